@@ -1,0 +1,127 @@
+"""Host-side mirror of the reference's codec classes (same names, argument meaning and error
+behaviour), calling the sm_100a kernels through the C ABI.
+
+Mirrors (paths relative to /root/reference/):
+  Inflate            lib/src/codecs/zlib/inflate.dart:12-116
+  ZLibDecoder(Web)   lib/src/codecs/zlib_decoder.dart:14-35, codecs/zlib/_zlib_decoder_web.dart:14-107
+  GZipDecoder(Web)   lib/src/codecs/gzip_decoder.dart:14-30, codecs/zlib/_gzip_decoder_web.dart:14-58
+  inflateBuffer      lib/src/codecs/zlib/inflate_buffer.dart:7
+
+In the Dart package these classes stay Dart and bind libb200z.so with dart:ffi (dart/);
+no Dart SDK exists in the build image, so the parity tests drive this Python mirror instead.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+from . import _ffi
+from .streams import BIG_ENDIAN, InputMemoryStream, OutputMemoryStream
+
+
+def _grow_call(fn, in_addr, in_len, first_cap):
+    """Call fn(out_addr, cap) -> (rc, out_len); retry with a larger buffer on E_NOSPC."""
+    cap = max(first_cap, 1 << 12)
+    while True:
+        out = (C.c_uint8 * cap)()
+        rc, n = fn(C.addressof(out), cap)
+        if rc == _ffi.E_NOSPC and cap < (1 << 40):
+            cap = max(cap * 2, n + (n >> 3))
+            continue
+        return rc, out, n
+
+
+class Inflate:
+    """`Inflate(bytes)` / `Inflate.stream(input, output:)`: all work happens in the constructor
+    (inflate.dart:23-40); bad data never raises -- decoding stops and the partial output is kept
+    (inflate.dart:150-151); `RangeError` cases raise DartRangeError."""
+
+    def __init__(self, data=None, output: OutputMemoryStream | None = None, uncompressed_size: int | None = None,
+                 _input: InputMemoryStream | None = None):
+        self._input = _input if _input is not None else InputMemoryStream(data if data is not None else b"")
+        self._output = output if output is not None else OutputMemoryStream(size=uncompressed_size)
+        self.status = _ffi.U_EOS
+        self._inflate(uncompressed_size)
+
+    @classmethod
+    def stream(cls, input: InputMemoryStream | None, output: OutputMemoryStream | None = None,
+               uncompressed_size: int | None = None) -> "Inflate":
+        return cls(None, output=output, uncompressed_size=uncompressed_size,
+                   _input=input if input is not None else InputMemoryStream(b""))
+
+    def _inflate(self, size_hint):
+        L = _ffi.ensure_init()
+        view = self._input.buffer[self._input.position:]
+        if len(view) == 0:
+            return
+        addr, n, keep = _ffi.as_buffer(view)
+        out_len, used, ust = C.c_size_t(0), C.c_size_t(0), C.c_int32(0)
+
+        def call(out_addr, cap):
+            rc = L.b200z_inflate_raw(addr, n, out_addr, cap, C.byref(out_len), C.byref(used), C.byref(ust))
+            return rc, out_len.value
+
+        rc, out, got = _grow_call(call, addr, n, size_hint or 4 * n + 1024)
+        self.status = ust.value
+        if got:
+            self._output.write_bytes(C.string_at(out, got))
+        self._input.position += used.value
+        _ffi.check(rc)
+
+    def get_bytes(self) -> bytes:
+        return self._output.get_bytes()
+
+
+def inflate_buffer(data) -> bytes:  # inflate_buffer.dart:7 (web variant: Inflate(data).getBytes())
+    return Inflate(data).get_bytes()
+
+
+class _FramedDecoder:
+    _fn = None
+    _has_raw = True
+
+    def decode_bytes(self, data, verify: bool = False, raw: bool = False) -> bytes:
+        """decodeBytes ignores decodeStream's bool and returns whatever was written
+        (_gzip_decoder_web.dart:19-24, _zlib_decoder_web.dart:21-28)."""
+        out = OutputMemoryStream()
+        self.decode_stream(InputMemoryStream(data), out, verify=verify, raw=raw)
+        return out.get_bytes()
+
+    def decode_stream(self, input: InputMemoryStream, output: OutputMemoryStream, verify: bool = False,
+                      raw: bool = False) -> bool:
+        L = _ffi.ensure_init()
+        view = input.buffer[input.position:]
+        addr, n, keep = _ffi.as_buffer(view)
+        out_len = C.c_size_t(0)
+        rc, out, got = _grow_call(lambda oa, cap: self._call(L, addr, n, verify, raw, oa, cap, out_len),
+                                  addr, n, self._first_cap(L, addr, n))
+        if got:
+            output.write_bytes(C.string_at(out, got))
+        input.position = len(input.buffer)
+        if rc == _ffi.E_DATA:
+            return False
+        _ffi.check(rc)
+        return True
+
+
+class ZLibDecoderWeb(_FramedDecoder):
+    def _first_cap(self, L, addr, n):
+        return 4 * n + 1024
+
+    def _call(self, L, addr, n, verify, raw, oa, cap, out_len):
+        rc = L.b200z_zlib_decode(addr, n, int(verify), int(raw), oa, cap, C.byref(out_len))
+        return rc, out_len.value
+
+
+class GZipDecoderWeb(_FramedDecoder):
+    def _first_cap(self, L, addr, n):
+        return L.b200z_gzip_bound(addr, n) or 4 * n + 1024
+
+    def _call(self, L, addr, n, verify, raw, oa, cap, out_len):
+        rc = L.b200z_gzip_decode(addr, n, int(verify), oa, cap, C.byref(out_len))
+        return rc, out_len.value
+
+
+# The platform-dispatched names (zlib_decoder.dart:14, gzip_decoder.dart:14) bind the same backend:
+# this is the `platformZLibDecoder` / `platformGZipDecoder` seam (_zlib_decoder.dart:1, _gzip_decoder.dart:1).
+ZLibDecoder = ZLibDecoderWeb
+GZipDecoder = GZipDecoderWeb

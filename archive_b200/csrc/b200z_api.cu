@@ -1,0 +1,688 @@
+// b200z_api.cu -- the C ABI (include/b200z.h): context, staging, and the host-side framing logic
+// that sits between the reference's codec classes and the kernels.
+//
+// Host logic restated here (reference, paths relative to /root/reference/):
+//   lib/src/codecs/zlib/_gzip_decoder_web.dart:27-138   member loop + header skip
+//   lib/src/codecs/zlib/_zlib_decoder_web.dart:31-107   stream loop + FCHECK/FDICT + Adler verify
+// The byte-level work (Huffman decode, LZ77, Adler-32) runs on the GPU; nothing here decodes.
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+#include <vector>
+
+#include "b200z_internal.h"
+
+namespace b200z {
+
+static thread_local char t_err[512] = "";
+static void set_err(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(t_err, sizeof t_err, fmt, ap);
+  va_end(ap);
+}
+
+static std::atomic<uint64_t> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = n + (n >> 3) + 4096;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      p = nullptr;
+      return e;
+    }
+    cap = want;
+    return cudaSuccess;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+struct PinBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = n + (n >> 2) + 4096;
+    cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+      p = nullptr;
+      return e;
+    }
+    cap = want;
+    return cudaSuccess;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct Ctx {
+  std::mutex mu;
+  bool inited = false;
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  DevBuf d_in, d_out, d_ws, d_meta, d_small;
+  PinBuf h_meta;
+};
+static Ctx g;
+
+#define CU(x)                                                                       \
+  do {                                                                              \
+    cudaError_t e__ = (x);                                                          \
+    if (e__ != cudaSuccess) {                                                       \
+      set_err("%s failed: %s (%s:%d)", #x, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return B200Z_E_NODEVICE;                                                      \
+    }                                                                               \
+  } while (0)
+
+static int require_init() {
+  if (!g.inited) {
+    set_err("b200z_init has not been called (or no CUDA device): there is no CPU fallback");
+    return B200Z_E_NODEVICE;
+  }
+  return B200Z_OK;
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------------------------
+// Adler-32 on the device (adler32.dart:29-52).  s1 = 1 + sum b_i ; s2 = n + sum (n - i) b_i  (mod 65521)
+// Each block reduces a 64 KiB tile to (sum, weighted sum); the host folds the per-tile pairs (a few
+// integers per 64 KiB -- framing arithmetic, not a pass over the data).
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t ADLER_TILE = 1u << 16;
+__global__ void __launch_bounds__(256) k_adler_tiles(const uint8_t *__restrict__ p, size_t n, uint64_t *__restrict__ part) {
+  const size_t base = (size_t)blockIdx.x * ADLER_TILE;
+  const uint32_t len = (uint32_t)min((size_t)ADLER_TILE, n - base);
+  uint64_t s = 0, ws = 0;  // ws = sum (len - i) * b_i  within the tile
+  for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) {
+    uint32_t b = p[base + i];
+    s += b;
+    ws += (uint64_t)(len - i) * b;
+  }
+  __shared__ uint64_t sh[2][8];
+  for (int d = 16; d >= 1; d >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, d);
+    ws += __shfl_xor_sync(0xffffffffu, ws, d);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sh[0][threadIdx.x >> 5] = s;
+    sh[1][threadIdx.x >> 5] = ws;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint64_t a = 0, b = 0;
+    for (int i = 0; i < 8; ++i) {
+      a += sh[0][i];
+      b += sh[1][i];
+    }
+    part[2 * blockIdx.x] = a;
+    part[2 * blockIdx.x + 1] = b;
+  }
+}
+
+// device buffer -> adler32 (blocking)
+static int device_adler32(const uint8_t *d, size_t n, uint32_t *out) {
+  const uint32_t MOD = 65521;
+  if (n == 0) {
+    *out = 1;
+    return B200Z_OK;
+  }
+  size_t tiles = (n + ADLER_TILE - 1) / ADLER_TILE;
+  CU(g.d_small.reserve(tiles * 16));
+  k_adler_tiles<<<(unsigned)tiles, 256, 0, g.stream>>>(d, n, (uint64_t *)g.d_small.p);
+  count_launch();
+  CU(cudaGetLastError());
+  std::vector<uint64_t> part(tiles * 2);
+  CU(cudaMemcpyAsync(part.data(), g.d_small.p, tiles * 16, cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  uint64_t s1 = 1, s2 = 0;
+  for (size_t t = 0; t < tiles; ++t) {
+    uint64_t len = (t + 1 == tiles) ? n - t * ADLER_TILE : ADLER_TILE;
+    uint64_t ts = part[2 * t] % MOD, tw = part[2 * t + 1] % MOD;
+    // appending a tile: s2' = s2 + len * s1 + tw ; s1' = s1 + ts
+    s2 = (s2 + (len % MOD) * s1 + tw) % MOD;
+    s1 = (s1 + ts) % MOD;
+  }
+  *out = (uint32_t)((s2 << 16) | s1);
+  return B200Z_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// batch plumbing
+// ---------------------------------------------------------------------------------------------
+struct MetaLayout {
+  size_t n;
+  size_t off_in_off, off_out_off, off_in_len, off_out_cap, off_out_len, off_status, off_in_used, bytes;
+  explicit MetaLayout(size_t n_) : n(n_) {
+    size_t o = 0;
+    off_in_off = o;
+    o += 8 * n;
+    off_out_off = o;
+    o += 8 * n;
+    off_in_len = o;
+    o += 4 * n;
+    off_out_cap = o;
+    o += 4 * n;
+    off_out_len = o;
+    o += 4 * n;
+    off_status = o;
+    o += 4 * n;
+    off_in_used = o;
+    o += 4 * n;
+    bytes = align_up(o, 256);
+  }
+  size_t inputs_bytes() const { return off_out_len; }
+};
+
+static size_t workspace_bytes(size_t n_units, size_t total_out_cap) {
+  return align_up(total_out_cap * 4 + 256, 256) + align_up(n_units * 4, 256);
+}
+
+// Runs one batch whose compressed bytes are ALREADY in g.d_in (at offset 0 = in_base) and whose
+// output goes to g.d_out.  Meta arrays are host arrays; results are copied back into them.
+static int run_batch_on_staged(const uint64_t *in_off, const uint32_t *in_len, const uint64_t *out_off,
+                               const uint32_t *out_cap, uint32_t *out_len, int32_t *status, uint32_t *in_used,
+                               size_t n, size_t out_extent) {
+  MetaLayout ml(n);
+  CU(g.h_meta.reserve(ml.bytes));
+  CU(g.d_meta.reserve(ml.bytes));
+  uint8_t *hm = (uint8_t *)g.h_meta.p;
+  memcpy(hm + ml.off_in_off, in_off, 8 * n);
+  memcpy(hm + ml.off_out_off, out_off, 8 * n);
+  memcpy(hm + ml.off_in_len, in_len, 4 * n);
+  memcpy(hm + ml.off_out_cap, out_cap, 4 * n);
+  CU(cudaMemcpyAsync(g.d_meta.p, hm, ml.inputs_bytes(), cudaMemcpyHostToDevice, g.stream));
+  const size_t ws = workspace_bytes(n, out_extent);
+  CU(g.d_ws.reserve(ws));
+  uint8_t *dm = (uint8_t *)g.d_meta.p;
+  InflateBatch b;
+  b.in_base = (const uint8_t *)g.d_in.p;
+  b.in_off = (const uint64_t *)(dm + ml.off_in_off);
+  b.in_len = (const uint32_t *)(dm + ml.off_in_len);
+  b.out_base = (uint8_t *)g.d_out.p;
+  b.out_off = (const uint64_t *)(dm + ml.off_out_off);
+  b.out_cap = (const uint32_t *)(dm + ml.off_out_cap);
+  b.out_len = (uint32_t *)(dm + ml.off_out_len);
+  b.status = (int32_t *)(dm + ml.off_status);
+  b.in_used = (uint32_t *)(dm + ml.off_in_used);
+  b.n_units = n;
+  b.workspace = g.d_ws.p;
+  b.tok_bytes = align_up(out_extent * 4 + 256, 256);
+  CU(launch_inflate(b, g.stream));
+  CU(cudaMemcpyAsync(hm + ml.off_out_len, dm + ml.off_out_len, ml.bytes - ml.off_out_len, cudaMemcpyDeviceToHost,
+                     g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  memcpy(out_len, hm + ml.off_out_len, 4 * n);
+  memcpy(status, hm + ml.off_status, 4 * n);
+  memcpy(in_used, hm + ml.off_in_used, 4 * n);
+  return B200Z_OK;
+}
+
+static int stage_input(const uint8_t *in, size_t n) {
+  CU(g.d_in.reserve(n + 64));
+  if (n) CU(cudaMemcpyAsync(g.d_in.p, in, n, cudaMemcpyHostToDevice, g.stream));
+  return B200Z_OK;
+}
+
+// largest possible DEFLATE expansion: a 258-byte match costs at least 2 bits
+static size_t max_inflate_out(size_t in_len) {
+  const size_t lim = (size_t)0xffffffffu;
+  if (in_len > lim / 1040) return lim;
+  return in_len * 1040 + 1024;
+}
+
+// one stream from staged input at [pos, in_total): returns unit results
+struct OneResult {
+  uint32_t out_len, in_used;
+  int32_t status;
+};
+static int run_one_staged(size_t pos, size_t in_total, size_t out_pos, size_t out_cap_total, OneResult *r) {
+  uint64_t io = pos, oo = out_pos;
+  size_t avail_in = in_total - pos;
+  uint32_t il = (uint32_t)(avail_in > 0xfffffff0u ? 0xfffffff0u : avail_in);
+  size_t room = out_cap_total - out_pos;
+  size_t mx = max_inflate_out(il);
+  if (room > mx) room = mx;
+  uint32_t oc = (uint32_t)(room > 0xfffffff0u ? 0xfffffff0u : room);
+  CU(g.d_out.reserve(out_pos + oc + 64));
+  return run_batch_on_staged(&io, &il, &oo, &oc, &r->out_len, &r->status, &r->in_used, 1, out_pos + oc);
+}
+
+static inline uint32_t le32(const uint8_t *p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }
+static inline uint32_t le16(const uint8_t *p) { return p[0] | (p[1] << 8); }
+
+// _readHeader (_gzip_decoder_web.dart:60-138).  Returns 1 ok, 0 "not gzip" (-> zlib fallback), -1 = the
+// Dart code would have thrown (readByte past the end).  *bsize = BGZF 'BC' member size hint or 0.
+static int gzip_header(const uint8_t *in, size_t n, size_t pos, size_t *hdr_end, size_t *bsize) {
+  *bsize = 0;
+  if (pos + 2 > n) return -1;
+  if (le16(in + pos) != 0x8b1f) return 0;
+  if (pos + 3 > n) return -1;
+  if (in[pos + 2] != 8) return 0;
+  if (pos + 10 > n) return -1;
+  uint8_t flags = in[pos + 3];
+  size_t p = pos + 10;
+  if (flags & 0x04) {
+    if (p + 2 > n) return -1;
+    size_t xlen = le16(in + p);
+    p += 2;
+    size_t xend = p + xlen;
+    if (xend > n) xend = n;  // readBytes clamps (input_stream.dart:132-136)
+    // look for the BGZF subfield  'B' 'C' SLEN=2  BSIZE(u16) = member size - 1
+    size_t q = p;
+    while (q + 4 <= xend) {
+      size_t slen = le16(in + q + 2);
+      if (in[q] == 'B' && in[q + 1] == 'C' && slen == 2 && q + 6 <= xend) *bsize = (size_t)le16(in + q + 4) + 1;
+      q += 4 + slen;
+    }
+    p = xend;
+  }
+  if (flags & 0x08) {
+    while (p < n && in[p] != 0) ++p;
+    if (p < n) ++p;
+  }
+  if (flags & 0x10) {
+    while (p < n && in[p] != 0) ++p;
+    if (p < n) ++p;
+  }
+  if (flags & 0x02) {
+    if (p + 2 > n) return -1;
+    p += 2;
+  }
+  *hdr_end = p;
+  return 1;
+}
+
+static int zlib_decode_staged(const uint8_t *in, size_t in_len, size_t pos, int verify, int raw, int big_endian,
+                              size_t out_pos, size_t out_cap, size_t *out_len_total);
+
+// GZip member loop on staged input.
+static int gzip_decode_staged(const uint8_t *in, size_t in_len, int verify, size_t out_cap, size_t *out_len_total) {
+  size_t pos = 0, out_pos = 0;
+  std::vector<uint64_t> v_in_off, v_out_off;
+  std::vector<uint32_t> v_in_len, v_out_cap, v_out_len, v_in_used;
+  std::vector<int32_t> v_status;
+  std::vector<size_t> v_next;
+  while (pos < in_len) {
+    // -------- gather a run of members that carry a size hint (BGZF 'BC' + ISIZE) --------
+    v_in_off.clear(); v_out_off.clear(); v_in_len.clear(); v_out_cap.clear(); v_next.clear();
+    size_t p = pos, o = out_pos;
+    while (p < in_len) {
+      size_t hdr_end, bsize;
+      int h = gzip_header(in, in_len, p, &hdr_end, &bsize);
+      if (h != 1 || bsize == 0) break;
+      size_t next = p + bsize;
+      if (next > in_len || next < hdr_end + 8) break;
+      uint32_t isize = le32(in + next - 4);
+      v_in_off.push_back(hdr_end);
+      v_in_len.push_back((uint32_t)(next - hdr_end));
+      v_out_off.push_back(o);
+      v_out_cap.push_back(isize);
+      v_next.push_back(next);
+      o += isize;
+      p = next;
+    }
+    size_t nb = v_in_off.size();
+    if (nb > 0) {
+      if (o > out_cap) {
+        *out_len_total = o;  // best knowledge of what is needed so far
+        set_err("gzip_decode: output needs at least %zu bytes, out_cap %zu", o, out_cap);
+        return B200Z_E_NOSPC;
+      }
+      CU(g.d_out.reserve(o + 64));
+      v_out_len.resize(nb); v_status.resize(nb); v_in_used.resize(nb);
+      int rc = run_batch_on_staged(v_in_off.data(), v_in_len.data(), v_out_off.data(), v_out_cap.data(),
+                                   v_out_len.data(), v_status.data(), v_in_used.data(), nb, o);
+      if (rc) return rc;
+      // accept the prefix whose hints were exact; anything else is redone the slow, hint-free way
+      size_t k = 0;
+      for (; k < nb; ++k) {
+        bool ok = v_status[k] == B200Z_U_DONE && v_out_len[k] == v_out_cap[k] &&
+                  (size_t)v_in_off[k] + v_in_used[k] + 8 == v_next[k];
+        if (!ok) break;
+      }
+      if (k > 0) {
+        pos = v_next[k - 1];
+        out_pos = v_out_off[k - 1] + v_out_len[k - 1];
+      }
+      if (k == nb) continue;
+    }
+    if (pos >= in_len) break;
+    // -------- one member without (valid) hints: decode it alone to learn where it ends --------
+    size_t hdr_end, bsize;
+    int h = gzip_header(in, in_len, pos, &hdr_end, &bsize);
+    if (h < 0) {
+      *out_len_total = out_pos;
+      set_err("gzip_decode: truncated header (Dart: RangeError)");
+      return B200Z_E_THROW;
+    }
+    if (h == 0)  // no gzip header: fall back to zlib on the same little-endian stream (:31-37)
+      return zlib_decode_staged(in, in_len, pos, verify, 0, /*big_endian=*/0, out_pos, out_cap, out_len_total);
+    OneResult r;
+    int rc = run_one_staged(hdr_end, in_len, out_pos, out_cap, &r);
+    if (rc) return rc;
+    out_pos += r.out_len;
+    *out_len_total = out_pos;
+    if (r.status == B200Z_U_NOSPC) {
+      set_err("gzip_decode: out_cap %zu too small", out_cap);
+      return B200Z_E_NOSPC;
+    }
+    if (r.status == B200Z_U_RANGE || r.status == B200Z_U_THROW) {
+      set_err("gzip_decode: member at %zu: Dart would throw RangeError (status %d)", pos, r.status);
+      return B200Z_E_THROW;
+    }
+    size_t after = hdr_end + r.in_used;
+    if (r.status != B200Z_U_DONE && r.status != B200Z_U_EOS) {
+      set_err("gzip_decode: member at %zu stopped with status %d", pos, r.status);
+      return B200Z_E_DATA;  // DESIGN.md "Divergences": reference keeps parsing from an unspecified position
+    }
+    if (after + 8 > in_len) {  // readUint32 x2 past the end (:40-41)
+      set_err("gzip_decode: truncated trailer (Dart: RangeError)");
+      return B200Z_E_THROW;
+    }
+    pos = after + 8;
+  }
+  *out_len_total = out_pos;
+  return B200Z_OK;
+}
+
+// _zlib_decoder_web.dart:31-107 on staged input.
+static int zlib_decode_staged(const uint8_t *in, size_t in_len, size_t pos, int verify, int raw, int big_endian,
+                              size_t out_pos, size_t out_cap, size_t *out_len_total) {
+  *out_len_total = out_pos;
+  while (pos < in_len) {
+    if (!raw) {
+      if (pos + 2 > in_len) {
+        set_err("zlib_decode: truncated header (Dart: RangeError)");
+        return B200Z_E_THROW;
+      }
+      uint32_t cmf = in[pos], flg = in[pos + 1];
+      pos += 2;
+      if ((cmf & 8) != 8) {  // :57 (sic)
+        set_err("zlib_decode: method != deflate");
+        return B200Z_E_DATA;
+      }
+      if (((cmf * 256) + flg) % 31 != 0) {
+        set_err("zlib_decode: bad FCHECK");
+        return B200Z_E_DATA;
+      }
+      if ((flg & 32) != 0) {
+        if (pos + 4 > in_len) {
+          set_err("zlib_decode: truncated DICTID (Dart: RangeError)");
+          return B200Z_E_THROW;
+        }
+        set_err("zlib_decode: FDICT not supported");
+        return B200Z_E_DATA;
+      }
+    }
+    // The reference commits stream k's bytes when stream k+1 starts or at the end (:82-84,:101-103);
+    // a failed Adler check drops only the failing stream.  Decoding straight into the final position
+    // and rolling the length back gives the same observable result.
+    OneResult r;
+    int rc = run_one_staged(pos, in_len, out_pos, out_cap, &r);
+    if (rc) return rc;
+    if (r.status == B200Z_U_NOSPC) {
+      *out_len_total = out_pos + r.out_len;
+      set_err("zlib_decode: out_cap %zu too small", out_cap);
+      return B200Z_E_NOSPC;
+    }
+    if (r.status == B200Z_U_RANGE || r.status == B200Z_U_THROW) {
+      set_err("zlib_decode: Dart would throw RangeError (status %d)", r.status);
+      return B200Z_E_THROW;
+    }
+    if (r.status == B200Z_U_BADCODE) {
+      *out_len_total = out_pos + r.out_len;
+      set_err("zlib_decode: unusable Huffman code set");
+      return B200Z_E_DATA;
+    }
+    pos += r.in_used;
+    if (r.status == B200Z_U_STOP) {
+      // Inflate gave up: the reference's stream position is then wherever its byte-wise bit buffer had
+      // got to (not rewound) -- unspecified; stop here with the partial output (DESIGN.md "Divergences").
+      *out_len_total = out_pos + r.out_len;
+      set_err("zlib_decode: inflate stopped early");
+      return B200Z_E_DATA;
+    }
+    if (!raw) {
+      if (pos + 4 > in_len) {
+        set_err("zlib_decode: truncated Adler-32 (Dart: RangeError)");
+        return B200Z_E_THROW;
+      }
+      uint32_t stored = big_endian ? ((uint32_t)in[pos] << 24 | in[pos + 1] << 16 | in[pos + 2] << 8 | in[pos + 3])
+                                   : le32(in + pos);
+      pos += 4;
+      if (verify) {
+        uint32_t a;
+        rc = device_adler32((const uint8_t *)g.d_out.p + out_pos, r.out_len, &a);
+        if (rc) return rc;
+        if (a != stored) {
+          set_err("zlib_decode: Adler-32 mismatch");
+          return B200Z_E_DATA;  // this stream's bytes are dropped (:91-94)
+        }
+      }
+    }
+    out_pos += r.out_len;
+    *out_len_total = out_pos;
+  }
+  return B200Z_OK;
+}
+
+}  // namespace b200z
+
+using namespace b200z;
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+const char *b200z_version(void) { return "b200z 0.1 (sm_100a)"; }
+const char *b200z_last_error(void) { return t_err; }
+uint64_t b200z_launch_count(void) { return g_launches.load(); }
+
+int b200z_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int b200z_init(int device, uint32_t flags) {
+  (void)flags;
+  std::lock_guard<std::mutex> lk(g.mu);
+  if (g.inited && g.device == device) return B200Z_OK;
+  int n = b200z_device_count();
+  if (n <= 0 || device < 0 || device >= n) {
+    set_err("b200z_init: CUDA device %d not available (%d visible): there is no CPU fallback", device, n);
+    return B200Z_E_NODEVICE;
+  }
+  CU(cudaSetDevice(device));
+  if (!g.stream) CU(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  g.device = device;
+  g.inited = true;
+  return B200Z_OK;
+}
+
+void b200z_shutdown(void) {
+  std::lock_guard<std::mutex> lk(g.mu);
+  if (!g.inited) return;
+  cudaSetDevice(g.device);
+  cudaStreamSynchronize(g.stream);
+  g.d_in.release(); g.d_out.release(); g.d_ws.release(); g.d_meta.release(); g.d_small.release();
+  g.h_meta.release();
+  cudaStreamDestroy(g.stream);
+  g.stream = nullptr;
+  g.inited = false;
+}
+
+void *b200z_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    set_err("b200z_host_alloc(%zu) failed", bytes);
+    return nullptr;
+  }
+  return p;
+}
+void b200z_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
+size_t b200z_inflate_workspace_bytes(size_t n_units, size_t total_in_bytes, size_t total_out_cap) {
+  (void)total_in_bytes;
+  return workspace_bytes(n_units, total_out_cap);
+}
+
+int b200z_inflate_batch_device(const uint8_t *d_in_base, const uint64_t *d_in_off, const uint32_t *d_in_len,
+                               uint8_t *d_out_base, const uint64_t *d_out_off, const uint32_t *d_out_cap,
+                               uint32_t *d_out_len, int32_t *d_status, uint32_t *d_in_used, size_t n_units,
+                               void *d_workspace, size_t workspace_bytes_, void *cuda_stream) {
+  int rc = require_init();
+  if (rc) return rc;
+  if (n_units == 0) return B200Z_OK;
+  const size_t ntok_bytes = align_up(n_units * 4, 256);
+  if (workspace_bytes_ < ntok_bytes + 256) {
+    set_err("inflate_batch_device: workspace too small");
+    return B200Z_E_ARG;
+  }
+  InflateBatch b;
+  b.in_base = d_in_base; b.in_off = d_in_off; b.in_len = d_in_len;
+  b.out_base = d_out_base; b.out_off = d_out_off; b.out_cap = d_out_cap;
+  b.out_len = d_out_len; b.status = d_status; b.in_used = d_in_used;
+  b.n_units = n_units;
+  b.workspace = d_workspace;
+  b.tok_bytes = workspace_bytes_ - ntok_bytes;
+  cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : g.stream;
+  CU(launch_inflate(b, s));
+  return B200Z_OK;
+}
+
+int b200z_inflate_batch(const uint8_t *in_base, size_t in_bytes, const uint64_t *in_off, const uint32_t *in_len,
+                        uint8_t *out_base, size_t out_bytes, const uint64_t *out_off, const uint32_t *out_cap,
+                        uint32_t *out_len, int32_t *status, uint32_t *in_used, size_t n_units) {
+  int rc = require_init();
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(g.mu);
+  CU(cudaSetDevice(g.device));
+  for (size_t u = 0; u < n_units; ++u) {
+    if (in_off[u] + in_len[u] > in_bytes || out_off[u] + out_cap[u] > out_bytes) {
+      set_err("inflate_batch: unit %zu exceeds the buffers", u);
+      return B200Z_E_ARG;
+    }
+  }
+  rc = stage_input(in_base, in_bytes);
+  if (rc) return rc;
+  CU(g.d_out.reserve(out_bytes + 64));
+  rc = run_batch_on_staged(in_off, in_len, out_off, out_cap, out_len, status, in_used, n_units, out_bytes);
+  if (rc) return rc;
+  if (out_bytes) CU(cudaMemcpyAsync(out_base, g.d_out.p, out_bytes, cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  return B200Z_OK;
+}
+
+int b200z_inflate_raw(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_cap, size_t *out_len,
+                      size_t *in_consumed, int32_t *unit_status) {
+  int rc = require_init();
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(g.mu);
+  CU(cudaSetDevice(g.device));
+  if (in_len > 0xfffffff0u) {
+    set_err("inflate_raw: streams above 4 GiB are not supported");
+    return B200Z_E_ARG;
+  }
+  rc = stage_input(in, in_len);
+  if (rc) return rc;
+  OneResult r{0, 0, B200Z_U_EOS};
+  if (in_len > 0) {
+    rc = run_one_staged(0, in_len, 0, out_cap, &r);
+    if (rc) return rc;
+    if (r.out_len) CU(cudaMemcpyAsync(out, g.d_out.p, r.out_len, cudaMemcpyDeviceToHost, g.stream));
+    CU(cudaStreamSynchronize(g.stream));
+  }
+  if (out_len) *out_len = r.out_len;
+  if (in_consumed) *in_consumed = r.in_used;
+  if (unit_status) *unit_status = r.status;
+  if (r.status == B200Z_U_NOSPC) {
+    set_err("inflate_raw: out_cap %zu too small", out_cap);
+    return B200Z_E_NOSPC;
+  }
+  if (r.status == B200Z_U_RANGE || r.status == B200Z_U_THROW) {
+    set_err("inflate_raw: Dart would throw RangeError (unit status %d)", r.status);
+    return B200Z_E_THROW;
+  }
+  return B200Z_OK;  // STOP / BADCODE: reference keeps the partial output silently
+}
+
+size_t b200z_gzip_bound(const uint8_t *in, size_t in_len) {
+  size_t pos = 0, total = 0;
+  while (pos < in_len) {
+    size_t hdr_end, bsize;
+    int h = gzip_header(in, in_len, pos, &hdr_end, &bsize);
+    if (h != 1 || bsize == 0) return 0;
+    size_t next = pos + bsize;
+    if (next > in_len || next < hdr_end + 8) return 0;
+    total += le32(in + next - 4);
+    pos = next;
+  }
+  return total;
+}
+
+int b200z_gzip_decode(const uint8_t *in, size_t in_len, int verify, uint8_t *out, size_t out_cap, size_t *out_len) {
+  int rc = require_init();
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(g.mu);
+  CU(cudaSetDevice(g.device));
+  rc = stage_input(in, in_len);
+  if (rc) return rc;
+  size_t n = 0;
+  rc = gzip_decode_staged(in, in_len, verify, out_cap, &n);
+  if (out_len) *out_len = n;
+  if (rc == B200Z_E_NOSPC || rc == B200Z_E_NODEVICE) return rc;
+  if (n > out_cap) n = out_cap;
+  if (n) CU(cudaMemcpyAsync(out, g.d_out.p, n, cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  return rc;
+}
+
+int b200z_zlib_decode(const uint8_t *in, size_t in_len, int verify, int raw, uint8_t *out, size_t out_cap,
+                      size_t *out_len) {
+  int rc = require_init();
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(g.mu);
+  CU(cudaSetDevice(g.device));
+  rc = stage_input(in, in_len);
+  if (rc) return rc;
+  size_t n = 0;
+  rc = zlib_decode_staged(in, in_len, 0, verify, raw, /*big_endian=*/1, 0, out_cap, &n);
+  if (out_len) *out_len = n;
+  if (rc == B200Z_E_NOSPC || rc == B200Z_E_NODEVICE) return rc;
+  if (n > out_cap) n = out_cap;
+  if (n) CU(cudaMemcpyAsync(out, g.d_out.p, n, cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,521 @@
+// inflate_decode.cuh -- per-stream DEFLATE decode logic shared by the sm_100a kernel
+// (inflate_kernels.cu) and the host-side logic emulation used by the CPU tests.
+//
+// Restates (reference, paths relative to /root/reference/):
+//   lib/src/codecs/zlib/inflate.dart:104-401, lib/src/codecs/zlib/_huffman_table.dart:9-46
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/b200z.h"
+
+#ifndef B200Z_LBITS
+#define B200Z_LBITS 9
+#endif
+#ifndef B200Z_DBITS
+#define B200Z_DBITS 7
+#endif
+
+#ifdef __CUDA_ARCH__
+#define B200Z_LDG(p) __ldg(p)
+#define B200Z_BREV(x) __brev(x)
+#else
+#define B200Z_LDG(p) (*(p))
+static inline uint32_t b200z_host_brev(uint32_t v) {
+  v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
+  v = ((v >> 2) & 0x33333333u) | ((v & 0x33333333u) << 2);
+  v = ((v >> 4) & 0x0f0f0f0fu) | ((v & 0x0f0f0f0fu) << 4);
+  v = ((v >> 8) & 0x00ff00ffu) | ((v & 0x00ff00ffu) << 8);
+  return (v >> 16) | (v << 16);
+}
+#define B200Z_BREV(x) b200z_host_brev(x)
+#endif
+#ifdef __CUDACC__
+#define B200Z_HD __device__ __forceinline__
+#define B200Z_CONST __constant__
+#else
+#define B200Z_HD inline
+#define B200Z_CONST static const
+#include <algorithm>
+using std::max;
+using std::min;
+#endif
+
+namespace b200z {
+
+// ---------------------------------------------------------------------------------------------
+// constants (inflate.dart:738-894)
+// ---------------------------------------------------------------------------------------------
+B200Z_CONST uint8_t c_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+// length symbol 257+i -> (base << 4) | extra_bits
+B200Z_CONST uint16_t c_len_tab[32] = {
+    (3 << 4) | 0,   (4 << 4) | 0,   (5 << 4) | 0,   (6 << 4) | 0,   (7 << 4) | 0,   (8 << 4) | 0,
+    (9 << 4) | 0,   (10 << 4) | 0,  (11 << 4) | 1,  (13 << 4) | 1,  (15 << 4) | 1,  (17 << 4) | 1,
+    (19 << 4) | 2,  (23 << 4) | 2,  (27 << 4) | 2,  (31 << 4) | 2,  (35 << 4) | 3,  (43 << 4) | 3,
+    (51 << 4) | 3,  (59 << 4) | 3,  (67 << 4) | 4,  (83 << 4) | 4,  (99 << 4) | 4,  (115 << 4) | 4,
+    (131 << 4) | 5, (163 << 4) | 5, (195 << 4) | 5, (227 << 4) | 5, (258 << 4) | 0, 0, 0, 0};
+// distance symbol -> (base << 4) | extra_bits
+B200Z_CONST uint32_t c_dist_tab[32] = {
+    (1 << 4) | 0,     (2 << 4) | 0,     (3 << 4) | 0,      (4 << 4) | 0,      (5 << 4) | 1,      (7 << 4) | 1,
+    (9 << 4) | 2,     (13 << 4) | 2,    (17 << 4) | 3,     (25 << 4) | 3,     (33 << 4) | 4,     (49 << 4) | 4,
+    (65 << 4) | 5,    (97 << 4) | 5,    (129 << 4) | 6,    (193 << 4) | 6,    (257 << 4) | 7,    (385 << 4) | 7,
+    (513 << 4) | 8,   (769 << 4) | 8,   (1025 << 4) | 9,   (1537 << 4) | 9,   (2049 << 4) | 10,  (3073 << 4) | 10,
+    (4097 << 4) | 11, (6145 << 4) | 11, (8193 << 4) | 12,  (12289 << 4) | 12, (16385 << 4) | 13, (24577 << 4) | 13,
+    0, 0};
+
+// token encoding (uint32):
+//   literal : 0x80000000 | byte
+//   match   : (len << 16) | dist          len 1..258 (bit 31/30 clear), dist 1..32768
+//   stored  : 0x40000000 | (pos >> 30) << 16 | len (3..65535), followed by ONE payload word =
+//             pos & 0x3fffffff (pos = byte offset of the run in the unit's input; top bits 00 so a
+//             payload never looks like a stored token); the pair never straddles a group of 32
+//             tokens (a nop pads).
+//   nop     : 0
+#define TOK_LIT 0x80000000u
+#define TOK_STORED 0x40000000u
+
+constexpr int LBITS = B200Z_LBITS;  // primary literal/length LUT bits
+constexpr int DBITS = B200Z_DBITS;  // primary distance LUT bits
+constexpr int LUT_HALFWORDS = (1 << LBITS) + (1 << DBITS);
+constexpr int LANE_STRIDE_WORDS = LUT_HALFWORDS / 2 + 1;  // +1 word: same index -> different bank per lane
+constexpr int CONST_WORDS = 16 + 32;                       // len table (32 x u16) + dist table (32 x u32)
+
+static inline size_t inflate_decode_smem_bytes(int warps_per_block, int units_per_warp) {
+  return (size_t)(CONST_WORDS + warps_per_block * units_per_warp * LANE_STRIDE_WORDS) * 4;
+}
+
+// Canonical-code side tables for codes longer than the LUT (rare): per lane, in local memory.
+struct SlowTab {
+  uint16_t first[16];  // first canonical code of each length
+  uint16_t count[16];  // number of codes of each length
+  uint16_t offs[16];   // index into perm of the first symbol of each length
+  uint16_t perm[288];  // symbols sorted by (length, symbol)
+  uint8_t maxlen;      // HuffmanTable.maxCodeLength (_huffman_table.dart:12-15)
+};
+struct SlowTabD {
+  uint16_t first[16];
+  uint16_t count[16];
+  uint16_t offs[16];
+  uint8_t perm[32];
+  uint8_t maxlen;
+};
+
+// ---------------------------------------------------------------------------------------------
+// bit reader: LSB-first (inflate.dart:159-184), refilled 32 aligned bits at a time.
+//   rem_bits() is the exact number of stream bits not yet consumed; it is what the reference's
+//   "isEOS while _bitBufferLen < n" tests (inflate.dart:166-168,192-195) see.
+// ---------------------------------------------------------------------------------------------
+struct BitReader {
+  const uint32_t *w;  // aligned word base of the unit
+  uint64_t buf;
+  int cnt;          // bits in buf (may include `pad` invalid bits once widx >= nw)
+  uint32_t widx;    // next word to load
+  uint32_t nw;      // words covering the unit
+  uint32_t lead;    // byte offset of the unit inside word 0
+  uint32_t in_len;  // unit bytes
+
+  B200Z_HD void seek(uint32_t byte_pos) {
+    uint32_t a = lead + byte_pos;
+    widx = a >> 2;
+    uint32_t sh = (a & 3) * 8;
+    uint32_t v = (widx < nw) ? B200Z_LDG(w + widx) : 0u;
+    widx++;
+    buf = (uint64_t)(v >> sh);
+    cnt = 32 - (int)sh;
+  }
+  B200Z_HD void refill() {
+    if (cnt < 32) {
+      uint32_t v = (widx < nw) ? B200Z_LDG(w + widx) : 0u;
+      widx++;
+      buf |= (uint64_t)v << cnt;
+      cnt += 32;
+    }
+  }
+  // all bits in buf valid and >= 32 of them after refill()
+  B200Z_HD bool fast() const { return widx < nw; }
+  B200Z_HD long long rem_bits() const {
+    return (long long)cnt + 32ll * ((long long)nw - (long long)widx) -
+           (32ll * nw - 8ll * ((long long)lead + in_len));
+  }
+  B200Z_HD uint32_t peek(int n) const { return (uint32_t)buf & ((1u << n) - 1u); }
+  B200Z_HD void drop(int n) {
+    buf >>= n;
+    cnt -= n;
+  }
+  // _readBits: -1 when fewer than n bits remain (then nothing is consumed that matters)
+  B200Z_HD int read_bits_checked(int n) {
+    if (n == 0) return 0;
+    refill();
+    if (!fast() && rem_bits() < n) return -1;
+    int v = (int)peek(n);
+    drop(n);
+    return v;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Build the LUT + slow tables for one alphabet from code lengths (HuffmanTable ctor restated for a
+// two-level layout).  Returns false when the set is over-subscribed (reference: later writes win in
+// a flat table -- garbage; here: B200Z_U_BADCODE).
+// ---------------------------------------------------------------------------------------------
+template <int TBITS, typename PermT>
+B200Z_HD bool build_table(const uint8_t *lens, int n, uint16_t *lut, uint16_t *first,
+                                            uint16_t *count, uint16_t *offs, PermT *perm, uint8_t *maxlen) {
+  for (int l = 0; l < 16; ++l) count[l] = 0;
+  int mx = 0;
+  for (int i = 0; i < n; ++i) {
+    int l = lens[i];
+    count[l]++;
+    mx = max(mx, l);
+  }
+  *maxlen = (uint8_t)mx;
+  count[0] = 0;
+  // Kraft check
+  int left = 1;
+  bool over = false;
+  for (int l = 1; l < 16; ++l) {
+    left <<= 1;
+    left -= count[l];
+    if (left < 0) over = true;
+  }
+  uint16_t next[16];
+  {
+    int code = 0, o = 0;
+    for (int l = 1; l < 16; ++l) {
+      code = (code + count[l - 1]) << 1;
+      first[l] = (uint16_t)code;
+      next[l] = (uint16_t)code;
+      offs[l] = (uint16_t)o;
+      o += count[l];
+    }
+    first[0] = 0;
+    offs[0] = 0;
+  }
+  uint32_t *lut32 = reinterpret_cast<uint32_t *>(lut);
+  for (int i = 0; i < (1 << TBITS) / 2; ++i) lut32[i] = 0;
+  if (over) return false;
+  uint16_t run[16];
+  for (int l = 0; l < 16; ++l) run[l] = offs[l];
+  for (int s = 0; s < n; ++s) {
+    int l = lens[s];
+    if (l == 0) continue;
+    uint32_t c = next[l]++;
+    perm[run[l]++] = (PermT)s;
+    if (l <= TBITS) {
+      uint32_t r = B200Z_BREV(c) >> (32 - l);
+      uint16_t e = (uint16_t)((s << 4) | l);
+      for (uint32_t j = r; j < (1u << TBITS); j += (1u << l)) lut[j] = e;
+    }
+  }
+  return true;
+}
+
+// canonical decode of a code longer than TBITS (or a hole).  Returns length, 0 = no code matches.
+template <int TBITS, typename PermT>
+B200Z_HD int slow_decode(uint32_t bits15, const uint16_t *first, const uint16_t *count,
+                                           const uint16_t *offs, const PermT *perm, int maxlen, int *sym) {
+  uint32_t rev = B200Z_BREV(bits15) >> 17;  // first stream bit = MSB of a 15-bit value
+  for (int l = 1; l <= maxlen; ++l) {
+    uint32_t code = rev >> (15 - l);
+    uint32_t d = code - first[l];
+    if (d < count[l]) {
+      *sym = perm[offs[l] + d];
+      return l;
+    }
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// One stream: DEFLATE bits -> token stream.  Runs as one LANE of k_inflate_decode (and, compiled as
+// plain C++, inside tests/host_emul to check the logic against the oracle without a GPU).
+// ---------------------------------------------------------------------------------------------
+struct UnitResult {
+  uint32_t ntok, out_len, in_used;
+  int32_t status;
+};
+
+B200Z_HD UnitResult inflate_decode_unit(const uint8_t *in, uint32_t in_len, uint32_t cap, uint32_t *tok,
+                                        uint16_t *lut_l, uint16_t *lut_d, const uint16_t *s_len_tab,
+                                        const uint32_t *s_dist_tab) {
+  SlowTab sl;
+  SlowTabD sd;
+  uint8_t lens[320];
+
+  BitReader br;
+  {
+    uintptr_t a = reinterpret_cast<uintptr_t>(in);
+    br.lead = (uint32_t)(a & 3);
+    br.w = reinterpret_cast<const uint32_t *>(a - br.lead);
+    br.in_len = in_len;
+    br.nw = (uint32_t)(((uint64_t)br.lead + br.in_len + 3) >> 2);
+    br.seek(0);
+  }
+  uint32_t nt = 0;
+  uint32_t olen = 0;
+  int st = B200Z_U_EOS;
+  bool in_block = false;
+  bool final_block = false;
+  int maxl = 0, maxd = 0;
+
+  for (;;) {
+    if (!in_block) {
+      // ---------------- block boundary: _inflate loop + _parseBlock (inflate.dart:111-156) -------------
+      if (final_block) {
+        st = B200Z_U_DONE;
+        break;
+      }
+      br.refill();
+      if (br.rem_bits() < 8) {  // isEOS: every byte already pulled into the bit buffer
+        st = B200Z_U_EOS;
+        break;
+      }
+      uint32_t hdr = br.peek(3);
+      br.drop(3);
+      final_block = hdr & 1;
+      uint32_t type = hdr >> 1;
+      if (type == 0) {
+        // ---- stored (inflate.dart:213-235) ----
+        int k = (int)(br.rem_bits() & 7);
+        br.drop(k);
+        long long rem_bytes = br.rem_bits() >> 3;
+        uint32_t pos = br.in_len - (uint32_t)rem_bytes;
+        long long len = -1, nlen;
+        if (rem_bytes >= 2) {
+          br.refill();
+          len = br.peek(16);
+          br.drop(16);
+          rem_bytes -= 2;
+          pos += 2;
+        } else {
+          rem_bytes = 0;  // the short read swallowed what was left
+          pos = br.in_len;
+        }
+        if (rem_bytes >= 2) {
+          br.refill();
+          nlen = (long long)br.peek(16) ^ 0xffff;
+          br.drop(16);
+          rem_bytes -= 2;
+          pos += 2;
+        } else {
+          nlen = -1ll ^ 0xffff;
+          rem_bytes = 0;
+          pos = br.in_len;
+        }
+        if (len != 0 && len != nlen) {
+          st = B200Z_U_STOP;
+          break;
+        }
+        if (len > rem_bytes) {
+          st = B200Z_U_STOP;
+          break;
+        }
+        if (len > 0) {
+          if ((unsigned long long)olen + len > cap) {
+            st = B200Z_U_NOSPC;
+            break;
+          }
+          if (len < 3) {
+            const uint8_t *src = reinterpret_cast<const uint8_t *>(br.w) + br.lead + pos;
+            for (int i = 0; i < (int)len; ++i) tok[nt++] = TOK_LIT | src[i];
+          } else {
+            if ((nt & 31) == 31) tok[nt++] = 0;
+            tok[nt++] = TOK_STORED | ((pos >> 30) << 16) | (uint32_t)len;
+            tok[nt++] = pos & 0x3fffffffu;
+          }
+          olen += (uint32_t)len;
+        }
+        br.seek(pos + (uint32_t)len);
+        continue;
+      } else if (type == 1) {
+        // ---- fixed tables (inflate.dart:408-735): 288 lit/len lengths, 30 distance lengths ----
+        for (int i = 0; i < 288; ++i) lens[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8;
+        build_table<LBITS, uint16_t>(lens, 288, lut_l, sl.first, sl.count, sl.offs, sl.perm, &sl.maxlen);
+        for (int i = 0; i < 30; ++i) lens[i] = 5;
+        build_table<DBITS, uint8_t>(lens, 30, lut_d, sd.first, sd.count, sd.offs, sd.perm, &sd.maxlen);
+      } else if (type == 2) {
+        // ---- dynamic (inflate.dart:239-298) ----
+        int hlit = br.read_bits_checked(5);
+        if (hlit < 0) { st = B200Z_U_STOP; break; }
+        hlit += 257;
+        if (hlit > 288) { st = B200Z_U_STOP; break; }
+        int hdist = br.read_bits_checked(5);
+        if (hdist < 0) { st = B200Z_U_STOP; break; }
+        hdist += 1;
+        if (hdist > 32) { st = B200Z_U_STOP; break; }
+        int hclen = br.read_bits_checked(4);
+        if (hclen < 0) { st = B200Z_U_STOP; break; }
+        hclen += 4;
+        if (hclen > 19) { st = B200Z_U_STOP; break; }
+        for (int i = 0; i < 19; ++i) lens[i] = 0;
+        bool bad = false;
+        for (int i = 0; i < hclen; ++i) {
+          int l = br.read_bits_checked(3);
+          if (l < 0) { bad = true; break; }
+          lens[c_order[i]] = (uint8_t)l;
+        }
+        if (bad) { st = B200Z_U_STOP; break; }
+        // code-length alphabet: 7-bit LUT in the (not yet built) lit/len LUT area
+        uint8_t clmax;
+        {
+          uint16_t f[16], c[16], o[16];
+          uint8_t pm[19];
+          if (!build_table<7, uint8_t>(lens, 19, lut_l, f, c, o, pm, &clmax)) { st = B200Z_U_BADCODE; break; }
+        }
+        // _decode (inflate.dart:345-401)
+        const int num = hlit + hdist;
+        int i = 0, prev = 0;
+        int err = 0;
+        while (i < num) {
+          br.refill();
+          if (!br.fast() && br.rem_bits() < clmax) { err = B200Z_U_STOP; break; }
+          uint32_t e = lut_l[br.peek(7)];
+          int l = e & 15;
+          int code = e >> 4;
+          // l == 0: hole in an incomplete set -- the reference's flat table yields (len 0, sym 0)
+          // (_huffman_table.dart:22), i.e. a zero length for this symbol and no bits consumed.
+          br.drop(l);
+          int repeat;
+          if (code < 16) {
+            lens[i++] = (uint8_t)code;
+            prev = code;
+            continue;
+          } else if (code == 16) {
+            repeat = br.read_bits_checked(2);
+            if (repeat < 0) { err = B200Z_U_STOP; break; }
+            repeat += 3;
+          } else if (code == 17) {
+            repeat = br.read_bits_checked(3);
+            if (repeat < 0) { err = B200Z_U_STOP; break; }
+            repeat += 3;
+            prev = 0;
+          } else {
+            repeat = br.read_bits_checked(7);
+            if (repeat < 0) { err = B200Z_U_STOP; break; }
+            repeat += 11;
+            prev = 0;
+          }
+          if (i + repeat > num) { err = B200Z_U_THROW; break; }
+          for (int k = 0; k < repeat; ++k) lens[i++] = (uint8_t)prev;
+        }
+        if (err) { st = err; break; }
+        for (int k = hdist; k < 32; ++k) lens[hlit + k] = 0;
+        bool ok = build_table<DBITS, uint8_t>(lens + hlit, hdist, lut_d, sd.first, sd.count, sd.offs, sd.perm, &sd.maxlen);
+        ok = build_table<LBITS, uint16_t>(lens, hlit, lut_l, sl.first, sl.count, sl.offs, sl.perm, &sl.maxlen) && ok;
+        if (!ok) { st = B200Z_U_BADCODE; break; }
+      } else {
+        st = B200Z_U_STOP;
+        break;
+      }
+      maxl = sl.maxlen;
+      maxd = sd.maxlen;
+      in_block = true;
+    }
+
+    // ---------------- one token: _decodeHuffman (inflate.dart:300-343) -------------------------------
+    br.refill();
+    const bool careful = !br.fast();
+    if (careful && br.rem_bits() < maxl) {  // _readCodeByTable short read (quirk Q1)
+      st = B200Z_U_STOP;
+      break;
+    }
+    uint32_t e = lut_l[br.peek(LBITS)];
+    int n = e & 15;
+    int sym = e >> 4;
+    if (n == 0) {
+      n = slow_decode<LBITS, uint16_t>(br.peek(15), sl.first, sl.count, sl.offs, sl.perm, maxl, &sym);
+      if (n == 0) {  // hole: reference would emit literal 0 for ever (or until OOM)
+        st = B200Z_U_BADCODE;
+        break;
+      }
+    }
+    br.drop(n);
+    if (sym < 256) {
+      if (olen >= cap) {
+        st = B200Z_U_NOSPC;
+        break;
+      }
+      tok[nt++] = TOK_LIT | (uint32_t)sym;
+      olen++;
+      continue;
+    }
+    if (sym == 256) {
+      in_block = false;
+      continue;
+    }
+    if (sym > 285) {
+      st = B200Z_U_STOP;
+      break;
+    }
+    uint32_t le = s_len_tab[sym - 257];
+    int lx = le & 15;
+    int mlen = (int)(le >> 4);
+    if (!careful) {
+      mlen += (int)br.peek(lx);
+      br.drop(lx);
+    } else {
+      int x = 0;
+      if (lx) {
+        if (br.rem_bits() < lx) x = -1;  // _readBits -> -1 is ADDED to the base (inflate.dart:323)
+        else { x = (int)br.peek(lx); br.drop(lx); }
+      }
+      mlen += x;
+    }
+    br.refill();
+    const bool careful2 = !br.fast();
+    if (careful2 && br.rem_bits() < maxd) {
+      st = B200Z_U_STOP;
+      break;
+    }
+    uint32_t de = lut_d[br.peek(DBITS)];
+    int dn = de & 15;
+    int dsym = de >> 4;
+    if (dn == 0) {
+      dn = slow_decode<DBITS, uint8_t>(br.peek(15), sd.first, sd.count, sd.offs, sd.perm, maxd, &dsym);
+      if (dn == 0) dsym = 0;  // hole in the flat table: (len 0, sym 0) (_huffman_table.dart:22)
+    }
+    br.drop(dn);
+    if (dsym > 29) {
+      st = B200Z_U_STOP;
+      break;
+    }
+    uint32_t dd = s_dist_tab[dsym];
+    int dx = dd & 15;
+    int dist = (int)(dd >> 4);
+    if (!careful2) {
+      dist += (int)br.peek(dx);
+      br.drop(dx);
+    } else {
+      int x = 0;
+      if (dx) {
+        if (br.rem_bits() < dx) x = -1;
+        else { x = (int)br.peek(dx); br.drop(dx); }
+      }
+      dist += x;
+    }
+    // writeBackReference (output_memory_stream.dart:79-98)
+    if (dist <= 0 || (uint32_t)dist > olen) {  // dist 0 only via a truncated extra-bits read
+      st = B200Z_U_RANGE;
+      break;
+    }
+    if (olen + (uint32_t)mlen > cap) {
+      st = B200Z_U_NOSPC;
+      break;
+    }
+    tok[nt++] = ((uint32_t)mlen << 16) | (uint32_t)dist;
+    olen += (uint32_t)mlen;
+  }
+
+  UnitResult r;
+  r.ntok = nt;
+  r.out_len = olen;
+  r.status = st;
+  {
+    long long rem = br.rem_bits();
+    if (rem < 0) rem = 0;
+    r.in_used = br.in_len - (uint32_t)(rem >> 3);  // whole unread bytes are given back (inflate.dart:337-340)
+  }
+  return r;
+}
+
+}  // namespace b200z

@@ -1,0 +1,251 @@
+// inflate_kernels.cu -- sm_100a DEFLATE decode for batches of independent raw DEFLATE streams.
+//
+// Replaces (reference, paths relative to /root/reference/):
+//   lib/src/codecs/zlib/inflate.dart:104-401   Inflate._inflate/_parseBlock/_parseDynamicHuffmanBlock/
+//                                              _decodeHuffman/_decode/_readBits/_readCodeByTable
+//   lib/src/codecs/zlib/_huffman_table.dart:9-46  HuffmanTable
+//   lib/src/util/output_memory_stream.dart:41-98  writeByte / writeBackReference
+//
+// Two kernels (DESIGN.md "K1"):
+//   k_inflate_decode  lane-per-stream: every lane of a warp walks its OWN stream in SIMT lockstep
+//                     (table lookup -> shift -> next lookup is a serial chain per stream, so the
+//                     only data parallelism is across streams).  Per-lane Huffman LUTs live in shared
+//                     memory; the compressed bytes are read through L1 in aligned 32-bit words.  The
+//                     output of this phase is a TOKEN stream per unit (literal / match / stored-run),
+//                     not bytes: resolving LZ77 copies needs the warp, not a lane.
+//   k_inflate_expand  warp-per-stream: turns tokens into bytes.  32 tokens -> warp prefix sum of
+//                     lengths -> every lane owns ONE OUTPUT BYTE of a 32-byte window, finds its token
+//                     by a shuffle binary search, and resolves out[p] = out[p - dist] (chasing through
+//                     bytes of the same window that are not written yet).
+#include "b200z_internal.h"
+#include "inflate_decode.cuh"
+
+#include <stdlib.h>
+
+namespace b200z {
+
+// ---------------------------------------------------------------------------------------------
+// phase 1
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(B200Z_DECODE_THREADS)
+k_inflate_decode(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__ in_off,
+                 const uint32_t *__restrict__ in_len, const uint64_t *__restrict__ out_off,
+                 const uint32_t *__restrict__ out_cap, uint32_t *__restrict__ tokens,
+                 uint32_t *__restrict__ ntok, uint32_t *__restrict__ out_len, int32_t *__restrict__ status,
+                 uint32_t *__restrict__ in_used, uint32_t n_units, int units_per_warp) {
+  extern __shared__ uint32_t smem[];
+  uint16_t *s_len_tab = reinterpret_cast<uint16_t *>(smem);
+  uint32_t *s_dist_tab = smem + 16;
+  for (int i = threadIdx.x; i < 32; i += blockDim.x) {
+    s_len_tab[i] = c_len_tab[i];
+    s_dist_tab[i] = c_dist_tab[i];
+  }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const int warp_in_block = threadIdx.x >> 5;
+  const uint32_t gwarp = blockIdx.x * (blockDim.x >> 5) + warp_in_block;
+  if (lane >= units_per_warp) return;
+  const uint32_t unit = gwarp * units_per_warp + lane;
+  if (unit >= n_units) return;
+
+  uint16_t *lut_l = reinterpret_cast<uint16_t *>(smem + CONST_WORDS + (warp_in_block * units_per_warp + lane) * LANE_STRIDE_WORDS);
+  uint16_t *lut_d = lut_l + (1 << LBITS);
+
+  uint32_t *tok = tokens + out_off[unit];  // token region mirrors the output layout (<= 1 token per byte)
+  const UnitResult r = inflate_decode_unit(in_base + in_off[unit], in_len[unit], out_cap[unit], tok, lut_l, lut_d,
+                                           s_len_tab, s_dist_tab);
+  ntok[unit] = r.ntok;
+  out_len[unit] = r.out_len;
+  status[unit] = r.status;
+  in_used[unit] = r.in_used;
+}
+
+// ---------------------------------------------------------------------------------------------
+// phase 2
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t tok_len(uint32_t t, bool payload) {
+  if (payload) return 0;
+  if (t & TOK_LIT) return 1;
+  if (t & TOK_STORED) return t & 0xffff;
+  return t >> 16;
+}
+
+__global__ void __launch_bounds__(B200Z_EXPAND_THREADS)
+k_inflate_expand(const uint32_t *__restrict__ tokens, const uint32_t *__restrict__ ntok,
+                 const uint8_t *__restrict__ in_base, const uint64_t *__restrict__ in_off,
+                 uint8_t *out_base, const uint64_t *__restrict__ out_off, uint32_t n_units) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t unit = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; unit < n_units; unit += warps) {
+    const uint32_t *T = tokens + out_off[unit];
+    const uint32_t nt = ntok[unit];
+    uint8_t *out = out_base + out_off[unit];
+    const uint8_t *in = in_base + in_off[unit];
+    uint32_t pos0 = 0;
+    for (uint32_t g = 0; g < nt; g += 32) {
+      uint32_t t = (g + lane < nt) ? T[g + lane] : 0u;
+      uint32_t tprev = __shfl_up_sync(FULL, t, 1);
+      const bool payload = lane > 0 && (tprev >> 30) == 1u;  // payload words have top bits 00: no chains
+      uint32_t len = tok_len(t, payload);
+      // inclusive prefix sum of lengths
+      uint32_t incl = len;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        uint32_t v = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += v;
+      }
+      const uint32_t total = __shfl_sync(FULL, incl, 31);
+      const uint32_t start = incl - len;  // relative to pos0
+      const bool is_stored = !payload && (t & 0xC0000000u) == TOK_STORED;
+      unsigned stored_mask = __ballot_sync(FULL, is_stored);
+
+      if (stored_mask == 0) {
+        // ---- byte-parallel windows ----
+        for (uint32_t w = 0; w < total; w += 32) {
+          const uint32_t p = w + lane;
+          const bool active = p < total;
+          // first j with incl_j > p
+          int j = 0;
+#pragma unroll
+          for (int s = 16; s >= 1; s >>= 1) {
+            uint32_t v = __shfl_sync(FULL, incl, j + s - 1);
+            if (v <= p) j += s;
+          }
+          j &= 31;
+          uint32_t tj = __shfl_sync(FULL, t, j);
+          uint32_t sj = __shfl_sync(FULL, start, j);
+          bool have = !active || (tj & TOK_LIT);
+          uint32_t byte = tj & 0xff;
+          int src = 0;
+          if (!have) {
+            uint32_t dist = tj & 0xffff;
+            src = (int)p - (int)dist;
+            if (src >= (int)sj) {  // overlapping run: fold whole periods back before the match
+              int k = (src - (int)sj) / (int)dist + 1;
+              src -= k * (int)dist;
+            }
+          }
+          // chase sources that are still inside this (unwritten) window
+          while (__any_sync(FULL, !have && src >= (int)w)) {
+            const bool need = !have && src >= (int)w;
+            uint32_t q = need ? (uint32_t)src : 0u;
+            int j2 = 0;
+#pragma unroll
+            for (int s = 16; s >= 1; s >>= 1) {
+              uint32_t v = __shfl_sync(FULL, incl, j2 + s - 1);
+              if (v <= q) j2 += s;
+            }
+            j2 &= 31;
+            uint32_t t2 = __shfl_sync(FULL, t, j2);
+            uint32_t s2 = __shfl_sync(FULL, start, j2);
+            if (need) {
+              if (t2 & TOK_LIT) {
+                byte = t2 & 0xff;
+                have = true;
+              } else {
+                uint32_t d2 = t2 & 0xffff;
+                src = (int)q - (int)d2;
+                if (src >= (int)s2) {
+                  int k = (src - (int)s2) / (int)d2 + 1;
+                  src -= k * (int)d2;
+                }
+              }
+            }
+          }
+          if (active) {
+            if (!have) byte = out[(long long)pos0 + src];
+            out[pos0 + p] = (uint8_t)byte;
+          }
+          __syncwarp();
+        }
+      } else {
+        // ---- rare: group holds a stored run -> walk the 32 tokens in order, warp-cooperatively ----
+        for (int i = 0; i < 32; ++i) {
+          uint32_t ti = __shfl_sync(FULL, t, i);
+          uint32_t li = __shfl_sync(FULL, len, i);
+          uint32_t si = __shfl_sync(FULL, start, i);
+          uint32_t nx = __shfl_sync(FULL, t, (i + 1) & 31);
+          if (li == 0) continue;
+          uint8_t *dst = out + pos0 + si;
+          if (ti & TOK_LIT) {
+            if (lane == 0) dst[0] = (uint8_t)ti;
+          } else if ((stored_mask >> i) & 1u) {
+            const uint8_t *srcp = in + (((size_t)((ti >> 16) & 3u) << 30) | nx);
+            for (uint32_t b = lane; b < li; b += 32) dst[b] = srcp[b];
+          } else {
+            uint32_t dist = ti & 0xffff;
+            const uint8_t *srcp = dst - dist;
+            if (dist >= li) {
+              for (uint32_t b = lane; b < li; b += 32) dst[b] = srcp[b];
+            } else {
+              for (uint32_t b = lane; b < li; b += 32) dst[b] = srcp[b % dist];
+            }
+          }
+          __syncwarp();
+        }
+      }
+      pos0 += total;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------------
+static int g_num_sms = 0;
+
+cudaError_t launch_inflate(const InflateBatch &b, cudaStream_t stream) {
+  if (b.n_units == 0) return cudaSuccess;
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  // Streams per warp.  Decode is latency-bound per stream, so what matters first is that every
+  // scheduler has a warp; beyond that, packing more streams into a warp only saves issue slots.
+  const int warps_per_block = B200Z_DECODE_THREADS / 32;
+  int upw = 32;
+  {
+    static int forced = -1;
+    if (forced < 0) {
+      const char *e = getenv("B200Z_UPW");
+      forced = e ? atoi(e) : 0;
+    }
+    if (forced >= 1 && forced <= 32) {
+      upw = forced;
+    } else {
+      const uint64_t target_warps = (uint64_t)g_num_sms * 4;
+      while (upw > 1 && (b.n_units + upw - 1) / upw < target_warps) upw >>= 1;
+    }
+  }
+  const uint64_t n_warps = (b.n_units + upw - 1) / upw;
+  const unsigned blocks = (unsigned)((n_warps + warps_per_block - 1) / warps_per_block);
+  const size_t smem = inflate_decode_smem_bytes(warps_per_block, upw);
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(k_inflate_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_smem = smem;
+  }
+  uint32_t *tokens = reinterpret_cast<uint32_t *>(b.workspace);
+  uint32_t *ntok = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(b.workspace) + b.tok_bytes);
+  k_inflate_decode<<<blocks, B200Z_DECODE_THREADS, smem, stream>>>(
+      b.in_base, b.in_off, b.in_len, b.out_off, b.out_cap, tokens, ntok, b.out_len, b.status, b.in_used,
+      (uint32_t)b.n_units, upw);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const int ewarps = B200Z_EXPAND_THREADS / 32;
+  uint64_t eblocks = (b.n_units + ewarps - 1) / ewarps;
+  const uint64_t max_blocks = (uint64_t)g_num_sms * (2048 / B200Z_EXPAND_THREADS) * 4;
+  if (eblocks > max_blocks) eblocks = max_blocks;
+  k_inflate_expand<<<(unsigned)eblocks, B200Z_EXPAND_THREADS, 0, stream>>>(tokens, ntok, b.in_base, b.in_off, b.out_base,
+                                                                           b.out_off, (uint32_t)b.n_units);
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace b200z

@@ -1,0 +1,106 @@
+/*
+ * b200z.h -- C ABI of libb200z.so: B200 (sm_100a) DEFLATE / BZip2 block codecs behind the
+ * Dart `archive` package's codec classes.
+ *
+ * The reference (brendan-duncan/archive 4.2.0) is pure Dart and has no FFI of its own; the
+ * entry points below are what a `dart:ffi` binding for its codec hot path binds (see
+ * INTEGRATION.md and dart/lib/src/b200z_ffi.dart).  Each entry point cites the reference
+ * interface it replaces (paths relative to /root/reference/).
+ *
+ * Conventions
+ *   - plain pointers + sizes, no C++ / torch types; every call is blocking.
+ *   - one process drives ONE GPU (b200z_init(device)); multi-GPU = one process per GPU,
+ *     units sharded by the caller (bench.py / torchrun), see DESIGN.md "Multi-GPU".
+ *   - return value: 0 (B200Z_OK) or a negative B200Z_E_* code.  The reference's error
+ *     convention on this path is "stop, keep partial output, never throw"
+ *     (inflate.dart:150-151,166-168; bzip2_decoder.dart:32-78): data errors therefore still
+ *     produce the partial output the reference would have produced, and the per-stream
+ *     status says why decoding stopped.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     B200Z_E_NODEVICE.
+ */
+#ifndef B200Z_H
+#define B200Z_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes -------------------------------------------------------------------- */
+#define B200Z_OK 0
+#define B200Z_E_NODEVICE (-1) /* no CUDA device / b200z_init not called / CUDA runtime error   */
+#define B200Z_E_ARG (-2)      /* invalid argument (Deflate._init returning false, deflate.dart:107-118) */
+#define B200Z_E_NOSPC (-3)    /* out_cap too small; *out_len = bytes needed when known          */
+#define B200Z_E_DATA (-4)     /* decodeStream() returned false (bad header / adler / crc)       */
+#define B200Z_E_THROW (-5)    /* the Dart code would have thrown (RangeError: distance > output,
+                                 output_memory_stream.dart:83-86; code-length overrun inflate.dart:359) */
+#define B200Z_E_INTERNAL (-6)
+
+/* per-unit status written by the batch decoders (int32) */
+#define B200Z_U_DONE 0       /* BFINAL block decoded (inflate.dart:155)                          */
+#define B200Z_U_EOS 1        /* input exhausted before a final block (inflate.dart:111 loop end)  */
+#define B200Z_U_STOP (-1)    /* _parseBlock returned false: bad block type / code / short read    */
+#define B200Z_U_NOSPC (-2)   /* unit output would exceed out_cap                                  */
+#define B200Z_U_RANGE (-3)   /* back-reference before start of output (Dart RangeError)           */
+#define B200Z_U_BADCODE (-4) /* over-subscribed or unusable Huffman code set (reference would
+                                decode garbage / never terminate; see DESIGN.md "Divergences")    */
+#define B200Z_U_THROW (-5)   /* code-length run overruns HLIT+HDIST (Dart RangeError)             */
+#define B200Z_U_TOKCAP (-6)  /* internal token buffer too small (library retries)                 */
+
+/* ---- lifetime ------------------------------------------------------------------------ */
+int b200z_init(int device, uint32_t flags); /* selects the GPU for this process; idempotent  */
+void b200z_shutdown(void);
+const char *b200z_last_error(void); /* thread-local, never NULL                      */
+int b200z_device_count(void);       /* 0 when no CUDA device is visible              */
+const char *b200z_version(void);
+
+/* pinned host memory for callers that want full-speed PCIe copies (Dart: Pointer<Uint8>) */
+void *b200z_host_alloc(size_t bytes);
+void b200z_host_free(void *p);
+
+/* ---- single stream, reference class semantics ---------------------------------------- */
+/* Inflate(bytes).getBytes()  -- inflate.dart:23-28,102.  Raw DEFLATE.  *in_consumed is where
+ * the reference leaves the input stream (inflate.dart:337-340).  *unit_status = B200Z_U_*.  */
+int b200z_inflate_raw(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_cap,
+                      size_t *out_len, size_t *in_consumed, int32_t *unit_status);
+
+/* GZipDecoderWeb().decodeBytes -- _gzip_decoder_web.dart:19-58 (member loop, header skip,
+ * CRC/ISIZE read and ignored, zlib fallback when there is no gzip header).                */
+int b200z_gzip_decode(const uint8_t *in, size_t in_len, int verify, uint8_t *out, size_t out_cap,
+                      size_t *out_len);
+/* ZLibDecoderWeb().decodeBytes -- _zlib_decoder_web.dart:21-107 (stream loop, Adler-32 when
+ * verify, raw = no wrapper).                                                               */
+int b200z_zlib_decode(const uint8_t *in, size_t in_len, int verify, int raw, uint8_t *out,
+                      size_t out_cap, size_t *out_len);
+/* Upper bound for the output of b200z_gzip_decode / b200z_zlib_decode, from the framing's own
+ * size fields where present (ISIZE), else 0 = unknown (call with a guess, retry on E_NOSPC). */
+size_t b200z_gzip_bound(const uint8_t *in, size_t in_len);
+
+/* ---- batched independent units (what the kernels run) --------------------------------- */
+/* n_units raw DEFLATE streams: unit u reads in_base[in_off[u] .. +in_len[u]) and writes
+ * out_base[out_off[u] .. +out_cap[u]).  Per unit: out_len, status (B200Z_U_*), in_used.
+ * Host-pointer variant: copies in, runs, copies out (the end-to-end path).                  */
+int b200z_inflate_batch(const uint8_t *in_base, size_t in_bytes, const uint64_t *in_off,
+                        const uint32_t *in_len, uint8_t *out_base, size_t out_bytes,
+                        const uint64_t *out_off, const uint32_t *out_cap, uint32_t *out_len,
+                        int32_t *status, uint32_t *in_used, size_t n_units);
+/* Device-pointer variant: every pointer is device memory on the b200z_init device; work is
+ * enqueued on `cuda_stream` (a cudaStream_t, NULL = the library's stream) and NOT synchronised.
+ * `workspace` must hold b200z_inflate_workspace_bytes(...) bytes.                           */
+size_t b200z_inflate_workspace_bytes(size_t n_units, size_t total_in_bytes, size_t total_out_cap);
+int b200z_inflate_batch_device(const uint8_t *d_in_base, const uint64_t *d_in_off,
+                               const uint32_t *d_in_len, uint8_t *d_out_base,
+                               const uint64_t *d_out_off, const uint32_t *d_out_cap,
+                               uint32_t *d_out_len, int32_t *d_status, uint32_t *d_in_used,
+                               size_t n_units, void *d_workspace, size_t workspace_bytes,
+                               void *cuda_stream);
+
+/* Number of kernel launches issued by this library since b200z_init (bench.py gpu_launches). */
+uint64_t b200z_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200Z_H */
