@@ -500,6 +500,10 @@ extern "C" {
 const char *b200z_version(void) { return "b200z 0.1 (sm_100a)"; }
 const char *b200z_last_error(void) { return t_err; }
 uint64_t b200z_launch_count(void) { return g_launches.load(); }
+void b200z_profile_enable(int on) { profile_enable(on != 0); }
+int b200z_profile_read(double *decode_ms, double *expand_ms, uint64_t *n_batches) {
+  return profile_read(decode_ms, expand_ms, n_batches) ? B200Z_E_NODEVICE : B200Z_OK;
+}
 
 int b200z_device_count(void) {
   int n = 0;

@@ -34,5 +34,7 @@ struct InflateBatch {
 
 cudaError_t launch_inflate(const InflateBatch &b, cudaStream_t stream);
 void count_launch();
+void profile_enable(bool on);
+int profile_read(double *decode_ms, double *expand_ms, uint64_t *n);
 
 }  // namespace b200z

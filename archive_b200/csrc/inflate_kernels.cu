@@ -22,6 +22,8 @@
 
 #include <stdlib.h>
 
+#include <vector>
+
 namespace b200z {
 
 // ---------------------------------------------------------------------------------------------
@@ -196,6 +198,28 @@ k_inflate_expand(const uint32_t *__restrict__ tokens, const uint32_t *__restrict
 // ---------------------------------------------------------------------------------------------
 static int g_num_sms = 0;
 
+// optional per-kernel timing (CUDA events on the launching stream; bench.py's roofline breakdown)
+struct ProfTriple { cudaEvent_t a, b, c; };
+static bool g_prof = false;
+static std::vector<ProfTriple> g_prof_events;
+void profile_enable(bool on) { g_prof = on; }
+int profile_read(double *decode_ms, double *expand_ms, uint64_t *n) {
+  *decode_ms = *expand_ms = 0;
+  *n = 0;
+  for (auto &t : g_prof_events) {
+    if (cudaEventSynchronize(t.c) != cudaSuccess) return -1;
+    float d = 0, e = 0;
+    cudaEventElapsedTime(&d, t.a, t.b);
+    cudaEventElapsedTime(&e, t.b, t.c);
+    *decode_ms += d;
+    *expand_ms += e;
+    ++*n;
+    cudaEventDestroy(t.a); cudaEventDestroy(t.b); cudaEventDestroy(t.c);
+  }
+  g_prof_events.clear();
+  return 0;
+}
+
 cudaError_t launch_inflate(const InflateBatch &b, cudaStream_t stream) {
   if (b.n_units == 0) return cudaSuccess;
   if (!g_num_sms) {
@@ -232,12 +256,18 @@ cudaError_t launch_inflate(const InflateBatch &b, cudaStream_t stream) {
   }
   uint32_t *tokens = reinterpret_cast<uint32_t *>(b.workspace);
   uint32_t *ntok = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(b.workspace) + b.tok_bytes);
+  ProfTriple pt{};
+  if (g_prof) {
+    cudaEventCreate(&pt.a); cudaEventCreate(&pt.b); cudaEventCreate(&pt.c);
+    cudaEventRecord(pt.a, stream);
+  }
   k_inflate_decode<<<blocks, B200Z_DECODE_THREADS, smem, stream>>>(
       b.in_base, b.in_off, b.in_len, b.out_off, b.out_cap, tokens, ntok, b.out_len, b.status, b.in_used,
       (uint32_t)b.n_units, upw);
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
+  if (g_prof) cudaEventRecord(pt.b, stream);
   const int ewarps = B200Z_EXPAND_THREADS / 32;
   uint64_t eblocks = (b.n_units + ewarps - 1) / ewarps;
   const uint64_t max_blocks = (uint64_t)g_num_sms * (2048 / B200Z_EXPAND_THREADS) * 4;
@@ -245,6 +275,10 @@ cudaError_t launch_inflate(const InflateBatch &b, cudaStream_t stream) {
   k_inflate_expand<<<(unsigned)eblocks, B200Z_EXPAND_THREADS, 0, stream>>>(tokens, ntok, b.in_base, b.in_off, b.out_base,
                                                                            b.out_off, (uint32_t)b.n_units);
   count_launch();
+  if (g_prof) {
+    cudaEventRecord(pt.c, stream);
+    g_prof_events.push_back(pt);
+  }
   return cudaGetLastError();
 }
 

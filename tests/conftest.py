@@ -1,0 +1,38 @@
+"""Test tiers (mirrors the reference's single `dart test` tier, SURVEY.md section 4, split by device):
+  -m "not gpu": oracle vs the reference's golden vectors, host logic, C-ABI surface, kernel-logic emulation
+  -m gpu      : parity tests proper -- CUDA path through the C ABI vs the oracle."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # checker libraries (test infrastructure): the oracle and the host emulation of the decode logic
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
+    emul = os.path.join(ROOT, "tests", "host_emul")
+    src = os.path.join(emul, "emul_decode.cpp")
+    so = os.path.join(emul, "libemul.so")
+    hdr = os.path.join(ROOT, "archive_b200", "csrc", "inflate_decode.cuh")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.run(["g++", "-O1", "-g", "-fPIC", "-shared", "-std=c++17", "-x", "c++", src, "-o", so], check=True)
+
+
+def pytest_collection_modifyitems(config, items):
+    try:
+        import torch
+        has = torch.cuda.is_available()
+    except Exception:
+        has = False
+    if has:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device in this container")
+    for it in items:
+        if "gpu" in it.keywords:
+            it.add_marker(skip)

@@ -1,0 +1,66 @@
+"""ctypes access to oracle/liboracle.so -- TEST INFRASTRUCTURE (checker only, never the product path)."""
+import ctypes as C
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OK, FALSE, THROW, RUNAWAY = 0, 1, 2, 3
+
+_L = None
+
+
+def L():
+    global _L
+    if _L is None:
+        _L = C.CDLL(os.path.join(ROOT, "oracle", "liboracle.so"))
+        _L.orc_crc32.restype = C.c_uint32
+        _L.orc_adler32.restype = C.c_uint32
+        _L.orc_set_runaway_limit(C.c_int64(1 << 24))
+    return _L
+
+
+def _take(out, n):
+    r = C.string_at(out, n.value)
+    L().orc_free(out)
+    return r
+
+
+def inflate(data: bytes):
+    """-> (status, output, consumed)"""
+    out, n, c = C.POINTER(C.c_uint8)(), C.c_size_t(), C.c_size_t()
+    st = L().orc_inflate_bytes(data, C.c_size_t(len(data)), C.byref(out), C.byref(n), C.byref(c))
+    return st, _take(out, n), c.value
+
+
+def gzip_decode(data: bytes, verify=False):
+    out, n = C.POINTER(C.c_uint8)(), C.c_size_t()
+    st = L().orc_gzip_decode_bytes(data, C.c_size_t(len(data)), int(verify), C.byref(out), C.byref(n))
+    return st, _take(out, n)
+
+
+def zlib_decode(data: bytes, verify=False, raw=False):
+    out, n = C.POINTER(C.c_uint8)(), C.c_size_t()
+    st = L().orc_zlib_decode_bytes(data, C.c_size_t(len(data)), int(verify), int(raw), C.byref(out), C.byref(n))
+    return st, _take(out, n)
+
+
+def crc32(data: bytes, crc=0):
+    return L().orc_crc32(data, C.c_size_t(len(data)), C.c_uint32(crc))
+
+
+def adler32(data: bytes, adler=1):
+    return L().orc_adler32(data, C.c_size_t(len(data)), C.c_uint32(adler))
+
+
+_E = None
+
+
+def emul_inflate(data: bytes, cap: int = 1 << 20):
+    """The CUDA kernel's per-stream decode logic compiled for the host (tests/host_emul).
+    -> (unit_status, output, in_used, ntok)"""
+    global _E
+    if _E is None:
+        _E = C.CDLL(os.path.join(ROOT, "tests", "host_emul", "libemul.so"))
+    out = (C.c_uint8 * max(cap, 1))()
+    ol, iu, st, nt = C.c_uint32(), C.c_uint32(), C.c_int32(), C.c_uint32()
+    _E.emul_inflate(data, len(data), out, cap, C.byref(ol), C.byref(iu), C.byref(st), C.byref(nt))
+    return st.value, bytes(out[:ol.value]), iu.value, nt.value
