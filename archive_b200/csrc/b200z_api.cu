@@ -46,6 +46,26 @@ struct DevBuf {
     cap = want;
     return cudaSuccess;
   }
+  // grow but keep the first `keep` bytes (decoded members already sitting in the buffer)
+  cudaError_t reserve_keep(size_t n, size_t keep, cudaStream_t s) {
+    if (n <= cap) return cudaSuccess;
+    size_t want = n + (n >> 2) + 4096;
+    void *np = nullptr;
+    cudaError_t e = cudaMalloc(&np, want);
+    if (e != cudaSuccess) return e;
+    if (p && keep) {
+      e = cudaMemcpyAsync(np, p, keep < cap ? keep : cap, cudaMemcpyDeviceToDevice, s);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+      if (e != cudaSuccess) {
+        cudaFree(np);
+        return e;
+      }
+    }
+    if (p) cudaFree(p);
+    p = np;
+    cap = want;
+    return cudaSuccess;
+  }
   void release() {
     if (p) cudaFree(p);
     p = nullptr;
@@ -80,7 +100,7 @@ struct Ctx {
   std::mutex mu;
   bool inited = false;
   int device = -1;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, s_h2d = nullptr, s_d2h = nullptr;
   DevBuf d_in, d_out, d_ws, d_meta, d_small;
   PinBuf h_meta;
 };
@@ -265,7 +285,7 @@ static int run_one_staged(size_t pos, size_t in_total, size_t out_pos, size_t ou
   size_t mx = max_inflate_out(il);
   if (room > mx) room = mx;
   uint32_t oc = (uint32_t)(room > 0xfffffff0u ? 0xfffffff0u : room);
-  CU(g.d_out.reserve(out_pos + oc + 64));
+  CU(g.d_out.reserve_keep(out_pos + oc + 64, out_pos, g.stream));
   return run_batch_on_staged(&io, &il, &oo, &oc, &r->out_len, &r->status, &r->in_used, 1, out_pos + oc);
 }
 
@@ -318,8 +338,8 @@ static int zlib_decode_staged(const uint8_t *in, size_t in_len, size_t pos, int 
                               size_t out_pos, size_t out_cap, size_t *out_len_total);
 
 // GZip member loop on staged input.
-static int gzip_decode_staged(const uint8_t *in, size_t in_len, int verify, size_t out_cap, size_t *out_len_total) {
-  size_t pos = 0, out_pos = 0;
+static int gzip_decode_staged(const uint8_t *in, size_t in_len, int verify, size_t out_cap, size_t *out_len_total,
+                              size_t pos = 0, size_t out_pos = 0) {
   std::vector<uint64_t> v_in_off, v_out_off;
   std::vector<uint32_t> v_in_len, v_out_cap, v_out_len, v_in_used;
   std::vector<int32_t> v_status;
@@ -350,7 +370,7 @@ static int gzip_decode_staged(const uint8_t *in, size_t in_len, int verify, size
         set_err("gzip_decode: output needs at least %zu bytes, out_cap %zu", o, out_cap);
         return B200Z_E_NOSPC;
       }
-      CU(g.d_out.reserve(o + 64));
+      CU(g.d_out.reserve_keep(o + 64, out_pos, g.stream));
       v_out_len.resize(nb); v_status.resize(nb); v_in_used.resize(nb);
       int rc = run_batch_on_staged(v_in_off.data(), v_in_len.data(), v_out_off.data(), v_out_cap.data(),
                                    v_out_len.data(), v_status.data(), v_in_used.data(), nb, o);
@@ -404,6 +424,137 @@ static int gzip_decode_staged(const uint8_t *in, size_t in_len, int verify, size
     pos = after + 8;
   }
   *out_len_total = out_pos;
+  return B200Z_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// End-to-end fast path for the common shape: a run of members that all carry size hints.  The run is cut
+// into chunks; chunk c's host->device copy, its two kernels and chunk c-1's device->host copy run on
+// three streams, so the PCIe transfers hide behind each other and behind the decode.  Every hint is
+// verified afterwards; the first member whose hint was not exact ends the accepted prefix and the
+// caller continues from there on the slow, hint-free path (same bytes out either way).
+// ---------------------------------------------------------------------------------------------
+static int gzip_fast_path(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_cap, size_t *pos_io,
+                          size_t *out_pos_io, size_t *needed) {
+  struct M { size_t hdr_end, next; uint32_t isize; };
+  std::vector<M> ms;
+  size_t p = *pos_io, o = *out_pos_io;
+  while (p < in_len) {
+    size_t hdr_end, bsize;
+    if (gzip_header(in, in_len, p, &hdr_end, &bsize) != 1 || bsize == 0) break;
+    size_t next = p + bsize;
+    if (next > in_len || next < hdr_end + 8) break;
+    uint32_t isize = le32(in + next - 4);
+    ms.push_back({hdr_end, next, isize});
+    o += isize;
+    p = next;
+  }
+  const size_t nb = ms.size();
+  if (nb == 0) return B200Z_OK;
+  if (o > out_cap) {
+    *needed = o;
+    set_err("gzip_decode: output needs at least %zu bytes, out_cap %zu", o, out_cap);
+    return B200Z_E_NOSPC;
+  }
+  const size_t in_lo = *pos_io, in_hi = p, out_lo = *out_pos_io;
+  // chunks: ~16 per call, at least 4 MiB of compressed bytes each
+  size_t target = (in_hi - in_lo) / 16;
+  if (target < (4u << 20)) target = 4u << 20;
+  std::vector<size_t> cut{0};
+  {
+    size_t acc_start = in_lo;
+    for (size_t i = 0; i < nb; ++i)
+      if (ms[i].next - acc_start >= target && i + 1 < nb) {
+        cut.push_back(i + 1);
+        acc_start = ms[i].next;
+      }
+    cut.push_back(nb);
+  }
+  const size_t nchunks = cut.size() - 1;
+  MetaLayout ml(nb);
+  CU(g.h_meta.reserve(ml.bytes));
+  CU(g.d_meta.reserve(ml.bytes));
+  CU(g.d_in.reserve(in_len + 64));
+  CU(g.d_out.reserve_keep(o + 64, out_lo, g.stream));
+  uint8_t *hm = (uint8_t *)g.h_meta.p, *dm = (uint8_t *)g.d_meta.p;
+  uint64_t *h_in_off = (uint64_t *)(hm + ml.off_in_off), *h_out_off = (uint64_t *)(hm + ml.off_out_off);
+  uint32_t *h_in_len = (uint32_t *)(hm + ml.off_in_len), *h_out_cap = (uint32_t *)(hm + ml.off_out_cap);
+  size_t max_chunk_out = 0;
+  std::vector<size_t> chunk_out_lo(nchunks + 1);
+  {
+    size_t oo = out_lo;
+    for (size_t c = 0; c < nchunks; ++c) {
+      chunk_out_lo[c] = oo;
+      size_t rel = 0;
+      for (size_t i = cut[c]; i < cut[c + 1]; ++i) {
+        h_in_off[i] = ms[i].hdr_end;
+        h_in_len[i] = (uint32_t)(ms[i].next - ms[i].hdr_end);
+        h_out_off[i] = rel;  // relative to the chunk's slice of d_out
+        h_out_cap[i] = ms[i].isize;
+        rel += ms[i].isize;
+      }
+      oo += rel;
+      if (rel > max_chunk_out) max_chunk_out = rel;
+    }
+    chunk_out_lo[nchunks] = oo;
+  }
+  size_t max_units = 0;
+  for (size_t c = 0; c < nchunks; ++c) max_units = cut[c + 1] - cut[c] > max_units ? cut[c + 1] - cut[c] : max_units;
+  const size_t ws = workspace_bytes(max_units, max_chunk_out);
+  CU(g.d_ws.reserve(ws));
+  std::vector<cudaEvent_t> ev_in(nchunks), ev_k(nchunks);
+  for (size_t c = 0; c < nchunks; ++c) {
+    CU(cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ev_k[c], cudaEventDisableTiming));
+  }
+  CU(cudaMemcpyAsync(dm, hm, ml.inputs_bytes(), cudaMemcpyHostToDevice, g.s_h2d));
+  int rc = B200Z_OK;
+  for (size_t c = 0; c < nchunks && rc == B200Z_OK; ++c) {
+    const size_t a = cut[c], b = cut[c + 1];
+    const size_t lo = c == 0 ? in_lo : ms[a - 1].next, hi = ms[b - 1].next;
+    CU(cudaMemcpyAsync((uint8_t *)g.d_in.p + lo, in + lo, hi - lo, cudaMemcpyHostToDevice, g.s_h2d));
+    CU(cudaEventRecord(ev_in[c], g.s_h2d));
+    CU(cudaStreamWaitEvent(g.stream, ev_in[c], 0));
+    InflateBatch bt;
+    bt.in_base = (const uint8_t *)g.d_in.p;
+    bt.in_off = (const uint64_t *)(dm + ml.off_in_off) + a;
+    bt.in_len = (const uint32_t *)(dm + ml.off_in_len) + a;
+    bt.out_base = (uint8_t *)g.d_out.p + chunk_out_lo[c];
+    bt.out_off = (const uint64_t *)(dm + ml.off_out_off) + a;
+    bt.out_cap = (const uint32_t *)(dm + ml.off_out_cap) + a;
+    bt.out_len = (uint32_t *)(dm + ml.off_out_len) + a;
+    bt.status = (int32_t *)(dm + ml.off_status) + a;
+    bt.in_used = (uint32_t *)(dm + ml.off_in_used) + a;
+    bt.n_units = b - a;
+    bt.workspace = g.d_ws.p;
+    bt.tok_bytes = ws - align_up(max_units * 4, 256);
+    CU(launch_inflate(bt, g.stream));
+    CU(cudaEventRecord(ev_k[c], g.stream));
+    CU(cudaStreamWaitEvent(g.s_d2h, ev_k[c], 0));
+    const size_t ob = chunk_out_lo[c + 1] - chunk_out_lo[c];
+    if (ob) CU(cudaMemcpyAsync(out + chunk_out_lo[c], (uint8_t *)g.d_out.p + chunk_out_lo[c], ob, cudaMemcpyDeviceToHost, g.s_d2h));
+  }
+  CU(cudaMemcpyAsync(hm + ml.off_out_len, dm + ml.off_out_len, ml.bytes - ml.off_out_len, cudaMemcpyDeviceToHost, g.s_d2h));
+  CU(cudaStreamSynchronize(g.s_d2h));
+  CU(cudaStreamSynchronize(g.stream));
+  for (size_t c = 0; c < nchunks; ++c) {
+    cudaEventDestroy(ev_in[c]);
+    cudaEventDestroy(ev_k[c]);
+  }
+  const uint32_t *r_len = (const uint32_t *)(hm + ml.off_out_len), *r_used = (const uint32_t *)(hm + ml.off_in_used);
+  const int32_t *r_st = (const int32_t *)(hm + ml.off_status);
+  size_t k = 0;
+  for (; k < nb; ++k) {
+    bool ok = r_st[k] == B200Z_U_DONE && r_len[k] == ms[k].isize && ms[k].hdr_end + r_used[k] + 8 == ms[k].next;
+    if (!ok) break;
+  }
+  if (k > 0) {
+    *pos_io = ms[k - 1].next;
+    size_t oo = out_lo;
+    for (size_t i = 0; i < k; ++i) oo += ms[i].isize;
+    *out_pos_io = oo;
+  }
   return B200Z_OK;
 }
 
@@ -524,7 +675,11 @@ int b200z_init(int device, uint32_t flags) {
     return B200Z_E_NODEVICE;
   }
   CU(cudaSetDevice(device));
-  if (!g.stream) CU(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  if (!g.stream) {
+    CU(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&g.s_h2d, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&g.s_d2h, cudaStreamNonBlocking));
+  }
   g.device = device;
   g.inited = true;
   return B200Z_OK;
@@ -538,7 +693,9 @@ void b200z_shutdown(void) {
   g.d_in.release(); g.d_out.release(); g.d_ws.release(); g.d_meta.release(); g.d_small.release();
   g.h_meta.release();
   cudaStreamDestroy(g.stream);
-  g.stream = nullptr;
+  cudaStreamDestroy(g.s_h2d);
+  cudaStreamDestroy(g.s_d2h);
+  g.stream = g.s_h2d = g.s_d2h = nullptr;
   g.inited = false;
 }
 
@@ -659,16 +816,29 @@ int b200z_gzip_decode(const uint8_t *in, size_t in_len, int verify, uint8_t *out
   if (rc) return rc;
   std::lock_guard<std::mutex> lk(g.mu);
   CU(cudaSetDevice(g.device));
-  rc = stage_input(in, in_len);
-  if (rc) return rc;
-  size_t n = 0;
-  rc = gzip_decode_staged(in, in_len, verify, out_cap, &n);
+  size_t pos = 0, out_pos = 0, needed = 0;
+  rc = gzip_fast_path(in, in_len, out, out_cap, &pos, &out_pos, &needed);
+  if (rc) {
+    if (out_len) *out_len = needed;
+    return rc;
+  }
+  size_t n = out_pos;
+  if (pos < in_len) {
+    // whatever the hinted run did not cover (no hints, a lying hint, the zlib fall-back): generic path
+    const size_t done_out = out_pos;
+    rc = stage_input(in, in_len);
+    if (rc) return rc;
+    rc = gzip_decode_staged(in, in_len, verify, out_cap, &n, pos, out_pos);
+    if (out_len) *out_len = n;
+    if (rc == B200Z_E_NOSPC || rc == B200Z_E_NODEVICE) return rc;
+    size_t hi = n > out_cap ? out_cap : n;
+    if (hi > done_out)
+      CU(cudaMemcpyAsync(out + done_out, (uint8_t *)g.d_out.p + done_out, hi - done_out, cudaMemcpyDeviceToHost, g.stream));
+    CU(cudaStreamSynchronize(g.stream));
+    return rc;
+  }
   if (out_len) *out_len = n;
-  if (rc == B200Z_E_NOSPC || rc == B200Z_E_NODEVICE) return rc;
-  if (n > out_cap) n = out_cap;
-  if (n) CU(cudaMemcpyAsync(out, g.d_out.p, n, cudaMemcpyDeviceToHost, g.stream));
-  CU(cudaStreamSynchronize(g.stream));
-  return rc;
+  return B200Z_OK;
 }
 
 int b200z_zlib_decode(const uint8_t *in, size_t in_len, int verify, int raw, uint8_t *out, size_t out_cap,

@@ -17,9 +17,11 @@
 #endif
 
 #ifdef __CUDA_ARCH__
+#define B200Z_ANY(x) __any_sync(0xffffffffu, (x))
 #define B200Z_LDG(p) __ldg(p)
 #define B200Z_BREV(x) __brev(x)
 #else
+#define B200Z_ANY(x) (x)
 #define B200Z_LDG(p) (*(p))
 static inline uint32_t b200z_host_brev(uint32_t v) {
   v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
@@ -235,7 +237,7 @@ struct UnitResult {
   int32_t status;
 };
 
-B200Z_HD UnitResult inflate_decode_unit(const uint8_t *in, uint32_t in_len, uint32_t cap, uint32_t *tok,
+B200Z_HD UnitResult inflate_decode_unit(bool active, const uint8_t *in, uint32_t in_len, uint32_t cap, uint32_t *tok,
                                         uint16_t *lut_l, uint16_t *lut_d, const uint16_t *s_len_tab,
                                         const uint32_t *s_dist_tab) {
   SlowTab sl;
@@ -258,17 +260,19 @@ B200Z_HD UnitResult inflate_decode_unit(const uint8_t *in, uint32_t in_len, uint
   bool final_block = false;
   int maxl = 0, maxd = 0;
 
-  for (;;) {
+  bool done = !active;
+  while (B200Z_ANY(!done)) {  // warp-uniform: every lane reconverges here once per token
+    if (!done) do {
     if (!in_block) {
       // ---------------- block boundary: _inflate loop + _parseBlock (inflate.dart:111-156) -------------
       if (final_block) {
         st = B200Z_U_DONE;
-        break;
+        done = true; break;
       }
       br.refill();
       if (br.rem_bits() < 8) {  // isEOS: every byte already pulled into the bit buffer
         st = B200Z_U_EOS;
-        break;
+        done = true; break;
       }
       uint32_t hdr = br.peek(3);
       br.drop(3);
@@ -304,16 +308,16 @@ B200Z_HD UnitResult inflate_decode_unit(const uint8_t *in, uint32_t in_len, uint
         }
         if (len != 0 && len != nlen) {
           st = B200Z_U_STOP;
-          break;
+          done = true; break;
         }
         if (len > rem_bytes) {
           st = B200Z_U_STOP;
-          break;
+          done = true; break;
         }
         if (len > 0) {
           if ((unsigned long long)olen + len > cap) {
             st = B200Z_U_NOSPC;
-            break;
+            done = true; break;
           }
           if (len < 3) {
             const uint8_t *src = reinterpret_cast<const uint8_t *>(br.w) + br.lead + pos;
@@ -326,7 +330,7 @@ B200Z_HD UnitResult inflate_decode_unit(const uint8_t *in, uint32_t in_len, uint
           olen += (uint32_t)len;
         }
         br.seek(pos + (uint32_t)len);
-        continue;
+        break;  // next token
       } else if (type == 1) {
         // ---- fixed tables (inflate.dart:408-735): 288 lit/len lengths, 30 distance lengths ----
         for (int i = 0; i < 288; ++i) lens[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8;
@@ -336,17 +340,17 @@ B200Z_HD UnitResult inflate_decode_unit(const uint8_t *in, uint32_t in_len, uint
       } else if (type == 2) {
         // ---- dynamic (inflate.dart:239-298) ----
         int hlit = br.read_bits_checked(5);
-        if (hlit < 0) { st = B200Z_U_STOP; break; }
+        if (hlit < 0) { st = B200Z_U_STOP; done = true; break; }
         hlit += 257;
-        if (hlit > 288) { st = B200Z_U_STOP; break; }
+        if (hlit > 288) { st = B200Z_U_STOP; done = true; break; }
         int hdist = br.read_bits_checked(5);
-        if (hdist < 0) { st = B200Z_U_STOP; break; }
+        if (hdist < 0) { st = B200Z_U_STOP; done = true; break; }
         hdist += 1;
-        if (hdist > 32) { st = B200Z_U_STOP; break; }
+        if (hdist > 32) { st = B200Z_U_STOP; done = true; break; }
         int hclen = br.read_bits_checked(4);
-        if (hclen < 0) { st = B200Z_U_STOP; break; }
+        if (hclen < 0) { st = B200Z_U_STOP; done = true; break; }
         hclen += 4;
-        if (hclen > 19) { st = B200Z_U_STOP; break; }
+        if (hclen > 19) { st = B200Z_U_STOP; done = true; break; }
         for (int i = 0; i < 19; ++i) lens[i] = 0;
         bool bad = false;
         for (int i = 0; i < hclen; ++i) {
@@ -354,13 +358,13 @@ B200Z_HD UnitResult inflate_decode_unit(const uint8_t *in, uint32_t in_len, uint
           if (l < 0) { bad = true; break; }
           lens[c_order[i]] = (uint8_t)l;
         }
-        if (bad) { st = B200Z_U_STOP; break; }
+        if (bad) { st = B200Z_U_STOP; done = true; break; }
         // code-length alphabet: 7-bit LUT in the (not yet built) lit/len LUT area
         uint8_t clmax;
         {
           uint16_t f[16], c[16], o[16];
           uint8_t pm[19];
-          if (!build_table<7, uint8_t>(lens, 19, lut_l, f, c, o, pm, &clmax)) { st = B200Z_U_BADCODE; break; }
+          if (!build_table<7, uint8_t>(lens, 19, lut_l, f, c, o, pm, &clmax)) { st = B200Z_U_BADCODE; done = true; break; }
         }
         // _decode (inflate.dart:345-401)
         const int num = hlit + hdist;
@@ -398,14 +402,14 @@ B200Z_HD UnitResult inflate_decode_unit(const uint8_t *in, uint32_t in_len, uint
           if (i + repeat > num) { err = B200Z_U_THROW; break; }
           for (int k = 0; k < repeat; ++k) lens[i++] = (uint8_t)prev;
         }
-        if (err) { st = err; break; }
+        if (err) { st = err; done = true; break; }
         for (int k = hdist; k < 32; ++k) lens[hlit + k] = 0;
         bool ok = build_table<DBITS, uint8_t>(lens + hlit, hdist, lut_d, sd.first, sd.count, sd.offs, sd.perm, &sd.maxlen);
         ok = build_table<LBITS, uint16_t>(lens, hlit, lut_l, sl.first, sl.count, sl.offs, sl.perm, &sl.maxlen) && ok;
-        if (!ok) { st = B200Z_U_BADCODE; break; }
+        if (!ok) { st = B200Z_U_BADCODE; done = true; break; }
       } else {
         st = B200Z_U_STOP;
-        break;
+        done = true; break;
       }
       maxl = sl.maxlen;
       maxd = sd.maxlen;
@@ -417,7 +421,7 @@ B200Z_HD UnitResult inflate_decode_unit(const uint8_t *in, uint32_t in_len, uint
     const bool careful = !br.fast();
     if (careful && br.rem_bits() < maxl) {  // _readCodeByTable short read (quirk Q1)
       st = B200Z_U_STOP;
-      break;
+      done = true; break;
     }
     uint32_t e = lut_l[br.peek(LBITS)];
     int n = e & 15;
@@ -426,26 +430,26 @@ B200Z_HD UnitResult inflate_decode_unit(const uint8_t *in, uint32_t in_len, uint
       n = slow_decode<LBITS, uint16_t>(br.peek(15), sl.first, sl.count, sl.offs, sl.perm, maxl, &sym);
       if (n == 0) {  // hole: reference would emit literal 0 for ever (or until OOM)
         st = B200Z_U_BADCODE;
-        break;
+        done = true; break;
       }
     }
     br.drop(n);
     if (sym < 256) {
       if (olen >= cap) {
         st = B200Z_U_NOSPC;
-        break;
+        done = true; break;
       }
       tok[nt++] = TOK_LIT | (uint32_t)sym;
       olen++;
-      continue;
+      break;  // next token
     }
     if (sym == 256) {
       in_block = false;
-      continue;
+      break;  // next token
     }
     if (sym > 285) {
       st = B200Z_U_STOP;
-      break;
+      done = true; break;
     }
     uint32_t le = s_len_tab[sym - 257];
     int lx = le & 15;
@@ -465,7 +469,7 @@ B200Z_HD UnitResult inflate_decode_unit(const uint8_t *in, uint32_t in_len, uint
     const bool careful2 = !br.fast();
     if (careful2 && br.rem_bits() < maxd) {
       st = B200Z_U_STOP;
-      break;
+      done = true; break;
     }
     uint32_t de = lut_d[br.peek(DBITS)];
     int dn = de & 15;
@@ -477,7 +481,7 @@ B200Z_HD UnitResult inflate_decode_unit(const uint8_t *in, uint32_t in_len, uint
     br.drop(dn);
     if (dsym > 29) {
       st = B200Z_U_STOP;
-      break;
+      done = true; break;
     }
     uint32_t dd = s_dist_tab[dsym];
     int dx = dd & 15;
@@ -496,14 +500,15 @@ B200Z_HD UnitResult inflate_decode_unit(const uint8_t *in, uint32_t in_len, uint
     // writeBackReference (output_memory_stream.dart:79-98)
     if (dist <= 0 || (uint32_t)dist > olen) {  // dist 0 only via a truncated extra-bits read
       st = B200Z_U_RANGE;
-      break;
+      done = true; break;
     }
     if (olen + (uint32_t)mlen > cap) {
       st = B200Z_U_NOSPC;
-      break;
+      done = true; break;
     }
     tok[nt++] = ((uint32_t)mlen << 16) | (uint32_t)dist;
     olen += (uint32_t)mlen;
+    } while (0);
   }
 
   UnitResult r;

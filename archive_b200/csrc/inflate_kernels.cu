@@ -47,16 +47,20 @@ k_inflate_decode(const uint8_t *__restrict__ in_base, const uint64_t *__restrict
   const int lane = threadIdx.x & 31;
   const int warp_in_block = threadIdx.x >> 5;
   const uint32_t gwarp = blockIdx.x * (blockDim.x >> 5) + warp_in_block;
-  if (lane >= units_per_warp) return;
+  // every lane stays in the decode loop (it votes once per token so the warp reconverges); lanes without
+  // a stream are born finished
   const uint32_t unit = gwarp * units_per_warp + lane;
-  if (unit >= n_units) return;
+  const bool active = lane < units_per_warp && unit < n_units;
 
-  uint16_t *lut_l = reinterpret_cast<uint16_t *>(smem + CONST_WORDS + (warp_in_block * units_per_warp + lane) * LANE_STRIDE_WORDS);
+  uint16_t *lut_l = reinterpret_cast<uint16_t *>(smem + CONST_WORDS +
+                                                 (warp_in_block * units_per_warp + (active ? lane : 0)) * LANE_STRIDE_WORDS);
   uint16_t *lut_d = lut_l + (1 << LBITS);
 
-  uint32_t *tok = tokens + out_off[unit];  // token region mirrors the output layout (<= 1 token per byte)
-  const UnitResult r = inflate_decode_unit(in_base + in_off[unit], in_len[unit], out_cap[unit], tok, lut_l, lut_d,
-                                           s_len_tab, s_dist_tab);
+  // token region mirrors the output layout (<= 1 token per output byte)
+  const UnitResult r = inflate_decode_unit(active, active ? in_base + in_off[unit] : nullptr, active ? in_len[unit] : 0u,
+                                           active ? out_cap[unit] : 0u, active ? tokens + out_off[unit] : nullptr, lut_l,
+                                           lut_d, s_len_tab, s_dist_tab);
+  if (!active) return;
   ntok[unit] = r.ntok;
   out_len[unit] = r.out_len;
   status[unit] = r.status;

@@ -225,7 +225,8 @@ def main():
     d_used = torch.zeros(n, dtype=torch.int32, device=dev)
     ws_bytes = L.b200z_inflate_workspace_bytes(n, C_bytes, U_bytes)
     d_ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)  # a real (non-NULL) stream: the library launches on it, the events time it
+    torch.cuda.set_stream(stream)
 
     def step():
         rc = L.b200z_inflate_batch_device(d_in.data_ptr(), d_in_off.data_ptr(), d_in_len.data_ptr(), d_out.data_ptr(),

@@ -1,0 +1,116 @@
+// dart:ffi binding of include/b200z.h.  NOT compiled or run in the build image (no Dart SDK there):
+// it is the reference-side stub INTEGRATION.md describes, written to the letter of the C ABI.
+// The Python ctypes mirror (archive_b200/_ffi.py) binds the same symbols and IS exercised by the tests.
+import 'dart:ffi';
+import 'dart:io' show Platform;
+import 'dart:typed_data';
+
+import 'package:ffi/ffi.dart';
+
+const b200zOk = 0;
+const b200zENoDevice = -1;
+const b200zEArg = -2;
+const b200zENoSpc = -3;
+const b200zEData = -4;
+const b200zEThrow = -5;
+
+typedef _InitC = Int32 Function(Int32 device, Uint32 flags);
+typedef _InitD = int Function(int device, int flags);
+typedef _ErrC = Pointer<Utf8> Function();
+typedef _HostAllocC = Pointer<Uint8> Function(Size bytes);
+typedef _HostAllocD = Pointer<Uint8> Function(int bytes);
+typedef _HostFreeC = Void Function(Pointer<Uint8> p);
+typedef _HostFreeD = void Function(Pointer<Uint8> p);
+typedef _InflateRawC = Int32 Function(Pointer<Uint8> inp, Size inLen, Pointer<Uint8> out, Size outCap,
+    Pointer<Size> outLen, Pointer<Size> inConsumed, Pointer<Int32> unitStatus);
+typedef _InflateRawD = int Function(Pointer<Uint8> inp, int inLen, Pointer<Uint8> out, int outCap,
+    Pointer<Size> outLen, Pointer<Size> inConsumed, Pointer<Int32> unitStatus);
+typedef _GzipDecodeC = Int32 Function(
+    Pointer<Uint8> inp, Size inLen, Int32 verify, Pointer<Uint8> out, Size outCap, Pointer<Size> outLen);
+typedef _GzipDecodeD = int Function(
+    Pointer<Uint8> inp, int inLen, int verify, Pointer<Uint8> out, int outCap, Pointer<Size> outLen);
+typedef _ZlibDecodeC = Int32 Function(Pointer<Uint8> inp, Size inLen, Int32 verify, Int32 raw,
+    Pointer<Uint8> out, Size outCap, Pointer<Size> outLen);
+typedef _ZlibDecodeD = int Function(Pointer<Uint8> inp, int inLen, int verify, int raw,
+    Pointer<Uint8> out, int outCap, Pointer<Size> outLen);
+typedef _BoundC = Size Function(Pointer<Uint8> inp, Size inLen);
+typedef _BoundD = int Function(Pointer<Uint8> inp, int inLen);
+typedef _Bz2DecodeC = Int32 Function(
+    Pointer<Uint8> inp, Size inLen, Int32 verify, Pointer<Uint8> out, Size outCap, Pointer<Size> outLen);
+typedef _Bz2DecodeD = int Function(
+    Pointer<Uint8> inp, int inLen, int verify, Pointer<Uint8> out, int outCap, Pointer<Size> outLen);
+
+class B200ZException implements Exception {
+  final int code;
+  final String message;
+  B200ZException(this.code, this.message);
+  @override
+  String toString() => 'B200ZException($code): $message';
+}
+
+/// One process drives one GPU (b200z_init(device)); every call blocks.
+class B200Z {
+  static B200Z? _instance;
+  final DynamicLibrary _lib;
+  late final _InitD _init = _lib.lookupFunction<_InitC, _InitD>('b200z_init');
+  late final _ErrC _lastError = _lib.lookupFunction<_ErrC, _ErrC>('b200z_last_error');
+  late final _HostAllocD hostAlloc = _lib.lookupFunction<_HostAllocC, _HostAllocD>('b200z_host_alloc');
+  late final _HostFreeD hostFree = _lib.lookupFunction<_HostFreeC, _HostFreeD>('b200z_host_free');
+  late final _InflateRawD inflateRaw = _lib.lookupFunction<_InflateRawC, _InflateRawD>('b200z_inflate_raw');
+  late final _GzipDecodeD gzipDecode = _lib.lookupFunction<_GzipDecodeC, _GzipDecodeD>('b200z_gzip_decode');
+  late final _ZlibDecodeD zlibDecode = _lib.lookupFunction<_ZlibDecodeC, _ZlibDecodeD>('b200z_zlib_decode');
+  late final _BoundD gzipBound = _lib.lookupFunction<_BoundC, _BoundD>('b200z_gzip_bound');
+  late final _Bz2DecodeD bzip2Decode = _lib.lookupFunction<_Bz2DecodeC, _Bz2DecodeD>('b200z_bzip2_decode');
+
+  B200Z._(this._lib);
+
+  static B200Z get instance {
+    if (_instance == null) {
+      final path = Platform.environment['B200Z_LIB'] ?? 'libb200z.so';
+      final z = B200Z._(DynamicLibrary.open(path));
+      final device = int.parse(Platform.environment['LOCAL_RANK'] ?? '0');
+      final rc = z._init(device, 0);
+      if (rc != b200zOk) {
+        throw B200ZException(rc, z.lastError); // no CPU fallback: fail loudly
+      }
+      _instance = z;
+    }
+    return _instance!;
+  }
+
+  String get lastError => _lastError().toDartString();
+
+  /// Copies [bytes] into pinned native memory (full-speed PCIe); caller frees with [hostFree].
+  Pointer<Uint8> toNative(List<int> bytes) {
+    final p = hostAlloc(bytes.isEmpty ? 1 : bytes.length);
+    if (p == nullptr) throw B200ZException(b200zENoDevice, lastError);
+    p.asTypedList(bytes.length).setAll(0, bytes);
+    return p;
+  }
+
+  /// Runs [call](out, cap, outLen) growing the output buffer on B200Z_E_NOSPC; returns a Dart-owned copy.
+  /// A B200Z_E_DATA result still yields the partial output (the reference keeps it too) with ok == false.
+  (Uint8List, bool) grow(int firstCap, int Function(Pointer<Uint8>, int, Pointer<Size>) call) {
+    var cap = firstCap < 4096 ? 4096 : firstCap;
+    final outLen = calloc<Size>();
+    try {
+      while (true) {
+        final out = hostAlloc(cap);
+        try {
+          final rc = call(out, cap, outLen);
+          if (rc == b200zENoSpc) {
+            cap = cap * 2 > outLen.value ? cap * 2 : outLen.value + (outLen.value >> 3);
+            continue;
+          }
+          if (rc == b200zEThrow) throw RangeError(lastError);
+          if (rc != b200zOk && rc != b200zEData) throw B200ZException(rc, lastError);
+          return (Uint8List.fromList(out.asTypedList(outLen.value)), rc == b200zOk);
+        } finally {
+          hostFree(out);
+        }
+      }
+    } finally {
+      calloc.free(outLen);
+    }
+  }
+}

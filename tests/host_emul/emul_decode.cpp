@@ -39,7 +39,7 @@ extern "C" int emul_inflate(const uint8_t *in, uint32_t in_len, uint8_t *out, ui
   memcpy(p, in, in_len);
   std::vector<uint32_t> tok((size_t)cap + 64);
   std::vector<uint16_t> lut((1 << B200Z_LBITS) + (1 << B200Z_DBITS) + 8);
-  UnitResult r = inflate_decode_unit(p, in_len, cap, tok.data(), lut.data(), lut.data() + (1 << B200Z_LBITS),
+  UnitResult r = inflate_decode_unit(true, p, in_len, cap, tok.data(), lut.data(), lut.data() + (1 << B200Z_LBITS),
                                      c_len_tab, c_dist_tab);
   expand(tok.data(), r.ntok, p, out);
   *out_len = r.out_len;

@@ -211,11 +211,19 @@ def test_synthetic_units_config1_and_config2_shapes():
     dyn = [synth.deflate_raw(c, 6, 9) for c in chunks]
     assert dyn[0][0] & 7 == 0b101
     units = fixed + dyn
+    units = [u + b"\0\0" for u in units]  # >= 2 pad bytes: the reference's short-read quirk Q1 cannot fire
     res = inflate_batch(units, [65536] * len(units))
     for i, (st, out, used) in enumerate(res):
-        ost, oout, oused = orc.inflate(units[i] + b"\0\0")
-        assert st == 0 and out == oout and used == len(units[i]), i
+        ost, oout, oused = orc.inflate(units[i])
+        assert st == 0 and out == oout and used == len(units[i]) - 2 == oused, i
         assert out == (chunks[i] if i < 8 else chunks[i - 8])
+    # and WITHOUT padding the quirk must be reproduced bit for bit: the EOB (and whatever follows a short
+    # read) is lost exactly as in inflate.dart:192-195
+    raw_units = [u[:-2] for u in units]
+    res = inflate_batch(raw_units, [65536] * len(raw_units))
+    for i, (st, out, used) in enumerate(res):
+        ost, oout, oused = orc.inflate(raw_units[i])
+        assert out == oout and st in (0, -1), i
 
 
 def test_gzip_members_hinted_and_unhinted(a):
