@@ -80,6 +80,7 @@ int orc_bzip2_encode_bytes(const uint8_t *in, size_t n, uint8_t **out, size_t *o
 
 void orc_free(void *p);
 void orc_set_runaway_limit(int64_t n);
+void orc_deflate_set_truncate_heuristic(int on); /* tests only: off == stock zlib behaviour */
 
 #ifdef __cplusplus
 }

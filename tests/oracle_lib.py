@@ -64,3 +64,32 @@ def emul_inflate(data: bytes, cap: int = 1 << 20):
     ol, iu, st, nt = C.c_uint32(), C.c_uint32(), C.c_int32(), C.c_uint32()
     _E.emul_inflate(data, len(data), out, cap, C.byref(ol), C.byref(iu), C.byref(st), C.byref(nt))
     return st.value, bytes(out[:ol.value]), iu.value, nt.value
+
+
+def deflate(data: bytes, level=6, window_bits=15):
+    """-> (status, compressed, crc32_of_input)"""
+    out, n, crc = C.POINTER(C.c_uint8)(), C.c_size_t(), C.c_uint32()
+    st = L().orc_deflate_bytes(data, C.c_size_t(len(data)), level, window_bits, C.byref(out), C.byref(n), C.byref(crc))
+    return st, _take(out, n), crc.value
+
+
+def zlib_encode(data: bytes, level=6, window_bits=15, raw=False):
+    out, n = C.POINTER(C.c_uint8)(), C.c_size_t()
+    st = L().orc_zlib_encode_bytes(data, C.c_size_t(len(data)), level, window_bits, int(raw), C.byref(out), C.byref(n))
+    return st, _take(out, n)
+
+
+def gzip_encode(data: bytes, level=6, mtime=0):
+    out, n = C.POINTER(C.c_uint8)(), C.c_size_t()
+    st = L().orc_gzip_encode_bytes(data, C.c_size_t(len(data)), level, C.c_uint32(mtime), C.byref(out), C.byref(n))
+    return st, _take(out, n)
+
+
+def bzip2_decode(data: bytes, verify=True):
+    out, n = C.POINTER(C.c_uint8)(), C.c_size_t()
+    st = L().orc_bzip2_decode_bytes(data, C.c_size_t(len(data)), int(verify), C.byref(out), C.byref(n))
+    return st, _take(out, n)
+
+
+def set_truncate_heuristic(on: bool):
+    L().orc_deflate_set_truncate_heuristic(int(on))
