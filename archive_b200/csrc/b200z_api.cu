@@ -101,6 +101,8 @@ struct Ctx {
   bool inited = false;
   int device = -1;
   cudaStream_t stream = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+  static const int kCompStreams = 8;
+  cudaStream_t s_comp[kCompStreams] = {};
   DevBuf d_in, d_out, d_ws, d_meta, d_small;
   PinBuf h_meta;
 };
@@ -458,8 +460,9 @@ static int gzip_fast_path(const uint8_t *in, size_t in_len, uint8_t *out, size_t
     return B200Z_E_NOSPC;
   }
   const size_t in_lo = *pos_io, in_hi = p, out_lo = *out_pos_io;
-  // chunks: ~16 per call, at least 4 MiB of compressed bytes each
-  size_t target = (in_hi - in_lo) / 16;
+  // chunks: ~8 per call (one compute stream each, so their kernels overlap: a stream's decode time is set by
+  // its token count, not by how many streams run beside it), at least 4 MiB of compressed bytes each
+  size_t target = (in_hi - in_lo) / Ctx::kCompStreams;
   if (target < (4u << 20)) target = 4u << 20;
   std::vector<size_t> cut{0};
   {
@@ -501,7 +504,10 @@ static int gzip_fast_path(const uint8_t *in, size_t in_len, uint8_t *out, size_t
   }
   size_t max_units = 0;
   for (size_t c = 0; c < nchunks; ++c) max_units = cut[c + 1] - cut[c] > max_units ? cut[c + 1] - cut[c] : max_units;
-  const size_t ws = workspace_bytes(max_units, max_chunk_out);
+  (void)max_units;
+  (void)max_chunk_out;
+  const size_t tok_region = align_up((o - out_lo) * 4 + 256, 256);  // token layout mirrors the output layout
+  const size_t ws = tok_region + align_up(nb * 4, 256);
   CU(g.d_ws.reserve(ws));
   std::vector<cudaEvent_t> ev_in(nchunks), ev_k(nchunks);
   for (size_t c = 0; c < nchunks; ++c) {
@@ -515,7 +521,8 @@ static int gzip_fast_path(const uint8_t *in, size_t in_len, uint8_t *out, size_t
     const size_t lo = c == 0 ? in_lo : ms[a - 1].next, hi = ms[b - 1].next;
     CU(cudaMemcpyAsync((uint8_t *)g.d_in.p + lo, in + lo, hi - lo, cudaMemcpyHostToDevice, g.s_h2d));
     CU(cudaEventRecord(ev_in[c], g.s_h2d));
-    CU(cudaStreamWaitEvent(g.stream, ev_in[c], 0));
+    cudaStream_t cs = g.s_comp[c % Ctx::kCompStreams];
+    CU(cudaStreamWaitEvent(cs, ev_in[c], 0));
     InflateBatch bt;
     bt.in_base = (const uint8_t *)g.d_in.p;
     bt.in_off = (const uint64_t *)(dm + ml.off_in_off) + a;
@@ -527,17 +534,16 @@ static int gzip_fast_path(const uint8_t *in, size_t in_len, uint8_t *out, size_t
     bt.status = (int32_t *)(dm + ml.off_status) + a;
     bt.in_used = (uint32_t *)(dm + ml.off_in_used) + a;
     bt.n_units = b - a;
-    bt.workspace = g.d_ws.p;
-    bt.tok_bytes = ws - align_up(max_units * 4, 256);
-    CU(launch_inflate(bt, g.stream));
-    CU(cudaEventRecord(ev_k[c], g.stream));
+    bt.workspace = (uint8_t *)g.d_ws.p + (chunk_out_lo[c] - out_lo) * 4;
+    bt.tok_bytes = (tok_region + a * 4) - (chunk_out_lo[c] - out_lo) * 4;  // -> this chunk's slice of the count array
+    CU(launch_inflate(bt, cs));
+    CU(cudaEventRecord(ev_k[c], cs));
     CU(cudaStreamWaitEvent(g.s_d2h, ev_k[c], 0));
     const size_t ob = chunk_out_lo[c + 1] - chunk_out_lo[c];
     if (ob) CU(cudaMemcpyAsync(out + chunk_out_lo[c], (uint8_t *)g.d_out.p + chunk_out_lo[c], ob, cudaMemcpyDeviceToHost, g.s_d2h));
   }
   CU(cudaMemcpyAsync(hm + ml.off_out_len, dm + ml.off_out_len, ml.bytes - ml.off_out_len, cudaMemcpyDeviceToHost, g.s_d2h));
   CU(cudaStreamSynchronize(g.s_d2h));
-  CU(cudaStreamSynchronize(g.stream));
   for (size_t c = 0; c < nchunks; ++c) {
     cudaEventDestroy(ev_in[c]);
     cudaEventDestroy(ev_k[c]);
@@ -679,6 +685,7 @@ int b200z_init(int device, uint32_t flags) {
     CU(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&g.s_h2d, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&g.s_d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < Ctx::kCompStreams; ++i) CU(cudaStreamCreateWithFlags(&g.s_comp[i], cudaStreamNonBlocking));
   }
   g.device = device;
   g.inited = true;
@@ -695,6 +702,7 @@ void b200z_shutdown(void) {
   cudaStreamDestroy(g.stream);
   cudaStreamDestroy(g.s_h2d);
   cudaStreamDestroy(g.s_d2h);
+  for (int i = 0; i < Ctx::kCompStreams; ++i) cudaStreamDestroy(g.s_comp[i]);
   g.stream = g.s_h2d = g.s_d2h = nullptr;
   g.inited = false;
 }

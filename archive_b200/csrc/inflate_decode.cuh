@@ -13,14 +13,35 @@
 #define B200Z_LBITS 9
 #endif
 #ifndef B200Z_DBITS
-#define B200Z_DBITS 7
+#define B200Z_DBITS 9
 #endif
 
 #ifdef __CUDA_ARCH__
+// 32-bit shared-window addressing for the per-lane LUTs: keeps the hot loop free of 64-bit generic pointers
+#define B200Z_SADDR(p) ((uint32_t)__cvta_generic_to_shared(p))
+__device__ __forceinline__ uint32_t b200z_lds16(uint32_t base, uint32_t idx) {
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(base + idx * 2u));
+  return v;
+}
+__device__ __forceinline__ uint32_t b200z_lds32(uint32_t base, uint32_t idx) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + idx * 4u));
+  return v;
+}
+#define B200Z_LDS16(base, idx) b200z_lds16(base, idx)
+#define B200Z_LDS32(base, idx) b200z_lds32(base, idx)
+#define B200Z_PREFETCH(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
+typedef uint32_t b200z_saddr;
 #define B200Z_ANY(x) __any_sync(0xffffffffu, (x))
 #define B200Z_LDG(p) __ldg(p)
 #define B200Z_BREV(x) __brev(x)
 #else
+#define B200Z_SADDR(p) (p)
+#define B200Z_LDS16(base, idx) ((uint32_t)((const uint16_t *)(base))[idx])
+#define B200Z_LDS32(base, idx) (((const uint32_t *)(base))[idx])
+#define B200Z_PREFETCH(p) ((void)0)
+typedef const void *b200z_saddr;
 #define B200Z_ANY(x) (x)
 #define B200Z_LDG(p) (*(p))
 static inline uint32_t b200z_host_brev(uint32_t v) {
@@ -80,7 +101,7 @@ constexpr int LBITS = B200Z_LBITS;  // primary literal/length LUT bits
 constexpr int DBITS = B200Z_DBITS;  // primary distance LUT bits
 constexpr int LUT_HALFWORDS = (1 << LBITS) + (1 << DBITS);
 constexpr int LANE_STRIDE_WORDS = LUT_HALFWORDS / 2 + 1;  // +1 word: same index -> different bank per lane
-constexpr int CONST_WORDS = 16 + 32;                       // len table (32 x u16) + dist table (32 x u32)
+constexpr int CONST_WORDS = 16 + 32 + 64;                  // len table (32 x u16) + dist table (32 x u32) + xtab (64 x u32)
 
 static inline size_t inflate_decode_smem_bytes(int warps_per_block, int units_per_warp) {
   return (size_t)(CONST_WORDS + warps_per_block * units_per_warp * LANE_STRIDE_WORDS) * 4;
@@ -128,6 +149,17 @@ struct BitReader {
   B200Z_HD void refill() {
     if (cnt < 32) {
       uint32_t v = (widx < nw) ? B200Z_LDG(w + widx) : 0u;
+      widx++;
+      buf |= (uint64_t)v << cnt;
+      cnt += 32;
+    }
+  }
+  // bulk-path refill: as refill(), plus an L1 prefetch two 128-byte lines ahead whenever the stream enters a
+  // new line (a lane's miss stalls its whole warp, so the latency has to be hidden up front)
+  B200Z_HD void refill_bulk() {
+    if (cnt < 32) {
+      uint32_t v = B200Z_LDG(w + widx);
+      if ((widx & 31u) == 0u && widx + 96u < nw) B200Z_PREFETCH(w + widx + 64);
       widx++;
       buf |= (uint64_t)v << cnt;
       cnt += 32;
@@ -239,7 +271,8 @@ struct UnitResult {
 
 B200Z_HD UnitResult inflate_decode_unit(bool active, const uint8_t *in, uint32_t in_len, uint32_t cap, uint32_t *tok,
                                         uint16_t *lut_l, uint16_t *lut_d, const uint16_t *s_len_tab,
-                                        const uint32_t *s_dist_tab) {
+                                        const uint32_t *s_dist_tab, const uint32_t *s_xtab) {
+  const b200z_saddr lutl_s = B200Z_SADDR(lut_l), lutd_s = B200Z_SADDR(lut_d), xtab_s = B200Z_SADDR(s_xtab);
   SlowTab sl;
   SlowTabD sd;
   uint8_t lens[320];
@@ -259,10 +292,79 @@ B200Z_HD UnitResult inflate_decode_unit(bool active, const uint8_t *in, uint32_t
   bool in_block = false;
   bool final_block = false;
   int maxl = 0, maxd = 0;
+  bool mode_dist = false;  // bulk path: the next symbol is a distance code
+  uint32_t mlen_pending = 0;
 
   bool done = !active;
   while (B200Z_ANY(!done)) {  // warp-uniform: every lane reconverges here once per token
     if (!done) do {
+    if (in_block && (mode_dist || br.widx + 2u <= br.nw)) {
+      // ---------------- bulk path: ONE SYMBOL per turn, the same instructions for literal/length and
+      // distance symbols (a lane that has just read a length code reads its distance code on the next
+      // turn), so the lanes of a warp stay converged.  >= 64 stream bits are still unloaded when a
+      // literal/length symbol starts, so no end-of-stream test is needed here (a token is <= 48 bits);
+      // everything near the end of the stream goes through the exact per-token path below.
+      br.refill_bulk();
+      const bool dm = mode_dist;
+      const uint32_t bits = (uint32_t)br.buf;
+      uint32_t e = B200Z_LDS16(dm ? lutd_s : lutl_s, bits & (dm ? ((1u << DBITS) - 1u) : ((1u << LBITS) - 1u)));
+      int n = (int)(e & 15u);
+      int sym = (int)(e >> 4);
+      if (n == 0) {
+        if (dm) {
+          n = slow_decode<DBITS, uint8_t>(bits & 0x7fffu, sd.first, sd.count, sd.offs, sd.perm, maxd, &sym);
+          if (n == 0) sym = 0;  // hole in the flat table: (len 0, sym 0) (_huffman_table.dart:22)
+        } else {
+          n = slow_decode<LBITS, uint16_t>(bits & 0x7fffu, sl.first, sl.count, sl.offs, sl.perm, maxl, &sym);
+          if (n == 0) {
+            st = B200Z_U_BADCODE;
+            done = true; break;
+          }
+        }
+      }
+      br.drop(n);
+      // base + extra bits: lengths at [0,32), distances at [32,64); literals/EOB read the all-zero entry 63
+      const uint32_t xi = dm ? 32u + (uint32_t)sym : (sym > 256 ? (uint32_t)(sym - 257) : 63u);
+      const uint32_t x = B200Z_LDS32(xtab_s, xi & 63u);
+      const int xb = (int)(x & 15u);
+      const uint32_t val = (x >> 4) + ((uint32_t)br.buf & ((1u << xb) - 1u));
+      br.drop(xb);
+      if (!dm) {
+        if (sym < 256) {
+          if (olen >= cap) {
+            st = B200Z_U_NOSPC;
+            done = true; break;
+          }
+          tok[nt++] = TOK_LIT | (uint32_t)sym;
+          olen++;
+        } else if (sym == 256) {
+          in_block = false;
+        } else if (sym > 285) {
+          st = B200Z_U_STOP;
+          done = true; break;
+        } else {
+          mlen_pending = val;
+          mode_dist = true;
+        }
+      } else {
+        mode_dist = false;
+        if (sym > 29) {
+          st = B200Z_U_STOP;
+          done = true; break;
+        }
+        if (val > olen) {  // writeBackReference before the start of the output (output_memory_stream.dart:83-86)
+          st = B200Z_U_RANGE;
+          done = true; break;
+        }
+        if (olen + mlen_pending > cap) {
+          st = B200Z_U_NOSPC;
+          done = true; break;
+        }
+        tok[nt++] = (mlen_pending << 16) | val;
+        olen += mlen_pending;
+      }
+      break;  // next symbol
+    }
     if (!in_block) {
       // ---------------- block boundary: _inflate loop + _parseBlock (inflate.dart:111-156) -------------
       if (final_block) {

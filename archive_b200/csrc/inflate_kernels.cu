@@ -38,9 +38,12 @@ k_inflate_decode(const uint8_t *__restrict__ in_base, const uint64_t *__restrict
   extern __shared__ uint32_t smem[];
   uint16_t *s_len_tab = reinterpret_cast<uint16_t *>(smem);
   uint32_t *s_dist_tab = smem + 16;
+  uint32_t *s_xtab = smem + 48;  // [0,32) length symbols, [32,64) distance symbols: (base << 4) | extra_bits
   for (int i = threadIdx.x; i < 32; i += blockDim.x) {
     s_len_tab[i] = c_len_tab[i];
     s_dist_tab[i] = c_dist_tab[i];
+    s_xtab[i] = c_len_tab[i];
+    s_xtab[32 + i] = c_dist_tab[i];
   }
   __syncthreads();
 
@@ -59,7 +62,7 @@ k_inflate_decode(const uint8_t *__restrict__ in_base, const uint64_t *__restrict
   // token region mirrors the output layout (<= 1 token per output byte)
   const UnitResult r = inflate_decode_unit(active, active ? in_base + in_off[unit] : nullptr, active ? in_len[unit] : 0u,
                                            active ? out_cap[unit] : 0u, active ? tokens + out_off[unit] : nullptr, lut_l,
-                                           lut_d, s_len_tab, s_dist_tab);
+                                           lut_d, s_len_tab, s_dist_tab, s_xtab);
   if (!active) return;
   ntok[unit] = r.ntok;
   out_len[unit] = r.out_len;

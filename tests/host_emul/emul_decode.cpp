@@ -39,8 +39,13 @@ extern "C" int emul_inflate(const uint8_t *in, uint32_t in_len, uint8_t *out, ui
   memcpy(p, in, in_len);
   std::vector<uint32_t> tok((size_t)cap + 64);
   std::vector<uint16_t> lut((1 << B200Z_LBITS) + (1 << B200Z_DBITS) + 8);
+  uint32_t xtab[64];
+  for (int i = 0; i < 32; ++i) {
+    xtab[i] = c_len_tab[i];
+    xtab[32 + i] = c_dist_tab[i];
+  }
   UnitResult r = inflate_decode_unit(true, p, in_len, cap, tok.data(), lut.data(), lut.data() + (1 << B200Z_LBITS),
-                                     c_len_tab, c_dist_tab);
+                                     c_len_tab, c_dist_tab, xtab);
   expand(tok.data(), r.ntok, p, out);
   *out_len = r.out_len;
   *in_used = r.in_used;
