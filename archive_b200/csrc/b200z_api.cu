@@ -534,6 +534,7 @@ static int gzip_fast_path(const uint8_t *in, size_t in_len, uint8_t *out, size_t
     bt.status = (int32_t *)(dm + ml.off_status) + a;
     bt.in_used = (uint32_t *)(dm + ml.off_in_used) + a;
     bt.n_units = b - a;
+    bt.share = (int)(nchunks < (size_t)Ctx::kCompStreams ? nchunks : (size_t)Ctx::kCompStreams);
     bt.workspace = (uint8_t *)g.d_ws.p + (chunk_out_lo[c] - out_lo) * 4;
     bt.tok_bytes = (tok_region + a * 4) - (chunk_out_lo[c] - out_lo) * 4;  // -> this chunk's slice of the count array
     CU(launch_inflate(bt, cs));

@@ -30,6 +30,7 @@ struct InflateBatch {
   size_t n_units;
   void *workspace;   // [tok_bytes of tokens][n_units x u32 token counts]
   size_t tok_bytes;  // 4 * extent of the output layout, rounded up to 256
+  int share = 1;     // how many batches run concurrently on the device (sizes the streams-per-warp choice)
 };
 
 cudaError_t launch_inflate(const InflateBatch &b, cudaStream_t stream);
