@@ -125,3 +125,32 @@ class GZipDecoderWeb(_FramedDecoder):
 # this is the `platformZLibDecoder` / `platformGZipDecoder` seam (_zlib_decoder.dart:1, _gzip_decoder.dart:1).
 ZLibDecoder = ZLibDecoderWeb
 GZipDecoder = GZipDecoderWeb
+
+
+class BZip2Decoder:
+    """BZip2Decoder().decodeBytes / decodeStream (lib/src/codecs/bzip2_decoder.dart:12-88): CRCs are compared only
+    when `verify`; decodeStream returns False on any data error and keeps the blocks decoded before it."""
+
+    def decode_bytes(self, data, verify: bool = False) -> bytes:
+        out = OutputMemoryStream()
+        self.decode_stream(InputMemoryStream(data), out, verify=verify)
+        return out.get_bytes()
+
+    def decode_stream(self, input: InputMemoryStream, output: OutputMemoryStream, verify: bool = False) -> bool:
+        L = _ffi.ensure_init()
+        view = input.buffer[input.position:]
+        addr, n, keep = _ffi.as_buffer(view)
+        out_len = C.c_size_t(0)
+
+        def call(oa, cap):
+            rc = L.b200z_bzip2_decode(addr, n, int(verify), oa, cap, C.byref(out_len))
+            return rc, out_len.value
+
+        rc, out, got = _grow_call(call, addr, n, 6 * n + 4096)
+        if got:
+            output.write_bytes(C.string_at(out, got))
+        input.position = len(input.buffer)
+        if rc == _ffi.E_DATA:
+            return False
+        _ffi.check(rc)
+        return True

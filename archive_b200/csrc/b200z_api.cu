@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <mutex>
 #include <vector>
@@ -103,7 +104,7 @@ struct Ctx {
   cudaStream_t stream = nullptr, s_h2d = nullptr, s_d2h = nullptr;
   static const int kCompStreams = 8;
   cudaStream_t s_comp[kCompStreams] = {};
-  DevBuf d_in, d_out, d_ws, d_meta, d_small;
+  DevBuf d_in, d_out, d_ws, d_meta, d_small, d_bz;
   PinBuf h_meta;
 };
 static Ctx g;
@@ -648,6 +649,270 @@ static int zlib_decode_staged(const uint8_t *in, size_t in_len, size_t pos, int 
 
 }  // namespace b200z
 
+
+// =============================================================================================
+// BZip2Decoder.decodeBytes / decodeStream  (bzip2_decoder.dart:13-88)
+// Host side: stream header, ordering + chain validation of the block candidates the scan kernel finds,
+// stored-CRC comparison.  All bit/byte work is in bzip2_kernels.cu.
+// =============================================================================================
+namespace b200z {
+
+struct Carver {  // carve typed arrays out of one device allocation
+  uint8_t *p;
+  size_t off = 0;
+  explicit Carver(void *base) : p((uint8_t *)base) {}
+  template <typename T>
+  T *take(size_t n) {
+    off = align_up(off, 256);
+    T *r = p ? (T *)(p + off) : nullptr;
+    off += n * sizeof(T);
+    return r;
+  }
+};
+
+static inline uint32_t be32_at_bit(const uint8_t *in, size_t n, uint64_t bit) {
+  uint64_t v = 0;
+  size_t b0 = (size_t)(bit >> 3);
+  for (int i = 0; i < 5; ++i) v = (v << 8) | (b0 + i < n ? in[b0 + i] : 0);
+  return (uint32_t)(v >> (8 - (bit & 7)));
+}
+
+static int bzip2_decode_impl(const uint8_t *in, size_t in_len, int verify, uint8_t *out, size_t out_cap, size_t *out_len) {
+  *out_len = 0;
+  // 'B' 'Z' 'h' level: each is a readByte() that throws at EOS (bz2_bit_reader.dart:17-20)
+  static const uint8_t sig[3] = {0x42, 0x5a, 0x68};
+  for (int i = 0; i < 3; ++i) {
+    if ((size_t)i >= in_len) {
+      set_err("bzip2: truncated signature (Dart: RangeError)");
+      return B200Z_E_THROW;
+    }
+    if (in[i] != sig[i]) {
+      set_err("bzip2: bad signature");
+      return B200Z_E_DATA;
+    }
+  }
+  if (in_len < 4) {
+    set_err("bzip2: truncated header (Dart: RangeError)");
+    return B200Z_E_THROW;
+  }
+  const int level = (int)in[3] - 0x30;
+  if (level < 0 || level > 9) {
+    set_err("bzip2: bad block size");
+    return B200Z_E_DATA;
+  }
+  if (in_len == 4) return B200Z_OK;  // while (!input.isEOS) never runs
+  const uint32_t nblock_max = (uint32_t)level * 100000u;
+  const uint64_t total_bits = (uint64_t)in_len * 8;
+
+  int rc = stage_input(in, in_len);
+  if (rc) return rc;
+  CU(cudaMemsetAsync((uint8_t *)g.d_in.p + in_len, 0, 64, g.stream));
+
+  // ---- K6: candidates ----
+  const uint32_t cand_cap = 1u << 20;
+  CU(g.d_small.reserve((size_t)cand_cap * 8 + 256));
+  unsigned long long *d_cand = (unsigned long long *)((uint8_t *)g.d_small.p + 256);
+  uint32_t *d_ncand = (uint32_t *)g.d_small.p;
+  CU(bz2_launch_scan((const uint8_t *)g.d_in.p, in_len, d_cand, d_ncand, cand_cap, g.stream));
+  uint32_t ncand = 0;
+  CU(cudaMemcpyAsync(&ncand, d_ncand, 4, cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  if (ncand > cand_cap) {
+    set_err("bzip2: more than %u magic candidates", cand_cap);
+    return B200Z_E_INTERNAL;
+  }
+  std::vector<unsigned long long> cand(ncand);
+  if (ncand) CU(cudaMemcpy(cand.data(), d_cand, (size_t)ncand * 8, cudaMemcpyDeviceToHost));
+  std::sort(cand.begin(), cand.end(), [](unsigned long long a, unsigned long long b) {
+    return (a & ~(1ull << 63)) < (b & ~(1ull << 63));
+  });
+  std::vector<unsigned long long> blk_bits;
+  std::vector<uint32_t> blk_of_cand(ncand, 0xffffffffu);
+  for (uint32_t i = 0; i < ncand; ++i)
+    if (!(cand[i] >> 63)) {
+      blk_of_cand[i] = (uint32_t)blk_bits.size();
+      blk_bits.push_back(cand[i]);
+    }
+  const uint32_t nb = (uint32_t)blk_bits.size();
+
+  // ---- device arrays ----
+  const uint32_t chunks_max = (nblock_max + 1023) / 1024;
+  auto carve = [&](void *base, uint32_t nbk) {
+    Carver c(base);
+    struct A {
+      unsigned long long *blk_bit, *end_bit, *block_out, *block_off;
+      uint32_t *rec_val, *rec_pos, *n_rec, *nblock, *orig_ptr, *rnd, *chist, *tt, *seg_len, *seg_next, *seg_off, *slice_state,
+          *slice_out, *block_crc;
+      int32_t *status, *irregular;
+      uint8_t *sym8, *raw;
+      BzChainHost *chain;
+      size_t bytes;
+    } a;
+    a.blk_bit = c.take<unsigned long long>(nbk);
+    a.end_bit = c.take<unsigned long long>(nbk);
+    a.block_out = c.take<unsigned long long>(nbk);
+    a.block_off = c.take<unsigned long long>(nbk + 1);
+    a.n_rec = c.take<uint32_t>(nbk);
+    a.nblock = c.take<uint32_t>(nbk);
+    a.orig_ptr = c.take<uint32_t>(nbk);
+    a.rnd = c.take<uint32_t>(nbk);
+    a.status = c.take<int32_t>(nbk);
+    a.irregular = c.take<int32_t>(nbk);
+    a.block_crc = c.take<uint32_t>(nbk);
+    a.chain = c.take<BzChainHost>(nbk);
+    a.seg_len = c.take<uint32_t>((size_t)nbk * 4098);
+    a.seg_next = c.take<uint32_t>((size_t)nbk * 4098);
+    a.seg_off = c.take<uint32_t>((size_t)nbk * 4098);
+    a.slice_state = c.take<uint32_t>((size_t)nbk * 1024);
+    a.slice_out = c.take<uint32_t>((size_t)nbk * 1024);
+    a.chist = c.take<uint32_t>((size_t)nbk * chunks_max * 256);
+    a.rec_val = c.take<uint32_t>((size_t)nbk * nblock_max);
+    a.rec_pos = c.take<uint32_t>((size_t)nbk * nblock_max);
+    a.tt = c.take<uint32_t>((size_t)nbk * nblock_max);
+    a.sym8 = c.take<uint8_t>((size_t)nbk * nblock_max);
+    a.raw = c.take<uint8_t>((size_t)nbk * nblock_max);
+    a.bytes = align_up(c.off, 256);
+    return a;
+  };
+  const uint32_t nbk = nb ? nb : 1;
+  auto sz = carve(nullptr, nbk);
+  CU(g.d_bz.reserve(sz.bytes));
+  auto A = carve(g.d_bz.p, nbk);
+
+  // ---- K7 on every candidate (speculative: a magic-looking bit pattern inside a block just decodes to junk) ----
+  std::vector<uint32_t> h_nrec(nb), h_nblock(nb), h_optr(nb), h_rnd(nb);
+  std::vector<unsigned long long> h_end(nb);
+  std::vector<int32_t> h_st(nb);
+  if (nb) {
+    CU(cudaMemcpyAsync(A.blk_bit, blk_bits.data(), (size_t)nb * 8, cudaMemcpyHostToDevice, g.stream));
+    Bz2Entropy e;
+    e.words = (const uint32_t *)g.d_in.p;
+    e.n_bytes = in_len;
+    e.blk_bit = A.blk_bit;
+    e.n_blocks = nb;
+    e.nblock_max = nblock_max;
+    e.rec_val = A.rec_val; e.rec_pos = A.rec_pos; e.n_rec = A.n_rec; e.nblock = A.nblock; e.orig_ptr = A.orig_ptr;
+    e.randomised = A.rnd; e.end_bit = A.end_bit; e.status = A.status;
+    CU(bz2_launch_entropy(e, g.stream));
+    CU(cudaMemcpyAsync(h_nrec.data(), A.n_rec, nb * 4, cudaMemcpyDeviceToHost, g.stream));
+    CU(cudaMemcpyAsync(h_nblock.data(), A.nblock, nb * 4, cudaMemcpyDeviceToHost, g.stream));
+    CU(cudaMemcpyAsync(h_optr.data(), A.orig_ptr, nb * 4, cudaMemcpyDeviceToHost, g.stream));
+    CU(cudaMemcpyAsync(h_rnd.data(), A.rnd, nb * 4, cudaMemcpyDeviceToHost, g.stream));
+    CU(cudaMemcpyAsync(h_end.data(), A.end_bit, (size_t)nb * 8, cudaMemcpyDeviceToHost, g.stream));
+    CU(cudaMemcpyAsync(h_st.data(), A.status, nb * 4, cudaMemcpyDeviceToHost, g.stream));
+    CU(cudaStreamSynchronize(g.stream));
+  }
+
+  // ---- walk the chain exactly as decodeStream's loop does (:46-87) ----
+  std::vector<BzChainHost> chain;
+  std::vector<uint32_t> stored_crc;
+  int final_rc = B200Z_OK;
+  bool have_eos = false;
+  uint32_t eos_crc = 0;
+  uint64_t pos = 32;
+  size_t ci = 0;
+  for (;;) {
+    if ((pos + 7) / 8 >= in_len) break;  // input.isEOS: every byte has been pulled into the bit reader
+    if (pos + 48 > total_bits) {          // _readBlockType reads 6 bytes
+      set_err("bzip2: truncated block header (Dart: RangeError)");
+      final_rc = B200Z_E_THROW;
+      break;
+    }
+    while (ci < ncand && (cand[ci] & ~(1ull << 63)) < pos) ++ci;
+    if (ci >= ncand || (cand[ci] & ~(1ull << 63)) != pos) {
+      set_err("bzip2: no block signature at bit %llu", (unsigned long long)pos);
+      final_rc = B200Z_E_DATA;  // _readBlockType -> -1 -> false
+      break;
+    }
+    if (pos + 80 > total_bits) {  // 4 CRC bytes follow either magic
+      set_err("bzip2: truncated CRC (Dart: RangeError)");
+      final_rc = B200Z_E_THROW;
+      break;
+    }
+    const uint32_t crc_field = be32_at_bit(in, in_len, pos + 48);
+    if (cand[ci] >> 63) {
+      have_eos = true;
+      eos_crc = crc_field;
+      break;  // end of stream: whatever follows is ignored (:83-84)
+    }
+    const uint32_t k = blk_of_cand[ci];
+    if (h_st[k] == -2) {
+      set_err("bzip2: block at bit %llu reads past the end (Dart: RangeError)", (unsigned long long)pos);
+      final_rc = B200Z_E_THROW;
+      break;
+    }
+    if (h_st[k] != 0) {
+      set_err("bzip2: data error in the block at bit %llu", (unsigned long long)pos);
+      final_rc = B200Z_E_DATA;
+      break;
+    }
+    if (h_rnd[k]) {
+      // randomised blocks (obsolete since bzip2 0.9.5; the reference's variant of that path also differs from
+      // libbzip2) are not implemented on the device
+      set_err("bzip2: randomised block at bit %llu is not supported", (unsigned long long)pos);
+      final_rc = B200Z_E_DATA;
+      break;
+    }
+    chain.push_back({k, h_nblock[k], h_nrec[k], h_optr[k]});
+    stored_crc.push_back(crc_field);
+    pos = h_end[k];
+  }
+
+  // ---- K8 on the chain ----
+  const uint32_t nc = (uint32_t)chain.size();
+  std::vector<unsigned long long> h_off(nc + 1, 0);
+  std::vector<uint32_t> h_crc(nc);
+  std::vector<int32_t> h_irr(nc);
+  if (nc) {
+    CU(g.d_out.reserve(out_cap + 64));
+    CU(cudaMemcpyAsync(A.chain, chain.data(), (size_t)nc * sizeof(BzChainHost), cudaMemcpyHostToDevice, g.stream));
+    Bz2Ibwt w;
+    w.chain = A.chain; w.n_chain = nc; w.nblock_max = nblock_max;
+    w.rec_val = A.rec_val; w.rec_pos = A.rec_pos; w.sym8 = A.sym8; w.chist = A.chist; w.tt = A.tt;
+    w.seg_len = A.seg_len; w.seg_next = A.seg_next; w.seg_off = A.seg_off; w.irregular = A.irregular; w.raw = A.raw;
+    w.slice_state = A.slice_state; w.slice_out = A.slice_out; w.block_out = A.block_out; w.block_off = A.block_off;
+    w.block_crc = A.block_crc; w.out = (uint8_t *)g.d_out.p; w.out_cap = out_cap;
+    CU(bz2_launch_ibwt(w, g.stream));
+    CU(cudaMemcpyAsync(h_off.data(), A.block_off, (size_t)(nc + 1) * 8, cudaMemcpyDeviceToHost, g.stream));
+    CU(cudaMemcpyAsync(h_crc.data(), A.block_crc, (size_t)nc * 4, cudaMemcpyDeviceToHost, g.stream));
+    CU(cudaMemcpyAsync(h_irr.data(), A.irregular, (size_t)nc * 4, cudaMemcpyDeviceToHost, g.stream));
+    CU(cudaStreamSynchronize(g.stream));
+  }
+  // blocks are committed in order; the first bad one ends the stream (its bytes are already written when the
+  // reference compares the CRC, :58-66)
+  size_t n_out = 0;
+  uint32_t combined = 0;
+  for (uint32_t i = 0; i < nc; ++i) {
+    if (h_irr[i]) {
+      set_err("bzip2: block %u: corrupt BWT cycle", i);
+      final_rc = B200Z_E_DATA;
+      break;
+    }
+    n_out = (size_t)h_off[i + 1];
+    if (verify && h_crc[i] != stored_crc[i]) {
+      set_err("bzip2: block %u CRC mismatch", i);
+      final_rc = B200Z_E_DATA;
+      have_eos = false;
+      break;
+    }
+    combined = ((combined << 1) | (combined >> 31)) ^ h_crc[i];
+  }
+  if (final_rc == B200Z_OK && have_eos && verify && eos_crc != combined) {
+    set_err("bzip2: combined CRC mismatch");
+    final_rc = B200Z_E_DATA;
+  }
+  *out_len = n_out;
+  if (n_out > out_cap) {
+    set_err("bzip2: output needs %zu bytes, out_cap %zu", n_out, out_cap);
+    return B200Z_E_NOSPC;
+  }
+  if (n_out) CU(cudaMemcpyAsync(out, g.d_out.p, n_out, cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  return final_rc;
+}
+
+}  // namespace b200z
+
 using namespace b200z;
 
 // =============================================================================================
@@ -658,6 +923,17 @@ extern "C" {
 const char *b200z_version(void) { return "b200z 0.1 (sm_100a)"; }
 const char *b200z_last_error(void) { return t_err; }
 uint64_t b200z_launch_count(void) { return g_launches.load(); }
+
+int b200z_bzip2_decode(const uint8_t *in, size_t in_len, int verify, uint8_t *out, size_t out_cap, size_t *out_len) {
+  int rc = require_init();
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(g.mu);
+  CU(cudaSetDevice(g.device));
+  size_t n = 0;
+  rc = bzip2_decode_impl(in, in_len, verify, out, out_cap, &n);
+  if (out_len) *out_len = n;
+  return rc;
+}
 void b200z_profile_enable(int on) { profile_enable(on != 0); }
 int b200z_profile_read(double *decode_ms, double *expand_ms, uint64_t *n_batches) {
   return profile_read(decode_ms, expand_ms, n_batches) ? B200Z_E_NODEVICE : B200Z_OK;
@@ -698,7 +974,7 @@ void b200z_shutdown(void) {
   if (!g.inited) return;
   cudaSetDevice(g.device);
   cudaStreamSynchronize(g.stream);
-  g.d_in.release(); g.d_out.release(); g.d_ws.release(); g.d_meta.release(); g.d_small.release();
+  g.d_in.release(); g.d_out.release(); g.d_ws.release(); g.d_meta.release(); g.d_small.release(); g.d_bz.release();
   g.h_meta.release();
   cudaStreamDestroy(g.stream);
   cudaStreamDestroy(g.s_h2d);

@@ -34,6 +34,42 @@ struct InflateBatch {
 };
 
 cudaError_t launch_inflate(const InflateBatch &b, cudaStream_t stream);
+
+// ---- BZip2 (bzip2_kernels.cu) ----
+struct Bz2Entropy {  // K7, one warp per candidate block
+  const uint32_t *words;
+  uint64_t n_bytes;
+  const unsigned long long *blk_bit;  // bit position of each candidate's 48-bit magic
+  uint32_t n_blocks, nblock_max;
+  uint32_t *rec_val, *rec_pos;  // [n_blocks][nblock_max]
+  uint32_t *n_rec, *nblock, *orig_ptr, *randomised;
+  unsigned long long *end_bit;
+  int32_t *status;
+};
+struct Bz2Ibwt {  // K8 over the validated chain
+  const void *chain;  // BzChain[n_chain] (device)
+  uint32_t n_chain, nblock_max;
+  const uint32_t *rec_val, *rec_pos;
+  uint8_t *sym8;    // [n_chain][nblock_max]
+  uint32_t *chist;  // [n_chain][chunks_max][256]
+  uint32_t *tt;     // [n_chain][nblock_max]
+  uint32_t *seg_len, *seg_next, *seg_off;  // [n_chain][4098]
+  int32_t *irregular;                      // [n_chain]
+  uint8_t *raw;                            // [n_chain][nblock_max]
+  uint32_t *slice_state, *slice_out;       // [n_chain][1024]
+  unsigned long long *block_out, *block_off;  // [n_chain], [n_chain + 1]
+  uint32_t *block_crc;                         // [n_chain]
+  uint8_t *out;
+  unsigned long long out_cap;
+};
+struct BzChainHost {
+  uint32_t cand, nblock, n_rec, orig_ptr;
+};
+size_t bz2_entropy_smem();
+cudaError_t bz2_launch_scan(const uint8_t *d_in, uint64_t n_bytes, unsigned long long *d_cand, uint32_t *d_ncand,
+                            uint32_t cap, cudaStream_t s);
+cudaError_t bz2_launch_entropy(const Bz2Entropy &a, cudaStream_t s);
+cudaError_t bz2_launch_ibwt(const Bz2Ibwt &a, cudaStream_t s);
 void count_launch();
 void profile_enable(bool on);
 int profile_read(double *decode_ms, double *expand_ms, uint64_t *n);

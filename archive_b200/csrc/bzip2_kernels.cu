@@ -1,0 +1,827 @@
+// bzip2_kernels.cu -- sm_100a BZip2 block decode.
+//
+// Replaces (reference, paths relative to /root/reference/):
+//   lib/src/codecs/bzip2_decoder.dart:90-111    _readBlockType         -> k_bz2_scan      (K6)
+//   lib/src/codecs/bzip2_decoder.dart:113-388   _readCompressed part 1 -> k_bz2_entropy   (K7)
+//       (symbol map, selectors, code lengths, _hbCreateDecodeTables :774-813, _getMtfVal :732-772,
+//        MTF + RUNA/RUNB)
+//   lib/src/codecs/bzip2_decoder.dart:397-439   cftab + T^-1            -> k_bz2_expand / k_bz2_chunk_hist /
+//                                                                          k_bz2_chunk_scan / k_bz2_build_tt
+//   lib/src/codecs/bzip2_decoder.dart:610-727   pointer chase + un-RLE  -> k_bz2_walk_len / _order / _emit,
+//                                                                          k_bz2_rle_count / k_bz2_rle_emit
+//   lib/src/codecs/bzip2/bzip2.dart:11-14       CRC (0x04c11db7, MSB first) -> inside k_bz2_rle_emit
+//
+// Shape of the work (DESIGN.md "K6-K8"): the entropy stage is one serial chain per block (a table switch
+// every 50 symbols + an MTF list), so K7 runs ONE WARP PER BLOCK -- the warp builds the decode LUTs together,
+// lane 0 walks the bits and emits (byte, run) records.  Everything after it is data parallel: records ->
+// bytes, a stable counting sort builds T, the single cycle of T is cut at ~4096 splitters and walked by one
+// thread per segment, and RLE1 + CRC are scans over a 5-state automaton / an associative CRC combine.
+#include <stdint.h>
+
+#include "b200z_internal.h"
+
+namespace b200z {
+
+// ---------------------------------------------------------------------------------------------
+// MSB-first bit reader over 32-bit big-endian words (bz2_bit_reader.dart:12-44)
+// ---------------------------------------------------------------------------------------------
+struct BzBits {
+  const uint32_t *w;   // 4-byte aligned base of the whole stream
+  uint64_t buf;        // next bit = bit 63
+  int cnt;             // valid bits in buf
+  uint64_t next_word;  // index of the next word to load
+  uint64_t n_words;    // words that contain stream bytes
+  __device__ __forceinline__ void seek(uint64_t bitpos) {
+    next_word = bitpos >> 5;
+    uint32_t sh = (uint32_t)(bitpos & 31);
+    uint32_t v = next_word < n_words ? __byte_perm(__ldg(w + next_word), 0, 0x0123) : 0u;
+    next_word++;
+    buf = ((uint64_t)v << 32) << sh;
+    cnt = 32 - (int)sh;
+  }
+  __device__ __forceinline__ void refill() {
+    if (cnt <= 32) {
+      uint32_t v = next_word < n_words ? __byte_perm(__ldg(w + next_word), 0, 0x0123) : 0u;
+      if ((next_word & 31u) == 0u) asm volatile("prefetch.global.L1 [%0];" ::"l"(w + next_word + 64));
+      next_word++;
+      buf |= (uint64_t)v << (32 - cnt);
+      cnt += 32;
+    }
+  }
+  __device__ __forceinline__ uint32_t get(int n) {  // 1..24 bits
+    refill();
+    uint32_t x = (uint32_t)(buf >> (64 - n));
+    buf <<= n;
+    cnt -= n;
+    return x;
+  }
+  __device__ __forceinline__ uint64_t bitpos() const { return next_word * 32 - (uint64_t)cnt; }
+};
+
+// ---------------------------------------------------------------------------------------------
+// K6: every bit offset is tested for the block magic 0x314159265359 and the end-of-stream magic
+// 0x177245385090 (bzip2.dart compressedMagic / eosMagic).  cand = bit position of the magic | type << 63.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_bz2_scan(const uint8_t *__restrict__ in, uint64_t n_bytes,
+                                                  unsigned long long *__restrict__ cand, uint32_t *__restrict__ n_cand,
+                                                  uint32_t cap) {
+  const uint64_t MAGIC_BLK = 0x314159265359ull, MAGIC_EOS = 0x177245385090ull;
+  uint64_t b0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (b0 >= n_bytes) return;
+  // 11 bytes cover 4 byte offsets x 8 bit shifts x 48 bits
+  uint8_t by[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) by[i] = (b0 + i < n_bytes) ? in[b0 + i] : 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (b0 + k + 6 > n_bytes) break;  // fewer than 48 bits left even at shift 0
+    uint64_t v = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v = (v << 8) | by[k + i];
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+      uint64_t m = (v << s) >> 16;
+      bool blk = m == MAGIC_BLK, eos = m == MAGIC_EOS;
+      if (blk || eos) {
+        uint64_t bit = (b0 + k) * 8 + s;
+        if (bit + 48 <= n_bytes * 8) {
+          uint32_t slot = atomicAdd(n_cand, 1u);
+          if (slot < cap) cand[slot] = bit | (eos ? (1ull << 63) : 0ull);
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K7: entropy decode of one block per warp.
+// ---------------------------------------------------------------------------------------------
+constexpr int BZ_LUT_BITS = 10;
+constexpr int BZ_MAX_SEL = 18002;  // bzMaxSelectors (bzip2_decoder.dart:847)
+
+struct BzSmem {
+  uint16_t lut[6][1 << BZ_LUT_BITS];  // (sym << 5) | len ; 0 = needs the limit/base walk
+  int32_t limit[6][24];
+  int32_t base[6][24];
+  uint16_t perm[6][258];
+  uint8_t len[6][258];
+  uint8_t minlen[6];
+  uint8_t selector[BZ_MAX_SEL + 2];
+  uint8_t mtf[256];
+  uint8_t seq2unseq[256];
+};
+
+// status per block
+#define BZ_OK 0
+#define BZ_DATA (-1)    // _readCompressed returned -1 -> decodeStream returns false
+#define BZ_THROW (-2)   // the Dart code would have thrown (read past the end / selector overrun)
+
+__global__ void __launch_bounds__(32)
+k_bz2_entropy(const uint32_t *__restrict__ words, uint64_t n_bytes, const unsigned long long *__restrict__ blk_bit,
+              uint32_t n_blocks, uint32_t nblock_max, uint32_t *__restrict__ rec_val, uint32_t *__restrict__ rec_pos,
+              uint32_t *__restrict__ n_rec, uint32_t *__restrict__ nblock_out, uint32_t *__restrict__ orig_ptr,
+              uint32_t *__restrict__ randomised, unsigned long long *__restrict__ end_bit, int32_t *__restrict__ status) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  BzSmem &S = *reinterpret_cast<BzSmem *>(smraw);
+  const uint32_t b = blockIdx.x;
+  if (b >= n_blocks) return;
+  const int lane = threadIdx.x;
+  const uint64_t total_bits = n_bytes * 8;
+  __shared__ int s_groups, s_alpha, s_err;
+  __shared__ unsigned long long s_bitpos;
+
+  BzBits br;
+  br.w = words;
+  br.n_words = (n_bytes + 3) >> 2;
+  int err = 0;
+  uint32_t rnd = 0, optr = 0;
+  int n_groups = 0, n_sel = 0, alpha = 0, n_in_use = 0;
+
+  if (lane == 0) {
+    // header: after the 48-bit magic and the 32-bit stored CRC (bzip2_decoder.dart:113-218)
+    br.seek(blk_bit[b] + 48 + 32);
+    rnd = br.get(1);
+    optr = br.get(8);
+    optr = (optr << 8) | br.get(8);
+    optr = (optr << 8) | br.get(8);
+    uint32_t used16 = br.get(16);
+    for (int i = 0; i < 16; ++i) {
+      if (used16 & (0x8000u >> i)) {
+        uint32_t m = br.get(16);
+        for (int j = 0; j < 16; ++j)
+          if (m & (0x8000u >> j)) S.seq2unseq[n_in_use++] = (uint8_t)(i * 16 + j);
+      }
+    }
+    if (n_in_use == 0) err = BZ_DATA;
+    alpha = n_in_use + 2;
+    if (!err) {
+      n_groups = (int)br.get(3);
+      if (n_groups < 2 || n_groups > 6) err = BZ_DATA;
+    }
+    if (!err) {
+      n_sel = (int)br.get(15);
+      if (n_sel < 1) err = BZ_DATA;
+    }
+    if (!err) {
+      uint8_t pos[6];
+      for (int i = 0; i < n_groups; ++i) pos[i] = (uint8_t)i;
+      for (int i = 0; i < n_sel && !err; ++i) {
+        int j = 0;
+        while (br.get(1)) {
+          j++;
+          if (j >= n_groups) {
+            err = BZ_DATA;
+            break;
+          }
+        }
+        if (err) break;
+        if (i >= BZ_MAX_SEL) {  // _selectorMtf[i]: RangeError (bzip2_decoder.dart:168)
+          err = BZ_THROW;
+          break;
+        }
+        // undo the selector MTF on the fly (:172-186): same result as the reference's second loop
+        uint8_t tmp = pos[j];
+        for (int v = j; v > 0; --v) pos[v] = pos[v - 1];
+        pos[0] = tmp;
+        S.selector[i] = tmp;
+        if (br.bitpos() > total_bits) {
+          err = BZ_THROW;
+          break;
+        }
+      }
+    }
+    if (!err) {
+      for (int t = 0; t < n_groups && !err; ++t) {
+        int c = (int)br.get(5);
+        for (int i = 0; i < alpha && !err; ++i) {
+          for (;;) {
+            if (c < 1 || c > 20) {
+              err = BZ_DATA;
+              break;
+            }
+            if (br.get(1) == 0) break;
+            if (br.get(1) == 0) c++;
+            else c--;
+          }
+          S.len[t][i] = (uint8_t)c;
+        }
+        if (br.bitpos() > total_bits) err = BZ_THROW;
+      }
+    }
+    if (!err) {
+      // _hbCreateDecodeTables (:774-813) per table
+      for (int t = 0; t < n_groups; ++t) {
+        int mn = 32, mx = 0;
+        for (int i = 0; i < alpha; ++i) {
+          int l = S.len[t][i];
+          mx = l > mx ? l : mx;
+          mn = l < mn ? l : mn;
+        }
+        S.minlen[t] = (uint8_t)mn;
+        for (int i = 0; i < 258; ++i) S.perm[t][i] = 0;  // Int32List(bzMaxAlphaSize) starts zeroed (:234)
+        int pp = 0;
+        for (int i = mn; i <= mx; i++)
+          for (int j = 0; j < alpha; j++)
+            if (S.len[t][j] == i) S.perm[t][pp++] = (uint16_t)j;
+        int32_t *base = S.base[t], *limit = S.limit[t];
+        for (int i = 0; i < 23; i++) base[i] = 0;
+        for (int i = 0; i < alpha; i++) base[S.len[t][i] + 1]++;
+        for (int i = 1; i < 23; i++) base[i] += base[i - 1];
+        for (int i = 0; i < 23; i++) limit[i] = 0;
+        int32_t vec = 0;
+        for (int i = mn; i <= mx; i++) {
+          vec += (base[i + 1] - base[i]);
+          limit[i] = vec - 1;
+          vec <<= 1;
+        }
+        for (int i = mn + 1; i <= mx; i++) base[i] = ((limit[i - 1] + 1) << 1) - base[i];
+      }
+    }
+    s_groups = n_groups;
+    s_alpha = alpha;
+    s_err = err;
+    s_bitpos = br.bitpos();
+  }
+  __syncwarp();
+  n_groups = s_groups;
+  alpha = s_alpha;
+  if (s_err == 0) {
+    // The whole warp fills the LUTs.  Entry for a 10-bit prefix = what _getMtfVal's limit/base walk (:747-771)
+    // decides from those bits alone, so any code-length set (valid or not) decodes exactly as in the reference.
+    for (int t = 0; t < n_groups; ++t) {
+      const int mn = S.minlen[t];
+      for (int v = lane; v < (1 << BZ_LUT_BITS); v += 32) {
+        uint16_t e = 0;
+        for (int zn = mn; zn <= BZ_LUT_BITS; ++zn) {
+          if (zn < 1) continue;
+          int32_t zvec = v >> (BZ_LUT_BITS - zn);
+          if (zvec <= S.limit[t][zn]) {
+            int32_t idx = zvec - S.base[t][zn];
+            if (idx < 0 || idx >= 258) e = (uint16_t)((0x3ff << 5) | zn);  // data error marker
+            else e = (uint16_t)((S.perm[t][idx] << 5) | zn);
+            break;
+          }
+        }
+        S.lut[t][v] = e;
+      }
+    }
+  }
+  __syncwarp();
+  if (lane != 0) return;
+
+  uint32_t nrec = 0, nblock = 0;
+  if (!err) {
+    for (int i = 0; i < 256; ++i) S.mtf[i] = (uint8_t)i;
+    const int eob = n_in_use + 1;
+    uint32_t *rv = rec_val + (size_t)b * nblock_max;
+    uint32_t *rp = rec_pos + (size_t)b * nblock_max;
+    int gpos = 0, gno = -1, tsel = 0;
+    int run_n = 0;       // number of RUNA/RUNB symbols in the open run
+    uint32_t run_es = 0;  // value accumulated so far (es + 1 in the reference's terms)
+    for (;;) {
+      // ---- _getMtfVal (:732-772) ----
+      if (gpos == 0) {
+        gno++;
+        if (gno >= n_sel) {
+          err = BZ_DATA;  // reference returns -1 here (then spins to the block limit and fails)
+          break;
+        }
+        gpos = 50;
+        tsel = S.selector[gno];
+      }
+      gpos--;
+      br.refill();
+      uint32_t e = S.lut[tsel][(uint32_t)(br.buf >> (64 - BZ_LUT_BITS))];
+      int zn = e & 31;
+      int sym = e >> 5;
+      if (zn == 0) {
+        // code longer than the LUT (or a minLen above it): the reference's walk from LUT_BITS+1 (or minLen) on
+        zn = S.minlen[tsel] > BZ_LUT_BITS + 1 ? S.minlen[tsel] : BZ_LUT_BITS + 1;
+        for (;;) {
+          if (zn > 20) {
+            err = BZ_DATA;
+            break;
+          }
+          int32_t zvec = (int32_t)(br.buf >> (64 - zn));
+          if (zvec <= S.limit[tsel][zn]) {
+            int32_t idx = zvec - S.base[tsel][zn];
+            if (idx < 0 || idx >= 258) err = BZ_DATA;
+            else sym = S.perm[tsel][idx];
+            break;
+          }
+          zn++;
+        }
+        if (err) break;
+      } else if (sym == 0x3ff) {
+        err = BZ_DATA;
+        break;
+      }
+      br.buf <<= zn;
+      br.cnt -= zn;
+      // ---- MTF / run-length (:276-388) ----
+      if (sym <= 1) {
+        if (run_n >= 21) {  // N >= 2*1024*1024 (:291)
+          err = BZ_DATA;
+          break;
+        }
+        run_es += (uint32_t)(sym + 1) << run_n;
+        run_n++;
+        continue;
+      }
+      if (run_n) {
+        if (nblock + run_es > nblock_max) {  // (:313-316)
+          err = BZ_DATA;
+          break;
+        }
+        rv[nrec] = (run_es << 8) | S.seq2unseq[S.mtf[0]];
+        rp[nrec] = nblock;
+        nrec++;
+        nblock += run_es;
+        run_n = 0;
+        run_es = 0;
+      }
+      if (sym == eob) break;
+      if (nblock >= nblock_max) {  // (:326-329)
+        err = BZ_DATA;
+        break;
+      }
+      {
+        int nn = sym - 1;
+        uint8_t uc = S.mtf[nn];
+        for (int k = nn; k > 0; --k) S.mtf[k] = S.mtf[k - 1];
+        S.mtf[0] = uc;
+        rv[nrec] = (1u << 8) | S.seq2unseq[uc];
+        rp[nrec] = nblock;
+        nrec++;
+        nblock++;
+      }
+      if ((nrec & 1023u) == 0u && br.bitpos() > total_bits) {
+        err = BZ_THROW;
+        break;
+      }
+    }
+    if (!err && optr >= nblock) err = BZ_DATA;  // (:399-402) also covers nblock == 0
+  }
+  uint64_t endp = err ? s_bitpos : br.bitpos();
+  if (!err) endp = br.bitpos();
+  if (br.bitpos() > total_bits) err = BZ_THROW;  // some read went past the end: InputStream.readByte throws
+  n_rec[b] = nrec;
+  nblock_out[b] = nblock;
+  orig_ptr[b] = optr;
+  randomised[b] = rnd;
+  end_bit[b] = endp;
+  status[b] = err;
+}
+
+// ---------------------------------------------------------------------------------------------
+// records -> bytes (the low byte of tt[] in the reference, bzip2_decoder.dart:318,380)
+// grid.y = block index in the chain list
+// ---------------------------------------------------------------------------------------------
+struct BzChain {           // one entry per block that is on the validated chain
+  uint32_t cand;           // index into the K7 per-candidate arrays
+  uint32_t nblock;
+  uint32_t n_rec;
+  uint32_t orig_ptr;
+};
+
+__global__ void __launch_bounds__(256)
+k_bz2_expand(const BzChain *__restrict__ chain, const uint32_t *__restrict__ rec_val, const uint32_t *__restrict__ rec_pos,
+             uint32_t nblock_max, uint8_t *__restrict__ sym8) {
+  const BzChain c = chain[blockIdx.y];
+  const uint32_t *rv = rec_val + (size_t)c.cand * nblock_max, *rp = rec_pos + (size_t)c.cand * nblock_max;
+  uint8_t *dst = sym8 + (size_t)blockIdx.y * nblock_max;
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < c.n_rec; r += gridDim.x * blockDim.x) {
+    uint32_t v = rv[r], p = rp[r];
+    uint8_t ch = (uint8_t)v;
+    uint32_t n = v >> 8;
+    for (uint32_t j = 0; j < n; ++j) dst[p + j] = ch;
+  }
+}
+
+// per-warp-chunk (1024 positions) histograms
+constexpr int BZ_CHUNK = 1024;
+__global__ void __launch_bounds__(128)
+k_bz2_chunk_hist(const BzChain *__restrict__ chain, const uint8_t *__restrict__ sym8, uint32_t nblock_max,
+                 uint32_t chunks_max, uint32_t *__restrict__ chist) {
+  __shared__ uint32_t h[4][256];
+  const BzChain c = chain[blockIdx.y];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t chunk = blockIdx.x * 4 + warp;
+  for (int i = lane; i < 256; i += 32) h[warp][i] = 0;
+  __syncwarp();
+  const uint32_t lo = chunk * BZ_CHUNK;
+  const uint8_t *src = sym8 + (size_t)blockIdx.y * nblock_max;
+  if (lo < c.nblock) {
+    uint32_t hi = min(lo + BZ_CHUNK, c.nblock);
+    for (uint32_t i = lo + lane; i < hi; i += 32) atomicAdd(&h[warp][src[i]], 1u);
+  }
+  __syncwarp();
+  if (chunk < chunks_max) {
+    uint32_t *dst = chist + ((size_t)blockIdx.y * chunks_max + chunk) * 256;
+    for (int i = lane; i < 256; i += 32) dst[i] = h[warp][i];
+  }
+}
+
+// cftab (:407-432) + per-chunk start offsets: chist[chunk][c] becomes the first T index chunk `chunk` uses for byte c
+__global__ void __launch_bounds__(256)
+k_bz2_chunk_scan(const BzChain *__restrict__ chain, uint32_t chunks_max, uint32_t *__restrict__ chist) {
+  __shared__ uint32_t tot[256];
+  const BzChain c = chain[blockIdx.x];
+  const uint32_t nchunks = (c.nblock + BZ_CHUNK - 1) / BZ_CHUNK;
+  uint32_t *base = chist + (size_t)blockIdx.x * chunks_max * 256;
+  const int v = threadIdx.x;
+  uint32_t s = 0;
+  for (uint32_t k = 0; k < nchunks; ++k) s += base[(size_t)k * 256 + v];
+  tot[v] = s;
+  __syncthreads();
+  if (v == 0) {
+    uint32_t run = 0;
+    for (int i = 0; i < 256; ++i) {
+      uint32_t t = tot[i];
+      tot[i] = run;
+      run += t;
+    }
+  }
+  __syncthreads();
+  uint32_t run = tot[v];
+  for (uint32_t k = 0; k < nchunks; ++k) {
+    uint32_t t = base[(size_t)k * 256 + v];
+    base[(size_t)k * 256 + v] = run;
+    run += t;
+  }
+}
+
+// T^-1 (:435-439): tt[cftab[uc]++] |= i << 8 as a stable counting sort, one warp per 1024-position chunk
+__global__ void __launch_bounds__(128)
+k_bz2_build_tt(const BzChain *__restrict__ chain, const uint8_t *__restrict__ sym8, uint32_t nblock_max,
+               uint32_t chunks_max, const uint32_t *__restrict__ chist, uint32_t *__restrict__ tt) {
+  __shared__ uint32_t cnt[4][256];
+  const BzChain c = chain[blockIdx.y];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t chunk = blockIdx.x * 4 + warp;
+  const uint32_t lo = chunk * BZ_CHUNK;
+  if (lo >= c.nblock) return;
+  const uint32_t *cb = chist + ((size_t)blockIdx.y * chunks_max + chunk) * 256;
+  for (int i = lane; i < 256; i += 32) cnt[warp][i] = cb[i];
+  __syncwarp();
+  const uint8_t *src = sym8 + (size_t)blockIdx.y * nblock_max;
+  uint32_t *T = tt + (size_t)blockIdx.y * nblock_max;
+  const uint32_t hi = min(lo + BZ_CHUNK, c.nblock);
+  for (uint32_t g = lo; g < hi; g += 32) {
+    const uint32_t i = g + lane;
+    const bool act = i < hi;
+    const uint32_t ch = act ? src[i] : 0x100u + lane;  // inactive lanes never match anyone
+    const unsigned m = __match_any_sync(0xffffffffu, ch);
+    const uint32_t rank = __popc(m & ((1u << lane) - 1u));
+    uint32_t basev = act ? cnt[warp][ch] : 0;
+    __syncwarp();
+    if (act) {
+      T[basev + rank] = (i << 8) | ch;
+      if (rank == 0) cnt[warp][ch] = basev + __popc(m);
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the cycle walk (:610-727 reads tPos = tt[tPos] one byte at a time): cut at splitters, walk in parallel
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t BZ_SPLIT = 4096;
+
+struct BzWalkGeom {
+  uint32_t stride, kb, tpos0, start_id;
+};
+__device__ __forceinline__ BzWalkGeom bz_geom(const BzChain &c, const uint32_t *T) {
+  BzWalkGeom g;
+  g.stride = (c.nblock + BZ_SPLIT - 1) / BZ_SPLIT;
+  if (g.stride == 0) g.stride = 1;
+  g.kb = (c.nblock + g.stride - 1) / g.stride;
+  g.tpos0 = T[c.orig_ptr] >> 8;  // (:443)
+  g.start_id = (g.tpos0 % g.stride == 0) ? g.tpos0 / g.stride : g.kb;
+  return g;
+}
+
+__global__ void __launch_bounds__(256)
+k_bz2_walk_len(const BzChain *__restrict__ chain, const uint32_t *__restrict__ tt, uint32_t nblock_max,
+               uint32_t *__restrict__ seg_len, uint32_t *__restrict__ seg_next) {
+  const BzChain c = chain[blockIdx.y];
+  if (c.nblock == 0) return;
+  const uint32_t *T = tt + (size_t)blockIdx.y * nblock_max;
+  const BzWalkGeom g = bz_geom(c, T);
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j > g.kb) return;
+  uint32_t *sl = seg_len + (size_t)blockIdx.y * (BZ_SPLIT + 2), *sn = seg_next + (size_t)blockIdx.y * (BZ_SPLIT + 2);
+  if (j == g.kb && g.start_id != g.kb) {  // the start coincides with a regular splitter
+    sl[j] = 0;
+    sn[j] = g.start_id;
+    return;
+  }
+  uint32_t cur = (j == g.kb) ? g.tpos0 : j * g.stride;
+  uint32_t n = 0;
+  do {
+    cur = T[cur] >> 8;
+    n++;
+  } while (!(cur % g.stride == 0 || cur == g.tpos0) && n < c.nblock);
+  sl[j] = n;
+  sn[j] = (cur == g.tpos0) ? g.start_id : cur / g.stride;
+}
+
+// one thread per block: order of the segments along the cycle; irregular (repeating) chains only arise from
+// corrupt data and are flagged
+__global__ void k_bz2_walk_order(const BzChain *__restrict__ chain, uint32_t n_chain, const uint32_t *__restrict__ tt,
+                                 uint32_t nblock_max, const uint32_t *__restrict__ seg_len,
+                                 const uint32_t *__restrict__ seg_next, uint32_t *__restrict__ seg_off,
+                                 int32_t *__restrict__ irregular) {
+  const uint32_t bi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bi >= n_chain) return;
+  const BzChain c = chain[bi];
+  irregular[bi] = 0;
+  if (c.nblock == 0) return;
+  const uint32_t *T = tt + (size_t)bi * nblock_max;
+  const BzWalkGeom g = bz_geom(c, T);
+  const uint32_t *sl = seg_len + (size_t)bi * (BZ_SPLIT + 2), *sn = seg_next + (size_t)bi * (BZ_SPLIT + 2);
+  uint32_t *so = seg_off + (size_t)bi * (BZ_SPLIT + 2);
+  for (uint32_t j = 0; j <= g.kb; ++j) so[j] = 0xffffffffu;
+  uint32_t seg = g.start_id, off = 0, visited = 0;
+  while (off < c.nblock) {
+    if (seg > g.kb || so[seg] != 0xffffffffu || sl[seg] == 0 || ++visited > g.kb + 1) {
+      irregular[bi] = 1;
+      return;
+    }
+    so[seg] = off;
+    off += sl[seg];
+    seg = sn[seg];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_bz2_walk_emit(const BzChain *__restrict__ chain, const uint32_t *__restrict__ tt, uint32_t nblock_max,
+                const uint32_t *__restrict__ seg_len, const uint32_t *__restrict__ seg_off, uint8_t *__restrict__ raw) {
+  const BzChain c = chain[blockIdx.y];
+  if (c.nblock == 0) return;
+  const uint32_t *T = tt + (size_t)blockIdx.y * nblock_max;
+  const BzWalkGeom g = bz_geom(c, T);
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j > g.kb) return;
+  const uint32_t off = seg_off[(size_t)blockIdx.y * (BZ_SPLIT + 2) + j];
+  if (off == 0xffffffffu) return;
+  uint32_t n = seg_len[(size_t)blockIdx.y * (BZ_SPLIT + 2) + j];
+  if (off + n > c.nblock) n = c.nblock - off;
+  uint32_t cur = (j == g.kb) ? g.tpos0 : j * g.stride;
+  uint8_t *dst = raw + (size_t)blockIdx.y * nblock_max + off;
+  for (uint32_t i = 0; i < n; ++i) {
+    uint32_t t = T[cur];
+    dst[i] = (uint8_t)t;
+    cur = t >> 8;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// RLE1 (:610-727): 4 equal bytes are followed by a count byte.  State s = number of equal data bytes ending
+// at the previous position (1..4), 0 = fresh (start, or the previous byte was a count).  Input per position:
+// eq = (raw[i] == raw[i-1]).  Transition: 4 -> 0 (this byte is a COUNT); 0 -> 1; 1..3 -> eq ? s+1 : 1.
+// A map over the 5 states is packed 3 bits per state; maps compose associatively, so the state in front of
+// every slice comes from a scan.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t rle_step(uint32_t s, bool eq) { return s == 4 ? 0u : (s == 0 ? 1u : (eq ? s + 1u : 1u)); }
+__device__ __forceinline__ uint32_t map_identity() { return 0u | (1u << 3) | (2u << 6) | (3u << 9) | (4u << 12); }
+__device__ __forceinline__ uint32_t map_get(uint32_t m, uint32_t s) { return (m >> (3 * s)) & 7u; }
+__device__ __forceinline__ uint32_t map_compose(uint32_t first, uint32_t then) {  // then(first(s))
+  uint32_t r = 0;
+#pragma unroll
+  for (uint32_t s = 0; s < 5; ++s) r |= map_get(then, map_get(first, s)) << (3 * s);
+  return r;
+}
+
+// bzip2 CRC helpers (MSB-first, poly 0x04c11db7).  mulmod: polynomial product mod P of two 32-bit residues.
+__device__ __forceinline__ uint32_t bzcrc_mulmod(uint32_t a, uint32_t b) {
+  uint32_t r = 0;
+#pragma unroll 4
+  for (int i = 0; i < 32; ++i) {
+    if (b & 0x80000000u) r ^= a;  // processed from the top: Horner in x
+    b <<= 1;
+    if (i != 31) r = (r << 1) ^ ((r & 0x80000000u) ? 0x04c11db7u : 0u);
+  }
+  return r;
+}
+// x^(8n) mod P
+__device__ uint32_t bzcrc_xpow8(uint64_t n) {
+  uint32_t result = 1u;           // x^0
+  uint32_t sq = 0x00000100u;      // x^8
+  while (n) {
+    if (n & 1) result = bzcrc_mulmod(result, sq);
+    sq = bzcrc_mulmod(sq, sq);
+    n >>= 1;
+  }
+  return result;
+}
+
+constexpr int BZ_RLE_THREADS = 1024;
+
+// pass 1: per-block decoded size
+__global__ void __launch_bounds__(BZ_RLE_THREADS)
+k_bz2_rle_count(const BzChain *__restrict__ chain, const uint8_t *__restrict__ raw, uint32_t nblock_max,
+                uint32_t *__restrict__ slice_state, uint32_t *__restrict__ slice_out, unsigned long long *__restrict__ block_out) {
+  __shared__ uint32_t sm_map[BZ_RLE_THREADS];
+  __shared__ uint32_t sm_cnt[BZ_RLE_THREADS];
+  const BzChain c = chain[blockIdx.x];
+  const uint8_t *src = raw + (size_t)blockIdx.x * nblock_max;
+  const uint32_t t = threadIdx.x;
+  const uint32_t per = (c.nblock + BZ_RLE_THREADS - 1) / BZ_RLE_THREADS;
+  const uint32_t lo = min(t * per, c.nblock), hi = min(lo + per, c.nblock);
+  // slice map
+  uint32_t m = map_identity();
+  {
+    uint32_t st[5] = {0, 1, 2, 3, 4};
+    uint8_t prev = lo > 0 ? src[lo - 1] : 0;
+    for (uint32_t i = lo; i < hi; ++i) {
+      uint8_t x = src[i];
+      bool eq = (i > 0) && x == prev;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) st[k] = rle_step(st[k], eq);
+      prev = x;
+    }
+    m = st[0] | (st[1] << 3) | (st[2] << 6) | (st[3] << 9) | (st[4] << 12);
+  }
+  sm_map[t] = m;
+  __syncthreads();
+  // exclusive scan of maps (Hillis-Steele, order preserving)
+  for (int d = 1; d < BZ_RLE_THREADS; d <<= 1) {
+    uint32_t mine = sm_map[t];
+    uint32_t left = t >= (uint32_t)d ? sm_map[t - d] : map_identity();
+    __syncthreads();
+    sm_map[t] = map_compose(left, mine);
+    __syncthreads();
+  }
+  const uint32_t incl_prev = t > 0 ? sm_map[t - 1] : map_identity();
+  uint32_t s = map_get(incl_prev, 0);  // state in front of the slice, from the fresh state at the block start
+  slice_state[(size_t)blockIdx.x * BZ_RLE_THREADS + t] = s;
+  // slice output size
+  uint32_t outn = 0;
+  {
+    uint8_t prev = lo > 0 ? src[lo - 1] : 0;
+    for (uint32_t i = lo; i < hi; ++i) {
+      uint8_t x = src[i];
+      bool eq = (i > 0) && x == prev;
+      outn += (s == 4) ? (uint32_t)x : 1u;
+      s = rle_step(s, eq);
+      prev = x;
+    }
+  }
+  sm_cnt[t] = outn;
+  __syncthreads();
+  for (int d = 1; d < BZ_RLE_THREADS; d <<= 1) {
+    uint32_t v = t >= (uint32_t)d ? sm_cnt[t - d] : 0;
+    __syncthreads();
+    sm_cnt[t] += v;
+    __syncthreads();
+  }
+  slice_out[(size_t)blockIdx.x * BZ_RLE_THREADS + t] = sm_cnt[t] - outn;  // exclusive
+  if (t == BZ_RLE_THREADS - 1) block_out[blockIdx.x] = sm_cnt[t];
+}
+
+// exclusive scan of the block sizes (a few hundred values)
+__global__ void k_bz2_offsets(const unsigned long long *__restrict__ block_out, uint32_t n_chain,
+                              unsigned long long *__restrict__ block_off) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long run = 0;
+    for (uint32_t i = 0; i < n_chain; ++i) {
+      block_off[i] = run;
+      run += block_out[i];
+    }
+    block_off[n_chain] = run;
+  }
+}
+
+// pass 2: write the decoded bytes + the block CRC
+__global__ void __launch_bounds__(BZ_RLE_THREADS)
+k_bz2_rle_emit(const BzChain *__restrict__ chain, const uint8_t *__restrict__ raw, uint32_t nblock_max,
+               const uint32_t *__restrict__ slice_state, const uint32_t *__restrict__ slice_out,
+               const unsigned long long *__restrict__ block_off, unsigned long long out_cap, uint8_t *__restrict__ out,
+               uint32_t *__restrict__ block_crc) {
+  __shared__ uint32_t crc_tab[256];
+  __shared__ uint32_t sm_crc[BZ_RLE_THREADS];
+  __shared__ uint32_t sm_len[BZ_RLE_THREADS];
+  const BzChain c = chain[blockIdx.x];
+  const uint32_t t = threadIdx.x;
+  if (t < 256) {
+    uint32_t v = t << 24;
+    for (int k = 0; k < 8; ++k) v = (v & 0x80000000u) ? (v << 1) ^ 0x04c11db7u : v << 1;
+    crc_tab[t] = v;
+  }
+  __syncthreads();
+  const uint8_t *src = raw + (size_t)blockIdx.x * nblock_max;
+  const uint32_t per = (c.nblock + BZ_RLE_THREADS - 1) / BZ_RLE_THREADS;
+  const uint32_t lo = min(t * per, c.nblock), hi = min(lo + per, c.nblock);
+  uint32_t s = slice_state[(size_t)blockIdx.x * BZ_RLE_THREADS + t];
+  const unsigned long long o0 = block_off[blockIdx.x] + slice_out[(size_t)blockIdx.x * BZ_RLE_THREADS + t];
+  unsigned long long o = o0;
+  uint32_t crc = 0;  // register started at 0: R(0, slice)
+  uint8_t prev = lo > 0 ? src[lo - 1] : 0;
+  for (uint32_t i = lo; i < hi; ++i) {
+    uint8_t x = src[i];
+    bool eq = (i > 0) && x == prev;
+    if (s == 4) {
+      for (uint32_t k = 0; k < x; ++k) {
+        if (o < out_cap) out[o] = prev;
+        o++;
+        crc = (crc << 8) ^ crc_tab[(crc >> 24) ^ prev];
+      }
+    } else {
+      if (o < out_cap) out[o] = x;
+      o++;
+      crc = (crc << 8) ^ crc_tab[(crc >> 24) ^ x];
+    }
+    s = rle_step(s, eq);
+    prev = x;
+  }
+  // combine: R(init, A||B) = R(init, A) * x^(8|B|) ^ R(0, B)
+  sm_crc[t] = crc;
+  sm_len[t] = (uint32_t)(o - o0);
+  __syncthreads();
+  for (int d = 1; d < BZ_RLE_THREADS; d <<= 1) {
+    uint32_t cl = 0, ll = 0;
+    const bool has = t >= (uint32_t)d;
+    if (has) {
+      cl = sm_crc[t - d];
+      ll = sm_len[t - d];
+    }
+    __syncthreads();
+    if (has) {
+      sm_crc[t] = bzcrc_mulmod(cl, bzcrc_xpow8(sm_len[t])) ^ sm_crc[t];
+      sm_len[t] += ll;
+    }
+    __syncthreads();
+  }
+  if (t == BZ_RLE_THREADS - 1) {
+    // whole block with the real initial register 0xffffffff, then the final xor (bzip2.dart:9,16-18)
+    uint32_t r = bzcrc_mulmod(0xffffffffu, bzcrc_xpow8(sm_len[t])) ^ sm_crc[t];
+    block_crc[blockIdx.x] = r ^ 0xffffffffu;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------------
+size_t bz2_entropy_smem() { return sizeof(BzSmem); }
+
+cudaError_t bz2_launch_scan(const uint8_t *d_in, uint64_t n_bytes, unsigned long long *d_cand, uint32_t *d_ncand, uint32_t cap,
+                            cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(d_ncand, 0, 4, s);
+  if (e != cudaSuccess) return e;
+  uint64_t threads = (n_bytes + 3) / 4;
+  unsigned blocks = (unsigned)((threads + 255) / 256);
+  if (blocks == 0) return cudaSuccess;
+  k_bz2_scan<<<blocks, 256, 0, s>>>(d_in, n_bytes, d_cand, d_ncand, cap);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t bz2_launch_entropy(const Bz2Entropy &a, cudaStream_t s) {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(k_bz2_entropy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BzSmem));
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  if (a.n_blocks == 0) return cudaSuccess;
+  k_bz2_entropy<<<a.n_blocks, 32, sizeof(BzSmem), s>>>(a.words, a.n_bytes, a.blk_bit, a.n_blocks, a.nblock_max, a.rec_val,
+                                                       a.rec_pos, a.n_rec, a.nblock, a.orig_ptr, a.randomised, a.end_bit,
+                                                       a.status);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t bz2_launch_ibwt(const Bz2Ibwt &a, cudaStream_t s) {
+  if (a.n_chain == 0) return cudaSuccess;
+  const BzChain *chain = reinterpret_cast<const BzChain *>(a.chain);
+  const uint32_t chunks_max = (a.nblock_max + BZ_CHUNK - 1) / BZ_CHUNK;
+  dim3 g1(64, a.n_chain);
+  k_bz2_expand<<<g1, 256, 0, s>>>(chain, a.rec_val, a.rec_pos, a.nblock_max, a.sym8);
+  count_launch();
+  dim3 g2((chunks_max + 3) / 4, a.n_chain);
+  k_bz2_chunk_hist<<<g2, 128, 0, s>>>(chain, a.sym8, a.nblock_max, chunks_max, a.chist);
+  count_launch();
+  k_bz2_chunk_scan<<<a.n_chain, 256, 0, s>>>(chain, chunks_max, a.chist);
+  count_launch();
+  k_bz2_build_tt<<<g2, 128, 0, s>>>(chain, a.sym8, a.nblock_max, chunks_max, a.chist, a.tt);
+  count_launch();
+  dim3 g3((BZ_SPLIT + 2 + 255) / 256, a.n_chain);
+  k_bz2_walk_len<<<g3, 256, 0, s>>>(chain, a.tt, a.nblock_max, a.seg_len, a.seg_next);
+  count_launch();
+  k_bz2_walk_order<<<(a.n_chain + 63) / 64, 64, 0, s>>>(chain, a.n_chain, a.tt, a.nblock_max, a.seg_len, a.seg_next,
+                                                         a.seg_off, a.irregular);
+  count_launch();
+  k_bz2_walk_emit<<<g3, 256, 0, s>>>(chain, a.tt, a.nblock_max, a.seg_len, a.seg_off, a.raw);
+  count_launch();
+  k_bz2_rle_count<<<a.n_chain, BZ_RLE_THREADS, 0, s>>>(chain, a.raw, a.nblock_max, a.slice_state, a.slice_out, a.block_out);
+  count_launch();
+  k_bz2_offsets<<<1, 32, 0, s>>>(a.block_out, a.n_chain, a.block_off);
+  count_launch();
+  k_bz2_rle_emit<<<a.n_chain, BZ_RLE_THREADS, 0, s>>>(chain, a.raw, a.nblock_max, a.slice_state, a.slice_out, a.block_off,
+                                                     a.out_cap, a.out, a.block_crc);
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace b200z

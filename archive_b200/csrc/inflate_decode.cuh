@@ -34,6 +34,8 @@ __device__ __forceinline__ uint32_t b200z_lds32(uint32_t base, uint32_t idx) {
 #define B200Z_PREFETCH(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
 typedef uint32_t b200z_saddr;
 #define B200Z_ANY(x) __any_sync(0xffffffffu, (x))
+#define B200Z_ALL(x) __all_sync(0xffffffffu, (x))
+#define B200Z_LDG128(p) __ldg(reinterpret_cast<const uint4 *>(p))
 #define B200Z_LDG(p) __ldg(p)
 #define B200Z_BREV(x) __brev(x)
 #else
@@ -43,6 +45,11 @@ typedef uint32_t b200z_saddr;
 #define B200Z_PREFETCH(p) ((void)0)
 typedef const void *b200z_saddr;
 #define B200Z_ANY(x) (x)
+#define B200Z_ALL(x) (x)
+#ifndef __CUDACC__
+struct uint4 { uint32_t x, y, z, w; };
+#endif
+#define B200Z_LDG128(p) (*reinterpret_cast<const uint4 *>(p))
 #define B200Z_LDG(p) (*(p))
 static inline uint32_t b200z_host_brev(uint32_t v) {
   v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
@@ -129,7 +136,11 @@ struct SlowTabD {
 //   "isEOS while _bitBufferLen < n" tests (inflate.dart:166-168,192-195) see.
 // ---------------------------------------------------------------------------------------------
 struct BitReader {
-  const uint32_t *w;  // aligned word base of the unit
+  const uint32_t *w;  // 16-byte aligned word base of the unit
+  // bulk-path input queue: `cur` = the 16-byte block q_blk of the stream, `nxt` = block q_blk + 1, requested a
+  // whole block (several symbols) before it is needed, so a miss to L2/HBM is not on the critical path
+  uint4 cur, nxt;
+  uint32_t q_blk;
   uint64_t buf;
   int cnt;          // bits in buf (may include `pad` invalid bits once widx >= nw)
   uint32_t widx;    // next word to load
@@ -154,12 +165,22 @@ struct BitReader {
       cnt += 32;
     }
   }
-  // bulk-path refill: as refill(), plus an L1 prefetch two 128-byte lines ahead whenever the stream enters a
-  // new line (a lane's miss stalls its whole warp, so the latency has to be hidden up front)
+  B200Z_HD uint4 load_blk(uint32_t b) const {  // words [4b, 4b+4); blocks past the stream read as zero
+    uint4 z;
+    z.x = z.y = z.z = z.w = 0u;
+    return (b * 4u < nw) ? B200Z_LDG128(w + (size_t)b * 4u) : z;
+  }
+  // bulk-path refill through the register queue (only valid while widx < nw)
   B200Z_HD void refill_bulk() {
     if (cnt < 32) {
-      uint32_t v = B200Z_LDG(w + widx);
-      if ((widx & 31u) == 0u && widx + 96u < nw) B200Z_PREFETCH(w + widx + 64);
+      const uint32_t b = widx >> 2;
+      if (b != q_blk) {
+        cur = (b == q_blk + 1u) ? nxt : load_blk(b);
+        nxt = load_blk(b + 1u);
+        q_blk = b;
+      }
+      const uint32_t k = widx & 3u;
+      const uint32_t v = k == 0u ? cur.x : k == 1u ? cur.y : k == 2u ? cur.z : cur.w;
       widx++;
       buf |= (uint64_t)v << cnt;
       cnt += 32;
@@ -280,10 +301,13 @@ B200Z_HD UnitResult inflate_decode_unit(bool active, const uint8_t *in, uint32_t
   BitReader br;
   {
     uintptr_t a = reinterpret_cast<uintptr_t>(in);
-    br.lead = (uint32_t)(a & 3);
+    br.lead = (uint32_t)(a & 15);
     br.w = reinterpret_cast<const uint32_t *>(a - br.lead);
     br.in_len = in_len;
     br.nw = (uint32_t)(((uint64_t)br.lead + br.in_len + 3) >> 2);
+    br.q_blk = 0xfffffff0u;
+    br.cur.x = br.cur.y = br.cur.z = br.cur.w = 0u;
+    br.nxt = br.cur;
     br.seek(0);
   }
   uint32_t nt = 0;
@@ -297,6 +321,50 @@ B200Z_HD UnitResult inflate_decode_unit(bool active, const uint8_t *in, uint32_t
 
   bool done = !active;
   while (B200Z_ANY(!done)) {  // warp-uniform: every lane reconverges here once per token
+    // ---------------- bulk inner loop: warp-uniform, one symbol per lane per turn, (almost) branch free.
+    // A lane speculates the symbol from table look-ups alone and commits only if nothing special happened
+    // (end of block, invalid symbol, back-reference before the start, output full, near the end of the stream);
+    // anything special drops the whole warp to the exact step below for one turn.
+    for (;;) {
+      const bool can = !done && in_block && (mode_dist || br.widx + 2u <= br.nw);
+      if (!B200Z_ALL(done || can) || !B200Z_ANY(can)) break;
+      bool kick = false;
+      if (can) {
+        br.refill_bulk();
+        const bool dm = mode_dist;
+        const uint32_t bits = (uint32_t)br.buf;
+        const uint32_t e = B200Z_LDS16(dm ? lutd_s : lutl_s, bits & (dm ? ((1u << DBITS) - 1u) : ((1u << LBITS) - 1u)));
+        int n = (int)(e & 15u);
+        int sym = (int)(e >> 4);
+        if (n == 0) {  // code longer than the LUT (rare)
+          if (dm) {
+            n = slow_decode<DBITS, uint8_t>(bits & 0x7fffu, sd.first, sd.count, sd.offs, sd.perm, maxd, &sym);
+            if (n == 0) sym = 0;
+          } else {
+            n = slow_decode<LBITS, uint16_t>(bits & 0x7fffu, sl.first, sl.count, sl.offs, sl.perm, maxl, &sym);
+            kick = n == 0;
+          }
+        }
+        const uint32_t xi = dm ? 32u + (uint32_t)sym : (sym > 256 ? (uint32_t)(sym - 257) : 63u);
+        const uint32_t x = B200Z_LDS32(xtab_s, xi & 63u);
+        const uint32_t xb = x & 15u;
+        const uint32_t val = (x >> 4) + ((bits >> n) & ((1u << xb) - 1u));
+        const bool islit = !dm && sym < 256;
+        const bool islen = !dm && sym > 256;
+        const uint32_t nolen = olen + (islit ? 1u : dm ? mlen_pending : 0u);
+        kick = kick || (!dm && (sym == 256 || sym > 285)) || (dm && (sym > 29 || val > olen)) || nolen > cap;
+        if (!kick) {
+          const int tot = n + (int)xb;
+          br.buf >>= tot;
+          br.cnt -= tot;
+          if (islit || dm) tok[nt++] = islit ? (TOK_LIT | (uint32_t)sym) : ((mlen_pending << 16) | val);
+          olen = nolen;
+          if (islen) mlen_pending = val;
+          mode_dist = islen;
+        }
+      }
+      if (B200Z_ANY(kick)) break;
+    }
     if (!done) do {
     if (in_block && (mode_dist || br.widx + 2u <= br.nw)) {
       // ---------------- bulk path: ONE SYMBOL per turn, the same instructions for literal/length and

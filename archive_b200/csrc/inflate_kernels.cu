@@ -277,7 +277,14 @@ cudaError_t launch_inflate(const InflateBatch &b, cudaStream_t stream) {
   if (g_prof) cudaEventRecord(pt.b, stream);
   const int ewarps = B200Z_EXPAND_THREADS / 32;
   uint64_t eblocks = (b.n_units + ewarps - 1) / ewarps;
-  const uint64_t max_blocks = (uint64_t)g_num_sms * (2048 / B200Z_EXPAND_THREADS) * 4;
+  // resident expand warps x 32 KiB of LZ77 window each should stay inside the 126 MB L2
+  static int bps = -1;
+  if (bps < 0) {
+    const char *e = getenv("B200Z_EXPAND_BPS");
+    bps = e ? atoi(e) : 0;
+    if (bps <= 0) bps = 32;
+  }
+  const uint64_t max_blocks = (uint64_t)g_num_sms * (uint64_t)bps;
   if (eblocks > max_blocks) eblocks = max_blocks;
   k_inflate_expand<<<(unsigned)eblocks, B200Z_EXPAND_THREADS, 0, stream>>>(tokens, ntok, b.in_base, b.in_off, b.out_base,
                                                                            b.out_off, (uint32_t)b.n_units);

@@ -78,6 +78,12 @@ int b200z_zlib_decode(const uint8_t *in, size_t in_len, int verify, int raw, uin
  * size fields where present (ISIZE), else 0 = unknown (call with a guess, retry on E_NOSPC). */
 size_t b200z_gzip_bound(const uint8_t *in, size_t in_len);
 
+/* BZip2Decoder().decodeBytes(data, verify:) -- bzip2_decoder.dart:13-88.  Stops after the first end-of-stream
+ * block; CRCs are compared only when verify; B200Z_E_DATA == decodeStream returning false (the blocks decoded
+ * before the failure are kept, as in the reference).                                                    */
+int b200z_bzip2_decode(const uint8_t *in, size_t in_len, int verify, uint8_t *out, size_t out_cap,
+                       size_t *out_len);
+
 /* ---- batched independent units (what the kernels run) --------------------------------- */
 /* n_units raw DEFLATE streams: unit u reads in_base[in_off[u] .. +in_len[u]) and writes
  * out_base[out_off[u] .. +out_cap[u]).  Per unit: out_len, status (B200Z_U_*), in_used.

@@ -33,7 +33,7 @@ static void expand(const uint32_t *tok, uint32_t nt, const uint8_t *in, uint8_t 
 extern "C" int emul_inflate(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t cap, uint32_t *out_len,
                             uint32_t *in_used, int32_t *status, uint32_t *ntok_out) {
   // the kernel reads aligned 32-bit words: give the stream a padded, deliberately misaligned home
-  std::vector<uint8_t> home(in_len + 16, 0xA5);
+  std::vector<uint8_t> home(in_len + 64, 0xA5);
   uint8_t *p = home.data() + 4 + 1;
   while (((uintptr_t)p & 3) != 1) ++p;
   memcpy(p, in, in_len);

@@ -1,0 +1,94 @@
+"""Parity tests for the sm_100a BZip2 decode path (K6-K8), through the C ABI, against the oracle and libbz2.
+Fixtures: test/bzip2_test.dart:8-12 (test.bz2), io_test's test2.tar.bz2; seeded synthetic data incl. multi-block
+streams (no reference fixture has one), degenerate run patterns for the RLE1 automaton, and bad data."""
+import bz2
+import hashlib
+import json
+import os
+import random
+
+import pytest
+
+import oracle_lib as orc
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+MAN = json.load(open(os.path.join(G, "manifest.json")))
+
+
+def rd(n):
+    return open(os.path.join(G, n), "rb").read()
+
+
+@pytest.fixture(scope="module")
+def a():
+    import archive_b200
+    return archive_b200
+
+
+def test_fixtures(a):
+    for name in ("test.bz2", "test2.tar.bz2"):
+        out = a.BZip2Decoder().decode_bytes(rd(name), verify=True)
+        assert hashlib.sha256(out).hexdigest() == MAN[name]["sha256"], name
+        assert out == orc.bzip2_decode(rd(name))[1]
+    assert a.BZip2Decoder().decode_bytes(rd("test2.tar.bz2")) == rd("test2.tar")
+
+
+def test_roundtrip_cat_jpg(a):  # test/bzip2_test.dart:14-25 (decode side; libbz2 encodes)
+    z = bz2.compress(rd("cat.jpg"), 9)
+    assert a.BZip2Decoder().decode_bytes(z, verify=True) == rd("cat.jpg")
+
+
+def test_synthetic_vs_oracle(a):
+    from archive_b200 import synth
+    rng = random.Random(31)
+    big = synth.text(2_300_000, stream=7).tobytes()
+    cases = [big, b"", b"a", b"ab" * 5, b"aaaa", b"aaaaa", b"aaaa" * 100000, bytes([251]) * 70000,
+             bytes([4]) * 1000 + bytes([5]) * 9 + bytes([4]) * 5, bytes(rng.getrandbits(8) for _ in range(200000)),
+             big[:1000], bytes(rng.choice(b"ab") for _ in range(50000)),
+             b"".join(bytes([rng.randrange(4)]) * rng.choice([1, 3, 4, 5, 8, 9, 10, 255, 256, 259, 260]) for _ in range(3000))]
+    for d in cases:
+        for level in (1, 9):
+            z = bz2.compress(d, level)
+            ost, oout = orc.bzip2_decode(z, verify=True)
+            out = a.BZip2Decoder().decode_bytes(z, verify=True)
+            assert ost == orc.OK and out == oout == d, (len(d), level)
+
+
+def test_stops_at_first_eos_and_bad_data(a):
+    from archive_b200 import synth
+    d = synth.text(300000, stream=8).tobytes()
+    z = bz2.compress(d, 1)  # 4 blocks
+    out = a.OutputMemoryStream()
+    assert a.BZip2Decoder().decode_stream(a.InputMemoryStream(z + z), out) is True
+    assert out.get_bytes() == d  # the second stream is not decoded (bzip2_decoder.dart:83-84)
+    # bad signature -> false, nothing written
+    out = a.OutputMemoryStream()
+    assert a.BZip2Decoder().decode_stream(a.InputMemoryStream(b"BZx1" + z[4:]), out) is False
+    assert out.get_bytes() == b""
+    # a flipped bit inside the third block: blocks before it are kept, decodeStream is false (verify) or throws
+    bad = bytearray(z)
+    bad[len(z) * 5 // 8] ^= 0x10
+    ost, oout = orc.bzip2_decode(bytes(bad), verify=True)
+    out = a.OutputMemoryStream()
+    try:
+        ok = a.BZip2Decoder().decode_stream(a.InputMemoryStream(bytes(bad)), out, verify=True)
+        assert ok is False and ost in (orc.FALSE, orc.THROW)
+    except a.DartRangeError:
+        assert ost == orc.THROW
+    got = out.get_bytes()
+    assert d.startswith(got[:100000])  # at least the first block is intact and identical
+    # truncated stream: readByte past the end throws in the reference
+    with pytest.raises(a.DartRangeError):
+        a.BZip2Decoder().decode_bytes(z[:len(z) // 2])
+    assert orc.bzip2_decode(z[:len(z) // 2])[0] == orc.THROW
+
+
+def test_scale_multiblock(a):
+    """Config-4 shape at test size: one BZh9 stream of many 900 KB blocks; every block CRC and the combined CRC
+    are verified on the device path (verify=True) and the bytes equal the source."""
+    from archive_b200 import synth
+    d = synth.text(24 << 20, stream=12).tobytes()
+    z = bz2.compress(d, 9)
+    out = a.BZip2Decoder().decode_bytes(z, verify=True)
+    assert len(out) == len(d) and out == d
