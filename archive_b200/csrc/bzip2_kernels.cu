@@ -476,7 +476,9 @@ k_bz2_build_tt(const BzChain *__restrict__ chain, const uint8_t *__restrict__ sy
     uint32_t basev = act ? cnt[warp][ch] : 0;
     __syncwarp();
     if (act) {
-      T[basev + rank] = (i << 8) | ch;
+      // tt[j] keeps ITS OWN byte in bits 0-7 (written at :318/:380) and receives i in the upper bits (:437)
+      const uint32_t j = basev + rank;
+      T[j] = (i << 8) | src[j];
       if (rank == 0) cnt[warp][ch] = basev + __popc(m);
     }
     __syncwarp();

@@ -34,8 +34,13 @@ __device__ __forceinline__ uint32_t b200z_lds32(uint32_t base, uint32_t idx) {
 #define B200Z_PREFETCH(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
 typedef uint32_t b200z_saddr;
 #define B200Z_ANY(x) __any_sync(0xffffffffu, (x))
-#define B200Z_ALL(x) __all_sync(0xffffffffu, (x))
-#define B200Z_LDG128(p) __ldg(reinterpret_cast<const uint4 *>(p))
+#define B200Z_BALLOT(x) __ballot_sync(0xffffffffu, (x))
+__device__ __forceinline__ uint32_t b200z_opaque(uint32_t v) {
+  uint32_t o;
+  asm volatile("mov.b32 %0, %1;" : "=r"(o) : "r"(v));  // keeps a loop invariant in a register (no rematerialisation)
+  return o;
+}
+#define B200Z_OPAQUE(x) b200z_opaque(x)
 #define B200Z_LDG(p) __ldg(p)
 #define B200Z_BREV(x) __brev(x)
 #else
@@ -45,11 +50,8 @@ typedef uint32_t b200z_saddr;
 #define B200Z_PREFETCH(p) ((void)0)
 typedef const void *b200z_saddr;
 #define B200Z_ANY(x) (x)
-#define B200Z_ALL(x) (x)
-#ifndef __CUDACC__
-struct uint4 { uint32_t x, y, z, w; };
-#endif
-#define B200Z_LDG128(p) (*reinterpret_cast<const uint4 *>(p))
+#define B200Z_BALLOT(x) ((x) ? 1u : 0u)
+#define B200Z_OPAQUE(x) (x)
 #define B200Z_LDG(p) (*(p))
 static inline uint32_t b200z_host_brev(uint32_t v) {
   v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
@@ -137,10 +139,7 @@ struct SlowTabD {
 // ---------------------------------------------------------------------------------------------
 struct BitReader {
   const uint32_t *w;  // 16-byte aligned word base of the unit
-  // bulk-path input queue: `cur` = the 16-byte block q_blk of the stream, `nxt` = block q_blk + 1, requested a
-  // whole block (several symbols) before it is needed, so a miss to L2/HBM is not on the critical path
-  uint4 cur, nxt;
-  uint32_t q_blk;
+  uint32_t nextw;  // word `widx`, requested one refill ahead of its use (hides the L1/L2 latency)
   uint64_t buf;
   int cnt;          // bits in buf (may include `pad` invalid bits once widx >= nw)
   uint32_t widx;    // next word to load
@@ -154,36 +153,16 @@ struct BitReader {
     uint32_t sh = (a & 3) * 8;
     uint32_t v = (widx < nw) ? B200Z_LDG(w + widx) : 0u;
     widx++;
+    nextw = (widx < nw) ? B200Z_LDG(w + widx) : 0u;
     buf = (uint64_t)(v >> sh);
     cnt = 32 - (int)sh;
   }
   B200Z_HD void refill() {
     if (cnt < 32) {
-      uint32_t v = (widx < nw) ? B200Z_LDG(w + widx) : 0u;
-      widx++;
-      buf |= (uint64_t)v << cnt;
+      buf |= (uint64_t)nextw << cnt;
       cnt += 32;
-    }
-  }
-  B200Z_HD uint4 load_blk(uint32_t b) const {  // words [4b, 4b+4); blocks past the stream read as zero
-    uint4 z;
-    z.x = z.y = z.z = z.w = 0u;
-    return (b * 4u < nw) ? B200Z_LDG128(w + (size_t)b * 4u) : z;
-  }
-  // bulk-path refill through the register queue (only valid while widx < nw)
-  B200Z_HD void refill_bulk() {
-    if (cnt < 32) {
-      const uint32_t b = widx >> 2;
-      if (b != q_blk) {
-        cur = (b == q_blk + 1u) ? nxt : load_blk(b);
-        nxt = load_blk(b + 1u);
-        q_blk = b;
-      }
-      const uint32_t k = widx & 3u;
-      const uint32_t v = k == 0u ? cur.x : k == 1u ? cur.y : k == 2u ? cur.z : cur.w;
       widx++;
-      buf |= (uint64_t)v << cnt;
-      cnt += 32;
+      nextw = (widx < nw) ? B200Z_LDG(w + widx) : 0u;
     }
   }
   // all bits in buf valid and >= 32 of them after refill()
@@ -215,7 +194,8 @@ struct BitReader {
 // ---------------------------------------------------------------------------------------------
 template <int TBITS, typename PermT>
 B200Z_HD bool build_table(const uint8_t *lens, int n, uint16_t *lut, uint16_t *first,
-                                            uint16_t *count, uint16_t *offs, PermT *perm, uint8_t *maxlen) {
+                                            uint16_t *count, uint16_t *offs, PermT *perm, uint8_t *maxlen,
+                                            int lut_skip_eq = -1, int lut_skip_above = 0x7fffffff) {
   for (int l = 0; l < 16; ++l) count[l] = 0;
   int mx = 0;
   for (int i = 0; i < n; ++i) {
@@ -256,7 +236,7 @@ B200Z_HD bool build_table(const uint8_t *lens, int n, uint16_t *lut, uint16_t *f
     if (l == 0) continue;
     uint32_t c = next[l]++;
     perm[run[l]++] = (PermT)s;
-    if (l <= TBITS) {
+    if (l <= TBITS && s != lut_skip_eq && s <= lut_skip_above) {
       uint32_t r = B200Z_BREV(c) >> (32 - l);
       uint16_t e = (uint16_t)((s << 4) | l);
       for (uint32_t j = r; j < (1u << TBITS); j += (1u << l)) lut[j] = e;
@@ -305,9 +285,6 @@ B200Z_HD UnitResult inflate_decode_unit(bool active, const uint8_t *in, uint32_t
     br.w = reinterpret_cast<const uint32_t *>(a - br.lead);
     br.in_len = in_len;
     br.nw = (uint32_t)(((uint64_t)br.lead + br.in_len + 3) >> 2);
-    br.q_blk = 0xfffffff0u;
-    br.cur.x = br.cur.y = br.cur.z = br.cur.w = 0u;
-    br.nxt = br.cur;
     br.seek(0);
   }
   uint32_t nt = 0;
@@ -320,50 +297,48 @@ B200Z_HD UnitResult inflate_decode_unit(bool active, const uint8_t *in, uint32_t
   uint32_t mlen_pending = 0;
 
   bool done = !active;
-  while (B200Z_ANY(!done)) {  // warp-uniform: every lane reconverges here once per token
-    // ---------------- bulk inner loop: warp-uniform, one symbol per lane per turn, (almost) branch free.
-    // A lane speculates the symbol from table look-ups alone and commits only if nothing special happened
-    // (end of block, invalid symbol, back-reference before the start, output full, near the end of the stream);
-    // anything special drops the whole warp to the exact step below for one turn.
+  // loop invariants of the bulk loop, pinned in registers
+  const b200z_saddr lutl_r = B200Z_OPAQUE(lutl_s), lutd_r = B200Z_OPAQUE(lutd_s), xtab_r = B200Z_OPAQUE(xtab_s);
+  static_assert(LBITS == DBITS, "the bulk loop uses one index mask for both LUTs");
+  unsigned live;
+  while ((live = B200Z_BALLOT(!done)) != 0u) {  // warp-uniform: every lane reconverges here
+    // ---------------- bulk inner loop: warp-uniform, ONE SYMBOL per lane per turn, branch-light.  The same
+    // instructions decode a literal/length symbol or a distance symbol (a lane that has just read a length
+    // code reads its distance code on the next turn), so literal lanes and match lanes do not diverge.  A
+    // lane speculates the symbol from two table look-ups and commits only if nothing special happened:
+    // LUT miss (long code, end-of-block and invalid symbols are deliberately absent from the LUT),
+    // back-reference before the start, output full, or fewer than 64 unloaded bits left.  Anything special
+    // drops the warp to the exact step below for one turn.  (A token is <= 48 bits, so with >= 64 unloaded
+    // bits at its start no end-of-stream test is needed in here.)
+    bool fast_ok = !done && in_block;
     for (;;) {
-      const bool can = !done && in_block && (mode_dist || br.widx + 2u <= br.nw);
-      if (!B200Z_ALL(done || can) || !B200Z_ANY(can)) break;
-      bool kick = false;
-      if (can) {
-        br.refill_bulk();
-        const bool dm = mode_dist;
-        const uint32_t bits = (uint32_t)br.buf;
-        const uint32_t e = B200Z_LDS16(dm ? lutd_s : lutl_s, bits & (dm ? ((1u << DBITS) - 1u) : ((1u << LBITS) - 1u)));
-        int n = (int)(e & 15u);
-        int sym = (int)(e >> 4);
-        if (n == 0) {  // code longer than the LUT (rare)
-          if (dm) {
-            n = slow_decode<DBITS, uint8_t>(bits & 0x7fffu, sd.first, sd.count, sd.offs, sd.perm, maxd, &sym);
-            if (n == 0) sym = 0;
-          } else {
-            n = slow_decode<LBITS, uint16_t>(bits & 0x7fffu, sl.first, sl.count, sl.offs, sl.perm, maxl, &sym);
-            kick = n == 0;
-          }
-        }
-        const uint32_t xi = dm ? 32u + (uint32_t)sym : (sym > 256 ? (uint32_t)(sym - 257) : 63u);
-        const uint32_t x = B200Z_LDS32(xtab_s, xi & 63u);
-        const uint32_t xb = x & 15u;
-        const uint32_t val = (x >> 4) + ((bits >> n) & ((1u << xb) - 1u));
-        const bool islit = !dm && sym < 256;
-        const bool islen = !dm && sym > 256;
-        const uint32_t nolen = olen + (islit ? 1u : dm ? mlen_pending : 0u);
-        kick = kick || (!dm && (sym == 256 || sym > 285)) || (dm && (sym > 29 || val > olen)) || nolen > cap;
-        if (!kick) {
-          const int tot = n + (int)xb;
-          br.buf >>= tot;
-          br.cnt -= tot;
-          if (islit || dm) tok[nt++] = islit ? (TOK_LIT | (uint32_t)sym) : ((mlen_pending << 16) | val);
-          olen = nolen;
-          if (islen) mlen_pending = val;
-          mode_dist = islen;
-        }
+      const bool can = fast_ok && (mode_dist || br.widx + 2u <= br.nw);
+      if (B200Z_BALLOT(can) != live) break;
+      if (!can) continue;  // lanes whose stream is finished just keep voting
+      br.refill();
+      const bool dm = mode_dist;
+      const uint32_t bits = (uint32_t)br.buf;
+      const uint32_t e = B200Z_LDS16(dm ? lutd_r : lutl_r, bits & ((1u << LBITS) - 1u));
+      const uint32_t n = e & 15u;
+      const uint32_t sym = e >> 4;
+      const uint32_t xi = dm ? sym + 32u : (sym > 256u ? sym - 257u : 63u);
+      const uint32_t x = B200Z_LDS32(xtab_r, xi);
+      const uint32_t xb = x & 15u;
+      const uint32_t val = (x >> 4) + ((bits >> n) & ~(0xffffffffu << xb));
+      const bool islit = !dm && sym < 256u;
+      const bool islen = !dm && sym > 256u;
+      const uint32_t nolen = olen + (islit ? 1u : dm ? mlen_pending : 0u);
+      const bool special = n == 0u || (dm && val > olen) || nolen > cap;
+      if (!special) {
+        const uint32_t tot = n + xb;
+        br.buf >>= tot;
+        br.cnt -= (int)tot;
+        if (islit || dm) tok[nt++] = islit ? (TOK_LIT | sym) : ((mlen_pending << 16) | val);
+        olen = nolen;
+        mlen_pending = islen ? val : mlen_pending;
+        mode_dist = islen;
       }
-      if (B200Z_ANY(kick)) break;
+      fast_ok = !special;
     }
     if (!done) do {
     if (in_block && (mode_dist || br.widx + 2u <= br.nw)) {
@@ -372,7 +347,7 @@ B200Z_HD UnitResult inflate_decode_unit(bool active, const uint8_t *in, uint32_t
       // turn), so the lanes of a warp stay converged.  >= 64 stream bits are still unloaded when a
       // literal/length symbol starts, so no end-of-stream test is needed here (a token is <= 48 bits);
       // everything near the end of the stream goes through the exact per-token path below.
-      br.refill_bulk();
+      br.refill();
       const bool dm = mode_dist;
       const uint32_t bits = (uint32_t)br.buf;
       uint32_t e = B200Z_LDS16(dm ? lutd_s : lutl_s, bits & (dm ? ((1u << DBITS) - 1u) : ((1u << LBITS) - 1u)));
@@ -504,9 +479,9 @@ B200Z_HD UnitResult inflate_decode_unit(bool active, const uint8_t *in, uint32_t
       } else if (type == 1) {
         // ---- fixed tables (inflate.dart:408-735): 288 lit/len lengths, 30 distance lengths ----
         for (int i = 0; i < 288; ++i) lens[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8;
-        build_table<LBITS, uint16_t>(lens, 288, lut_l, sl.first, sl.count, sl.offs, sl.perm, &sl.maxlen);
+        build_table<LBITS, uint16_t>(lens, 288, lut_l, sl.first, sl.count, sl.offs, sl.perm, &sl.maxlen, 256, 285);
         for (int i = 0; i < 30; ++i) lens[i] = 5;
-        build_table<DBITS, uint8_t>(lens, 30, lut_d, sd.first, sd.count, sd.offs, sd.perm, &sd.maxlen);
+        build_table<DBITS, uint8_t>(lens, 30, lut_d, sd.first, sd.count, sd.offs, sd.perm, &sd.maxlen, -1, 29);
       } else if (type == 2) {
         // ---- dynamic (inflate.dart:239-298) ----
         int hlit = br.read_bits_checked(5);
@@ -574,8 +549,8 @@ B200Z_HD UnitResult inflate_decode_unit(bool active, const uint8_t *in, uint32_t
         }
         if (err) { st = err; done = true; break; }
         for (int k = hdist; k < 32; ++k) lens[hlit + k] = 0;
-        bool ok = build_table<DBITS, uint8_t>(lens + hlit, hdist, lut_d, sd.first, sd.count, sd.offs, sd.perm, &sd.maxlen);
-        ok = build_table<LBITS, uint16_t>(lens, hlit, lut_l, sl.first, sl.count, sl.offs, sl.perm, &sl.maxlen) && ok;
+        bool ok = build_table<DBITS, uint8_t>(lens + hlit, hdist, lut_d, sd.first, sd.count, sd.offs, sd.perm, &sd.maxlen, -1, 29);
+        ok = build_table<LBITS, uint16_t>(lens, hlit, lut_l, sl.first, sl.count, sl.offs, sl.perm, &sl.maxlen, 256, 285) && ok;
         if (!ok) { st = B200Z_U_BADCODE; done = true; break; }
       } else {
         st = B200Z_U_STOP;
