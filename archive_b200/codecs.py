@@ -154,3 +154,67 @@ class BZip2Decoder:
             return False
         _ffi.check(rc)
         return True
+
+
+class Deflate:
+    """`Deflate(bytes, level: 6, windowBits: 15)` (lib/src/codecs/zlib/deflate.dart:25-100): raw DEFLATE produced in the
+    constructor, `get_bytes()` / `take_bytes()`, and `crc32` of the consumed input.  Invalid parameters make the
+    reference's `getBytes()` throw LateInitializationError (`_init` returned false, :107-118): B200ZError(E_ARG) here."""
+
+    def __init__(self, data=b"", level: int = 6, window_bits: int = 15, output: OutputMemoryStream | None = None):
+        self._output = output if output is not None else OutputMemoryStream()
+        self.level = level
+        self.crc32 = 0
+        L = _ffi.ensure_init()
+        addr, n, keep = _ffi.as_buffer(data)
+        cap = L.b200z_deflate_bound(n)
+        out = (C.c_uint8 * cap)()
+        out_len, crc = C.c_size_t(0), C.c_uint32(0)
+        rc = L.b200z_deflate_raw(addr, n, level, window_bits, C.addressof(out), cap, C.byref(out_len), C.byref(crc))
+        _ffi.check(rc)
+        self.crc32 = crc.value
+        self._output.write_bytes(C.string_at(out, out_len.value))
+
+    def get_bytes(self) -> bytes:
+        return self._output.get_bytes()
+
+    def take_bytes(self) -> bytes:
+        b = self._output.get_bytes()
+        self._output.clear()
+        return b
+
+
+class ZLibEncoderWeb:
+    """ZLibEncoderWeb().encodeBytes(bytes, level:, windowBits:, raw:) -- _zlib_encoder_web.dart:17-73"""
+
+    def encode_bytes(self, data, level: int | None = None, window_bits: int | None = None, raw: bool = False) -> bytes:
+        L = _ffi.ensure_init()
+        addr, n, keep = _ffi.as_buffer(data)
+        cap = L.b200z_deflate_bound(n)
+        out = (C.c_uint8 * cap)()
+        out_len = C.c_size_t(0)
+        rc = L.b200z_zlib_encode(addr, n, 6 if level is None else level, 15 if window_bits is None else window_bits, int(raw),
+                                 C.addressof(out), cap, C.byref(out_len))
+        _ffi.check(rc)
+        return C.string_at(out, out_len.value)
+
+
+class GZipEncoderWeb:
+    """GZipEncoderWeb().encodeBytes(bytes, level:) -- _gzip_encoder_web.dart:17-100.  The reference stamps MTIME with the
+    wall clock (:82); pass `mtime` for reproducible bytes."""
+
+    def encode_bytes(self, data, level: int | None = None, mtime: int | None = None) -> bytes:
+        import time
+        L = _ffi.ensure_init()
+        addr, n, keep = _ffi.as_buffer(data)
+        cap = L.b200z_deflate_bound(n)
+        out = (C.c_uint8 * cap)()
+        out_len = C.c_size_t(0)
+        rc = L.b200z_gzip_encode(addr, n, 6 if level is None else level, int(time.time()) if mtime is None else mtime,
+                                 C.addressof(out), cap, C.byref(out_len))
+        _ffi.check(rc)
+        return C.string_at(out, out_len.value)
+
+
+ZLibEncoder = ZLibEncoderWeb
+GZipEncoder = GZipEncoderWeb

@@ -742,7 +742,7 @@ static int bzip2_decode_impl(const uint8_t *in, size_t in_len, int verify, uint8
     struct A {
       unsigned long long *blk_bit, *end_bit, *block_out, *block_off;
       uint32_t *rec_val, *rec_pos, *n_rec, *nblock, *orig_ptr, *rnd, *chist, *tt, *seg_len, *seg_next, *seg_off, *slice_state,
-          *slice_out, *block_crc;
+          *slice_out, *block_crc, *cycle_len;
       int32_t *status, *irregular;
       uint8_t *sym8, *raw;
       BzChainHost *chain;
@@ -759,6 +759,7 @@ static int bzip2_decode_impl(const uint8_t *in, size_t in_len, int verify, uint8
     a.status = c.take<int32_t>(nbk);
     a.irregular = c.take<int32_t>(nbk);
     a.block_crc = c.take<uint32_t>(nbk);
+    a.cycle_len = c.take<uint32_t>(nbk);
     a.chain = c.take<BzChainHost>(nbk);
     a.seg_len = c.take<uint32_t>((size_t)nbk * 4098);
     a.seg_next = c.take<uint32_t>((size_t)nbk * 4098);
@@ -869,7 +870,7 @@ static int bzip2_decode_impl(const uint8_t *in, size_t in_len, int verify, uint8
     Bz2Ibwt w;
     w.chain = A.chain; w.n_chain = nc; w.nblock_max = nblock_max;
     w.rec_val = A.rec_val; w.rec_pos = A.rec_pos; w.sym8 = A.sym8; w.chist = A.chist; w.tt = A.tt;
-    w.seg_len = A.seg_len; w.seg_next = A.seg_next; w.seg_off = A.seg_off; w.irregular = A.irregular; w.raw = A.raw;
+    w.seg_len = A.seg_len; w.seg_next = A.seg_next; w.seg_off = A.seg_off; w.irregular = A.irregular; w.cycle_len = A.cycle_len; w.raw = A.raw;
     w.slice_state = A.slice_state; w.slice_out = A.slice_out; w.block_out = A.block_out; w.block_off = A.block_off;
     w.block_crc = A.block_crc; w.out = (uint8_t *)g.d_out.p; w.out_cap = out_cap;
     CU(bz2_launch_ibwt(w, g.stream));
@@ -909,6 +910,142 @@ static int bzip2_decode_impl(const uint8_t *in, size_t in_len, int verify, uint8
   if (n_out) CU(cudaMemcpyAsync(out, g.d_out.p, n_out, cudaMemcpyDeviceToHost, g.stream));
   CU(cudaStreamSynchronize(g.stream));
   return final_rc;
+}
+
+}  // namespace b200z
+
+// =============================================================================================
+// Deflate(bytes, level:, windowBits:).getBytes() + crc32  (deflate.dart:25-100), and the encoder framing of
+// _zlib_encoder_web.dart:27-73 / _gzip_encoder_web.dart:27-100
+// =============================================================================================
+namespace b200z {
+
+// CRC-32 (reflected 0xEDB88320) combination, as in zlib's crc32_combine: crc(A||B) = crc(A) * x^(8|B|) + crc(B)
+static uint32_t crc_multmodp(uint32_t a, uint32_t b) {
+  uint32_t m = 1u << 31, p = 0;
+  for (;;) {
+    if (a & m) {
+      p ^= b;
+      if ((a & (m - 1)) == 0) break;
+    }
+    m >>= 1;
+    b = (b & 1) ? (b >> 1) ^ 0xEDB88320u : b >> 1;
+  }
+  return p;
+}
+static uint32_t crc_xpow8(uint64_t nbytes) {
+  uint32_t p = 1u << 31;      // x^0
+  uint32_t sq = 1u << 23;     // x^8 in the reflected representation (bit 31 = x^0)
+  while (nbytes) {
+    if (nbytes & 1) p = crc_multmodp(sq, p);
+    sq = crc_multmodp(sq, sq);
+    nbytes >>= 1;
+  }
+  return p;
+}
+static int device_crc32(const uint8_t *d, size_t n, uint32_t *out) {
+  const uint32_t TILE = 1u << 16;
+  if (n == 0) {
+    *out = 0;
+    return B200Z_OK;
+  }
+  size_t tiles = (n + TILE - 1) / TILE;
+  CU(g.d_small.reserve(tiles * 4 + 256));
+  CU(crc32_tiles_device(d, n, TILE, (uint32_t *)g.d_small.p, g.stream));
+  std::vector<uint32_t> part(tiles);
+  CU(cudaMemcpyAsync(part.data(), g.d_small.p, tiles * 4, cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  uint32_t crc = part[0];
+  const uint32_t xfull = crc_xpow8(TILE);
+  for (size_t t = 1; t < tiles; ++t) {
+    size_t len = (t + 1 == tiles) ? n - t * TILE : TILE;
+    crc = crc_multmodp(len == TILE ? xfull : crc_xpow8(len), crc) ^ part[t];
+  }
+  *out = crc;
+  return B200Z_OK;
+}
+
+// the old deflate_stored (deflate.dart:691-737) touches no data: its block list follows from the length alone
+static void stored_block_list(size_t n, std::vector<DeflStoredBlock> &out) {
+  const long long w_size = 32768, window_size = 65536, min_lookahead = 262;
+  const long long max_block_size = 65536 - 5 < 0xffff ? 65536 - 5 : 0xffff;
+  long long strstart = 0, block_start = 0, lookahead = 0, base = 0;  // base: absolute position of window index 0
+  long long in_pos = 0;
+  auto flush = [&](bool eof) {
+    out.push_back({(uint32_t)(base + block_start), (uint32_t)(strstart - block_start), eof ? 1u : 0u});
+    block_start = strstart;
+  };
+  auto fill_window = [&]() {
+    do {
+      long long more = window_size - lookahead - strstart;
+      if (more == 0 && strstart == 0 && lookahead == 0) {
+        more = w_size;
+      } else if (strstart >= w_size + w_size - min_lookahead) {
+        strstart -= w_size;
+        block_start -= w_size;
+        base += w_size;
+        more += w_size;
+      }
+      if (in_pos >= (long long)n) return;
+      long long len = (long long)n - in_pos;
+      if (len > more) len = more;
+      in_pos += len;
+      lookahead += len;
+    } while (lookahead < min_lookahead && in_pos < (long long)n);
+  };
+  for (;;) {
+    if (lookahead <= 1) {
+      fill_window();
+      if (lookahead == 0) break;
+    }
+    strstart += lookahead;
+    lookahead = 0;
+    const long long max_start = block_start + max_block_size;
+    if (strstart >= max_start) {
+      lookahead = strstart - max_start;
+      strstart = max_start;
+      flush(false);
+    }
+    if (strstart - block_start >= w_size - min_lookahead) flush(false);
+  }
+  flush(true);
+}
+
+// compresses d_in[0, n) (already staged in g.d_in) into g.d_out; returns the compressed size
+static int deflate_staged(size_t n, int level, int window_bits, size_t *out_len) {
+  if (window_bits < 9 || window_bits > 15 || level < 0 || level > 9) {
+    set_err("deflate: invalid level %d / windowBits %d (Dart: LateInitializationError)", level, window_bits);
+    return B200Z_E_ARG;
+  }
+  if (window_bits != 15) {
+    set_err("deflate: windowBits %d is not implemented on the device (only 15)", window_bits);
+    return B200Z_E_ARG;
+  }
+  if (level >= 1 && level <= 3) {
+    set_err("deflate: levels 1-3 (the serial deflate_fast strategy) are not implemented on the device yet");
+    return B200Z_E_ARG;
+  }
+  if (n >= (1ull << 30)) {
+    set_err("deflate: inputs of 1 GiB and more are not supported yet");
+    return B200Z_E_ARG;
+  }
+  const size_t cap = align_up(deflate_bound(n) + 16, 256);
+  CU(g.d_out.reserve(cap));
+  if (level == 0) {
+    std::vector<DeflStoredBlock> bl;
+    stored_block_list(n, bl);
+    const size_t ws = bl.size() * 64 + 1024;
+    CU(g.d_ws.reserve(ws));
+    CU(deflate_stored_device((const uint8_t *)g.d_in.p, bl.data(), (uint32_t)bl.size(), (uint8_t *)g.d_out.p, cap, g.d_ws.p,
+                             g.d_ws.cap, out_len, g.stream));
+    return B200Z_OK;
+  }
+  const size_t ws = deflate_workspace_bytes(n);
+  CU(g.d_ws.reserve(ws));
+  uint32_t stats[3];
+  CU(deflate_slow_device((const uint8_t *)g.d_in.p, n, level, (uint8_t *)g.d_out.p, cap, g.d_ws.p, g.d_ws.cap, out_len, stats,
+                         g.stream));
+  return B200Z_OK;
 }
 
 }  // namespace b200z
@@ -1080,6 +1217,110 @@ int b200z_inflate_raw(const uint8_t *in, size_t in_len, uint8_t *out, size_t out
     return B200Z_E_THROW;
   }
   return B200Z_OK;  // STOP / BADCODE: reference keeps the partial output silently
+}
+
+int b200z_deflate_raw(const uint8_t *in, size_t in_len, int level, int window_bits, uint8_t *out, size_t out_cap,
+                      size_t *out_len, uint32_t *crc32_of_input) {
+  int rc = require_init();
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(g.mu);
+  CU(cudaSetDevice(g.device));
+  rc = stage_input(in, in_len);
+  if (rc) return rc;
+  CU(cudaMemsetAsync((uint8_t *)g.d_in.p + in_len, 0, 64, g.stream));
+  size_t n = 0;
+  rc = deflate_staged(in_len, level, window_bits, &n);
+  if (rc) return rc;
+  if (out_len) *out_len = n;
+  if (n > out_cap) {
+    set_err("deflate: output needs %zu bytes, out_cap %zu", n, out_cap);
+    return B200Z_E_NOSPC;
+  }
+  if (n) CU(cudaMemcpyAsync(out, g.d_out.p, n, cudaMemcpyDeviceToHost, g.stream));
+  if (crc32_of_input) {
+    rc = device_crc32((const uint8_t *)g.d_in.p, in_len, crc32_of_input);
+    if (rc) return rc;
+  }
+  CU(cudaStreamSynchronize(g.stream));
+  return B200Z_OK;
+}
+
+size_t b200z_deflate_bound(size_t in_len) { return deflate_bound(in_len) + 32; }
+
+int b200z_zlib_encode(const uint8_t *in, size_t in_len, int level, int window_bits, int raw, uint8_t *out, size_t out_cap,
+                      size_t *out_len) {
+  int rc = require_init();
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(g.mu);
+  CU(cudaSetDevice(g.device));
+  rc = stage_input(in, in_len);
+  if (rc) return rc;
+  CU(cudaMemsetAsync((uint8_t *)g.d_in.p + in_len, 0, 64, g.stream));
+  size_t n = 0;
+  rc = deflate_staged(in_len, level, window_bits, &n);
+  if (rc) return rc;
+  const size_t total = raw ? n : n + 6;
+  if (out_len) *out_len = total;
+  if (total > out_cap) {
+    set_err("zlib_encode: output needs %zu bytes, out_cap %zu", total, out_cap);
+    return B200Z_E_NOSPC;
+  }
+  size_t o = 0;
+  if (!raw) {
+    // CMF / FLG with FLEVEL 0 for every level (_zlib_encoder_web.dart:44-60, quirk Q4)
+    int wb = window_bits < 0 ? 0 : window_bits > 15 ? 15 : window_bits;
+    int cmf = ((wb - 8) << 4) | 8, flag = 0, fcheck = 0;
+    while ((cmf * 256 + (flag | fcheck)) % 31 != 0) fcheck++;
+    out[o++] = (uint8_t)cmf;
+    out[o++] = (uint8_t)(flag | fcheck);
+  }
+  if (n) CU(cudaMemcpyAsync(out + o, g.d_out.p, n, cudaMemcpyDeviceToHost, g.stream));
+  o += n;
+  if (!raw) {
+    uint32_t ad;
+    rc = device_adler32((const uint8_t *)g.d_in.p, in_len, &ad);
+    if (rc) return rc;
+    out[o++] = (uint8_t)(ad >> 24);
+    out[o++] = (uint8_t)(ad >> 16);
+    out[o++] = (uint8_t)(ad >> 8);
+    out[o++] = (uint8_t)ad;
+  }
+  CU(cudaStreamSynchronize(g.stream));
+  return B200Z_OK;
+}
+
+int b200z_gzip_encode(const uint8_t *in, size_t in_len, int level, uint32_t mtime, uint8_t *out, size_t out_cap,
+                      size_t *out_len) {
+  int rc = require_init();
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(g.mu);
+  CU(cudaSetDevice(g.device));
+  rc = stage_input(in, in_len);
+  if (rc) return rc;
+  CU(cudaMemsetAsync((uint8_t *)g.d_in.p + in_len, 0, 64, g.stream));
+  size_t n = 0;
+  rc = deflate_staged(in_len, level, 15, &n);
+  if (rc) return rc;
+  const size_t total = n + 18;
+  if (out_len) *out_len = total;
+  if (total > out_cap) {
+    set_err("gzip_encode: output needs %zu bytes, out_cap %zu", total, out_cap);
+    return B200Z_E_NOSPC;
+  }
+  // header (_gzip_encoder_web.dart:77-90): magic, deflate, flags 0, MTIME, XFL 0, OS 255
+  size_t o = 0;
+  out[o++] = 0x1f; out[o++] = 0x8b; out[o++] = 8; out[o++] = 0;
+  for (int i = 0; i < 4; ++i) out[o++] = (uint8_t)(mtime >> (8 * i));
+  out[o++] = 0; out[o++] = 255;
+  if (n) CU(cudaMemcpyAsync(out + o, g.d_out.p, n, cudaMemcpyDeviceToHost, g.stream));
+  o += n;
+  uint32_t crc;
+  rc = device_crc32((const uint8_t *)g.d_in.p, in_len, &crc);
+  if (rc) return rc;
+  for (int i = 0; i < 4; ++i) out[o++] = (uint8_t)(crc >> (8 * i));
+  for (int i = 0; i < 4; ++i) out[o++] = (uint8_t)((uint32_t)in_len >> (8 * i));
+  CU(cudaStreamSynchronize(g.stream));
+  return B200Z_OK;
 }
 
 size_t b200z_gzip_bound(const uint8_t *in, size_t in_len) {

@@ -55,6 +55,7 @@ struct Bz2Ibwt {  // K8 over the validated chain
   uint32_t *tt;     // [n_chain][nblock_max]
   uint32_t *seg_len, *seg_next, *seg_off;  // [n_chain][4098]
   int32_t *irregular;                      // [n_chain]
+  uint32_t *cycle_len;                     // [n_chain]
   uint8_t *raw;                            // [n_chain][nblock_max]
   uint32_t *slice_state, *slice_out;       // [n_chain][1024]
   unsigned long long *block_out, *block_off;  // [n_chain], [n_chain + 1]
@@ -73,5 +74,17 @@ cudaError_t bz2_launch_ibwt(const Bz2Ibwt &a, cudaStream_t s);
 void count_launch();
 void profile_enable(bool on);
 int profile_read(double *decode_ms, double *expand_ms, uint64_t *n);
+
+// ---- Deflate (deflate_kernels.cu) ----
+struct DeflStoredBlock {
+  uint32_t start, len, eof;
+};
+size_t deflate_bound(size_t n);
+size_t deflate_workspace_bytes(size_t n);
+cudaError_t deflate_slow_device(const uint8_t *d_in, size_t n, int level, uint8_t *d_out, size_t out_cap, void *ws,
+                                size_t ws_bytes, size_t *out_len, uint32_t *stats, cudaStream_t s);
+cudaError_t deflate_stored_device(const uint8_t *d_in, const DeflStoredBlock *h_blocks, uint32_t n_blocks, uint8_t *d_out,
+                                  size_t out_cap, void *ws, size_t ws_bytes, size_t *out_len, cudaStream_t s);
+cudaError_t crc32_tiles_device(const uint8_t *d_in, size_t n, uint32_t tile, uint32_t *d_part, cudaStream_t s);
 
 }  // namespace b200z

@@ -528,16 +528,19 @@ k_bz2_walk_len(const BzChain *__restrict__ chain, const uint32_t *__restrict__ t
   sn[j] = (cur == g.tpos0) ? g.start_id : cur / g.stride;
 }
 
-// one thread per block: order of the segments along the cycle; irregular (repeating) chains only arise from
-// corrupt data and are flagged
+// one thread per block: order of the segments along the cycle.  T (built by a stable counting sort) is always a
+// permutation, so the walk from tPos0 returns to tPos0; for a PERIODIC block (e.g. "abab...", or long runs after
+// RLE1) that happens after cycle_len < nblock steps and the reference simply keeps going round
+// (bzip2_decoder.dart:648-650): raw[i] = raw[i mod cycle_len].
 __global__ void k_bz2_walk_order(const BzChain *__restrict__ chain, uint32_t n_chain, const uint32_t *__restrict__ tt,
                                  uint32_t nblock_max, const uint32_t *__restrict__ seg_len,
                                  const uint32_t *__restrict__ seg_next, uint32_t *__restrict__ seg_off,
-                                 int32_t *__restrict__ irregular) {
+                                 int32_t *__restrict__ irregular, uint32_t *__restrict__ cycle_len) {
   const uint32_t bi = blockIdx.x * blockDim.x + threadIdx.x;
   if (bi >= n_chain) return;
   const BzChain c = chain[bi];
   irregular[bi] = 0;
+  cycle_len[bi] = c.nblock;
   if (c.nblock == 0) return;
   const uint32_t *T = tt + (size_t)bi * nblock_max;
   const BzWalkGeom g = bz_geom(c, T);
@@ -546,14 +549,30 @@ __global__ void k_bz2_walk_order(const BzChain *__restrict__ chain, uint32_t n_c
   for (uint32_t j = 0; j <= g.kb; ++j) so[j] = 0xffffffffu;
   uint32_t seg = g.start_id, off = 0, visited = 0;
   while (off < c.nblock) {
-    if (seg > g.kb || so[seg] != 0xffffffffu || sl[seg] == 0 || ++visited > g.kb + 1) {
+    if (seg > g.kb || sl[seg] == 0 || ++visited > g.kb + 1) {
       irregular[bi] = 1;
+      return;
+    }
+    if (so[seg] != 0xffffffffu) {  // back at the start: the cycle is shorter than the block
+      if (seg != g.start_id) irregular[bi] = 1;
+      cycle_len[bi] = off;
       return;
     }
     so[seg] = off;
     off += sl[seg];
     seg = sn[seg];
   }
+}
+
+// periodic blocks: repeat the cycle
+__global__ void __launch_bounds__(256)
+k_bz2_periodic_fill(const BzChain *__restrict__ chain, const uint32_t *__restrict__ cycle_len, uint32_t nblock_max,
+                    uint8_t *__restrict__ raw) {
+  const BzChain c = chain[blockIdx.y];
+  const uint32_t cl = cycle_len[blockIdx.y];
+  if (cl == 0 || cl >= c.nblock) return;
+  uint8_t *dst = raw + (size_t)blockIdx.y * nblock_max;
+  for (uint32_t i = cl + blockIdx.x * blockDim.x + threadIdx.x; i < c.nblock; i += gridDim.x * blockDim.x) dst[i] = dst[i % cl];
 }
 
 __global__ void __launch_bounds__(256)
@@ -812,9 +831,11 @@ cudaError_t bz2_launch_ibwt(const Bz2Ibwt &a, cudaStream_t s) {
   k_bz2_walk_len<<<g3, 256, 0, s>>>(chain, a.tt, a.nblock_max, a.seg_len, a.seg_next);
   count_launch();
   k_bz2_walk_order<<<(a.n_chain + 63) / 64, 64, 0, s>>>(chain, a.n_chain, a.tt, a.nblock_max, a.seg_len, a.seg_next,
-                                                         a.seg_off, a.irregular);
+                                                         a.seg_off, a.irregular, a.cycle_len);
   count_launch();
   k_bz2_walk_emit<<<g3, 256, 0, s>>>(chain, a.tt, a.nblock_max, a.seg_len, a.seg_off, a.raw);
+  count_launch();
+  k_bz2_periodic_fill<<<dim3(64, a.n_chain), 256, 0, s>>>(chain, a.cycle_len, a.nblock_max, a.raw);
   count_launch();
   k_bz2_rle_count<<<a.n_chain, BZ_RLE_THREADS, 0, s>>>(chain, a.raw, a.nblock_max, a.slice_state, a.slice_out, a.block_out);
   count_launch();

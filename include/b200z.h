@@ -78,6 +78,19 @@ int b200z_zlib_decode(const uint8_t *in, size_t in_len, int verify, int raw, uin
  * size fields where present (ISIZE), else 0 = unknown (call with a guess, retry on E_NOSPC). */
 size_t b200z_gzip_bound(const uint8_t *in, size_t in_len);
 
+/* Deflate(bytes, level:, windowBits:).getBytes() and .crc32 -- deflate.dart:39-48,72-75,31.  Raw DEFLATE, byte-identical
+ * to the reference at the same level.  Levels 0 and 4-9 run on the device; 1-3 (deflate_fast) and windowBits != 15
+ * return B200Z_E_ARG for now.  Invalid level / windowBits (Deflate._init returning false) -> B200Z_E_ARG.            */
+int b200z_deflate_raw(const uint8_t *in, size_t in_len, int level, int window_bits, uint8_t *out, size_t out_cap,
+                      size_t *out_len, uint32_t *crc32_of_input);
+size_t b200z_deflate_bound(size_t in_len); /* output capacity that always suffices (+18 for gzip, +6 for zlib) */
+/* ZLibEncoderWeb().encodeBytes -- _zlib_encoder_web.dart:17-73 (header 78 01 at every level, Adler-32 trailer)      */
+int b200z_zlib_encode(const uint8_t *in, size_t in_len, int level, int window_bits, int raw, uint8_t *out,
+                      size_t out_cap, size_t *out_len);
+/* GZipEncoderWeb().encodeBytes -- _gzip_encoder_web.dart:17-100 (MTIME is "now" in the reference: a parameter here) */
+int b200z_gzip_encode(const uint8_t *in, size_t in_len, int level, uint32_t mtime, uint8_t *out, size_t out_cap,
+                      size_t *out_len);
+
 /* BZip2Decoder().decodeBytes(data, verify:) -- bzip2_decoder.dart:13-88.  Stops after the first end-of-stream
  * block; CRCs are compared only when verify; B200Z_E_DATA == decodeStream returning false (the blocks decoded
  * before the failure are kept, as in the reference).                                                    */
