@@ -93,3 +93,9 @@ def bzip2_decode(data: bytes, verify=True):
 
 def set_truncate_heuristic(on: bool):
     L().orc_deflate_set_truncate_heuristic(int(on))
+
+
+def bzip2_encode(data: bytes):
+    out, n = C.POINTER(C.c_uint8)(), C.c_size_t()
+    st = L().orc_bzip2_encode_bytes(data, C.c_size_t(len(data)), C.byref(out), C.byref(n))
+    return st, _take(out, n)

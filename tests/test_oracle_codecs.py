@@ -121,3 +121,29 @@ def test_bzip2_decode_errors():
     # stops at the first end-of-stream block: a second concatenated stream is NOT decoded (:83-84)
     st, out = orc.bzip2_decode(z + z)
     assert st == orc.OK and out == bz2.decompress(z)
+
+
+def test_bzip2_encode_single_block_equals_libbz2(corpus):
+    """the Dart encoder descends from libbzip2; for inputs that fit ONE block the oracle's output
+    must equal bz2.compress(x, 9) byte for byte (main sort, fallback sort < 10000, periodic blocks that exhaust the
+    work budget, RLE1 corner cases)."""
+    rng = random.Random(11)
+    t = corpus["text"]
+    cases = [t[:880000], b"", b"a", b"ab" * 5, b"aaaa" * 100000, bytes([251]) * 70000, corpus["rand"], t[:1000], t[:9999],
+             t[:10000], rd("cat.jpg"), bytes(rng.choice(b"ab") for _ in range(50000)), t[:37] * 20000, b"\0" * 800000,
+             b"".join(bytes([rng.randrange(4)]) * rng.choice([1, 3, 4, 5, 8, 9, 10, 255, 256, 259, 260]) for _ in range(3000))]
+    for d in cases:
+        st, z = orc.bzip2_encode(d)
+        assert st == orc.OK and z == bz2.compress(d, 9), len(d)
+
+
+def test_bzip2_encode_multiblock_roundtrip_and_block_boundary_quirk():
+    """test/bzip2_test.dart:14-25 is a round trip.  Across block boundaries the reference flushes the pending RLE1 run
+    at the end of EVERY block (_writeBlock, bzip2_encoder.dart:97-103) where libbzip2 carries it over, so multi-block
+    output legitimately differs from libbz2 while decoding to the same bytes."""
+    d = synth.text(2_000_000, stream=3).tobytes()
+    st, z = orc.bzip2_encode(d)
+    assert st == orc.OK and bz2.decompress(z) == d
+    assert orc.bzip2_decode(z, verify=True) == (orc.OK, d)
+    assert z != bz2.compress(d, 9)
+    assert z[:4] == b"BZh9"
