@@ -859,6 +859,13 @@ static int bzip2_decode_impl(const uint8_t *in, size_t in_len, int verify, uint8
     pos = h_end[k];
   }
 
+  if (getenv("B200Z_DEBUG")) {
+    fprintf(stderr, "[b200z] bzip2: %u candidates (%u block), chain %zu, rc so far %d, eos %d\n", ncand, nb, chain.size(),
+            final_rc, (int)have_eos);
+    for (uint32_t i = 0; i < nb && i < 16; ++i)
+      fprintf(stderr, "[b200z]   cand %u bit %llu st %d nblock %u nrec %u optr %u end %llu\n", i,
+              (unsigned long long)blk_bits[i], h_st[i], h_nblock[i], h_nrec[i], h_optr[i], (unsigned long long)h_end[i]);
+  }
   // ---- K8 on the chain ----
   const uint32_t nc = (uint32_t)chain.size();
   std::vector<unsigned long long> h_off(nc + 1, 0);
@@ -879,6 +886,10 @@ static int bzip2_decode_impl(const uint8_t *in, size_t in_len, int verify, uint8
     CU(cudaMemcpyAsync(h_irr.data(), A.irregular, (size_t)nc * 4, cudaMemcpyDeviceToHost, g.stream));
     CU(cudaStreamSynchronize(g.stream));
   }
+  if (getenv("B200Z_DEBUG"))
+    for (uint32_t i = 0; i < nc && i < 16; ++i)
+      fprintf(stderr, "[b200z]   chain %u off %llu..%llu crc %08x stored %08x irregular %d\n", i, (unsigned long long)h_off[i],
+              (unsigned long long)h_off[i + 1], h_crc[i], stored_crc[i], h_irr[i]);
   // blocks are committed in order; the first bad one ends the stream (its bytes are already written when the
   // reference compares the CRC, :58-66)
   size_t n_out = 0;
