@@ -955,7 +955,7 @@ static uint32_t crc_xpow8(uint64_t nbytes) {
   return p;
 }
 static int device_crc32(const uint8_t *d, size_t n, uint32_t *out) {
-  const uint32_t TILE = 1u << 16;
+  const uint32_t TILE = 1u << 13;
   if (n == 0) {
     *out = 0;
     return B200Z_OK;

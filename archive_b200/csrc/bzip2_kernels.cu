@@ -107,7 +107,7 @@ struct BzSmem {
   uint8_t len[6][258];
   uint8_t minlen[6];
   uint8_t selector[BZ_MAX_SEL + 2];
-  uint8_t mtf[256];
+  uint32_t mtfw[64];  // the MTF list, 4 entries per word (entry k = byte k%4 of word k/4)
   uint8_t seq2unseq[256];
 };
 
@@ -271,7 +271,7 @@ k_bz2_entropy(const uint32_t *__restrict__ words, uint64_t n_bytes, const unsign
 
   uint32_t nrec = 0, nblock = 0;
   if (!err) {
-    for (int i = 0; i < 256; ++i) S.mtf[i] = (uint8_t)i;
+    for (int i = 0; i < 64; ++i) S.mtfw[i] = (uint32_t)(4 * i) | ((uint32_t)(4 * i + 1) << 8) | ((uint32_t)(4 * i + 2) << 16) | ((uint32_t)(4 * i + 3) << 24);
     const int eob = n_in_use + 1;
     uint32_t *rv = rec_val + (size_t)b * nblock_max;
     uint32_t *rp = rec_pos + (size_t)b * nblock_max;
@@ -333,7 +333,7 @@ k_bz2_entropy(const uint32_t *__restrict__ words, uint64_t n_bytes, const unsign
           err = BZ_DATA;
           break;
         }
-        rv[nrec] = (run_es << 8) | S.seq2unseq[S.mtf[0]];
+        rv[nrec] = (run_es << 8) | S.seq2unseq[S.mtfw[0] & 0xffu];
         rp[nrec] = nblock;
         nrec++;
         nblock += run_es;
@@ -346,10 +346,19 @@ k_bz2_entropy(const uint32_t *__restrict__ words, uint64_t n_bytes, const unsign
         break;
       }
       {
-        int nn = sym - 1;
-        uint8_t uc = S.mtf[nn];
-        for (int k = nn; k > 0; --k) S.mtf[k] = S.mtf[k - 1];
-        S.mtf[0] = uc;
+        // move entry nn to the front, a word (4 entries) at a time (:331-378 does the same job with its 16x16 blocks)
+        const int nn = sym - 1, wi = nn >> 2, sh = (nn & 3) * 8;
+        uint32_t t = S.mtfw[wi];
+        const uint32_t uc = (t >> sh) & 0xffu;
+        uint32_t carry = uc;
+        for (int j = 0; j < wi; ++j) {
+          const uint32_t w = S.mtfw[j];
+          S.mtfw[j] = (w << 8) | carry;
+          carry = w >> 24;
+        }
+        const uint32_t below = sh ? (t & ((1u << sh) - 1u)) : 0u;          // entries under nn in this word
+        const uint32_t upto = sh == 24 ? 0xffffffffu : ((1u << (sh + 8)) - 1u);  // entries 0..nn of this word
+        S.mtfw[wi] = (t & ~upto) | (((below << 8) | carry) & upto);
         rv[nrec] = (1u << 8) | S.seq2unseq[uc];
         rp[nrec] = nblock;
         nrec++;

@@ -1,0 +1,6 @@
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest.log 2>&1; echo "rc=$?" >> gpurun_out/pytest.log
+timeout 1200 python scripts/bench_codecs.py > gpurun_out/bench_codecs.log 2>&1; echo "rc=$?" >> gpurun_out/bench_codecs.log
+DEFL_MIB=64 BZ_MIB=0 DEFL_CHECK_ORACLE=0 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_deflate.csv python scripts/bench_codecs.py > gpurun_out/ncu_defl.log 2>&1
+DEFL_MIB=1 BZ_MIB=128 DEFL_CHECK_ORACLE=0 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_bzip2.csv python scripts/bench_codecs.py > gpurun_out/ncu_bz2.log 2>&1
+grep -v Warn gpurun_out/pytest.log | tail -6 | cut -c1-200; tail -3 gpurun_out/bench_codecs.log | cut -c1-1200

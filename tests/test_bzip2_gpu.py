@@ -66,18 +66,20 @@ def test_stops_at_first_eos_and_bad_data(a):
     out = a.OutputMemoryStream()
     assert a.BZip2Decoder().decode_stream(a.InputMemoryStream(b"BZx1" + z[4:]), out) is False
     assert out.get_bytes() == b""
-    # a flipped bit inside the third block: blocks before it are kept, decodeStream is false (verify) or throws
+    # a flipped bit inside a block: whatever the reference makes of it (here: the block still decodes, to garbage, and
+    # fails its CRC -- its bytes are already written when the CRC is compared, bzip2_decoder.dart:58-66), the GPU path
+    # must produce the same bytes and the same verdict
     bad = bytearray(z)
     bad[len(z) * 5 // 8] ^= 0x10
     ost, oout = orc.bzip2_decode(bytes(bad), verify=True)
     out = a.OutputMemoryStream()
     try:
         ok = a.BZip2Decoder().decode_stream(a.InputMemoryStream(bytes(bad)), out, verify=True)
-        assert ok is False and ost in (orc.FALSE, orc.THROW)
+        assert ok is False and ost == orc.FALSE
+        assert out.get_bytes() == oout
     except a.DartRangeError:
         assert ost == orc.THROW
-    got = out.get_bytes()
-    assert d.startswith(got[:100000])  # at least the first block is intact and identical
+    assert out.get_bytes()[:90000] == d[:90000]  # the block before the damage is intact
     # truncated stream: readByte past the end throws in the reference
     with pytest.raises(a.DartRangeError):
         a.BZip2Decoder().decode_bytes(z[:len(z) // 2])
