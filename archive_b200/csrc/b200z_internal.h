@@ -10,7 +10,7 @@
 #define B200Z_LBITS 9  // literal/length primary LUT bits (2^9 x u16 per stream)
 #endif
 #ifndef B200Z_DBITS
-#define B200Z_DBITS 9  // distance primary LUT bits
+#define B200Z_DBITS 8  // distance primary LUT bits
 #endif
 #define B200Z_DECODE_THREADS 32   // one warp per block: finest block-scheduler granularity
 #define B200Z_EXPAND_THREADS 256

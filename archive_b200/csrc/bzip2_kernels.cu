@@ -278,13 +278,15 @@ k_bz2_entropy(const uint32_t *__restrict__ words, uint64_t n_bytes, const unsign
     int gpos = 0, gno = -1, tsel = 0;
     int run_n = 0;       // number of RUNA/RUNB symbols in the open run
     uint32_t run_es = 0;  // value accumulated so far (es + 1 in the reference's terms)
-    for (;;) {
-      // ---- _getMtfVal (:732-772) ----
+    uint32_t mtf0 = S.mtfw[0];  // entries 0..3 of the MTF list live in a register (most symbols land there)
+    // ---- _getMtfVal (:732-772); sets derr instead of returning -1 ----
+    int derr = 0;
+    auto decode = [&]() -> int {
       if (gpos == 0) {
         gno++;
         if (gno >= n_sel) {
-          err = BZ_DATA;  // reference returns -1 here (then spins to the block limit and fails)
-          break;
+          derr = BZ_DATA;  // reference returns -1 here (then spins to the block limit and fails)
+          return 0;
         }
         gpos = 50;
         tsel = S.selector[gno];
@@ -299,25 +301,37 @@ k_bz2_entropy(const uint32_t *__restrict__ words, uint64_t n_bytes, const unsign
         zn = S.minlen[tsel] > BZ_LUT_BITS + 1 ? S.minlen[tsel] : BZ_LUT_BITS + 1;
         for (;;) {
           if (zn > 20) {
-            err = BZ_DATA;
-            break;
+            derr = BZ_DATA;
+            return 0;
           }
           int32_t zvec = (int32_t)(br.buf >> (64 - zn));
           if (zvec <= S.limit[tsel][zn]) {
             int32_t idx = zvec - S.base[tsel][zn];
-            if (idx < 0 || idx >= 258) err = BZ_DATA;
-            else sym = S.perm[tsel][idx];
+            if (idx < 0 || idx >= 258) {
+              derr = BZ_DATA;
+              return 0;
+            }
+            sym = S.perm[tsel][idx];
             break;
           }
           zn++;
         }
-        if (err) break;
       } else if (sym == 0x3ff) {
-        err = BZ_DATA;
-        break;
+        derr = BZ_DATA;
+        return 0;
       }
       br.buf <<= zn;
       br.cnt -= zn;
+      return sym;
+    };
+    int sym = decode();
+    err = derr;
+    while (!err) {
+      // the NEXT symbol's Huffman decode does not depend on the MTF work of this one: start it first so the two
+      // dependency chains overlap (a decode error is acted on after this symbol, as in the reference's order)
+      const bool more = sym != eob;
+      int nsym = 0;
+      if (more) nsym = decode();
       // ---- MTF / run-length (:276-388) ----
       if (sym <= 1) {
         if (run_n >= 21) {  // N >= 2*1024*1024 (:291)
@@ -326,48 +340,62 @@ k_bz2_entropy(const uint32_t *__restrict__ words, uint64_t n_bytes, const unsign
         }
         run_es += (uint32_t)(sym + 1) << run_n;
         run_n++;
-        continue;
-      }
-      if (run_n) {
-        if (nblock + run_es > nblock_max) {  // (:313-316)
+      } else {
+        if (run_n) {
+          if (nblock + run_es > nblock_max) {  // (:313-316)
+            err = BZ_DATA;
+            break;
+          }
+          rv[nrec] = (run_es << 8) | S.seq2unseq[mtf0 & 0xffu];
+          rp[nrec] = nblock;
+          nrec++;
+          nblock += run_es;
+          run_n = 0;
+          run_es = 0;
+        }
+        if (sym == eob) break;
+        if (nblock >= nblock_max) {  // (:326-329)
           err = BZ_DATA;
           break;
         }
-        rv[nrec] = (run_es << 8) | S.seq2unseq[S.mtfw[0] & 0xffu];
-        rp[nrec] = nblock;
-        nrec++;
-        nblock += run_es;
-        run_n = 0;
-        run_es = 0;
-      }
-      if (sym == eob) break;
-      if (nblock >= nblock_max) {  // (:326-329)
-        err = BZ_DATA;
-        break;
-      }
-      {
-        // move entry nn to the front, a word (4 entries) at a time (:331-378 does the same job with its 16x16 blocks)
-        const int nn = sym - 1, wi = nn >> 2, sh = (nn & 3) * 8;
-        uint32_t t = S.mtfw[wi];
-        const uint32_t uc = (t >> sh) & 0xffu;
-        uint32_t carry = uc;
-        for (int j = 0; j < wi; ++j) {
-          const uint32_t w = S.mtfw[j];
-          S.mtfw[j] = (w << 8) | carry;
-          carry = w >> 24;
+        // move entry nn to the front (:331-378 does the same job with its 16x16 blocks)
+        const int nn = sym - 1;
+        uint32_t uc;
+        if (nn < 4) {
+          const int sh = nn * 8;
+          uc = (mtf0 >> sh) & 0xffu;
+          const uint32_t below = mtf0 & ((1u << sh) - 1u);
+          const uint32_t upto = sh == 24 ? 0xffffffffu : ((1u << (sh + 8)) - 1u);
+          mtf0 = (mtf0 & ~upto) | (((below << 8) | uc) & upto);
+        } else {
+          const int wi = nn >> 2, sh = (nn & 3) * 8;
+          const uint32_t t = S.mtfw[wi];
+          uc = (t >> sh) & 0xffu;
+          uint32_t carry = mtf0 >> 24;
+          mtf0 = (mtf0 << 8) | uc;
+          for (int j = 1; j < wi; ++j) {
+            const uint32_t w = S.mtfw[j];
+            S.mtfw[j] = (w << 8) | carry;
+            carry = w >> 24;
+          }
+          const uint32_t below = sh ? (t & ((1u << sh) - 1u)) : 0u;
+          const uint32_t upto = sh == 24 ? 0xffffffffu : ((1u << (sh + 8)) - 1u);
+          S.mtfw[wi] = (t & ~upto) | (((below << 8) | carry) & upto);
         }
-        const uint32_t below = sh ? (t & ((1u << sh) - 1u)) : 0u;          // entries under nn in this word
-        const uint32_t upto = sh == 24 ? 0xffffffffu : ((1u << (sh + 8)) - 1u);  // entries 0..nn of this word
-        S.mtfw[wi] = (t & ~upto) | (((below << 8) | carry) & upto);
         rv[nrec] = (1u << 8) | S.seq2unseq[uc];
         rp[nrec] = nblock;
         nrec++;
         nblock++;
+        if ((nrec & 1023u) == 0u && br.bitpos() > total_bits) {
+          err = BZ_THROW;
+          break;
+        }
       }
-      if ((nrec & 1023u) == 0u && br.bitpos() > total_bits) {
-        err = BZ_THROW;
+      if (derr) {
+        err = derr;
         break;
       }
+      sym = nsym;
     }
     if (!err && optr >= nblock) err = BZ_DATA;  // (:399-402) also covers nblock == 0
   }

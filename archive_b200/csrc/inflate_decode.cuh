@@ -13,7 +13,7 @@
 #define B200Z_LBITS 9
 #endif
 #ifndef B200Z_DBITS
-#define B200Z_DBITS 9
+#define B200Z_DBITS 8
 #endif
 
 #ifdef __CUDA_ARCH__
@@ -299,7 +299,6 @@ B200Z_HD UnitResult inflate_decode_unit(bool active, const uint8_t *in, uint32_t
   bool done = !active;
   // loop invariants of the bulk loop, pinned in registers
   const b200z_saddr lutl_r = B200Z_OPAQUE(lutl_s), lutd_r = B200Z_OPAQUE(lutd_s), xtab_r = B200Z_OPAQUE(xtab_s);
-  static_assert(LBITS == DBITS, "the bulk loop uses one index mask for both LUTs");
   unsigned live;
   while ((live = B200Z_BALLOT(!done)) != 0u) {  // warp-uniform: every lane reconverges here
     // ---------------- bulk inner loop: warp-uniform, ONE SYMBOL per lane per turn, branch-light.  The same
@@ -318,17 +317,28 @@ B200Z_HD UnitResult inflate_decode_unit(bool active, const uint8_t *in, uint32_t
       br.refill();
       const bool dm = mode_dist;
       const uint32_t bits = (uint32_t)br.buf;
-      const uint32_t e = B200Z_LDS16(dm ? lutd_r : lutl_r, bits & ((1u << LBITS) - 1u));
-      const uint32_t n = e & 15u;
-      const uint32_t sym = e >> 4;
+      const uint32_t e = B200Z_LDS16(dm ? lutd_r : lutl_r, bits & (dm ? ((1u << DBITS) - 1u) : ((1u << LBITS) - 1u)));
+      uint32_t n = e & 15u;
+      uint32_t sym = e >> 4;
+      bool odd = false;
+      if (n == 0u) {
+        // LUT miss (rare, divergent): a code longer than the LUT, or one of the symbols kept out of it.  Long codes
+        // are decoded here by the canonical walk; end-of-block / invalid symbols / holes go to the exact step.
+        int sy = 0;
+        const int ln = dm ? slow_decode<DBITS, uint8_t>(bits & 0x7fffu, sd.first, sd.count, sd.offs, sd.perm, maxd, &sy)
+                          : slow_decode<LBITS, uint16_t>(bits & 0x7fffu, sl.first, sl.count, sl.offs, sl.perm, maxl, &sy);
+        n = (uint32_t)ln;
+        sym = (uint32_t)sy;
+        odd = ln == 0 || (dm ? sy > 29 : (sy == 256 || sy > 285));
+      }
       const uint32_t xi = dm ? sym + 32u : (sym > 256u ? sym - 257u : 63u);
-      const uint32_t x = B200Z_LDS32(xtab_r, xi);
+      const uint32_t x = B200Z_LDS32(xtab_r, xi & 63u);
       const uint32_t xb = x & 15u;
       const uint32_t val = (x >> 4) + ((bits >> n) & ~(0xffffffffu << xb));
       const bool islit = !dm && sym < 256u;
       const bool islen = !dm && sym > 256u;
       const uint32_t nolen = olen + (islit ? 1u : dm ? mlen_pending : 0u);
-      const bool special = n == 0u || (dm && val > olen) || nolen > cap;
+      const bool special = odd || (dm && val > olen) || nolen > cap;
       if (!special) {
         const uint32_t tot = n + xb;
         br.buf >>= tot;
