@@ -248,9 +248,9 @@ cudaError_t launch_inflate(const InflateBatch &b, cudaStream_t stream) {
     if (forced >= 1 && forced <= 32) {
       upw = forced;
     } else {
-      // measured on B200 (profiles/): ~4 streams per warp with ~24+ warps per SM beats wider warps -- the loop is
-      // latency-bound per warp, so warps per scheduler matter more than lanes per instruction
-      const uint64_t target_warps = (uint64_t)g_num_sms * 24 / (uint64_t)(b.share > 0 ? b.share : 1);
+      // measured on B200 (profiles/r1_inflate_upw_sweep.md): 8 streams per warp at ~14 warps per SM is the best point for
+      // 16 Ki streams -- wider warps are latency-bound (too few warps per scheduler), narrower ones issue-bound
+      const uint64_t target_warps = (uint64_t)g_num_sms * 12 / (uint64_t)(b.share > 0 ? b.share : 1);
       while (upw > 1 && (b.n_units + upw - 1) / upw < target_warps) upw >>= 1;
     }
   }
