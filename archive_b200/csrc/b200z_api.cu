@@ -1028,16 +1028,8 @@ static int deflate_staged(size_t n, int level, int window_bits, size_t *out_len)
     set_err("deflate: invalid level %d / windowBits %d (Dart: LateInitializationError)", level, window_bits);
     return B200Z_E_ARG;
   }
-  if (window_bits != 15) {
-    set_err("deflate: windowBits %d is not implemented on the device (only 15)", window_bits);
-    return B200Z_E_ARG;
-  }
-  if (level >= 1 && level <= 3) {
-    set_err("deflate: levels 1-3 (the serial deflate_fast strategy) are not implemented on the device yet");
-    return B200Z_E_ARG;
-  }
-  if (n >= (1ull << 30)) {
-    set_err("deflate: inputs of 1 GiB and more are not supported yet");
+  if (n >= 0xffff0000ull) {
+    set_err("deflate: inputs of 4 GiB and more are not supported");
     return B200Z_E_ARG;
   }
   const size_t cap = align_up(deflate_bound(n) + 16, 256);
@@ -1054,7 +1046,7 @@ static int deflate_staged(size_t n, int level, int window_bits, size_t *out_len)
   const size_t ws = deflate_workspace_bytes(n);
   CU(g.d_ws.reserve(ws));
   uint32_t stats[3];
-  CU(deflate_slow_device((const uint8_t *)g.d_in.p, n, level, (uint8_t *)g.d_out.p, cap, g.d_ws.p, g.d_ws.cap, out_len, stats,
+  CU(deflate_slow_device((const uint8_t *)g.d_in.p, n, level, window_bits, (uint8_t *)g.d_out.p, cap, g.d_ws.p, g.d_ws.cap, out_len, stats,
                          g.stream));
   return B200Z_OK;
 }

@@ -81,8 +81,8 @@ struct DeflStoredBlock {
 };
 size_t deflate_bound(size_t n);
 size_t deflate_workspace_bytes(size_t n);
-cudaError_t deflate_slow_device(const uint8_t *d_in, size_t n, int level, uint8_t *d_out, size_t out_cap, void *ws,
-                                size_t ws_bytes, size_t *out_len, uint32_t *stats, cudaStream_t s);
+cudaError_t deflate_slow_device(const uint8_t *d_in, size_t n, int level, int window_bits, uint8_t *d_out, size_t out_cap,
+                                void *ws, size_t ws_bytes, size_t *out_len, uint32_t *stats, cudaStream_t s);
 cudaError_t deflate_stored_device(const uint8_t *d_in, const DeflStoredBlock *h_blocks, uint32_t n_blocks, uint8_t *d_out,
                                   size_t out_cap, void *ws, size_t ws_bytes, size_t *out_len, cudaStream_t s);
 cudaError_t crc32_tiles_device(const uint8_t *d_in, size_t n, uint32_t tile, uint32_t *d_part, cudaStream_t s);

@@ -79,8 +79,9 @@ int b200z_zlib_decode(const uint8_t *in, size_t in_len, int verify, int raw, uin
 size_t b200z_gzip_bound(const uint8_t *in, size_t in_len);
 
 /* Deflate(bytes, level:, windowBits:).getBytes() and .crc32 -- deflate.dart:39-48,72-75,31.  Raw DEFLATE, byte-identical
- * to the reference at the same level.  Levels 0 and 4-9 run on the device; 1-3 (deflate_fast) and windowBits != 15
- * return B200Z_E_ARG for now.  Invalid level / windowBits (Deflate._init returning false) -> B200Z_E_ARG.            */
+ * to the reference at the same level and windowBits (9..15).  Levels 4-9 are data parallel; 1-3 (deflate_fast, whose hash
+ * chains depend on the parse) run as one serial device thread per stream; 0 is stored.  Invalid level / windowBits
+ * (Deflate._init returning false, :107-118) -> B200Z_E_ARG.                                                          */
 int b200z_deflate_raw(const uint8_t *in, size_t in_len, int level, int window_bits, uint8_t *out, size_t out_cap,
                       size_t *out_len, uint32_t *crc32_of_input);
 size_t b200z_deflate_bound(size_t in_len); /* output capacity that always suffices (+18 for gzip, +6 for zlib) */

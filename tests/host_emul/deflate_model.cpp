@@ -44,7 +44,7 @@ struct Match {
 inline uint32_t hash3(const uint8_t *p) { return (((uint32_t)(p[0] & 31) << 10) ^ ((uint32_t)p[1] << 5) ^ p[2]) & 0x7fff; }
 
 // S1: both budgets in one chain walk.  `full` = result after `chain` candidates, `reduced` after `chain >> 2`.
-void match_table(const uint8_t *d, size_t n, const Cfg &c, std::vector<Match> &full, std::vector<Match> &reduced) {
+void match_table(const uint8_t *d, size_t n, const Cfg &c, int64_t max_dist, std::vector<Match> &full, std::vector<Match> &reduced) {
   full.assign(n, Match{0, 0});
   reduced.assign(n, Match{0, 0});
   std::vector<int64_t> head(32768, -1), prev(n, -1);
@@ -54,7 +54,7 @@ void match_table(const uint8_t *d, size_t n, const Cfg &c, std::vector<Match> &f
     int64_t cur = head[h];
     prev[p] = cur;
     head[h] = (int64_t)p;
-    const int64_t limit = (int64_t)p > MAX_DIST ? (int64_t)p - MAX_DIST : 0;
+    const int64_t limit = (int64_t)p > max_dist ? (int64_t)p - max_dist : 0;
     const size_t lookahead = n - p;
     const int nice = (size_t)c.nice > lookahead ? (int)lookahead : c.nice;
     int best = MIN_MATCH - 1;
@@ -63,7 +63,7 @@ void match_table(const uint8_t *d, size_t n, const Cfg &c, std::vector<Match> &f
     bool red_done = budget_red == 0;
     // first candidate: hashHead != 0 && strStart - hashHead <= MAX_DIST (:1036-1038); later ones: > limit (:1198)
     bool first = true;
-    while (first ? (cur >= 1 && (int64_t)p - cur <= MAX_DIST) : (cur > limit)) {
+    while (first ? (cur >= 1 && (int64_t)p - cur <= max_dist) : (cur > limit)) {
       first = false;
       // candidate length (exact common prefix, capped at MAX_MATCH and at the end of the data)
       size_t maxl = lookahead < (size_t)MAX_MATCH ? lookahead : (size_t)MAX_MATCH;
@@ -415,13 +415,13 @@ void compress_block(BitOut &b, const Token *t, size_t nt, const uint16_t *lt, co
 
 }  // namespace
 
-extern "C" int model_deflate(const uint8_t *d, size_t n, int level, uint8_t **out, size_t *out_len, uint64_t *n_tokens,
-                             uint64_t *n_blocks) {
+extern "C" int model_deflate_wb(const uint8_t *d, size_t n, int level, int window_bits, uint8_t **out, size_t *out_len,
+                                uint64_t *n_tokens, uint64_t *n_blocks) {
   if (level < 4 || level > 9) return -1;
   init_tabs();
   const Cfg &c = kCfg[level];
   std::vector<Match> full, red;
-  match_table(d, n, c, full, red);
+  match_table(d, n, c, ((int64_t)1 << window_bits) - MIN_LOOKAHEAD, full, red);
   std::vector<Token> toks;
   std::vector<uint32_t> tally_ss, next_ss;
   bool last_pending = false;
@@ -435,7 +435,20 @@ extern "C" int model_deflate(const uint8_t *d, size_t n, int level, uint8_t **ou
   uint32_t block_start = 0;
   uint64_t blocks = 0;
   const size_t NT = toks.size();
-  auto flush = [&](size_t t1, uint32_t strstart, bool eof) {
+  // window base (absolute position of window index 0) at the iteration that starts at position p: _fillWindow slides by
+  // wSize whenever lookahead < MIN_LOOKAHEAD and strStart >= 2 wSize - MIN_LOOKAHEAD (:816-857).  Blocks whose start has
+  // slid out (blockStart < 0 -> buf == -1, :677-680) cannot be stored.
+  const int64_t W = (int64_t)1 << window_bits;
+  auto window_base = [&](int64_t p) {
+    int64_t base = 0;
+    for (;;) {
+      int64_t loaded = base + 2 * W < (int64_t)n ? base + 2 * W : (int64_t)n;
+      if (loaded - p < MIN_LOOKAHEAD && p - base >= 2 * W - MIN_LOOKAHEAD) base += W;
+      else break;
+    }
+    return base;
+  };
+  auto flush = [&](size_t t1, uint32_t strstart, bool eof, int64_t iter_pos) {
     uint16_t lt[HEAP_SIZE * 2], dt[(2 * D_CODES + 1) * 2], bl[(2 * BL_CODES + 1) * 2];
     memset(lt, 0, sizeof lt);
     memset(dt, 0, sizeof dt);
@@ -461,7 +474,7 @@ extern "C" int model_deflate(const uint8_t *d, size_t n, int level, uint8_t **ou
     int64_t opt_lenb = (tb.opt_len + 3 + 7) >> 3, static_lenb = (tb.static_len + 3 + 7) >> 3;
     if (static_lenb <= opt_lenb) opt_lenb = static_lenb;
     const int64_t stored_len = (int64_t)strstart - block_start;
-    if (stored_len + 4 <= opt_lenb) {  // (buf != -1 assumed: see DESIGN.md)
+    if (stored_len + 4 <= opt_lenb && (int64_t)block_start >= window_base(iter_pos)) {
       bo.put(0 + (eof ? 1 : 0), 3);
       bo.align();
       o.push_back((uint8_t)stored_len);
@@ -504,16 +517,21 @@ extern "C" int model_deflate(const uint8_t *d, size_t n, int level, uint8_t **ou
     if (last_lit == 16383) fl = true;
     // the very last token is followed by the final flush, which takes precedence only if no flush fired here
     if (fl && !(i + 1 == NT && last_pending)) {
-      flush(i + 1, next_ss[i], false);
+      flush(i + 1, next_ss[i], false, tally_ss[i]);
       matches = 0;
       dsum = 0;
     }
   }
-  flush(NT, (uint32_t)n, true);
+  flush(NT, (uint32_t)n, true, (int64_t)n);
   *out = (uint8_t *)malloc(o.size() ? o.size() : 1);
   memcpy(*out, o.data(), o.size());
   *out_len = o.size();
   if (n_tokens) *n_tokens = NT;
   if (n_blocks) *n_blocks = blocks;
   return 0;
+}
+
+extern "C" int model_deflate(const uint8_t *d, size_t n, int level, uint8_t **out, size_t *out_len, uint64_t *n_tokens,
+                             uint64_t *n_blocks) {
+  return model_deflate_wb(d, n, level, 15, out, out_len, n_tokens, n_blocks);
 }

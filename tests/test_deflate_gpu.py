@@ -50,9 +50,9 @@ def test_level_0_stored(a, corpus):
         assert a.Deflate(d, level=0).get_bytes() == orc.deflate(d, 0)[1], name
 
 
-def test_reference_roundtrips(a):  # test/deflate_test.dart:12-44 (levels 0 / 9; level 1 is not on the device yet)
+def test_reference_roundtrips(a):  # test/deflate_test.dart:12-44 (levels 0 / 1 / 9)
     buf = bytes(i % 256 for i in range(0xfffff))
-    for level in (0, 9):
+    for level in (0, 1, 9):
         z = a.Deflate(buf, level=level).get_bytes()
         assert a.Inflate(z + b"\0\0").get_bytes() == buf
         assert zlib.decompress(z, -15) == buf
@@ -72,6 +72,24 @@ def test_encoder_framing(a, corpus):  # test/zlib_test.dart:15-55, test/gzip_tes
     assert a.GZipDecoderWeb().decode_bytes(two, verify=True) == bytes([1, 2, 3, 4, 5, 6])
     raw = a.ZLibEncoder().encode_bytes(d, raw=True)
     assert raw == orc.deflate(d, 6)[1]
+
+
+def test_levels_1_to_3_serial_strategy(a, corpus):
+    """deflate_fast (levels 1-3) is serial per stream on the device too; byte-identical, just not fast."""
+    for name in ("short", "mix", "zeros", "empty", "abc", "tail2"):
+        d = corpus[name][:200000]
+        for level in (1, 2, 3):
+            assert a.Deflate(d, level=level).get_bytes() == orc.deflate(d, level)[1], (name, level)
+
+
+def test_window_bits(a, corpus):
+    """windowBits 9..14 (deflate.dart:107-118): shorter match distances, and blocks whose start has slid out of the
+    window can no longer be stored (buf == -1, :677-680) -- incompressible data exercises that rule."""
+    for name in ("rand", "mix", "short", "rep"):
+        d = corpus[name][:150000]
+        for wb in (9, 11, 12, 14):
+            for level in (1, 6):
+                assert a.Deflate(d, level=level, window_bits=wb).get_bytes() == orc.deflate(d, level, wb)[1], (name, wb, level)
 
 
 def test_invalid_and_unsupported_parameters(a):

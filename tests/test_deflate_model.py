@@ -53,3 +53,23 @@ def test_model_exercises_the_early_flush_heuristic(model):
     z, ntok, nblk = model(t, 6)
     assert nblk > (ntok + 16382) // 16383 + 5
     assert z == orc.deflate(t, 6)[1]
+
+
+def test_model_window_bits_and_the_stored_block_rule():
+    """windowBits 9..15: MAX_DIST shrinks, and a block whose start has slid out of the 2 x wSize window (buf == -1,
+    deflate.dart:677-680 + the slide in _fillWindow :816-857) may not be stored.  Incompressible data hits that rule."""
+    so = os.path.join(HERE, "libdeflate_model.so")
+    M = C.CDLL(so)
+
+    def run(d, level, wb):
+        out, n, nt, nb = C.POINTER(C.c_uint8)(), C.c_size_t(), C.c_uint64(), C.c_uint64()
+        assert M.model_deflate_wb(d, C.c_size_t(len(d)), level, wb, C.byref(out), C.byref(n), C.byref(nt), C.byref(nb)) == 0
+        return C.string_at(out, n.value)
+
+    rng = random.Random(1)
+    t = synth.text(400000).tobytes()
+    rnd = bytes(rng.getrandbits(8) for _ in range(100000))
+    for d in (t, t[:5000] * 40, rnd, rnd[:30000] + t[:100000] + rnd[:50000], rnd[:16383], rnd[:16384], rnd[:33000]):
+        for wb in (9, 10, 12, 14, 15):
+            for level in (4, 6, 9):
+                assert run(d, level, wb) == orc.deflate(d, level, wb)[1], (len(d), wb, level)
