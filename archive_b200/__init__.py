@@ -1,5 +1,5 @@
 """archive_b200 -- B200 (sm_100a) implementation of the Inflate/Deflate and BZip2 block-codec hot path
 of the Dart `archive` package, behind the package's own class names.  See DESIGN.md."""
 from ._ffi import B200ZError, DartRangeError, LIB_PATH  # noqa: F401
-from .codecs import BZip2Decoder, Deflate, GZipDecoder, GZipEncoder, GZipEncoderWeb, ZLibEncoder, ZLibEncoderWeb, GZipDecoderWeb, Inflate, ZLibDecoder, ZLibDecoderWeb, inflate_buffer  # noqa: F401
+from .codecs import BZip2Decoder, BZip2Encoder, Deflate, GZipDecoder, GZipEncoder, GZipEncoderWeb, ZLibEncoder, ZLibEncoderWeb, GZipDecoderWeb, Inflate, ZLibDecoder, ZLibDecoderWeb, inflate_buffer  # noqa: F401
 from .streams import BIG_ENDIAN, LITTLE_ENDIAN, InputMemoryStream, OutputMemoryStream  # noqa: F401

@@ -156,6 +156,30 @@ class BZip2Decoder:
         return True
 
 
+class BZip2Encoder:
+    """BZip2Encoder().encodeBytes / encode / encodeStream (lib/src/codecs/bzip2_encoder.dart:15-81): one "BZh9"
+    stream; encodeStream returns True."""
+
+    def encode_bytes(self, data) -> bytes:
+        out = OutputMemoryStream()
+        self.encode_stream(InputMemoryStream(data), out)
+        return out.get_bytes()
+
+    encode = encode_bytes
+
+    def encode_stream(self, input: InputMemoryStream, output: OutputMemoryStream) -> bool:
+        L = _ffi.ensure_init()
+        view = input.buffer[input.position:]
+        addr, n, keep = _ffi.as_buffer(view)
+        cap = L.b200z_bzip2_bound(n)
+        out = (C.c_uint8 * cap)()
+        out_len = C.c_size_t(0)
+        _ffi.check(L.b200z_bzip2_encode(addr, n, C.addressof(out), cap, C.byref(out_len)))
+        output.write_bytes(C.string_at(out, out_len.value))
+        input.position = len(input.buffer)
+        return True
+
+
 class Deflate:
     """`Deflate(bytes, level: 6, windowBits: 15)` (lib/src/codecs/zlib/deflate.dart:25-100): raw DEFLATE produced in the
     constructor, `get_bytes()` / `take_bytes()`, and `crc32` of the consumed input.  Invalid parameters make the

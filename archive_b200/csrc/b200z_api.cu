@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "b200z_internal.h"
+#include "bzip2_enc.h"
 
 namespace b200z {
 
@@ -1075,6 +1076,48 @@ int b200z_bzip2_decode(const uint8_t *in, size_t in_len, int verify, uint8_t *ou
   return rc;
 }
 void b200z_profile_enable(int on) { profile_enable(on != 0); }
+int b200z_bzip2_encode(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_cap, size_t *out_len) {
+  int rc = require_init();
+  if (rc) return rc;
+  if (in_len >= 0xfff00000ull) {
+    set_err("bzip2 encode: inputs of 4 GiB and more are not supported");
+    return B200Z_E_ARG;
+  }
+  std::lock_guard<std::mutex> lk(g.mu);
+  CU(cudaSetDevice(g.device));
+  rc = stage_input(in, in_len);
+  if (rc) return rc;
+  size_t free_b = 0, total_b = 0;
+  CU(cudaMemGetInfo(&free_b, &total_b));
+  const size_t budget = free_b + g.d_ws.cap > ((size_t)2 << 30) ? (free_b + g.d_ws.cap) / 2 : ((size_t)1 << 30);
+  const bz2e::Plan plan = bz2e::plan(in_len, budget < ((size_t)24 << 30) ? budget : ((size_t)24 << 30));
+  const size_t cap = align_up(bz2e::bound(in_len) + 64, 256);
+  CU(g.d_out.reserve(cap));
+  CU(g.d_ws.reserve(plan.ws_bytes));
+  size_t n = 0;
+  bz2e::Stats st;
+  int r = bz2e::encode_device((const uint8_t *)g.d_in.p, in_len, (uint8_t *)g.d_out.p, cap, g.d_ws.p, plan, &n, &st,
+                              (void *)g.stream);
+  if (r == -3) {
+    set_err("bzip2 encode: internal output bound too small (%zu)", cap);
+    return B200Z_E_INTERNAL;
+  }
+  if (r != 0) {
+    cudaError_t e = cudaGetLastError();
+    set_err("bzip2 encode: device failure (%s)", cudaGetErrorString(e));
+    return B200Z_E_INTERNAL;
+  }
+  if (out_len) *out_len = n;
+  if (n > out_cap) {
+    set_err("bzip2 encode: output needs %zu bytes, out_cap %zu", n, out_cap);
+    return B200Z_E_NOSPC;
+  }
+  CU(cudaMemcpyAsync(out, g.d_out.p, n, cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  return B200Z_OK;
+}
+size_t b200z_bzip2_bound(size_t in_len) { return bz2e::bound(in_len); }
+
 int b200z_profile_read(double *decode_ms, double *expand_ms, uint64_t *n_batches) {
   return profile_read(decode_ms, expand_ms, n_batches) ? B200Z_E_NODEVICE : B200Z_OK;
 }

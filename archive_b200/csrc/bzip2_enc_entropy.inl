@@ -329,7 +329,6 @@ k_h_tables(const uint16_t *__restrict__ mtfv, const uint32_t *__restrict__ nmtf_
   __shared__ int s_weight[BZ_N_GROUPS][BZ_MAX_ALPHA * 2];
   __shared__ int s_parent[BZ_N_GROUPS][BZ_MAX_ALPHA * 2];
   __shared__ uint32_t s_tile[NET + 1];
-  __shared__ uint32_t s_red[512];
   __shared__ uint32_t s_misc[8];
   const uint32_t bl = blockIdx.x, t = threadIdx.x;
   const uint32_t nmtf = nmtf_a[bl];

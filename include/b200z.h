@@ -97,6 +97,11 @@ int b200z_gzip_encode(const uint8_t *in, size_t in_len, int level, uint32_t mtim
  * before the failure are kept, as in the reference).                                                    */
 int b200z_bzip2_decode(const uint8_t *in, size_t in_len, int verify, uint8_t *out, size_t out_cap,
                        size_t *out_len);
+/* BZip2Encoder().encodeBytes(data) -- bzip2_encoder.dart:15-81: always "BZh9", never randomised, the pending RLE1
+ * run is closed at every block end (which is where the bytes differ from libbzip2 on multi-block inputs).
+ * Inputs of 4 GiB and more: B200Z_E_ARG.                                                                       */
+int b200z_bzip2_encode(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_cap, size_t *out_len);
+size_t b200z_bzip2_bound(size_t in_len); /* output capacity that always suffices */
 
 /* ---- batched independent units (what the kernels run) --------------------------------- */
 /* n_units raw DEFLATE streams: unit u reads in_base[in_off[u] .. +in_len[u]) and writes

@@ -22,6 +22,15 @@ def pytest_configure(config):
     hdr = os.path.join(ROOT, "archive_b200", "csrc", "inflate_decode.cuh")
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
         subprocess.run(["g++", "-O1", "-g", "-fPIC", "-shared", "-std=c++17", "-x", "c++", src, "-o", so], check=True)
+    # the BZip2 encoder kernels, compiled against the CUDA execution-model emulation (tests/host_emul/cuda_emu.h)
+    csrc = os.path.join(ROOT, "archive_b200", "csrc")
+    src = os.path.join(emul, "bz2enc_emul.cpp")
+    so = os.path.join(emul, "libbz2enc_emul.so")
+    deps = [src, os.path.join(emul, "cuda_emu.h")] + [
+        os.path.join(csrc, f) for f in os.listdir(csrc) if f.startswith("bzip2_enc")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
+        subprocess.run(["g++", "-O2", "-g", "-fPIC", "-shared", "-std=c++17", "-I", emul, "-I", csrc, src, "-o", so],
+                       check=True)
 
 
 def pytest_collection_modifyitems(config, items):

@@ -99,3 +99,20 @@ def bzip2_encode(data: bytes):
     out, n = C.POINTER(C.c_uint8)(), C.c_size_t()
     st = L().orc_bzip2_encode_bytes(data, C.c_size_t(len(data)), C.byref(out), C.byref(n))
     return st, _take(out, n)
+
+
+_BE = None
+
+
+def emul_bzip2_encode(data: bytes):
+    """The device BZip2 encoder's kernels run on the CUDA emulation (tests/host_emul/bz2enc_emul.cpp).
+    -> (rc, output, stats[n_blocks, n_serial_blocks, rounds, _])"""
+    global _BE
+    if _BE is None:
+        _BE = C.CDLL(os.path.join(ROOT, "tests", "host_emul", "libbz2enc_emul.so"))
+    cap = len(data) + len(data) // 32 + 8192
+    out = (C.c_uint8 * (cap + 16))()
+    n = C.c_size_t()
+    st = (C.c_uint32 * 4)()
+    rc = _BE.emu_bzip2_encode(data, C.c_size_t(len(data)), out, C.c_size_t(cap), C.byref(n), st)
+    return rc, bytes(out[:n.value]), list(st)
