@@ -12,7 +12,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200z.so")
+LIB_PATH = os.environ.get("B200Z_LIB") or os.path.join(_HERE, "libb200z.so")
 
 OK, E_NODEVICE, E_ARG, E_NOSPC, E_DATA, E_THROW, E_INTERNAL = 0, -1, -2, -3, -4, -5, -6
 U_DONE, U_EOS, U_STOP, U_NOSPC, U_RANGE, U_BADCODE, U_THROW, U_TOKCAP = 0, 1, -1, -2, -3, -4, -5, -6

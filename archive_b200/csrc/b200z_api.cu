@@ -219,9 +219,7 @@ struct MetaLayout {
   size_t inputs_bytes() const { return off_out_len; }
 };
 
-static size_t workspace_bytes(size_t n_units, size_t total_out_cap) {
-  return align_up(total_out_cap * 4 + 256, 256) + align_up(n_units * 4, 256);
-}
+static size_t workspace_bytes(size_t n_units, size_t total_out_cap) { return inflate_ws_bytes(n_units, total_out_cap); }
 
 // Runs one batch whose compressed bytes are ALREADY in g.d_in (at offset 0 = in_base) and whose
 // output goes to g.d_out.  Meta arrays are host arrays; results are copied back into them.
@@ -251,8 +249,7 @@ static int run_batch_on_staged(const uint64_t *in_off, const uint32_t *in_len, c
   b.status = (int32_t *)(dm + ml.off_status);
   b.in_used = (uint32_t *)(dm + ml.off_in_used);
   b.n_units = n;
-  b.workspace = g.d_ws.p;
-  b.tok_bytes = align_up(out_extent * 4 + 256, 256);
+  b.ws = inflate_ws_carve(g.d_ws.p, n, out_extent);
   CU(launch_inflate(b, g.stream));
   CU(cudaMemcpyAsync(hm + ml.off_out_len, dm + ml.off_out_len, ml.bytes - ml.off_out_len, cudaMemcpyDeviceToHost,
                      g.stream));
@@ -508,9 +505,8 @@ static int gzip_fast_path(const uint8_t *in, size_t in_len, uint8_t *out, size_t
   for (size_t c = 0; c < nchunks; ++c) max_units = cut[c + 1] - cut[c] > max_units ? cut[c + 1] - cut[c] : max_units;
   (void)max_units;
   (void)max_chunk_out;
-  const size_t tok_region = align_up((o - out_lo) * 4 + 256, 256);  // token layout mirrors the output layout
-  const size_t ws = tok_region + align_up(nb * 4, 256);
-  CU(g.d_ws.reserve(ws));
+  CU(g.d_ws.reserve(inflate_ws_bytes(nb, o - out_lo)));  // token layout mirrors the output layout
+  const InflateWs ws_all = inflate_ws_carve(g.d_ws.p, nb, o - out_lo);
   std::vector<cudaEvent_t> ev_in(nchunks), ev_k(nchunks);
   for (size_t c = 0; c < nchunks; ++c) {
     CU(cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming));
@@ -537,8 +533,7 @@ static int gzip_fast_path(const uint8_t *in, size_t in_len, uint8_t *out, size_t
     bt.in_used = (uint32_t *)(dm + ml.off_in_used) + a;
     bt.n_units = b - a;
     bt.share = (int)(nchunks < (size_t)Ctx::kCompStreams ? nchunks : (size_t)Ctx::kCompStreams);
-    bt.workspace = (uint8_t *)g.d_ws.p + (chunk_out_lo[c] - out_lo) * 4;
-    bt.tok_bytes = (tok_region + a * 4) - (chunk_out_lo[c] - out_lo) * 4;  // -> this chunk's slice of the count array
+    bt.ws = inflate_ws_slice(ws_all, a, chunk_out_lo[c] - out_lo);
     CU(launch_inflate(bt, cs));
     CU(cudaEventRecord(ev_k[c], cs));
     CU(cudaStreamWaitEvent(g.s_d2h, ev_k[c], 0));
@@ -1192,9 +1187,9 @@ int b200z_inflate_batch_device(const uint8_t *d_in_base, const uint64_t *d_in_of
   int rc = require_init();
   if (rc) return rc;
   if (n_units == 0) return B200Z_OK;
-  const size_t ntok_bytes = align_up(n_units * 4, 256);
-  if (workspace_bytes_ < ntok_bytes + 256) {
-    set_err("inflate_batch_device: workspace too small");
+  const size_t extent = inflate_ws_extent_for(n_units, workspace_bytes_);
+  if (extent == 0) {
+    set_err("inflate_batch_device: workspace too small (size it with b200z_inflate_workspace_bytes)");
     return B200Z_E_ARG;
   }
   InflateBatch b;
@@ -1202,8 +1197,7 @@ int b200z_inflate_batch_device(const uint8_t *d_in_base, const uint64_t *d_in_of
   b.out_base = d_out_base; b.out_off = d_out_off; b.out_cap = d_out_cap;
   b.out_len = d_out_len; b.status = d_status; b.in_used = d_in_used;
   b.n_units = n_units;
-  b.workspace = d_workspace;
-  b.tok_bytes = workspace_bytes_ - ntok_bytes;
+  b.ws = inflate_ws_carve(d_workspace, n_units, extent);
   cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : g.stream;
   CU(launch_inflate(b, s));
   return B200Z_OK;

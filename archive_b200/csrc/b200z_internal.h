@@ -17,6 +17,19 @@
 
 namespace b200z {
 
+// Device workspace of one inflate batch (inflate_kernels.cu).  `extent` = size of the output layout in bytes.
+struct InflateWs {
+  uint32_t *tokens = nullptr;   // [extent] u32: unit u's own tokens start at word out_off[u] (<= 1 token per output byte)
+  uint32_t *htokens = nullptr;  // 7 helper planes of hstride words: helper k of unit u writes from plane k-1, word out_off[u] >> 2
+  size_t hstride = 0;
+  uint32_t *pieces = nullptr;   // [n_units][PIECE_WORDS]: which token runs make up the unit, in order
+  uint8_t *uscratch = nullptr;  // [n_units][USCRATCH_BYTES]: slow tables + helper boundary bitmaps
+};
+size_t inflate_ws_bytes(size_t n_units, size_t extent);
+size_t inflate_ws_extent_for(size_t n_units, size_t bytes);  // largest extent a workspace of `bytes` serves
+InflateWs inflate_ws_carve(void *ws, size_t n_units, size_t extent);
+InflateWs inflate_ws_slice(const InflateWs &w, size_t first_unit, size_t first_out_byte);
+
 struct InflateBatch {
   const uint8_t *in_base;
   const uint64_t *in_off;
@@ -28,8 +41,7 @@ struct InflateBatch {
   int32_t *status;
   uint32_t *in_used;
   size_t n_units;
-  void *workspace;   // [tok_bytes of tokens][n_units x u32 token counts]
-  size_t tok_bytes;  // 4 * extent of the output layout, rounded up to 256
+  InflateWs ws;
   int share = 1;     // how many batches run concurrently on the device (sizes the streams-per-warp choice)
 };
 

@@ -16,7 +16,24 @@
 #define B200Z_DBITS 8
 #endif
 
-#ifdef __CUDA_ARCH__
+#if defined(B200Z_EMU)
+// CPU emulation of the CUDA execution model (tests/host_emul/cuda_emu.h): real warp collectives, plain memory
+#define B200Z_SADDR(p) (p)
+#define B200Z_LDS16(base, idx) ((uint32_t)((const uint16_t *)(base))[idx])
+#define B200Z_LDS32(base, idx) (((const uint32_t *)(base))[idx])
+#define B200Z_PREFETCH(p) ((void)0)
+typedef const void *b200z_saddr;
+#define B200Z_ANY(x) __any_sync(0xffffffffu, (x))
+#define B200Z_BALLOT(x) __ballot_sync(0xffffffffu, (x))
+#define B200Z_SHFL(v, src) __shfl_sync(0xffffffffu, (v), (src))
+#define B200Z_SYNCWARP() __syncwarp()
+#define B200Z_OPAQUE(x) (x)
+#define B200Z_LDG(p) (*(p))
+#define B200Z_BREV(x) __brev(x)
+#define B200Z_POPC(x) __popc(x)
+#define B200Z_LDCG(p) (*(p))
+#define B200Z_REDOR(p, v) atomicOr((p), (v))
+#elif defined(__CUDA_ARCH__)
 // 32-bit shared-window addressing for the per-lane LUTs: keeps the hot loop free of 64-bit generic pointers
 #define B200Z_SADDR(p) ((uint32_t)__cvta_generic_to_shared(p))
 __device__ __forceinline__ uint32_t b200z_lds16(uint32_t base, uint32_t idx) {
@@ -35,6 +52,11 @@ __device__ __forceinline__ uint32_t b200z_lds32(uint32_t base, uint32_t idx) {
 typedef uint32_t b200z_saddr;
 #define B200Z_ANY(x) __any_sync(0xffffffffu, (x))
 #define B200Z_BALLOT(x) __ballot_sync(0xffffffffu, (x))
+#define B200Z_SHFL(v, src) __shfl_sync(0xffffffffu, (v), (src))
+#define B200Z_SYNCWARP() __syncwarp()
+#define B200Z_POPC(x) __popc(x)
+#define B200Z_LDCG(p) __ldcg(p)
+#define B200Z_REDOR(p, v) atomicOr((p), (v))
 __device__ __forceinline__ uint32_t b200z_opaque(uint32_t v) {
   uint32_t o;
   asm volatile("mov.b32 %0, %1;" : "=r"(o) : "r"(v));  // keeps a loop invariant in a register (no rematerialisation)
@@ -51,6 +73,11 @@ __device__ __forceinline__ uint32_t b200z_opaque(uint32_t v) {
 typedef const void *b200z_saddr;
 #define B200Z_ANY(x) (x)
 #define B200Z_BALLOT(x) ((x) ? 1u : 0u)
+#define B200Z_SHFL(v, src) (v)
+#define B200Z_SYNCWARP() ((void)0)
+#define B200Z_POPC(x) __builtin_popcount(x)
+#define B200Z_LDCG(p) (*(p))
+#define B200Z_REDOR(p, v) (*(p) |= (v))
 #define B200Z_OPAQUE(x) (x)
 #define B200Z_LDG(p) (*(p))
 static inline uint32_t b200z_host_brev(uint32_t v) {
@@ -62,7 +89,7 @@ static inline uint32_t b200z_host_brev(uint32_t v) {
 }
 #define B200Z_BREV(x) b200z_host_brev(x)
 #endif
-#ifdef __CUDACC__
+#if defined(__CUDACC__) && !defined(B200Z_EMU)
 #define B200Z_HD __device__ __forceinline__
 #define B200Z_CONST __constant__
 #else
@@ -108,7 +135,8 @@ B200Z_CONST uint32_t c_dist_tab[32] = {
 
 constexpr int LBITS = B200Z_LBITS;  // primary literal/length LUT bits
 constexpr int DBITS = B200Z_DBITS;  // primary distance LUT bits
-constexpr int LUT_HALFWORDS = (1 << LBITS) + (1 << DBITS);
+constexpr int SUBN = 160;           // second-level entries shared by the codes longer than LBITS / DBITS of one block
+constexpr int LUT_HALFWORDS = (1 << LBITS) + (1 << DBITS) + SUBN;
 constexpr int LANE_STRIDE_WORDS = LUT_HALFWORDS / 2 + 1;  // +1 word: same index -> different bank per lane
 constexpr int CONST_WORDS = 16 + 32 + 64;                  // len table (32 x u16) + dist table (32 x u32) + xtab (64 x u32)
 
@@ -117,14 +145,14 @@ static inline size_t inflate_decode_smem_bytes(int warps_per_block, int units_pe
 }
 
 // Canonical-code side tables for codes longer than the LUT (rare): per lane, in local memory.
-struct SlowTab {
+struct alignas(4) SlowTab {
   uint16_t first[16];  // first canonical code of each length
   uint16_t count[16];  // number of codes of each length
   uint16_t offs[16];   // index into perm of the first symbol of each length
   uint16_t perm[288];  // symbols sorted by (length, symbol)
   uint8_t maxlen;      // HuffmanTable.maxCodeLength (_huffman_table.dart:12-15)
 };
-struct SlowTabD {
+struct alignas(4) SlowTabD {
   uint16_t first[16];
   uint16_t count[16];
   uint16_t offs[16];
@@ -192,10 +220,15 @@ struct BitReader {
 // two-level layout).  Returns false when the set is over-subscribed (reference: later writes win in
 // a flat table -- garbage; here: B200Z_U_BADCODE).
 // ---------------------------------------------------------------------------------------------
+// Second level (sub != nullptr): a root slot shared by codes longer than TBITS holds a LINK = (sub_base << 7) |
+// (extra index bits << 4) | 0 -- the zero length nibble still reads as "miss" to code that does not know links -- and the
+// entry is found at sub[sub_base + next bits].  Symbols kept out of the LUT leave zero entries there too.  When the
+// pool of sub_cap entries (shared by the block's two alphabets, *sub_used so far) is exhausted the remaining long prefixes stay plain misses (the exact step decodes them).
 template <int TBITS, typename PermT>
 B200Z_HD bool build_table(const uint8_t *lens, int n, uint16_t *lut, uint16_t *first,
                                             uint16_t *count, uint16_t *offs, PermT *perm, uint8_t *maxlen,
-                                            int lut_skip_eq = -1, int lut_skip_above = 0x7fffffff) {
+                                            int lut_skip_eq = -1, int lut_skip_above = 0x7fffffff,
+                                            uint16_t *sub = nullptr, int sub_cap = 0, int *sub_used = nullptr) {
   for (int l = 0; l < 16; ++l) count[l] = 0;
   int mx = 0;
   for (int i = 0; i < n; ++i) {
@@ -242,6 +275,41 @@ B200Z_HD bool build_table(const uint8_t *lens, int n, uint16_t *lut, uint16_t *f
       for (uint32_t j = r; j < (1u << TBITS); j += (1u << l)) lut[j] = e;
     }
   }
+  if (sub != nullptr && mx > TBITS) {
+    // pass 1: the longest code under every root prefix, parked in the (still empty) root slot as a bare number > TBITS
+    for (int l = TBITS + 1; l < 16; ++l) next[l] = first[l];
+    for (int s = 0; s < n; ++s) {
+      const int l = lens[s];
+      if (l <= TBITS) continue;
+      const uint32_t r = B200Z_BREV((uint32_t)next[l]++) >> (32 - l);
+      uint16_t &slot = lut[r & ((1u << TBITS) - 1u)];
+      if (slot < (uint16_t)l) slot = (uint16_t)l;
+    }
+    // pass 2: allocate the prefix's block on first sight, then place the symbol
+    int used = *sub_used;
+    for (int l = TBITS + 1; l < 16; ++l) next[l] = first[l];
+    for (int s = 0; s < n; ++s) {
+      const int l = lens[s];
+      if (l <= TBITS) continue;
+      const uint32_t r = B200Z_BREV((uint32_t)next[l]++) >> (32 - l);
+      uint16_t &slot = lut[r & ((1u << TBITS) - 1u)];
+      if (slot != 0 && slot < 16) {  // still the parked length
+        const int sb = (int)slot - TBITS;
+        if (used + (1 << sb) <= sub_cap) {
+          slot = (uint16_t)((used << 7) | (sb << 4));
+          used += 1 << sb;
+        } else {
+          slot = 0;
+        }
+      }
+      if (slot == 0 || (slot & 15) != 0) continue;  // pool exhausted for this prefix
+      if (s == lut_skip_eq || s > lut_skip_above) continue;
+      const uint32_t sb = (slot >> 4) & 7u, base = slot >> 7;
+      const uint16_t e = (uint16_t)((s << 4) | l);
+      for (uint32_t j = r >> TBITS; j < (1u << sb); j += (1u << (l - TBITS))) sub[base + j] = e;
+    }
+    *sub_used = used;
+  }
   return true;
 }
 
@@ -270,13 +338,57 @@ struct UnitResult {
   int32_t status;
 };
 
+// Intra-stream speculation ("helpers").  A stream's symbols form one serial chain, and 16 Ki streams cannot fill a
+// B200; so every stream owns G lanes of a warp.  Lane 0 of the group (the MASTER) is the exact decoder.  When it has
+// parsed a block header it starts lanes 1..G-1 (HELPERS) at G-1 evenly spaced bit offsets of the rest of the input.
+// A helper decodes from its (wrong) offset with the master's tables; Huffman streams self-synchronise, so after a few
+// symbols its symbol boundaries coincide with the true ones.  Every helper marks the boundaries it passes in its first
+// SPEC_W bits in a bitmap (global memory, L2); a lane that runs into its successor's window tests each of its own boundaries
+// against that bitmap, and the first hit proves both parses identical from there on: helpers stop there ("linked"),
+// the master instead adopts the successor's tokens (and, through the links, those of the whole chain), adds their
+// output length, and resumes after the last adopted helper.  Helpers never take the exact path: anything unusual (end of
+// block, invalid symbol, end of input, scratch full) just ends them, and the master continues exactly from there.  The
+// tokens of a unit therefore live in PIECES (own region / helper regions); back-references of adopted tokens are range
+// checked by k_inflate_expand, which knows absolute positions.
+constexpr int SPEC_W = 2048;          // sync window (bits) = boundary bitmap of a helper
+constexpr int SPEC_BMW = SPEC_W / 32;  // words per bitmap
+constexpr int SPEC_MAX_G = 8;
+constexpr int SPEC_HSHIFT = 2;         // helper token region = unit capacity >> 2
+constexpr int PIECE_MAX = 30;
+constexpr int PIECE_WORDS = 2 + 3 * PIECE_MAX;  // [0] = count, then (src, start, count) from word 2: src 0 = own region, k = helper k
+constexpr int USCRATCH_BYTES = (SPEC_MAX_G - 1) * SPEC_BMW * 4;  // per unit: the helpers' boundary bitmaps
+constexpr uint32_t SPEC_BIAS = 0x40000000u;  // helpers count output bytes from here, so "distance > produced" never fires
+constexpr uint32_t SPEC_NOLINK = 0xffffffffu;
+
+struct SpecCtx {
+  int lane, sub, G;   // lane in the warp, index inside the stream's lane group (0 = master), lanes per stream
+  bool spec;          // warp-uniform: helpers are in use in this launch
+  uint32_t *hplane;   // helper k's token region = hplane + (k - 1) * hstride  [hcap words]
+  size_t hstride;
+  uint32_t hcap;
+  uint32_t *bm;       // global: helper k's boundary bitmap = bm + (k - 1) * SPEC_BMW
+  uint32_t *pieces;   // the unit's piece table (global)
+};
+
+B200Z_HD void piece_add(uint32_t *pieces, uint32_t &np, uint32_t src, uint32_t start, uint32_t count) {
+  if (count == 0 || !pieces) return;
+  pieces[2 + 3 * np] = src;
+  pieces[3 + 3 * np] = start;
+  pieces[4 + 3 * np] = count;
+  np++;
+}
+
 B200Z_HD UnitResult inflate_decode_unit(bool active, const uint8_t *in, uint32_t in_len, uint32_t cap, uint32_t *tok,
                                         uint16_t *lut_l, uint16_t *lut_d, const uint16_t *s_len_tab,
-                                        const uint32_t *s_dist_tab, const uint32_t *s_xtab) {
+                                        const uint32_t *s_dist_tab, const uint32_t *s_xtab, const SpecCtx &sc) {
   const b200z_saddr lutl_s = B200Z_SADDR(lut_l), lutd_s = B200Z_SADDR(lut_d), xtab_s = B200Z_SADDR(s_xtab);
+  uint16_t *sub_p = lut_d + (1 << DBITS);  // second-level pool (build_table)
   SlowTab sl;
   SlowTabD sd;
   uint8_t lens[320];
+  const bool is_master = sc.sub == 0;
+  const int gbase = sc.lane - sc.sub;  // the master's lane
+  const bool spec_on = sc.spec;  // warp-uniform
 
   BitReader br;
   {
@@ -295,12 +407,148 @@ B200Z_HD UnitResult inflate_decode_unit(bool active, const uint8_t *in, uint32_t
   int maxl = 0, maxd = 0;
   bool mode_dist = false;  // bulk path: the next symbol is a distance code
   uint32_t mlen_pending = 0;
+  uint32_t *tk = tok;      // where this lane's tokens go (master: the unit's region; helper: its own region)
+  uint32_t capx = cap;     // output bound the bulk loop tests (helpers: none, their byte count is biased)
+  uint32_t nt_limit = 0xffffffffu;  // token bound the bulk loop tests (helpers: end of their token region)
 
-  bool done = !active;
+  // ---- speculation state (see SpecCtx) ----
+  const uint32_t G = (uint32_t)sc.G;
+  uint32_t hst = 0;  // helper: 0 idle, 1 running, 2 stopped with results
+  bool h_fast = false;
+  // Role-exclusive state shares registers: a master reads its helpers' values (and helpers the master's commands)
+  // by shuffling the SAME variable from a lane of the other role.
+  uint32_t v0 = 0, v1 = 0, v2 = 0, v3 = 0, v4 = 0, v5 = is_master ? 0u : SPEC_NOLINK, v6 = 0;
+#define h_start_tok v0  /* helper: first token of the current run in its region      | master: cmd       */
+#define h_ntok v1       /* helper: tokens of the run                                 | master: cmd_p0    */
+#define h_rel_bytes v2  /* helper: bytes they produce                                | master: cmd_seg   */
+#define h_end_pos v3    /* helper: bit position where it stopped                     | master: m_h       */
+#define h_link_to v4    /* helper: the helper it met                                 | master: m_idx     */
+#define h_link v5       /* helper: token of h_link_to where the parses met / NOLINK  | master: np        */
+#define h_cur v6        /* helper: next free word of its token region                | master: piece_start */
+#define cmd v0
+#define cmd_p0 v1
+#define cmd_seg v2
+#define m_h v3
+#define m_idx v4
+#define np v5
+#define piece_start v6
+  bool m_stitch = false;  // master: adopting helper m_h from its token m_idx on
+  uint32_t sp_origin = 0, sp_seg = 0;  // bit position rel_bits counts from; bits between helper starts (0: none live)
+  uint32_t succ = G;                   // next helper this lane may meet
+  bool sync_hit = false;
+  uint32_t sync_off = 0, lb_rel = 0;
+
+  bool done = !active || !is_master;
   // loop invariants of the bulk loop, pinned in registers
   const b200z_saddr lutl_r = B200Z_OPAQUE(lutl_s), lutd_r = B200Z_OPAQUE(lutd_s), xtab_r = B200Z_OPAQUE(xtab_s);
-  unsigned live;
-  while ((live = B200Z_BALLOT(!done)) != 0u) {  // warp-uniform: every lane reconverges here
+  const b200z_saddr sub_r = B200Z_SADDR(sub_p);
+  for (;;) {  // warp-uniform: every lane reconverges here
+    if (G > 1u) {  // helpers live exactly as long as their master
+      const uint32_t md = B200Z_SHFL((uint32_t)done, gbase);
+      if (!is_master) done = md != 0u;
+    }
+    if (B200Z_BALLOT(!done) == 0u) break;
+    if (spec_on) {
+      B200Z_SYNCWARP();
+      // ---- commands of the master ----
+      const uint32_t c = B200Z_SHFL(cmd, gbase), c_p0 = B200Z_SHFL(cmd_p0, gbase), c_seg = B200Z_SHFL(cmd_seg, gbase);
+      if (is_master) {
+        cmd = 0;
+      } else if (c == 2u) {
+        hst = 0;
+      } else if (c == 1u && active) {
+        hst = 0;
+        uint32_t *bm_own = sc.bm + (sc.sub - 1) * SPEC_BMW;
+        for (int i = 0; i < SPEC_BMW; ++i) bm_own[i] = 0;
+        if (h_cur + 256u <= sc.hcap) {
+          const uint32_t start = c_p0 + c_seg * (uint32_t)sc.sub;
+          br.seek(start >> 3);
+          br.drop((int)(start & 7u));
+          in_block = true;
+          mode_dist = false;
+          mlen_pending = 0;
+          tk = sc.hplane + (size_t)(sc.sub - 1) * sc.hstride;
+          nt = h_cur;
+          h_start_tok = h_cur;
+          olen = SPEC_BIAS;
+          capx = 0xffffffffu;
+          nt_limit = sc.hcap - 2u;
+          sp_origin = start;
+          sp_seg = c_seg;
+          succ = (uint32_t)sc.sub + 1u;
+          sync_hit = false;
+          h_link = SPEC_NOLINK;
+          h_fast = true;
+          hst = 1;
+        }
+      }
+      // ---- a running helper that cannot go on in the bulk loop is finished ----
+      if (!is_master && hst == 1u && (!h_fast || !(mode_dist || br.widx + 2u <= br.nw))) {
+        const uint32_t pos = 32u * br.widx - (uint32_t)br.cnt - 8u * br.lead;  // bits consumed
+        h_end_pos = mode_dist ? sp_origin + lb_rel : pos;  // a pending length symbol is given back
+        if (!sync_hit && !h_fast && h_end_pos - sp_origin < (uint32_t)SPEC_W / 2u && br.widx + 4u <= br.nw) {
+          // Stopped by an impossible symbol (typically a chance end-of-block) while still decoding from the guessed
+          // offset, i.e. before it can have synchronised: nothing is lost by guessing again one bit further on.
+          uint32_t *bm_own = sc.bm + (sc.sub - 1) * SPEC_BMW;
+          for (int i = 0; i < SPEC_BMW; ++i) bm_own[i] = 0;
+          const uint32_t again = h_end_pos + 1u;
+          br.seek(again >> 3);
+          br.drop((int)(again & 7u));
+          mode_dist = false;
+          mlen_pending = 0;
+          nt = h_start_tok;
+          olen = SPEC_BIAS;
+          h_fast = true;
+        } else {
+        h_ntok = nt - h_start_tok;
+        h_rel_bytes = olen - SPEC_BIAS;
+        h_link = SPEC_NOLINK;
+        if (sync_hit) {
+          const uint32_t *bms = sc.bm + (succ - 1u) * SPEC_BMW;
+          uint32_t idx = 0;
+          for (uint32_t w = 0; w < (sync_off >> 5); ++w) idx += (uint32_t)B200Z_POPC(B200Z_LDCG(bms + w));
+          idx += (uint32_t)B200Z_POPC(B200Z_LDCG(bms + (sync_off >> 5)) & ((1u << (sync_off & 31u)) - 1u));
+          h_link = idx;
+          h_link_to = succ;
+        }
+        h_cur = (nt + 31u) & ~31u;
+        hst = 2;
+        }
+      }
+      // ---- the master adopts the chain of helpers it met ----
+      {
+        const int src = (is_master && m_stitch) ? gbase + (int)m_h : sc.lane;
+        const uint32_t r_hst = B200Z_SHFL(hst, src), r_start = B200Z_SHFL(h_start_tok, src), r_ntok = B200Z_SHFL(h_ntok, src);
+        const uint32_t r_rel = B200Z_SHFL(h_rel_bytes, src), r_end = B200Z_SHFL(h_end_pos, src);
+        const uint32_t r_link = B200Z_SHFL(h_link, src), r_to = B200Z_SHFL(h_link_to, src);
+        if (is_master && m_stitch && r_hst == 2u) {
+          const uint32_t *ht = sc.hplane + (size_t)(m_h - 1u) * sc.hstride + r_start;
+          uint32_t r0 = 0;  // bytes the helper produced before the token the parses met at
+          for (uint32_t i = 0; i < m_idx; ++i) {
+            const uint32_t t = B200Z_LDCG(ht + i);
+            r0 += (t & TOK_LIT) ? 1u : (t >> 16);
+          }
+          piece_add(sc.pieces, np, m_h, r_start + m_idx, r_ntok - m_idx);
+          olen += r_rel - r0;
+          if (r_link != SPEC_NOLINK) {
+            m_h = r_to;
+            m_idx = r_link;
+          } else {  // end of the chain: go on from where that helper stopped
+            br.seek(r_end >> 3);
+            br.drop((int)(r_end & 7u));
+            in_block = true;
+            mode_dist = false;
+            piece_start = nt;  // no gap: the unit's region holds at most one token per output byte
+            succ = m_h + 1u;
+            m_stitch = false;
+            if (olen > cap) {
+              st = B200Z_U_NOSPC;
+              done = true;
+            }
+          }
+        }
+      }
+    }
     // ---------------- bulk inner loop: warp-uniform, ONE SYMBOL per lane per turn, branch-light.  The same
     // instructions decode a literal/length symbol or a distance symbol (a lane that has just read a length
     // code reads its distance code on the next turn), so literal lanes and match lanes do not diverge.  A
@@ -309,48 +557,98 @@ B200Z_HD UnitResult inflate_decode_unit(bool active, const uint8_t *in, uint32_t
     // back-reference before the start, output full, or fewer than 64 unloaded bits left.  Anything special
     // drops the warp to the exact step below for one turn.  (A token is <= 48 bits, so with >= 64 unloaded
     // bits at its start no end-of-stream test is needed in here.)
-    bool fast_ok = !done && in_block;
-    for (;;) {
-      const bool can = fast_ok && (mode_dist || br.widx + 2u <= br.nw);
-      if (B200Z_BALLOT(can) != live) break;
-      if (!can) continue;  // lanes whose stream is finished just keep voting
-      br.refill();
-      const bool dm = mode_dist;
-      const uint32_t bits = (uint32_t)br.buf;
-      const uint32_t e = B200Z_LDS16(dm ? lutd_r : lutl_r, bits & (dm ? ((1u << DBITS) - 1u) : ((1u << LBITS) - 1u)));
-      uint32_t n = e & 15u;
-      uint32_t sym = e >> 4;
-      bool odd = false;
-      if (n == 0u) {
-        // LUT miss (rare, divergent): a code longer than the LUT, or one of the symbols kept out of it.  Long codes
-        // are decoded here by the canonical walk; end-of-block / invalid symbols / holes go to the exact step.
-        int sy = 0;
-        const int ln = dm ? slow_decode<DBITS, uint8_t>(bits & 0x7fffu, sd.first, sd.count, sd.offs, sd.perm, maxd, &sy)
-                          : slow_decode<LBITS, uint16_t>(bits & 0x7fffu, sl.first, sl.count, sl.offs, sl.perm, maxl, &sy);
-        n = (uint32_t)ln;
-        sym = (uint32_t)sy;
-        odd = ln == 0 || (dm ? sy > 29 : (sy == 256 || sy > 285));
+    const bool m_run = is_master && !done && !m_stitch;
+    const bool can0 = ((m_run && in_block) || (!is_master && hst == 1u)) && (mode_dist || br.widx + 2u <= br.nw);
+    const unsigned expect = B200Z_BALLOT(can0);
+    if (B200Z_BALLOT(m_run && !can0) == 0u && expect != 0u) {
+      bool fast_ok = can0;
+      // position bookkeeping of the speculation (rel_bits counts from this lane's own start)
+      uint32_t rel_bits = 32u * br.widx - (uint32_t)br.cnt - 8u * br.lead - sp_origin;
+      uint32_t succ_rel = (sp_seg != 0u && succ < G) ? (succ - (uint32_t)sc.sub) * sp_seg : 0xffffffffu;
+      bool mark = !is_master && spec_on;
+      for (;;) {
+        const bool can = fast_ok && (mode_dist || br.widx + 2u <= br.nw);
+        if (B200Z_BALLOT(can) != expect) break;
+        if (!can) continue;  // lanes that are finished or waiting just keep voting
+        br.refill();
+        const bool dm = mode_dist;
+        if (!dm) {
+          lb_rel = rel_bits;
+          if (rel_bits >= succ_rel) {  // inside the next helper's window: has it passed a boundary here?
+            const uint32_t off = rel_bits - succ_rel;
+            if (off < (uint32_t)SPEC_W) {
+              if ((B200Z_LDCG(sc.bm + (succ - 1u) * SPEC_BMW + (off >> 5)) >> (off & 31u)) & 1u) {
+                sync_hit = true;
+                sync_off = off;
+                fast_ok = false;
+                continue;
+              }
+            } else {  // through the window without meeting it: that helper is lost, look for the next one
+              succ++;
+              succ_rel = succ < G ? succ_rel + sp_seg : 0xffffffffu;
+            }
+          }
+          if (mark) {
+            if (rel_bits < (uint32_t)SPEC_W) B200Z_REDOR(sc.bm + (sc.sub - 1) * SPEC_BMW + (rel_bits >> 5), 1u << (rel_bits & 31u));
+            else mark = false;
+          }
+        }
+        const uint32_t bits = (uint32_t)br.buf;
+        const uint32_t e = B200Z_LDS16(dm ? lutd_r : lutl_r, bits & (dm ? ((1u << DBITS) - 1u) : ((1u << LBITS) - 1u)));
+        uint32_t n = e & 15u;
+        uint32_t sym = e >> 4;
+        bool odd = false;
+        if (n == 0u) {
+          // Root miss (rare, divergent).  A link leads to the second-level entry of a code longer than the root index;
+          // what is still a miss after that -- end of block, the invalid symbols, holes, an exhausted second-level
+          // pool -- takes the exact step (helpers just stop there).
+          if (e != 0u) {
+            const uint32_t sb = (e >> 4) & 7u, sbase = e >> 7;
+            const uint32_t e2 = B200Z_LDS16(sub_r, sbase + ((bits >> (dm ? DBITS : LBITS)) & ((1u << sb) - 1u)));
+            n = e2 & 15u;
+            sym = e2 >> 4;
+          }
+          odd = n == 0u;
+        }
+        const uint32_t xi = dm ? sym + 32u : (sym > 256u ? sym - 257u : 63u);
+        const uint32_t x = B200Z_LDS32(xtab_r, xi & 63u);
+        const uint32_t xb = x & 15u;
+        const uint32_t val = (x >> 4) + ((bits >> n) & ~(0xffffffffu << xb));
+        const bool islit = !dm && sym < 256u;
+        const bool islen = !dm && sym > 256u;
+        const uint32_t nolen = olen + (islit ? 1u : dm ? mlen_pending : 0u);
+        const bool special = odd || (dm && val > olen) || nolen > capx || nt >= nt_limit;
+        if (!special) {
+          const uint32_t tot = n + xb;
+          br.buf >>= tot;
+          br.cnt -= (int)tot;
+          rel_bits += tot;
+#ifdef B200Z_EXP_NOSTORE  // timing experiment only: how much of the turn is the scattered 4-byte token store?
+          if (islit || dm) nt++;
+#else
+          if (islit || dm) tk[nt++] = islit ? (TOK_LIT | sym) : ((mlen_pending << 16) | val);
+#endif
+          olen = nolen;
+          mlen_pending = islen ? val : mlen_pending;
+          mode_dist = islen;
+        }
+        fast_ok = !special;
       }
-      const uint32_t xi = dm ? sym + 32u : (sym > 256u ? sym - 257u : 63u);
-      const uint32_t x = B200Z_LDS32(xtab_r, xi & 63u);
-      const uint32_t xb = x & 15u;
-      const uint32_t val = (x >> 4) + ((bits >> n) & ~(0xffffffffu << xb));
-      const bool islit = !dm && sym < 256u;
-      const bool islen = !dm && sym > 256u;
-      const uint32_t nolen = olen + (islit ? 1u : dm ? mlen_pending : 0u);
-      const bool special = odd || (dm && val > olen) || nolen > cap;
-      if (!special) {
-        const uint32_t tot = n + xb;
-        br.buf >>= tot;
-        br.cnt -= (int)tot;
-        if (islit || dm) tok[nt++] = islit ? (TOK_LIT | sym) : ((mlen_pending << 16) | val);
-        olen = nolen;
-        mlen_pending = islen ? val : mlen_pending;
-        mode_dist = islen;
-      }
-      fast_ok = !special;
+      if (!is_master) h_fast = fast_ok;
     }
-    if (!done) do {
+    // ---- the master met a helper: close its own piece; the adoption runs at the top of the next turns ----
+    if (spec_on && is_master && sync_hit) {
+      const uint32_t *bms = sc.bm + (succ - 1u) * SPEC_BMW;
+      uint32_t idx = 0;
+      for (uint32_t w = 0; w < (sync_off >> 5); ++w) idx += (uint32_t)B200Z_POPC(B200Z_LDCG(bms + w));
+      idx += (uint32_t)B200Z_POPC(B200Z_LDCG(bms + (sync_off >> 5)) & ((1u << (sync_off & 31u)) - 1u));
+      piece_add(sc.pieces, np, 0u, piece_start, nt - piece_start);
+      m_h = succ;
+      m_idx = idx;
+      m_stitch = true;
+      sync_hit = false;
+    }
+    if (is_master && !done && !m_stitch) do {
     if (in_block && (mode_dist || br.widx + 2u <= br.nw)) {
       // ---------------- bulk path: ONE SYMBOL per turn, the same instructions for literal/length and
       // distance symbols (a lane that has just read a length code reads its distance code on the next
@@ -420,6 +718,11 @@ B200Z_HD UnitResult inflate_decode_unit(bool active, const uint8_t *in, uint32_t
     }
     if (!in_block) {
       // ---------------- block boundary: _inflate loop + _parseBlock (inflate.dart:111-156) -------------
+      if (sp_seg != 0u) {  // helpers of the block that just ended (they decode past its end-of-block symbol)
+        cmd = 2;
+        sp_seg = 0;
+        succ = G;
+      }
       if (final_block) {
         st = B200Z_U_DONE;
         done = true; break;
@@ -478,7 +781,7 @@ B200Z_HD UnitResult inflate_decode_unit(bool active, const uint8_t *in, uint32_t
             const uint8_t *src = reinterpret_cast<const uint8_t *>(br.w) + br.lead + pos;
             for (int i = 0; i < (int)len; ++i) tok[nt++] = TOK_LIT | src[i];
           } else {
-            if ((nt & 31) == 31) tok[nt++] = 0;
+            if (((nt - piece_start) & 31u) == 31u) tok[nt++] = 0;  // the pair must not straddle a group of 32 of its piece
             tok[nt++] = TOK_STORED | ((pos >> 30) << 16) | (uint32_t)len;
             tok[nt++] = pos & 0x3fffffffu;
           }
@@ -559,8 +862,10 @@ B200Z_HD UnitResult inflate_decode_unit(bool active, const uint8_t *in, uint32_t
         }
         if (err) { st = err; done = true; break; }
         for (int k = hdist; k < 32; ++k) lens[hlit + k] = 0;
-        bool ok = build_table<DBITS, uint8_t>(lens + hlit, hdist, lut_d, sd.first, sd.count, sd.offs, sd.perm, &sd.maxlen, -1, 29);
-        ok = build_table<LBITS, uint16_t>(lens, hlit, lut_l, sl.first, sl.count, sl.offs, sl.perm, &sl.maxlen, 256, 285) && ok;
+        int sub_used = 0;
+        for (int k = 0; k < SUBN / 2; ++k) reinterpret_cast<uint32_t *>(sub_p)[k] = 0;
+        bool ok = build_table<DBITS, uint8_t>(lens + hlit, hdist, lut_d, sd.first, sd.count, sd.offs, sd.perm, &sd.maxlen, -1, 29, sub_p, SUBN, &sub_used);
+        ok = build_table<LBITS, uint16_t>(lens, hlit, lut_l, sl.first, sl.count, sl.offs, sl.perm, &sl.maxlen, 256, 285, sub_p, SUBN, &sub_used) && ok;
         if (!ok) { st = B200Z_U_BADCODE; done = true; break; }
       } else {
         st = B200Z_U_STOP;
@@ -569,6 +874,18 @@ B200Z_HD UnitResult inflate_decode_unit(bool active, const uint8_t *in, uint32_t
       maxl = sl.maxlen;
       maxd = sd.maxlen;
       in_block = true;
+      if (spec_on && np + G + 2u <= (uint32_t)PIECE_MAX) {  // start the helpers on the rest of the input
+        br.refill();
+        const uint32_t p0 = 32u * br.widx - (uint32_t)br.cnt - 8u * br.lead, eb = 8u * br.in_len;
+        if (eb > p0 && (eb - p0) / G >= 2u * (uint32_t)SPEC_W) {
+          cmd = 1;
+          cmd_p0 = p0;
+          cmd_seg = (eb - p0) / G;
+          sp_origin = p0;
+          sp_seg = cmd_seg;
+          succ = 1;
+        }
+      }
     }
 
     // ---------------- one token: _decodeHuffman (inflate.dart:300-343) -------------------------------
@@ -666,6 +983,24 @@ B200Z_HD UnitResult inflate_decode_unit(bool active, const uint8_t *in, uint32_t
     } while (0);
   }
 
+  if (is_master && sc.pieces) {
+    piece_add(sc.pieces, np, 0u, piece_start, nt - piece_start);
+    sc.pieces[0] = np;
+  }
+#undef h_start_tok
+#undef h_ntok
+#undef h_rel_bytes
+#undef h_end_pos
+#undef h_link_to
+#undef h_link
+#undef h_cur
+#undef cmd
+#undef cmd_p0
+#undef cmd_seg
+#undef m_h
+#undef m_idx
+#undef np
+#undef piece_start
   UnitResult r;
   r.ntok = nt;
   r.out_len = olen;

@@ -17,7 +17,22 @@
 //                     lengths -> every lane owns ONE OUTPUT BYTE of a 32-byte window, finds its token
 //                     by a shuffle binary search, and resolves out[p] = out[p - dist] (chasing through
 //                     bytes of the same window that are not written yet).
+#ifdef B200Z_EMU  // CPU emulation build (tests/host_emul/inflate_emul.cpp): kernels only
+#include "cuda_emu.h"
+static uint32_t cuemu_dyn_smem[64 * 1024];
+#define B200Z_DECODE_THREADS 32
+#define B200Z_EXPAND_THREADS 256
+namespace b200z {
+struct InflateWs {
+  uint32_t *tokens = nullptr, *htokens = nullptr;
+  size_t hstride = 0;
+  uint32_t *pieces = nullptr;
+  uint8_t *uscratch = nullptr;
+};
+}  // namespace b200z
+#else
 #include "b200z_internal.h"
+#endif
 #include "inflate_decode.cuh"
 
 #include <stdlib.h>
@@ -29,13 +44,19 @@ namespace b200z {
 // ---------------------------------------------------------------------------------------------
 // phase 1
 // ---------------------------------------------------------------------------------------------
+#ifdef B200Z_EMU
+#define B200Z_DYN_SMEM(name) uint32_t *name = cuemu_dyn_smem
+#else
+#define B200Z_DYN_SMEM(name) extern __shared__ uint32_t name[]
+#endif
+
 __global__ void __launch_bounds__(B200Z_DECODE_THREADS)
 k_inflate_decode(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__ in_off,
                  const uint32_t *__restrict__ in_len, const uint64_t *__restrict__ out_off,
-                 const uint32_t *__restrict__ out_cap, uint32_t *__restrict__ tokens,
-                 uint32_t *__restrict__ ntok, uint32_t *__restrict__ out_len, int32_t *__restrict__ status,
-                 uint32_t *__restrict__ in_used, uint32_t n_units, int units_per_warp) {
-  extern __shared__ uint32_t smem[];
+                 const uint32_t *__restrict__ out_cap, InflateWs ws, uint32_t *__restrict__ out_len,
+                 int32_t *__restrict__ status, uint32_t *__restrict__ in_used, uint32_t n_units, int units_per_warp,
+                 int lanes_per_unit) {
+  B200Z_DYN_SMEM(smem);
   uint16_t *s_len_tab = reinterpret_cast<uint16_t *>(smem);
   uint32_t *s_dist_tab = smem + 16;
   uint32_t *s_xtab = smem + 48;  // [0,32) length symbols, [32,64) distance symbols: (base << 4) | extra_bits
@@ -50,21 +71,43 @@ k_inflate_decode(const uint8_t *__restrict__ in_base, const uint64_t *__restrict
   const int lane = threadIdx.x & 31;
   const int warp_in_block = threadIdx.x >> 5;
   const uint32_t gwarp = blockIdx.x * (blockDim.x >> 5) + warp_in_block;
-  // every lane stays in the decode loop (it votes once per token so the warp reconverges); lanes without
-  // a stream are born finished
-  const uint32_t unit = gwarp * units_per_warp + lane;
-  const bool active = lane < units_per_warp && unit < n_units;
+  // a stream owns lanes_per_unit consecutive lanes: the first decodes it exactly, the others are its speculative
+  // helpers (inflate_decode.cuh).  Every lane stays in the decode loop (it votes once per turn so the warp
+  // reconverges); lanes without a stream are born finished.
+  const int sidx = lane / lanes_per_unit, sub = lane % lanes_per_unit;
+  const uint32_t unit = gwarp * units_per_warp + sidx;
+  const bool active = sidx < units_per_warp && unit < n_units;
 
   uint16_t *lut_l = reinterpret_cast<uint16_t *>(smem + CONST_WORDS +
-                                                 (warp_in_block * units_per_warp + (active ? lane : 0)) * LANE_STRIDE_WORDS);
+                                                 (warp_in_block * units_per_warp + (active ? sidx : 0)) * LANE_STRIDE_WORDS);
   uint16_t *lut_d = lut_l + (1 << LBITS);
 
-  // token region mirrors the output layout (<= 1 token per output byte)
+  SpecCtx sc;
+  sc.lane = lane;
+  sc.sub = sub;
+  sc.G = lanes_per_unit;
+  sc.spec = lanes_per_unit > 1 && ws.htokens != nullptr;
+  sc.hplane = nullptr;
+  sc.hstride = ws.hstride;
+  sc.hcap = 0;
+  sc.bm = nullptr;
+  sc.pieces = nullptr;
+  uint32_t *tok = nullptr;
+  if (active) {
+    const uint64_t oo = out_off[unit];
+    const uint32_t cap = out_cap[unit];
+    tok = ws.tokens + oo;  // token region mirrors the output layout (<= 1 token per output byte)
+    if (lanes_per_unit > 1 && ws.htokens) {
+      sc.hplane = ws.htokens + (oo >> SPEC_HSHIFT);
+      sc.hcap = (uint32_t)(((oo + cap) >> SPEC_HSHIFT) - (oo >> SPEC_HSHIFT));
+    }
+    uint8_t *us = ws.uscratch + (size_t)unit * USCRATCH_BYTES;
+    sc.bm = reinterpret_cast<uint32_t *>(us);
+    sc.pieces = ws.pieces + (size_t)unit * PIECE_WORDS;
+  }
   const UnitResult r = inflate_decode_unit(active, active ? in_base + in_off[unit] : nullptr, active ? in_len[unit] : 0u,
-                                           active ? out_cap[unit] : 0u, active ? tokens + out_off[unit] : nullptr, lut_l,
-                                           lut_d, s_len_tab, s_dist_tab, s_xtab);
-  if (!active) return;
-  ntok[unit] = r.ntok;
+                                           active ? out_cap[unit] : 0u, tok, lut_l, lut_d, s_len_tab, s_dist_tab, s_xtab, sc);
+  if (!active || sub != 0) return;
   out_len[unit] = r.out_len;
   status[unit] = r.status;
   in_used[unit] = r.in_used;
@@ -81,19 +124,25 @@ __device__ __forceinline__ uint32_t tok_len(uint32_t t, bool payload) {
 }
 
 __global__ void __launch_bounds__(B200Z_EXPAND_THREADS)
-k_inflate_expand(const uint32_t *__restrict__ tokens, const uint32_t *__restrict__ ntok,
-                 const uint8_t *__restrict__ in_base, const uint64_t *__restrict__ in_off,
-                 uint8_t *out_base, const uint64_t *__restrict__ out_off, uint32_t n_units) {
+k_inflate_expand(InflateWs ws, const uint8_t *__restrict__ in_base, const uint64_t *__restrict__ in_off, uint8_t *out_base,
+                 const uint64_t *__restrict__ out_off, const uint32_t *__restrict__ out_cap, uint32_t *__restrict__ out_len,
+                 int32_t *__restrict__ status, uint32_t n_units) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t unit = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; unit < n_units; unit += warps) {
-    const uint32_t *T = tokens + out_off[unit];
-    const uint32_t nt = ntok[unit];
-    uint8_t *out = out_base + out_off[unit];
+    const uint64_t oo = out_off[unit];
+    const uint32_t cap = out_cap[unit];
+    const uint32_t *P = ws.pieces + (size_t)unit * PIECE_WORDS;
+    const uint32_t np = P[0];
+    uint8_t *out = out_base + oo;
     const uint8_t *in = in_base + in_off[unit];
     uint32_t pos0 = 0;
-    for (uint32_t g = 0; g < nt; g += 32) {
+    bool stop = false;
+    for (uint32_t pi = 0; pi < np && !stop; ++pi) {
+      const uint32_t src = P[2 + 3 * pi], pstart = P[3 + 3 * pi], nt = P[4 + 3 * pi];
+      const uint32_t *T = (src == 0 ? ws.tokens + oo : ws.htokens + (size_t)(src - 1) * ws.hstride + (oo >> SPEC_HSHIFT)) + pstart;
+    for (uint32_t g = 0; g < nt && !stop; g += 32) {
       uint32_t t = (g + lane < nt) ? T[g + lane] : 0u;
       uint32_t tprev = __shfl_up_sync(FULL, t, 1);
       const bool payload = lane > 0 && (tprev >> 30) == 1u;  // payload words have top bits 00: no chains
@@ -105,10 +154,39 @@ k_inflate_expand(const uint32_t *__restrict__ tokens, const uint32_t *__restrict
         uint32_t v = __shfl_up_sync(FULL, incl, d);
         if (lane >= d) incl += v;
       }
+      const bool is_stored = !payload && (t & 0xC0000000u) == TOK_STORED;
+      // Range checks of the reference, here because tokens adopted from helper lanes were decoded without knowing
+      // their absolute position: a back-reference before the start of the output throws (output_memory_stream.dart:
+      // 83-86), output beyond the caller's capacity is B200Z_U_NOSPC.  The unit ends with the last good token.
+      {
+        const bool is_match = !payload && len != 0u && (t & 0xC0000000u) == 0u;
+        const bool bad_range = is_match && (t & 0xffffu) > pos0 + (incl - len);
+        const bool bad_cap = len != 0u && pos0 + incl > cap;
+        const unsigned bad = __ballot_sync(FULL, bad_range || bad_cap);
+        if (bad) {
+          const int fb = __ffs((int)bad) - 1;
+          const bool r_range = __shfl_sync(FULL, (int)bad_range, fb) != 0;
+          if (lane >= fb) {
+            t = 0;
+            len = 0;
+          }
+          incl = len;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            uint32_t v = __shfl_up_sync(FULL, incl, d);
+            if (lane >= d) incl += v;
+          }
+          stop = true;
+          const uint32_t good = __shfl_sync(FULL, incl, 31);
+          if (lane == 0) {
+            status[unit] = r_range ? B200Z_U_RANGE : B200Z_U_NOSPC;
+            out_len[unit] = pos0 + good;
+          }
+        }
+      }
       const uint32_t total = __shfl_sync(FULL, incl, 31);
       const uint32_t start = incl - len;  // relative to pos0
-      const bool is_stored = !payload && (t & 0xC0000000u) == TOK_STORED;
-      unsigned stored_mask = __ballot_sync(FULL, is_stored);
+      unsigned stored_mask = __ballot_sync(FULL, is_stored && len != 0u);
 
       if (stored_mask == 0) {
         // ---- byte-parallel windows ----
@@ -127,19 +205,19 @@ k_inflate_expand(const uint32_t *__restrict__ tokens, const uint32_t *__restrict
           uint32_t sj = __shfl_sync(FULL, start, j);
           bool have = !active || (tj & TOK_LIT);
           uint32_t byte = tj & 0xff;
-          int src = 0;
+          int src2 = 0;
           if (!have) {
             uint32_t dist = tj & 0xffff;
-            src = (int)p - (int)dist;
-            if (src >= (int)sj) {  // overlapping run: fold whole periods back before the match
-              int k = (src - (int)sj) / (int)dist + 1;
-              src -= k * (int)dist;
+            src2 = (int)p - (int)dist;
+            if (src2 >= (int)sj) {  // overlapping run: fold whole periods back before the match
+              int k = (src2 - (int)sj) / (int)dist + 1;
+              src2 -= k * (int)dist;
             }
           }
           // chase sources that are still inside this (unwritten) window
-          while (__any_sync(FULL, !have && src >= (int)w)) {
-            const bool need = !have && src >= (int)w;
-            uint32_t q = need ? (uint32_t)src : 0u;
+          while (__any_sync(FULL, !have && src2 >= (int)w)) {
+            const bool need = !have && src2 >= (int)w;
+            uint32_t q = need ? (uint32_t)src2 : 0u;
             int j2 = 0;
 #pragma unroll
             for (int s = 16; s >= 1; s >>= 1) {
@@ -155,16 +233,16 @@ k_inflate_expand(const uint32_t *__restrict__ tokens, const uint32_t *__restrict
                 have = true;
               } else {
                 uint32_t d2 = t2 & 0xffff;
-                src = (int)q - (int)d2;
-                if (src >= (int)s2) {
-                  int k = (src - (int)s2) / (int)d2 + 1;
-                  src -= k * (int)d2;
+                src2 = (int)q - (int)d2;
+                if (src2 >= (int)s2) {
+                  int k = (src2 - (int)s2) / (int)d2 + 1;
+                  src2 -= k * (int)d2;
                 }
               }
             }
           }
           if (active) {
-            if (!have) byte = out[(long long)pos0 + src];
+            if (!have) byte = out[(long long)pos0 + src2];
             out[pos0 + p] = (uint8_t)byte;
           }
           __syncwarp();
@@ -197,9 +275,11 @@ k_inflate_expand(const uint32_t *__restrict__ tokens, const uint32_t *__restrict
       }
       pos0 += total;
     }
+    }
   }
 }
 
+#ifndef B200Z_EMU
 // ---------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------
@@ -225,6 +305,41 @@ int profile_read(double *decode_ms, double *expand_ms, uint64_t *n) {
   }
   g_prof_events.clear();
   return 0;
+}
+
+size_t inflate_ws_bytes(size_t n_units, size_t extent) {
+  const size_t tok = (extent * 4 + 511) & ~(size_t)255;
+  const size_t hstride = (extent >> SPEC_HSHIFT) + 64;
+  const size_t hb = ((SPEC_MAX_G - 1) * hstride * 4 + 255) & ~(size_t)255;
+  const size_t pb = (n_units * PIECE_WORDS * 4 + 255) & ~(size_t)255;
+  const size_t ub = (n_units * (size_t)USCRATCH_BYTES + 255) & ~(size_t)255;
+  return tok + hb + pb + ub + 256;
+}
+size_t inflate_ws_extent_for(size_t n_units, size_t bytes) {
+  const size_t fixed = inflate_ws_bytes(n_units, 0) + 1024;
+  if (bytes <= fixed) return 0;
+  return (bytes - fixed) / (4 + (SPEC_MAX_G - 1)) ;
+}
+InflateWs inflate_ws_carve(void *ws, size_t n_units, size_t extent) {
+  InflateWs w;
+  uint8_t *p = reinterpret_cast<uint8_t *>(ws);
+  const size_t tok = (extent * 4 + 511) & ~(size_t)255;
+  w.hstride = (extent >> SPEC_HSHIFT) + 64;
+  const size_t hb = ((SPEC_MAX_G - 1) * w.hstride * 4 + 255) & ~(size_t)255;
+  const size_t pb = (n_units * PIECE_WORDS * 4 + 255) & ~(size_t)255;
+  w.tokens = reinterpret_cast<uint32_t *>(p);
+  w.htokens = reinterpret_cast<uint32_t *>(p + tok);
+  w.pieces = reinterpret_cast<uint32_t *>(p + tok + hb);
+  w.uscratch = p + tok + hb + pb;
+  return w;
+}
+InflateWs inflate_ws_slice(const InflateWs &w, size_t first_unit, size_t first_out_byte) {
+  InflateWs s = w;
+  s.tokens = w.tokens + first_out_byte;
+  s.htokens = w.htokens + (first_out_byte >> SPEC_HSHIFT);
+  s.pieces = w.pieces + first_unit * PIECE_WORDS;
+  s.uscratch = w.uscratch + first_unit * (size_t)USCRATCH_BYTES;
+  return s;
 }
 
 cudaError_t launch_inflate(const InflateBatch &b, cudaStream_t stream) {
@@ -254,6 +369,18 @@ cudaError_t launch_inflate(const InflateBatch &b, cudaStream_t stream) {
       while (upw > 1 && (b.n_units + upw - 1) / upw < target_warps) upw >>= 1;
     }
   }
+  // lanes per stream: the lanes a warp has left over decode the same streams speculatively (inflate_decode.cuh)
+  int lpu = 32 / upw;
+  {
+    static int forced_g = -1;
+    if (forced_g < 0) {
+      const char *e = getenv("B200Z_SPEC_G");
+      forced_g = e ? atoi(e) : 0;
+    }
+    if (lpu > SPEC_MAX_G) lpu = SPEC_MAX_G;
+    if (forced_g >= 1 && forced_g < lpu) lpu = forced_g;
+    while (lpu & (lpu - 1)) lpu &= lpu - 1;
+  }
   const uint64_t n_warps = (b.n_units + upw - 1) / upw;
   const unsigned blocks = (unsigned)((n_warps + warps_per_block - 1) / warps_per_block);
   const size_t smem = inflate_decode_smem_bytes(warps_per_block, upw);
@@ -263,16 +390,14 @@ cudaError_t launch_inflate(const InflateBatch &b, cudaStream_t stream) {
     if (e != cudaSuccess) return e;
     attr_smem = smem;
   }
-  uint32_t *tokens = reinterpret_cast<uint32_t *>(b.workspace);
-  uint32_t *ntok = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(b.workspace) + b.tok_bytes);
   ProfTriple pt{};
   if (g_prof) {
     cudaEventCreate(&pt.a); cudaEventCreate(&pt.b); cudaEventCreate(&pt.c);
     cudaEventRecord(pt.a, stream);
   }
-  k_inflate_decode<<<blocks, B200Z_DECODE_THREADS, smem, stream>>>(
-      b.in_base, b.in_off, b.in_len, b.out_off, b.out_cap, tokens, ntok, b.out_len, b.status, b.in_used,
-      (uint32_t)b.n_units, upw);
+  k_inflate_decode<<<blocks, B200Z_DECODE_THREADS, smem, stream>>>(b.in_base, b.in_off, b.in_len, b.out_off, b.out_cap, b.ws,
+                                                                   b.out_len, b.status, b.in_used, (uint32_t)b.n_units, upw,
+                                                                   lpu);
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
@@ -288,8 +413,8 @@ cudaError_t launch_inflate(const InflateBatch &b, cudaStream_t stream) {
   }
   const uint64_t max_blocks = (uint64_t)g_num_sms * (uint64_t)bps;
   if (eblocks > max_blocks) eblocks = max_blocks;
-  k_inflate_expand<<<(unsigned)eblocks, B200Z_EXPAND_THREADS, 0, stream>>>(tokens, ntok, b.in_base, b.in_off, b.out_base,
-                                                                           b.out_off, (uint32_t)b.n_units);
+  k_inflate_expand<<<(unsigned)eblocks, B200Z_EXPAND_THREADS, 0, stream>>>(b.ws, b.in_base, b.in_off, b.out_base, b.out_off,
+                                                                           b.out_cap, b.out_len, b.status, (uint32_t)b.n_units);
   count_launch();
   if (g_prof) {
     cudaEventRecord(pt.c, stream);
@@ -297,5 +422,6 @@ cudaError_t launch_inflate(const InflateBatch &b, cudaStream_t stream) {
   }
   return cudaGetLastError();
 }
+#endif  // !B200Z_EMU
 
 }  // namespace b200z

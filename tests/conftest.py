@@ -22,6 +22,13 @@ def pytest_configure(config):
     hdr = os.path.join(ROOT, "archive_b200", "csrc", "inflate_decode.cuh")
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
         subprocess.run(["g++", "-O1", "-g", "-fPIC", "-shared", "-std=c++17", "-x", "c++", src, "-o", so], check=True)
+    # the inflate kernels (several lanes per stream) on the CUDA execution-model emulation
+    src = os.path.join(emul, "inflate_emul.cpp")
+    so = os.path.join(emul, "libinflate_emul.so")
+    deps = [src, os.path.join(emul, "cuda_emu.h"), hdr, os.path.join(ROOT, "archive_b200", "csrc", "inflate_kernels.cu")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
+        subprocess.run(["g++", "-O2", "-g", "-fPIC", "-shared", "-std=c++17", "-I", emul, "-I",
+                        os.path.join(ROOT, "archive_b200", "csrc"), src, "-o", so], check=True)
     # the BZip2 encoder kernels, compiled against the CUDA execution-model emulation (tests/host_emul/cuda_emu.h)
     csrc = os.path.join(ROOT, "archive_b200", "csrc")
     src = os.path.join(emul, "bz2enc_emul.cpp")

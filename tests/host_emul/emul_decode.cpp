@@ -38,14 +38,17 @@ extern "C" int emul_inflate(const uint8_t *in, uint32_t in_len, uint8_t *out, ui
   while (((uintptr_t)p & 3) != 1) ++p;
   memcpy(p, in, in_len);
   std::vector<uint32_t> tok((size_t)cap + 64);
-  std::vector<uint16_t> lut((1 << B200Z_LBITS) + (1 << B200Z_DBITS) + 8);
+  std::vector<uint16_t> lut(LUT_HALFWORDS + 8);
   uint32_t xtab[64];
   for (int i = 0; i < 32; ++i) {
     xtab[i] = c_len_tab[i];
     xtab[32 + i] = c_dist_tab[i];
   }
+  SpecCtx sc{};  // one lane per stream: no speculative helpers in this single-threaded build
+  sc.G = 1;
+  sc.spec = false;
   UnitResult r = inflate_decode_unit(true, p, in_len, cap, tok.data(), lut.data(), lut.data() + (1 << B200Z_LBITS),
-                                     c_len_tab, c_dist_tab, xtab);
+                                     c_len_tab, c_dist_tab, xtab, sc);
   expand(tok.data(), r.ntok, p, out);
   *out_len = r.out_len;
   *in_used = r.in_used;
