@@ -32,6 +32,12 @@ _lib = None
 _lock = threading.Lock()
 _u8p = C.POINTER(C.c_uint8)
 
+class Bz2Block(C.Structure):
+    """b200z_bz2_block (include/b200z.h)"""
+    _fields_ = [("start_bit", C.c_uint64), ("end_bit", C.c_uint64), ("out_bytes", C.c_uint64), ("crc_calc", C.c_uint32),
+                ("crc_stored", C.c_uint32), ("status", C.c_int32), ("flags", C.c_uint32)]
+
+
 _SIGS = {
     "b200z_init": (C.c_int, [C.c_int, C.c_uint32]),
     "b200z_shutdown": (None, []),
@@ -57,6 +63,8 @@ _SIGS = {
     "b200z_gzip_encode": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_uint32, C.c_void_p, C.c_size_t,
                                     C.POINTER(C.c_size_t)]),
     "b200z_bzip2_decode": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "b200z_bzip2_decode_shard": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t,
+                                           C.POINTER(C.c_size_t), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "b200z_bzip2_encode": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "b200z_bzip2_bound": (C.c_size_t, [C.c_size_t]),
     "b200z_inflate_batch": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,

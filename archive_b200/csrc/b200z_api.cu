@@ -673,7 +673,15 @@ static inline uint32_t be32_at_bit(const uint8_t *in, size_t n, uint64_t bit) {
   return (uint32_t)(v >> (8 - (bit & 7)));
 }
 
-static int bzip2_decode_impl(const uint8_t *in, size_t in_len, int verify, uint8_t *out, size_t out_cap, size_t *out_len) {
+// shard != nullptr: decode only this rank's share of the block candidates and report every block instead of walking the
+// chain (the ranks' reports are merged and validated by the caller, archive_b200/shard.py).
+struct Bz2Shard {
+  uint32_t rank, world;
+  b200z_bz2_block *blocks;
+  size_t blocks_cap, n_blocks;
+};
+static int bzip2_decode_impl(const uint8_t *in, size_t in_len, int verify, uint8_t *out, size_t out_cap, size_t *out_len,
+                             Bz2Shard *shard = nullptr) {
   *out_len = 0;
   // 'B' 'Z' 'h' level: each is a readByte() that throws at EOS (bz2_bit_reader.dart:17-20)
   static const uint8_t sig[3] = {0x42, 0x5a, 0x68};
@@ -733,6 +741,7 @@ static int bzip2_decode_impl(const uint8_t *in, size_t in_len, int verify, uint8
 
   // ---- device arrays ----
   const uint32_t chunks_max = (nblock_max + 1023) / 1024;
+  const uint32_t nb_all = nb ? nb : 1;
   auto carve = [&](void *base, uint32_t nbk) {
     Carver c(base);
     struct A {
@@ -744,7 +753,7 @@ static int bzip2_decode_impl(const uint8_t *in, size_t in_len, int verify, uint8
       BzChainHost *chain;
       size_t bytes;
     } a;
-    a.blk_bit = c.take<unsigned long long>(nbk);
+    a.blk_bit = c.take<unsigned long long>(nb_all);
     a.end_bit = c.take<unsigned long long>(nbk);
     a.block_out = c.take<unsigned long long>(nbk);
     a.block_off = c.take<unsigned long long>(nbk + 1);
@@ -771,7 +780,11 @@ static int bzip2_decode_impl(const uint8_t *in, size_t in_len, int verify, uint8
     a.bytes = align_up(c.off, 256);
     return a;
   };
-  const uint32_t nbk = nb ? nb : 1;
+  uint32_t nbk = nb ? nb : 1;
+  if (shard) {  // only this rank's share needs the big per-block arrays (blk_bit keeps all candidates: small)
+    const uint32_t lo = (uint32_t)((uint64_t)nb * shard->rank / shard->world), hi = (uint32_t)((uint64_t)nb * (shard->rank + 1) / shard->world);
+    nbk = hi > lo ? hi - lo : 1;
+  }
   auto sz = carve(nullptr, nbk);
   CU(g.d_bz.reserve(sz.bytes));
   auto A = carve(g.d_bz.p, nbk);
@@ -780,23 +793,30 @@ static int bzip2_decode_impl(const uint8_t *in, size_t in_len, int verify, uint8
   std::vector<uint32_t> h_nrec(nb), h_nblock(nb), h_optr(nb), h_rnd(nb);
   std::vector<unsigned long long> h_end(nb);
   std::vector<int32_t> h_st(nb);
-  if (nb) {
+  uint32_t k_lo = 0, k_hi = nb;  // candidates this call decodes
+  if (shard) {
+    k_lo = (uint32_t)((uint64_t)nb * shard->rank / shard->world);
+    k_hi = (uint32_t)((uint64_t)nb * (shard->rank + 1) / shard->world);
+  }
+  if (k_hi > k_lo) {
     CU(cudaMemcpyAsync(A.blk_bit, blk_bits.data(), (size_t)nb * 8, cudaMemcpyHostToDevice, g.stream));
     Bz2Entropy e;
     e.words = (const uint32_t *)g.d_in.p;
     e.n_bytes = in_len;
-    e.blk_bit = A.blk_bit;
-    e.n_blocks = nb;
+    e.blk_bit = A.blk_bit + k_lo;
+    e.n_blocks = k_hi - k_lo;
     e.nblock_max = nblock_max;
+    // block k of this call uses slot k - k_lo of every per-block array
     e.rec_val = A.rec_val; e.rec_pos = A.rec_pos; e.n_rec = A.n_rec; e.nblock = A.nblock; e.orig_ptr = A.orig_ptr;
     e.randomised = A.rnd; e.end_bit = A.end_bit; e.status = A.status;
     CU(bz2_launch_entropy(e, g.stream));
-    CU(cudaMemcpyAsync(h_nrec.data(), A.n_rec, nb * 4, cudaMemcpyDeviceToHost, g.stream));
-    CU(cudaMemcpyAsync(h_nblock.data(), A.nblock, nb * 4, cudaMemcpyDeviceToHost, g.stream));
-    CU(cudaMemcpyAsync(h_optr.data(), A.orig_ptr, nb * 4, cudaMemcpyDeviceToHost, g.stream));
-    CU(cudaMemcpyAsync(h_rnd.data(), A.rnd, nb * 4, cudaMemcpyDeviceToHost, g.stream));
-    CU(cudaMemcpyAsync(h_end.data(), A.end_bit, (size_t)nb * 8, cudaMemcpyDeviceToHost, g.stream));
-    CU(cudaMemcpyAsync(h_st.data(), A.status, nb * 4, cudaMemcpyDeviceToHost, g.stream));
+    const uint32_t m = k_hi - k_lo;
+    CU(cudaMemcpyAsync(h_nrec.data() + k_lo, A.n_rec, m * 4, cudaMemcpyDeviceToHost, g.stream));
+    CU(cudaMemcpyAsync(h_nblock.data() + k_lo, A.nblock, m * 4, cudaMemcpyDeviceToHost, g.stream));
+    CU(cudaMemcpyAsync(h_optr.data() + k_lo, A.orig_ptr, m * 4, cudaMemcpyDeviceToHost, g.stream));
+    CU(cudaMemcpyAsync(h_rnd.data() + k_lo, A.rnd, m * 4, cudaMemcpyDeviceToHost, g.stream));
+    CU(cudaMemcpyAsync(h_end.data() + k_lo, A.end_bit, (size_t)m * 8, cudaMemcpyDeviceToHost, g.stream));
+    CU(cudaMemcpyAsync(h_st.data() + k_lo, A.status, m * 4, cudaMemcpyDeviceToHost, g.stream));
     CU(cudaStreamSynchronize(g.stream));
   }
 
@@ -808,7 +828,16 @@ static int bzip2_decode_impl(const uint8_t *in, size_t in_len, int verify, uint8
   uint32_t eos_crc = 0;
   uint64_t pos = 32;
   size_t ci = 0;
-  for (;;) {
+  std::vector<uint32_t> chain_of(nb, 0xffffffffu);
+  if (shard) {
+    for (uint32_t k = k_lo; k < k_hi; ++k)
+      if (h_st[k] == 0 && !h_rnd[k]) {
+        chain_of[k] = (uint32_t)chain.size();
+        chain.push_back({k - k_lo, h_nblock[k], h_nrec[k], h_optr[k]});
+        stored_crc.push_back(blk_bits[k] + 80 <= total_bits ? be32_at_bit(in, in_len, blk_bits[k] + 48) : 0u);
+      }
+  }
+  for (; !shard;) {
     if ((pos + 7) / 8 >= in_len) break;  // input.isEOS: every byte has been pulled into the bit reader
     if (pos + 48 > total_bits) {          // _readBlockType reads 6 bytes
       set_err("bzip2: truncated block header (Dart: RangeError)");
@@ -886,6 +915,51 @@ static int bzip2_decode_impl(const uint8_t *in, size_t in_len, int verify, uint8
     for (uint32_t i = 0; i < nc && i < 16; ++i)
       fprintf(stderr, "[b200z]   chain %u off %llu..%llu crc %08x stored %08x irregular %d\n", i, (unsigned long long)h_off[i],
               (unsigned long long)h_off[i + 1], h_crc[i], stored_crc[i], h_irr[i]);
+  if (shard) {
+    // one report per candidate of the range + one per end-of-stream candidate (every rank reports those)
+    shard->n_blocks = 0;
+    auto push = [&](const b200z_bz2_block &b) {
+      if (shard->n_blocks < shard->blocks_cap) shard->blocks[shard->n_blocks] = b;
+      shard->n_blocks++;
+    };
+    for (uint32_t k = k_lo; k < k_hi; ++k) {
+      b200z_bz2_block b{};
+      b.start_bit = blk_bits[k];
+      b.end_bit = h_end[k];
+      b.status = h_st[k];
+      b.flags = h_rnd[k] ? B200Z_BZ2_RANDOMISED : 0u;
+      b.crc_stored = blk_bits[k] + 80 <= total_bits ? be32_at_bit(in, in_len, blk_bits[k] + 48) : 0u;
+      const uint32_t c = chain_of[k];
+      if (c != 0xffffffffu) {
+        b.out_bytes = h_off[c + 1] - h_off[c];
+        b.crc_calc = h_crc[c];
+        if (h_irr[c]) b.flags |= B200Z_BZ2_CORRUPT_CYCLE;
+      }
+      push(b);
+    }
+    for (uint32_t i = 0; i < ncand; ++i)
+      if (cand[i] >> 63) {
+        b200z_bz2_block b{};
+        b.start_bit = cand[i] & ~(1ull << 63);
+        b.end_bit = b.start_bit + 80;
+        b.flags = B200Z_BZ2_EOS;
+        b.crc_stored = b.start_bit + 80 <= total_bits ? be32_at_bit(in, in_len, b.start_bit + 48) : 0u;
+        push(b);
+      }
+    const size_t n_local = nc ? (size_t)h_off[nc] : 0;
+    *out_len = n_local;
+    if (shard->n_blocks > shard->blocks_cap) {
+      set_err("bzip2 shard: %zu block reports, capacity %zu", shard->n_blocks, shard->blocks_cap);
+      return B200Z_E_NOSPC;
+    }
+    if (n_local > out_cap) {
+      set_err("bzip2 shard: output needs %zu bytes, out_cap %zu", n_local, out_cap);
+      return B200Z_E_NOSPC;
+    }
+    if (n_local) CU(cudaMemcpyAsync(out, g.d_out.p, n_local, cudaMemcpyDeviceToHost, g.stream));
+    CU(cudaStreamSynchronize(g.stream));
+    return B200Z_OK;
+  }
   // blocks are committed in order; the first bad one ends the stream (its bytes are already written when the
   // reference compares the CRC, :58-66)
   size_t n_out = 0;
@@ -1071,6 +1145,24 @@ int b200z_bzip2_decode(const uint8_t *in, size_t in_len, int verify, uint8_t *ou
   return rc;
 }
 void b200z_profile_enable(int on) { profile_enable(on != 0); }
+int b200z_bzip2_decode_shard(const uint8_t *in, size_t in_len, uint32_t rank, uint32_t world, uint8_t *out, size_t out_cap,
+                             size_t *out_len, b200z_bz2_block *blocks, size_t blocks_cap, size_t *n_blocks) {
+  int rc = require_init();
+  if (rc) return rc;
+  if (world == 0 || rank >= world || !blocks) {
+    set_err("bzip2_decode_shard: bad rank/world");
+    return B200Z_E_ARG;
+  }
+  std::lock_guard<std::mutex> lk(g.mu);
+  CU(cudaSetDevice(g.device));
+  Bz2Shard sh{rank, world, blocks, blocks_cap, 0};
+  size_t n = 0;
+  rc = bzip2_decode_impl(in, in_len, 0, out, out_cap, &n, &sh);
+  if (out_len) *out_len = n;
+  if (n_blocks) *n_blocks = sh.n_blocks;
+  return rc;
+}
+
 int b200z_bzip2_encode(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_cap, size_t *out_len) {
   int rc = require_init();
   if (rc) return rc;

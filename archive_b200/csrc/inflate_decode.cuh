@@ -623,11 +623,7 @@ B200Z_HD UnitResult inflate_decode_unit(bool active, const uint8_t *in, uint32_t
           br.buf >>= tot;
           br.cnt -= (int)tot;
           rel_bits += tot;
-#ifdef B200Z_EXP_NOSTORE  // timing experiment only: how much of the turn is the scattered 4-byte token store?
-          if (islit || dm) nt++;
-#else
           if (islit || dm) tk[nt++] = islit ? (TOK_LIT | sym) : ((mlen_pending << 16) | val);
-#endif
           olen = nolen;
           mlen_pending = islen ? val : mlen_pending;
           mode_dist = islen;

@@ -29,3 +29,117 @@ def out_slices(out_len, ranges):
     out_len = np.asarray(out_len, dtype=np.int64)
     csum = np.concatenate([[0], np.cumsum(out_len)])
     return [(int(csum[lo]), int(csum[hi])) for lo, hi in ranges]
+
+
+# ---------------------------------------------------------------------------------------------
+# BZip2: blocks sharded over ranks
+# ---------------------------------------------------------------------------------------------
+BZ2_EOS, BZ2_RANDOMISED, BZ2_CORRUPT_CYCLE = 1, 2, 4
+
+
+def bz2_walk_chain(reports, in_len: int, verify: bool):
+    """Merge the block reports of all ranks and walk them exactly as BZip2Decoder.decodeStream does
+    (bzip2_decoder.dart:46-87): the stream is the chain of blocks in which every block starts on the bit where the
+    previous one ended, up to the first end-of-stream magic; CRCs are compared only when `verify`.
+    reports: iterable of (start_bit, end_bit, out_bytes, crc_calc, crc_stored, status, flags, rank, local_off).
+    -> (kind, chain, n_out): kind 'ok' | 'data' (decodeStream returns false) | 'throw' (RangeError); chain = the
+    reports that make up the output, in order; n_out = bytes of output that are kept."""
+    by_start = {}
+    for r in reports:
+        by_start.setdefault(r[0], r)  # every rank reports the EOS candidates: keep one
+    total_bits = in_len * 8
+    pos, chain, kind, eos = 32, [], "ok", None
+    while True:
+        if (pos + 7) // 8 >= in_len:
+            break
+        if pos + 48 > total_bits:
+            kind = "throw"
+            break
+        r = by_start.get(pos)
+        if r is None:
+            kind = "data"
+            break
+        if pos + 80 > total_bits:
+            kind = "throw"
+            break
+        if r[6] & BZ2_EOS:
+            eos = r
+            break
+        if r[5] == -2:
+            kind = "throw"
+            break
+        if r[5] != 0 or (r[6] & BZ2_RANDOMISED):
+            kind = "data"
+            break
+        chain.append(r)
+        pos = r[1]
+    n_out, combined, kept = 0, 0, []
+    for r in chain:
+        if r[6] & BZ2_CORRUPT_CYCLE:
+            kind = "data"
+            break
+        kept.append(r)
+        n_out += r[2]
+        if verify and r[3] != r[4]:
+            kind, eos = "data", None
+            break
+        combined = (((combined << 1) | (combined >> 31)) & 0xFFFFFFFF) ^ r[3]
+    if kind == "ok" and eos is not None and verify and eos[4] != combined:
+        kind = "data"
+    return kind, kept, n_out
+
+
+def bzip2_decode_sharded(data, verify: bool = False, group=None, rank=None, world=None, reports_in=None):
+    """Every rank passes the same BZip2 stream; rank r decodes its share of the blocks on its GPU
+    (b200z_bzip2_decode_shard), the per-block reports are exchanged (a few dozen bytes per block -- the only collective on
+    this path; the decoded bytes stay where they were produced), and every rank derives the same chain.
+    -> dict(kind, total, pieces): pieces = [(stream_offset, bytes)] this rank holds of the output."""
+    import ctypes as C
+
+    import torch.distributed as dist
+
+    from . import _ffi
+    L = _ffi.ensure_init()
+    use_dist = rank is None
+    if use_dist:
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+    addr, n, keep = _ffi.as_buffer(data)
+    cap_blocks = n // 4096 + 64
+    blocks = (_ffi.Bz2Block * cap_blocks)()
+    out_cap = n * 8 // world + (2 << 20)
+    while True:
+        out = (C.c_uint8 * out_cap)()
+        out_len, nb = C.c_size_t(0), C.c_size_t(0)
+        rc = L.b200z_bzip2_decode_shard(addr, n, rank, world, C.addressof(out), out_cap, C.byref(out_len), blocks,
+                                        cap_blocks, C.byref(nb))
+        if rc == _ffi.E_NOSPC and out_len.value > out_cap:
+            out_cap = out_len.value + 64
+            continue
+        _ffi.check(rc)
+        break
+    mine, off = [], 0
+    for i in range(nb.value):
+        b = blocks[i]
+        mine.append((b.start_bit, b.end_bit, b.out_bytes, b.crc_calc, b.crc_stored, b.status, b.flags, rank, off))
+        off += b.out_bytes
+    if not use_dist:  # the caller plays the other ranks itself (tests): it passes their reports in
+        reports = mine + list(reports_in or [])
+    elif world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine, group=group)
+        reports = [r for part in gathered for r in part]
+    else:
+        reports = mine
+    kind, chain, n_out = bz2_walk_chain(reports, n, verify)
+    pieces, pos = [], 0
+    view = memoryview(out)
+    for r in chain:
+        if r[7] == rank and r[2]:
+            if pieces and pieces[-1][0] + len(pieces[-1][1]) == pos and pieces[-1][2] + len(pieces[-1][1]) == r[8]:
+                o, v, lo = pieces[-1]
+                pieces[-1] = (o, view[lo:lo + len(v) + r[2]], lo)
+            else:
+                pieces.append((pos, view[r[8]:r[8] + r[2]], r[8]))
+        pos += r[2]
+    return {"kind": kind, "total": n_out, "pieces": [(o, v) for o, v, _ in pieces], "n_chain": len(chain), "reports": mine}

@@ -97,6 +97,25 @@ int b200z_gzip_encode(const uint8_t *in, size_t in_len, int level, uint32_t mtim
  * before the failure are kept, as in the reference).                                                    */
 int b200z_bzip2_decode(const uint8_t *in, size_t in_len, int verify, uint8_t *out, size_t out_cap,
                        size_t *out_len);
+/* One rank's share of a BZip2 stream (blocks are independent once the bit-level magic scan has found
+ * them; only the combined CRC and the output offsets chain across blocks).  Rank `rank` of `world` decodes the block
+ * candidates [n*rank/world, n*(rank+1)/world) into `out`, back to back, and reports EVERY candidate of its share plus
+ * the end-of-stream candidates: the caller merges the reports of all ranks, walks the chain as decodeStream does
+ * (bzip2_decoder.dart:46-87: a block must start where the previous one ended), checks the CRCs and derives the output
+ * offsets (archive_b200/shard.py: bzip2_decode_sharded).                                                         */
+typedef struct {
+  uint64_t start_bit, end_bit; /* position of the 48-bit magic; first bit after the block's last symbol */
+  uint64_t out_bytes;          /* decoded size (0 when the block could not be decoded)                  */
+  uint32_t crc_calc, crc_stored;
+  int32_t status;              /* 0 ok, -1 data error, -2 read past the end of the input               */
+  uint32_t flags;              /* B200Z_BZ2_*                                                           */
+} b200z_bz2_block;
+#define B200Z_BZ2_EOS 1u            /* an end-of-stream magic (crc_stored = the combined CRC) */
+#define B200Z_BZ2_RANDOMISED 2u     /* randomised block: not decoded                          */
+#define B200Z_BZ2_CORRUPT_CYCLE 4u  /* inverse BWT is not one cycle: not decoded              */
+int b200z_bzip2_decode_shard(const uint8_t *in, size_t in_len, uint32_t rank, uint32_t world, uint8_t *out,
+                             size_t out_cap, size_t *out_len, b200z_bz2_block *blocks, size_t blocks_cap,
+                             size_t *n_blocks);
 /* BZip2Encoder().encodeBytes(data) -- bzip2_encoder.dart:15-81: always "BZh9", never randomised, the pending RLE1
  * run is closed at every block end (which is where the bytes differ from libbzip2 on multi-block inputs).
  * Inputs of 4 GiB and more: B200Z_E_ARG.                                                                       */

@@ -1,0 +1,106 @@
+"""BZip2 block sharding: the host-side chain walk over merged per-rank block reports (CPU), its exchange
+between two gloo ranks (CPU), and -- on the GPU -- b200z_bzip2_decode_shard played for 1, 2 and 3 ranks on one device."""
+import bz2
+import os
+import socket
+
+import pytest
+
+from archive_b200 import shard
+
+
+def rep(start, end, out, crc, stored=None, status=0, flags=0, rank=0, off=0):
+    return (start, end, out, crc, crc if stored is None else stored, status, flags, rank, off)
+
+
+def comb(crcs):
+    c = 0
+    for x in crcs:
+        c = (((c << 1) | (c >> 31)) & 0xFFFFFFFF) ^ x
+    return c
+
+
+def test_chain_walk_rules():
+    n = 1000
+    good = [rep(32, 3000, 100, 11), rep(3000, 6000, 200, 22, rank=1), rep(6000, 6080, 0, 0, stored=comb([11, 22]), flags=shard.BZ2_EOS)]
+    assert shard.bz2_walk_chain(good, n, True)[::2] == ("ok", 300)
+    # a magic-looking pattern inside a block is reported but is not on the chain
+    junk = good + [rep(4000, 4100, 7, 1, status=-1)]
+    assert shard.bz2_walk_chain(junk, n, True)[::2] == ("ok", 300)
+    # gap: the second block does not start where the first ended -> false, first block kept
+    gap = [good[0], rep(3001, 6000, 200, 22), good[2]]
+    assert shard.bz2_walk_chain(gap, n, False)[::2] == ("data", 100)
+    # CRC mismatch is only seen with verify, and the bad block's bytes are already written (bzip2_decoder.dart:58-66)
+    bad = [good[0], rep(3000, 6000, 200, 22, stored=23, rank=1), good[2]]
+    assert shard.bz2_walk_chain(bad, n, False)[::2] == ("ok", 300)
+    assert shard.bz2_walk_chain(bad, n, True)[::2] == ("data", 300)
+    # combined CRC
+    eos_bad = good[:2] + [rep(6000, 6080, 0, 0, stored=5, flags=shard.BZ2_EOS)]
+    assert shard.bz2_walk_chain(eos_bad, n, True)[0] == "data" and shard.bz2_walk_chain(eos_bad, n, False)[0] == "ok"
+    # block that read past the end: RangeError; randomised: false
+    assert shard.bz2_walk_chain([good[0], rep(3000, 0, 0, 0, status=-2)], n, False)[::2] == ("throw", 100)
+    assert shard.bz2_walk_chain([good[0], rep(3000, 6000, 0, 0, flags=shard.BZ2_RANDOMISED)], n, False)[::2] == ("data", 100)
+    # stream that just ends after a block (no EOS): the loop stops at isEOS
+    assert shard.bz2_walk_chain([rep(32, 7995, 100, 11)], n, True)[::2] == ("ok", 100)
+    assert shard.bz2_walk_chain([rep(32, 7990, 100, 11)], n, True)[::2] == ("throw", 100)  # 10 bits left: _readBlockType throws
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine = [rep(32, 3000, 100, 11, rank=0)] if rank == 0 else [rep(3000, 6000, 200, 22, rank=1)]
+    mine.append(rep(6000, 6080, 0, 0, stored=comb([11, 22]), flags=shard.BZ2_EOS, rank=rank))
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine)
+    kind, chain, n_out = shard.bz2_walk_chain([r for part in gathered for r in part], 1000, True)
+    if rank == 0:
+        q.put((kind, n_out, [r[7] for r in chain]))
+    dist.destroy_process_group()
+
+
+def test_two_rank_report_exchange_gloo():
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    got = q.get(timeout=120)
+    for p in ps:
+        p.join(60)
+    assert got == ("ok", 300, [0, 1])
+
+
+@pytest.mark.gpu
+def test_shards_reassemble_on_one_gpu():
+    """Each 'rank' is a call of b200z_bzip2_decode_shard on the same device; the merged reports must give back the
+    stream, identically for every world size, and find corruption where the unsharded decoder finds it."""
+    import archive_b200
+    from archive_b200 import synth
+    src = synth.text(9_500_000, stream=77).tobytes()
+    z = bz2.compress(src, 9)
+    for world in (1, 2, 3):
+        parts = [shard.bzip2_decode_sharded(z, rank=r, world=world) for r in range(world)]
+        reports = [x for p in parts for x in p["reports"]]
+        kind, chain, n_out = shard.bz2_walk_chain(reports, len(z), True)
+        assert kind == "ok" and n_out == len(src)
+        out = bytearray(n_out)
+        for r, p in enumerate(parts):
+            others = [x for q, pp in enumerate(parts) if q != r for x in pp["reports"]]
+            mine = shard.bzip2_decode_sharded(z, verify=True, rank=r, world=world, reports_in=others)
+            assert mine["kind"] == "ok" and mine["total"] == len(src)
+            for off, v in mine["pieces"]:
+                out[off:off + len(v)] = v
+        assert bytes(out) == src
+    bad = bytearray(z)
+    bad[len(z) // 2] ^= 0x10
+    ref_ok = archive_b200.BZip2Decoder().decode_bytes(bytes(bad), verify=True)
+    parts = [shard.bzip2_decode_sharded(bytes(bad), rank=r, world=2) for r in range(2)]
+    kind, chain, n_out = shard.bz2_walk_chain([x for p in parts for x in p["reports"]], len(bad), True)
+    assert kind == "data" and n_out == len(ref_ok)
