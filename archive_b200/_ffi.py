@@ -38,6 +38,15 @@ class Bz2Block(C.Structure):
                 ("crc_stored", C.c_uint32), ("status", C.c_int32), ("flags", C.c_uint32)]
 
 
+class ZipEntry(C.Structure):
+    """b200z_zip_entry (include/b200z.h)"""
+    _fields_ = [("local_header_off", C.c_uint64), ("data_off", C.c_uint64), ("comp_size", C.c_uint64),
+                ("uncomp_size", C.c_uint64), ("hint_uncomp_size", C.c_uint64), ("name_off", C.c_uint64),
+                ("cd_name_off", C.c_uint64), ("name_len", C.c_uint32), ("cd_name_len", C.c_uint32), ("crc32", C.c_uint32),
+                ("method", C.c_uint32), ("flags", C.c_uint32), ("mod_time", C.c_uint32), ("mod_date", C.c_uint32),
+                ("ext_attr", C.c_uint32), ("version_made_by", C.c_uint32), ("has_data", C.c_uint32)]
+
+
 _SIGS = {
     "b200z_init": (C.c_int, [C.c_int, C.c_uint32]),
     "b200z_shutdown": (None, []),
@@ -63,6 +72,9 @@ _SIGS = {
     "b200z_gzip_encode": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_uint32, C.c_void_p, C.c_size_t,
                                     C.POINTER(C.c_size_t)]),
     "b200z_bzip2_decode": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "b200z_zip_list": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "b200z_zip_extract": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
     "b200z_bzip2_decode_shard": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t,
                                            C.POINTER(C.c_size_t), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "b200z_bzip2_encode": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),

@@ -1128,6 +1128,251 @@ using namespace b200z;
 // =============================================================================================
 // C ABI
 // =============================================================================================
+
+// ---------------------------------------------------------------------------------------------
+// ZIP container: directory parse on the host, members as ONE inflate batch
+// ---------------------------------------------------------------------------------------------
+static inline uint64_t le64(const uint8_t *p) { return (uint64_t)le32(p) | ((uint64_t)le32(p + 4) << 32); }
+
+// ZipDirectory._findSignature (zip_directory.dart:139-182): 1024-byte chunks from the end, each scanned backwards; a
+// signature that straddles two chunks, or lies in the last 4 bytes, is not seen.
+static long long zip_find_eocd(const uint8_t *z, size_t len) {
+  if (len <= 4) return -1;
+  const long long length = (long long)len - 4;
+  const long long chunk = length < 1024 ? length : 1024;
+  long long start = length - chunk;
+  while (start >= 0) {
+    for (long long cp = chunk - 4; cp >= 0; --cp)
+      if (le32(z + start + cp) == 0x06054b50u) return start + cp;
+    if (start > 0 && start < chunk) start = 0;
+    else start -= chunk;
+  }
+  return -1;
+}
+
+extern "C" int b200z_zip_list(const uint8_t *z, size_t len, b200z_zip_entry *entries, size_t cap, size_t *n_entries) {
+  if (n_entries) *n_entries = 0;
+  if (!z && len) return B200Z_E_ARG;
+  const long long fp = zip_find_eocd(z, len);
+  if (fp < 0) return B200Z_OK;  // ZipDirectory.read returns with no headers (zip_directory.dart:26-29)
+#define ZNEED(pos, k)                                                              \
+  if ((unsigned long long)(pos) + (k) > len) {                                      \
+    set_err("zip: read past the end at %llu (Dart: RangeError)", (unsigned long long)(pos)); \
+    return B200Z_E_THROW;                                                          \
+  }
+  ZNEED(fp, 22);
+  uint64_t cd_size = le32(z + fp + 12), cd_off = le32(z + fp + 16);
+  {
+    const size_t clen = le16(z + fp + 20);
+    ZNEED(fp + 22, clen);  // the comment is read (readString) before the zip64 records are looked at
+  }
+  // _readZip64Data :65-137
+  if (fp >= 20 && le32(z + fp - 20) == 0x07064b50u) {
+    const uint64_t z64 = le64(z + fp - 20 + 8);
+    if (z64 <= len && len - z64 >= 4 && le32(z + z64) == 0x06064b50u) {
+      ZNEED(z64, 56);
+      cd_size = le64(z + z64 + 40);
+      cd_off = le64(z + z64 + 48);
+    } else if (z64 > len || len - z64 < 4) {
+      ZNEED(z64, 4);
+    }
+  }
+  // central directory :50-63
+  size_t n = 0;
+  uint64_t p = cd_off;
+  const uint64_t cd_end = cd_off + cd_size;  // dirContent = input.subset(position, length)
+  while (p < cd_end) {
+    ZNEED(p, 4);
+    if (le32(z + p) != 0x02014b50u) break;
+    ZNEED(p, 46);
+    // ZipFileHeader.read (zip_file_header.dart:28-111)
+    const uint8_t *h = z + p;
+    b200z_zip_entry e;
+    memset(&e, 0, sizeof e);
+    e.version_made_by = le16(h + 4);
+    uint64_t comp = le32(h + 20), uncomp = le32(h + 24), lho = le32(h + 42);
+    const size_t fn_len = le16(h + 28), ex_len = le16(h + 30), cm_len = le16(h + 32);
+    uint32_t disk = le16(h + 34);
+    e.ext_attr = le32(h + 38);
+    ZNEED(p + 46, fn_len + ex_len + cm_len);
+    e.cd_name_off = p + 46;
+    e.cd_name_len = (uint32_t)fn_len;
+    if (ex_len >= 4) {  // :48-98 -- shorter extra fields are ignored
+      const uint8_t *x = h + 46 + fn_len;
+      size_t xo = 0;
+      while (ex_len - xo >= 4) {
+        const uint32_t id = le16(x + xo);
+        size_t size = le16(x + xo + 2);
+        xo += 4;
+        if (xo + size > ex_len) {
+          set_err("zip: extra field overruns its record (Dart: RangeError)");
+          return B200Z_E_THROW;
+        }
+        if (id == 1) {
+          size_t q = xo;
+          if (size >= 8 && uncomp == 0xffffffffu) { uncomp = le64(x + q); q += 8; size -= 8; }
+          if (size >= 8 && comp == 0xffffffffu) { comp = le64(x + q); q += 8; size -= 8; }
+          if (size >= 8 && lho == 0xffffffffu) { lho = le64(x + q); q += 8; size -= 8; }
+          if (size >= 4 && disk == 0xffffu) { disk = le32(x + q); q += 4; size -= 4; }
+          xo = q + size;
+        } else {
+          xo += size;
+        }
+      }
+    }
+    (void)disk;
+    p += 46 + fn_len + ex_len + cm_len;
+    // ZipFile.read at the local header (zip_file.dart:73-149)
+    e.local_header_off = lho;
+    e.comp_size = comp;
+    e.uncomp_size = uncomp;
+    e.hint_uncomp_size = uncomp;
+    ZNEED(lho, 4);
+    if (le32(z + lho) == 0x04034b50u) {
+      ZNEED(lho, 30);
+      const uint8_t *l = z + lho;
+      e.flags = le16(l + 6);
+      e.method = le16(l + 8);
+      e.mod_time = le16(l + 10);
+      e.mod_date = le16(l + 12);
+      e.crc32 = le32(l + 14);
+      const size_t lfn = le16(l + 26), lex = le16(l + 28);
+      ZNEED(lho + 30, lfn + lex);
+      e.name_off = lho + 30;
+      e.name_len = (uint32_t)lfn;
+      e.data_off = lho + 30 + lfn + lex;
+      e.has_data = 1;
+      if (e.data_off + comp > len) {  // readBytes hands out what is there
+        e.comp_size = len - e.data_off;
+      }
+      if (e.flags & 0x08) {  // data descriptor :137-148: CRC and the 32-bit sizes are replaced by what follows the data
+        uint64_t q = e.data_off + e.comp_size;
+        ZNEED(q, 4);
+        const uint32_t sig_or_crc = le32(z + q);
+        q += 4;
+        if (sig_or_crc == 0x08074b50u) {
+          ZNEED(q, 4);
+          e.crc32 = le32(z + q);
+          q += 4;
+        } else {
+          e.crc32 = sig_or_crc;
+        }
+        ZNEED(q, 8);
+        e.uncomp_size = le32(z + q + 4);
+      }
+    }
+    if (n < cap && entries) entries[n] = e;
+    n++;
+  }
+#undef ZNEED
+  if (n_entries) *n_entries = n;
+  if (n > cap && entries) {
+    set_err("zip: %zu entries, capacity %zu", n, cap);
+    return B200Z_E_NOSPC;
+  }
+  return B200Z_OK;
+}
+
+extern "C" int b200z_zip_extract(const uint8_t *z, size_t len, const b200z_zip_entry *entries, size_t n, uint8_t *out,
+                                 size_t out_cap, const uint64_t *out_off, const uint64_t *out_room, uint64_t *out_len,
+                                 int32_t *status, uint32_t flags) {
+  int rc = require_init();
+  if (rc) return rc;
+  if (n == 0) return B200Z_OK;
+  if (!entries || !out_off || !out_room || !out_len || !status) return B200Z_E_ARG;
+  std::lock_guard<std::mutex> lk(g.mu);
+  CU(cudaSetDevice(g.device));
+  // members: deflate -> one inflate batch; stored (and unknown methods, which the reference treats as stored,
+  // zip_file.dart:83) -> device copies; bzip2 -> one stream each, afterwards
+  std::vector<uint64_t> u_in_off, u_out_off;
+  std::vector<uint32_t> u_in_len, u_cap, u_idx;
+  std::vector<size_t> bz_idx;
+  uint64_t lo = ~0ull, hi = 0;
+  for (size_t i = 0; i < n; ++i) {
+    const b200z_zip_entry &e = entries[i];
+    out_len[i] = 0;
+    status[i] = B200Z_U_DONE;
+    if (!e.has_data) continue;
+    if (e.flags & 1u) {
+      status[i] = B200Z_ZIP_ENCRYPTED;
+      continue;
+    }
+    if (out_off[i] + out_room[i] > out_cap || e.data_off + e.comp_size > len) {
+      set_err("zip_extract: entry %zu lies outside the buffers", i);
+      return B200Z_E_ARG;
+    }
+    if (e.method == 8 || e.method == 12) {
+      if (e.comp_size > 0xfffffff0ull || out_room[i] > 0xfffffff0ull) {
+        status[i] = B200Z_ZIP_TOO_LARGE;
+        continue;
+      }
+    }
+    if (e.method == 12) {
+      bz_idx.push_back(i);
+      continue;
+    }
+    if (out_room[i]) {
+      lo = out_off[i] < lo ? out_off[i] : lo;
+      hi = out_off[i] + out_room[i] > hi ? out_off[i] + out_room[i] : hi;
+    }
+    if (e.method == 8) {
+      // ZipFile.getStream: ZLibDecoder().decodeBytes(compressed, raw: true) on exactly the member's bytes.  On the Dart
+      // VM that is dart:io's zlib; the pure-Dart Inflate wants maxCodeLength bits after the last code and
+      // so can drop the last symbols of such a stream.  Default: what the VM gives -- a few bytes that follow the
+      // member are made readable so the lookahead is satisfied; B200Z_ZIP_WEB_EOS: the pure-Dart behaviour.
+      uint64_t pad = 0;
+      if (!(flags & B200Z_ZIP_WEB_EOS)) {
+        pad = len - (e.data_off + e.comp_size);
+        if (pad > 8) pad = 8;
+      }
+      u_in_off.push_back(e.data_off);
+      u_in_len.push_back((uint32_t)(e.comp_size + pad));
+      u_out_off.push_back(out_off[i]);
+      u_cap.push_back((uint32_t)out_room[i]);
+      u_idx.push_back((uint32_t)i);
+    }
+  }
+  const bool any_dev = hi > lo;
+  if (any_dev || !u_idx.empty()) {
+    rc = stage_input(z, len);
+    if (rc) return rc;
+    CU(cudaMemsetAsync((uint8_t *)g.d_in.p + len, 0, 64, g.stream));
+    CU(g.d_out.reserve((hi ? hi : 1) + 64));
+  }
+  for (size_t i = 0; i < n; ++i) {
+    const b200z_zip_entry &e = entries[i];
+    if (!e.has_data || (e.flags & 1u) || e.method == 8 || e.method == 12) continue;
+    uint64_t k = e.comp_size < out_room[i] ? e.comp_size : out_room[i];
+    if (k) CU(cudaMemcpyAsync((uint8_t *)g.d_out.p + out_off[i], (const uint8_t *)g.d_in.p + e.data_off, k, cudaMemcpyDeviceToDevice, g.stream));
+    out_len[i] = e.comp_size;
+    if (e.comp_size > out_room[i]) status[i] = B200Z_U_NOSPC;
+  }
+  if (!u_idx.empty()) {
+    const size_t m = u_idx.size();
+    std::vector<uint32_t> r_len(m), r_used(m);
+    std::vector<int32_t> r_st(m);
+    rc = run_batch_on_staged(u_in_off.data(), u_in_len.data(), u_out_off.data(), u_cap.data(), r_len.data(), r_st.data(),
+                             r_used.data(), m, (size_t)hi);
+    if (rc) return rc;
+    for (size_t k = 0; k < m; ++k) {
+      out_len[u_idx[k]] = r_len[k];
+      status[u_idx[k]] = r_st[k];
+    }
+  }
+  if (any_dev) {
+    CU(cudaMemcpyAsync(out + lo, (const uint8_t *)g.d_out.p + lo, hi - lo, cudaMemcpyDeviceToHost, g.stream));
+    CU(cudaStreamSynchronize(g.stream));
+  }
+  for (size_t i : bz_idx) {  // BZip2Decoder().decodeStream(_rawContent, output) (zip_file.dart:189-192,239-245)
+    const b200z_zip_entry &e = entries[i];
+    size_t got = 0;
+    rc = bzip2_decode_impl(z + e.data_off, (size_t)e.comp_size, 0, out + out_off[i], (size_t)out_room[i], &got);
+    out_len[i] = got;
+    status[i] = rc == B200Z_OK ? B200Z_U_DONE : rc == B200Z_E_NOSPC ? B200Z_U_NOSPC : rc == B200Z_E_THROW ? B200Z_U_THROW : B200Z_U_STOP;
+  }
+  return B200Z_OK;
+}
+
 extern "C" {
 
 const char *b200z_version(void) { return "b200z 0.1 (sm_100a)"; }

@@ -1,0 +1,142 @@
+"""Host mirror of the reference's ZIP reader for the B200 path: `ZipDecoder().decode_bytes(data)` ->
+`Archive` of `ArchiveFile`s, as lib/src/codecs/zip_decoder.dart:18-81 builds it.  The directory is parsed by
+b200z_zip_list (ZipDirectory / ZipFileHeader / ZipFile.read), and -- this is the point of the batching -- ALL members are
+decompressed by ONE b200z_zip_extract call (every deflate member is a unit of the same inflate batch) instead of one
+Inflate per member on first access (zip_file.dart:201-248)."""
+from __future__ import annotations
+
+import ctypes as C
+
+from . import _ffi
+
+U_DONE, U_EOS, U_STOP, U_NOSPC = 0, 1, -1, -2
+ZIP_ENCRYPTED, ZIP_TOO_LARGE = -20, -21
+COMPRESSION = {0: "none", 8: "deflate", 12: "bzip2"}  # zip_file.dart:36-40; anything else is read as "none" (:83)
+
+
+def _name(raw: bytes) -> str:
+    try:  # InputStream.readString: UTF-8, falling back to one char per byte (input_stream.dart:140-149)
+        return raw.decode("utf-8")
+    except UnicodeDecodeError:
+        return raw.decode("latin-1")
+
+
+class ArchiveFile:
+    """archive_file.dart:14-130 (the fields ZipDecoder fills)."""
+
+    def __init__(self, name: str, size: int, is_file: bool = True):
+        self.name, self.size, self.is_file = name, size, is_file
+        self.mode = 0o644
+        self.crc32 = None
+        self.last_mod_time = 0
+        self.compression = None
+        self.symbolic_link = None
+        self.content = b"" if is_file else None
+        self.status = U_DONE  # unit status of the member's decode (include/b200z.h)
+
+    @property
+    def is_symbolic_link(self):
+        return bool(self.symbolic_link)
+
+    def read_bytes(self):
+        return self.content
+
+
+class Archive:
+    """archive.dart:6-60: files in directory order; a later entry with a name already present replaces the earlier."""
+
+    def __init__(self):
+        self.files, self._index = [], {}
+
+    def find(self, name):
+        i = self._index.get(name)
+        return None if i is None else self.files[i]
+
+    def add(self, f: ArchiveFile):
+        i = self._index.get(f.name)
+        if i is not None:
+            self.files[i] = f
+            return
+        self._index[f.name] = len(self.files)
+        self.files.append(f)
+
+    def __iter__(self):
+        return iter(self.files)
+
+    def __len__(self):
+        return len(self.files)
+
+
+class ZipDecoder:
+    def __init__(self, web_eos: bool = False):
+        # web_eos: the pure-Dart Inflate's end-of-stream behaviour; default is what the Dart VM's ZipDecoder
+        # gives (dart:io zlib): a member's last symbols are always decoded
+        self.flags = 1 if web_eos else 0
+        self.entries = []
+
+    def list(self, data):
+        L = _ffi.lib()
+        addr, n, keep = _ffi.as_buffer(data)
+        cnt = C.c_size_t(0)
+        _ffi.check(L.b200z_zip_list(addr, n, None, 0, C.byref(cnt)))
+        ents = (_ffi.ZipEntry * max(1, cnt.value))()
+        _ffi.check(L.b200z_zip_list(addr, n, ents, cnt.value, C.byref(cnt)))
+        self.entries = [ents[i] for i in range(cnt.value)]
+        return ents, cnt.value
+
+    def decode_bytes(self, data, verify: bool = False, password=None) -> Archive:
+        data = bytes(data) if not isinstance(data, (bytes, bytearray)) else data
+        ents, n = self.list(data)
+        contents, statuses = self._extract(data, ents, n)
+        archive = Archive()
+        for i in range(n):
+            e = ents[i]
+            name = _name(data[e.name_off:e.name_off + e.name_len]) if e.has_data else ""
+            is_dir = name.endswith("/") or name.endswith("\\")
+            entry = archive.find(name)
+            if entry is None:
+                entry = ArchiveFile(name, 0, is_file=False) if is_dir else ArchiveFile(name, e.uncomp_size if e.has_data else 0)
+                entry.compression = COMPRESSION.get(e.method, "none") if e.has_data else "none"
+                if not is_dir:
+                    entry.content, entry.status = contents[i], statuses[i]
+                archive.add(entry)
+            entry.mode = e.ext_attr >> 16
+            if (e.version_made_by >> 8) == 3 and (entry.mode & 0xF000) == 0xA000:  # unix symlink (:58-70)
+                try:
+                    entry.symbolic_link = contents[i].decode("utf-8")
+                except UnicodeDecodeError:
+                    pass
+            entry.crc32 = e.crc32
+            entry.last_mod_time = (e.mod_date << 16) | e.mod_time
+        return archive
+
+    def _extract(self, data, ents, n):
+        if n == 0:
+            return [], []
+        L = _ffi.ensure_init()
+        addr, zlen, keep = _ffi.as_buffer(data)
+        room = [max(int(ents[i].hint_uncomp_size), int(ents[i].uncomp_size), 1) if ents[i].has_data else 0 for i in range(n)]
+        contents, statuses = [b""] * n, [U_DONE] * n
+        todo = list(range(n))
+        while todo:
+            m = len(todo)
+            sub = (_ffi.ZipEntry * m)(*[ents[i] for i in todo])
+            off, tot = [], 0
+            for i in todo:
+                off.append(tot)
+                tot += (room[i] + 63) & ~63
+            out = (C.c_uint8 * max(tot, 1))()
+            a64 = lambda l: (C.c_uint64 * m)(*l)
+            out_len, st = (C.c_uint64 * m)(), (C.c_int32 * m)()
+            _ffi.check(L.b200z_zip_extract(addr, zlen, sub, m, C.addressof(out), max(tot, 1), a64(off),
+                                           a64([room[i] for i in todo]), out_len, st, self.flags))
+            again = []
+            for k, i in enumerate(todo):
+                statuses[i] = st[k]
+                if st[k] == U_NOSPC and room[i] < (1 << 32) - 64:  # the size fields lied: the data decide (grow and retry)
+                    room[i] = min(max(room[i] * 4, int(out_len[k]), int(ents[i].comp_size) * 4), (1 << 32) - 64)
+                    again.append(i)
+                    continue
+                contents[i] = C.string_at(C.addressof(out) + off[k], min(int(out_len[k]), room[i]))
+            todo = again
+        return contents, statuses

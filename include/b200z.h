@@ -122,6 +122,35 @@ int b200z_bzip2_decode_shard(const uint8_t *in, size_t in_len, uint32_t rank, ui
 int b200z_bzip2_encode(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_cap, size_t *out_len);
 size_t b200z_bzip2_bound(size_t in_len); /* output capacity that always suffices */
 
+/* ---- ZIP container: ZipDecoder / ZipDirectory / ZipFileHeader / ZipFile ------------------------------------
+ * b200z_zip_list   = ZipDirectory.read (zip_directory.dart:25-183) + ZipFileHeader.read (zip_file_header.dart:28-111)
+ *                    + ZipFile.read (zip_file.dart:73-149), host only: no device is needed.
+ * b200z_zip_extract = ZipFile.getStream / decompress (zip_file.dart:164-249) for ALL listed members at once: the deflate
+ *                    members are one batch of the inflate kernels, stored members are copies, bzip2 members are
+ *                    decoded one after the other.  Names are byte ranges of the archive (decoding them is the host
+ *                    language's business).  Encrypted members (ZipCrypto / AES) are reported, not decoded.        */
+typedef struct {
+  uint64_t local_header_off; /* ZipFileHeader.localHeaderOffset (zip64 applied)                               */
+  uint64_t data_off;         /* first byte of the member's data; valid when has_data                          */
+  uint64_t comp_size;        /* bytes of member data (central directory value, clipped to the archive)        */
+  uint64_t uncomp_size;      /* ZipFile.uncompressedSize: central directory value, or the data descriptor's   */
+  uint64_t hint_uncomp_size; /* the central directory value (a size hint only: the data decide)               */
+  uint64_t name_off, cd_name_off; /* file name in the local header (what ZipFile.filename is) / in the directory */
+  uint32_t name_len, cd_name_len;
+  uint32_t crc32, method, flags; /* from the local header (CRC from the data descriptor when flag bit 3 is set) */
+  uint32_t mod_time, mod_date, ext_attr, version_made_by;
+  uint32_t has_data;         /* 0: no local header signature at local_header_off -> empty content              */
+} b200z_zip_entry;
+int b200z_zip_list(const uint8_t *zip, size_t zip_len, b200z_zip_entry *entries, size_t cap, size_t *n_entries);
+#define B200Z_ZIP_WEB_EOS 1u      /* flags: pure-Dart Inflate end-of-stream behaviour instead of dart:io's  */
+#define B200Z_ZIP_ENCRYPTED (-20)  /* status: encrypted member, not decoded                                      */
+#define B200Z_ZIP_TOO_LARGE (-21)  /* status: member of 4 GiB or more                                            */
+/* Member i is written to out[out_off[i] .. +out_room[i]); out_len[i] = bytes it produced (may exceed the room:
+ * status B200Z_U_NOSPC), status[i] = B200Z_U_* / B200Z_ZIP_*.                                                    */
+int b200z_zip_extract(const uint8_t *zip, size_t zip_len, const b200z_zip_entry *entries, size_t n, uint8_t *out,
+                      size_t out_cap, const uint64_t *out_off, const uint64_t *out_room, uint64_t *out_len,
+                      int32_t *status, uint32_t flags);
+
 /* ---- batched independent units (what the kernels run) --------------------------------- */
 /* n_units raw DEFLATE streams: unit u reads in_base[in_off[u] .. +in_len[u]) and writes
  * out_base[out_off[u] .. +out_cap[u]).  Per unit: out_len, status (B200Z_U_*), in_used.

@@ -85,4 +85,12 @@ void orc_deflate_set_truncate_heuristic(int on); /* tests only: off == stock zli
 #ifdef __cplusplus
 }
 #endif
+/* ZIP container (zip.c): directory listing and member content. */
+typedef struct {
+  uint64_t local_header_off, data_off, comp_size, uncomp_size, hint_uncomp_size, name_off, cd_name_off;
+  uint32_t name_len, cd_name_len, crc32, method, flags, mod_time, mod_date, ext_attr, version_made_by, has_data;
+} orc_zip_entry;
+int orc_zip_list(const uint8_t *b, size_t blen, orc_zip_entry *out, size_t cap, size_t *n_out);
+int orc_zip_member(const uint8_t *b, size_t blen, const orc_zip_entry *e, int web_eos, uint8_t **out, size_t *out_len);
+
 #endif

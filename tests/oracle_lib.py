@@ -116,3 +116,29 @@ def emul_bzip2_encode(data: bytes):
     st = (C.c_uint32 * 4)()
     rc = _BE.emu_bzip2_encode(data, C.c_size_t(len(data)), out, C.c_size_t(cap), C.byref(n), st)
     return rc, bytes(out[:n.value]), list(st)
+
+
+class ZipEntry(C.Structure):
+    _fields_ = [("local_header_off", C.c_uint64), ("data_off", C.c_uint64), ("comp_size", C.c_uint64),
+                ("uncomp_size", C.c_uint64), ("hint_uncomp_size", C.c_uint64), ("name_off", C.c_uint64),
+                ("cd_name_off", C.c_uint64), ("name_len", C.c_uint32), ("cd_name_len", C.c_uint32), ("crc32", C.c_uint32),
+                ("method", C.c_uint32), ("flags", C.c_uint32), ("mod_time", C.c_uint32), ("mod_date", C.c_uint32),
+                ("ext_attr", C.c_uint32), ("version_made_by", C.c_uint32), ("has_data", C.c_uint32)]
+
+    def astuple(self):
+        return tuple(getattr(self, f) for f, _ in self._fields_)
+
+
+def zip_list(data: bytes):
+    """-> (status, [ZipEntry])"""
+    cap = 4096
+    ents = (ZipEntry * cap)()
+    n = C.c_size_t()
+    st = L().orc_zip_list(data, C.c_size_t(len(data)), ents, C.c_size_t(cap), C.byref(n))
+    return st, [ents[i] for i in range(min(n.value, cap))]
+
+
+def zip_member(data: bytes, entry, web_eos=False):
+    out, n = C.POINTER(C.c_uint8)(), C.c_size_t()
+    st = L().orc_zip_member(data, C.c_size_t(len(data)), C.byref(entry), int(web_eos), C.byref(out), C.byref(n))
+    return st, _take(out, n)
