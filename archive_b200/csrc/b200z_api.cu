@@ -225,7 +225,7 @@ static size_t workspace_bytes(size_t n_units, size_t total_out_cap) { return inf
 // output goes to g.d_out.  Meta arrays are host arrays; results are copied back into them.
 static int run_batch_on_staged(const uint64_t *in_off, const uint32_t *in_len, const uint64_t *out_off,
                                const uint32_t *out_cap, uint32_t *out_len, int32_t *status, uint32_t *in_used,
-                               size_t n, size_t out_extent) {
+                               size_t n, size_t out_extent, bool count_only = false) {
   MetaLayout ml(n);
   CU(g.h_meta.reserve(ml.bytes));
   CU(g.d_meta.reserve(ml.bytes));
@@ -250,6 +250,7 @@ static int run_batch_on_staged(const uint64_t *in_off, const uint32_t *in_len, c
   b.in_used = (uint32_t *)(dm + ml.off_in_used);
   b.n_units = n;
   b.ws = inflate_ws_carve(g.d_ws.p, n, out_extent);
+  b.count_only = count_only;
   CU(launch_inflate(b, g.stream));
   CU(cudaMemcpyAsync(hm + ml.off_out_len, dm + ml.off_out_len, ml.bytes - ml.off_out_len, cudaMemcpyDeviceToHost,
                      g.stream));
@@ -1347,6 +1348,90 @@ extern "C" int b200z_zip_extract(const uint8_t *z, size_t len, const b200z_zip_e
     out_len[i] = e.comp_size;
     if (e.comp_size > out_room[i]) status[i] = B200Z_U_NOSPC;
   }
+  // ---- flush points: a member that was written with Z_FULL_FLUSH every so often is many independent raw DEFLATE
+  // streams back to back (each ends with the byte-aligned empty stored block 00 00 FF FF and restarts the window).
+  // Candidates are found by a byte scan and PROVEN by a sizing pass (count-only decode of every piece: a piece must end
+  // exactly on its marker at a block boundary and must not reach back before its own start -- which also rejects
+  // Z_SYNC_FLUSH points, whose window continues); a member with any doubtful piece is decoded whole.
+  if (!u_idx.empty() && !(flags & B200Z_ZIP_NO_SPLIT)) {
+    bool worth = false;
+    for (size_t k = 0; k < u_idx.size(); ++k) worth = worth || u_in_len[k] >= (256u << 10);
+    if (worth) {
+      const uint32_t ccap = 1u << 22;
+      CU(g.d_small.reserve((size_t)ccap * 8 + 256));
+      unsigned long long *d_list = (unsigned long long *)((uint8_t *)g.d_small.p + 256);
+      uint32_t *d_cnt = (uint32_t *)g.d_small.p;
+      CU(launch_find_markers((const uint8_t *)g.d_in.p, len, d_list, d_cnt, ccap, g.stream));
+      uint32_t ncand = 0;
+      CU(cudaMemcpyAsync(&ncand, d_cnt, 4, cudaMemcpyDeviceToHost, g.stream));
+      CU(cudaStreamSynchronize(g.stream));
+      if (ncand > 0 && ncand <= ccap) {
+        std::vector<unsigned long long> cand(ncand);
+        CU(cudaMemcpy(cand.data(), d_list, (size_t)ncand * 8, cudaMemcpyDeviceToHost));
+        std::sort(cand.begin(), cand.end());
+        // pieces of every big member
+        std::vector<uint64_t> s_in_off, s_out_off;
+        std::vector<uint32_t> s_in_len, s_cap, s_member, first_seg(u_idx.size() + 1, 0);
+        for (size_t k = 0; k < u_idx.size(); ++k) {
+          first_seg[k] = (uint32_t)s_in_off.size();
+          if (u_in_len[k] < (256u << 10)) continue;
+          const uint64_t a0 = u_in_off[k], a1 = a0 + entries[u_idx[k]].comp_size, aend = a0 + u_in_len[k];
+          auto it = std::upper_bound(cand.begin(), cand.end(), a0);
+          uint64_t start = a0;
+          size_t pieces = 0;
+          for (; it != cand.end() && *it < a1; ++it) {
+            if (*it - start < 4096) continue;  // not worth a unit of its own
+            s_in_off.push_back(start);
+            s_in_len.push_back((uint32_t)(*it - start));
+            s_member.push_back((uint32_t)k);
+            start = *it;
+            pieces++;
+          }
+          if (pieces == 0) continue;
+          s_in_off.push_back(start);
+          s_in_len.push_back((uint32_t)(aend - start));
+          s_member.push_back((uint32_t)k);
+        }
+        first_seg[u_idx.size()] = (uint32_t)s_in_off.size();
+        const size_t ns = s_in_off.size();
+        if (ns) {
+          s_out_off.assign(ns, 0);
+          s_cap.assign(ns, 0xfffffff0u);
+          std::vector<uint32_t> a_len(ns), a_used(ns);
+          std::vector<int32_t> a_st(ns);
+          rc = run_batch_on_staged(s_in_off.data(), s_in_len.data(), s_out_off.data(), s_cap.data(), a_len.data(), a_st.data(),
+                                   a_used.data(), ns, 0, true);
+          if (rc) return rc;
+          // rebuild the unit list: proven members contribute their pieces, the others stay whole
+          std::vector<uint64_t> n_in_off, n_out_off;
+          std::vector<uint32_t> n_in_len, n_cap, n_idx;
+          for (size_t k = 0; k < u_idx.size(); ++k) {
+            const uint32_t f = first_seg[k], l = first_seg[k + 1];
+            bool ok = l > f;
+            uint64_t total = 0;
+            for (uint32_t q = f; q < l && ok; ++q) {
+              const bool last = q + 1 == l;
+              ok = last ? (a_st[q] == B200Z_U_DONE) : (a_st[q] == B200Z_U_EOS && a_used[q] == s_in_len[q]);
+              total += a_len[q];
+            }
+            ok = ok && total <= u_cap[k];
+            if (!ok) {
+              n_in_off.push_back(u_in_off[k]); n_in_len.push_back(u_in_len[k]); n_out_off.push_back(u_out_off[k]);
+              n_cap.push_back(u_cap[k]); n_idx.push_back(u_idx[k]);
+              continue;
+            }
+            uint64_t o = u_out_off[k];
+            for (uint32_t q = f; q < l; ++q) {
+              n_in_off.push_back(s_in_off[q]); n_in_len.push_back(s_in_len[q]); n_out_off.push_back(o);
+              n_cap.push_back(a_len[q]); n_idx.push_back(u_idx[k] | (q + 1 == l ? 0u : 0x80000000u));
+              o += a_len[q];
+            }
+          }
+          u_in_off.swap(n_in_off); u_in_len.swap(n_in_len); u_out_off.swap(n_out_off); u_cap.swap(n_cap); u_idx.swap(n_idx);
+        }
+      }
+    }
+  }
   if (!u_idx.empty()) {
     const size_t m = u_idx.size();
     std::vector<uint32_t> r_len(m), r_used(m);
@@ -1355,8 +1440,14 @@ extern "C" int b200z_zip_extract(const uint8_t *z, size_t len, const b200z_zip_e
                              r_used.data(), m, (size_t)hi);
     if (rc) return rc;
     for (size_t k = 0; k < m; ++k) {
-      out_len[u_idx[k]] = r_len[k];
-      status[u_idx[k]] = r_st[k];
+      const uint32_t i = u_idx[k] & 0x7fffffffu;
+      const bool inner = (u_idx[k] & 0x80000000u) != 0;  // a piece that is not the member's last
+      out_len[i] += r_len[k];
+      if (!inner) {
+        if (status[i] == B200Z_U_DONE) status[i] = r_st[k];
+      } else if (!(r_st[k] == B200Z_U_EOS && r_len[k] == u_cap[k])) {
+        status[i] = r_st[k] == B200Z_U_EOS || r_st[k] == B200Z_U_DONE ? B200Z_U_STOP : r_st[k];  // cannot happen after the sizing pass
+      }
     }
   }
   if (any_dev) {

@@ -43,9 +43,12 @@ struct InflateBatch {
   size_t n_units;
   InflateWs ws;
   int share = 1;     // how many batches run concurrently on the device (sizes the streams-per-warp choice)
+  bool count_only = false;  // sizes only: out_len / status / in_used, no tokens, no output bytes
 };
 
 cudaError_t launch_inflate(const InflateBatch &b, cudaStream_t stream);
+cudaError_t launch_find_markers(const uint8_t *d_in, size_t n, unsigned long long *d_list, uint32_t *d_count, uint32_t cap,
+                                cudaStream_t stream);
 
 // ---- BZip2 (bzip2_kernels.cu) ----
 struct Bz2Entropy {  // K7, one warp per candidate block

@@ -363,6 +363,7 @@ constexpr uint32_t SPEC_NOLINK = 0xffffffffu;
 struct SpecCtx {
   int lane, sub, G;   // lane in the warp, index inside the stream's lane group (0 = master), lanes per stream
   bool spec;          // warp-uniform: helpers are in use in this launch
+  bool count_only;    // warp-uniform: sizes only -- tokens are counted, not written (no expand follows)
   uint32_t *hplane;   // helper k's token region = hplane + (k - 1) * hstride  [hcap words]
   size_t hstride;
   uint32_t hcap;
@@ -386,6 +387,12 @@ B200Z_HD UnitResult inflate_decode_unit(bool active, const uint8_t *in, uint32_t
   SlowTab sl;
   SlowTabD sd;
   uint8_t lens[320];
+  const bool count_only = sc.count_only;
+#define B200Z_TOK(p, v)          \
+  do {                          \
+    if (!count_only) (p)[nt] = (v); \
+    nt++;                       \
+  } while (0)
   const bool is_master = sc.sub == 0;
   const int gbase = sc.lane - sc.sub;  // the master's lane
   const bool spec_on = sc.spec;  // warp-uniform
@@ -623,7 +630,7 @@ B200Z_HD UnitResult inflate_decode_unit(bool active, const uint8_t *in, uint32_t
           br.buf >>= tot;
           br.cnt -= (int)tot;
           rel_bits += tot;
-          if (islit || dm) tk[nt++] = islit ? (TOK_LIT | sym) : ((mlen_pending << 16) | val);
+          if (islit || dm) B200Z_TOK(tk, islit ? (TOK_LIT | sym) : ((mlen_pending << 16) | val));
           olen = nolen;
           mlen_pending = islen ? val : mlen_pending;
           mode_dist = islen;
@@ -682,7 +689,7 @@ B200Z_HD UnitResult inflate_decode_unit(bool active, const uint8_t *in, uint32_t
             st = B200Z_U_NOSPC;
             done = true; break;
           }
-          tok[nt++] = TOK_LIT | (uint32_t)sym;
+          B200Z_TOK(tok, TOK_LIT | (uint32_t)sym);
           olen++;
         } else if (sym == 256) {
           in_block = false;
@@ -707,7 +714,7 @@ B200Z_HD UnitResult inflate_decode_unit(bool active, const uint8_t *in, uint32_t
           st = B200Z_U_NOSPC;
           done = true; break;
         }
-        tok[nt++] = (mlen_pending << 16) | val;
+        B200Z_TOK(tok, (mlen_pending << 16) | val);
         olen += mlen_pending;
       }
       break;  // next symbol
@@ -775,11 +782,11 @@ B200Z_HD UnitResult inflate_decode_unit(bool active, const uint8_t *in, uint32_t
           }
           if (len < 3) {
             const uint8_t *src = reinterpret_cast<const uint8_t *>(br.w) + br.lead + pos;
-            for (int i = 0; i < (int)len; ++i) tok[nt++] = TOK_LIT | src[i];
+            for (int i = 0; i < (int)len; ++i) B200Z_TOK(tok, TOK_LIT | src[i]);
           } else {
-            if (((nt - piece_start) & 31u) == 31u) tok[nt++] = 0;  // the pair must not straddle a group of 32 of its piece
-            tok[nt++] = TOK_STORED | ((pos >> 30) << 16) | (uint32_t)len;
-            tok[nt++] = pos & 0x3fffffffu;
+            if (((nt - piece_start) & 31u) == 31u) B200Z_TOK(tok, 0u);  // the pair must not straddle a group of 32 of its piece
+            B200Z_TOK(tok, TOK_STORED | ((pos >> 30) << 16) | (uint32_t)len);
+            B200Z_TOK(tok, pos & 0x3fffffffu);
           }
           olen += (uint32_t)len;
         }
@@ -907,7 +914,7 @@ B200Z_HD UnitResult inflate_decode_unit(bool active, const uint8_t *in, uint32_t
         st = B200Z_U_NOSPC;
         done = true; break;
       }
-      tok[nt++] = TOK_LIT | (uint32_t)sym;
+      B200Z_TOK(tok, TOK_LIT | (uint32_t)sym);
       olen++;
       break;  // next token
     }
@@ -974,7 +981,7 @@ B200Z_HD UnitResult inflate_decode_unit(bool active, const uint8_t *in, uint32_t
       st = B200Z_U_NOSPC;
       done = true; break;
     }
-    tok[nt++] = ((uint32_t)mlen << 16) | (uint32_t)dist;
+    B200Z_TOK(tok, ((uint32_t)mlen << 16) | (uint32_t)dist);
     olen += (uint32_t)mlen;
     } while (0);
   }
@@ -983,6 +990,7 @@ B200Z_HD UnitResult inflate_decode_unit(bool active, const uint8_t *in, uint32_t
     piece_add(sc.pieces, np, 0u, piece_start, nt - piece_start);
     sc.pieces[0] = np;
   }
+#undef B200Z_TOK
 #undef h_start_tok
 #undef h_ntok
 #undef h_rel_bytes

@@ -55,7 +55,7 @@ k_inflate_decode(const uint8_t *__restrict__ in_base, const uint64_t *__restrict
                  const uint32_t *__restrict__ in_len, const uint64_t *__restrict__ out_off,
                  const uint32_t *__restrict__ out_cap, InflateWs ws, uint32_t *__restrict__ out_len,
                  int32_t *__restrict__ status, uint32_t *__restrict__ in_used, uint32_t n_units, int units_per_warp,
-                 int lanes_per_unit) {
+                 int lanes_per_unit, int count_only) {
   B200Z_DYN_SMEM(smem);
   uint16_t *s_len_tab = reinterpret_cast<uint16_t *>(smem);
   uint32_t *s_dist_tab = smem + 16;
@@ -86,7 +86,8 @@ k_inflate_decode(const uint8_t *__restrict__ in_base, const uint64_t *__restrict
   sc.lane = lane;
   sc.sub = sub;
   sc.G = lanes_per_unit;
-  sc.spec = lanes_per_unit > 1 && ws.htokens != nullptr;
+  sc.spec = lanes_per_unit > 1 && ws.htokens != nullptr && !count_only;
+  sc.count_only = count_only != 0;
   sc.hplane = nullptr;
   sc.hstride = ws.hstride;
   sc.hcap = 0;
@@ -97,13 +98,13 @@ k_inflate_decode(const uint8_t *__restrict__ in_base, const uint64_t *__restrict
     const uint64_t oo = out_off[unit];
     const uint32_t cap = out_cap[unit];
     tok = ws.tokens + oo;  // token region mirrors the output layout (<= 1 token per output byte)
-    if (lanes_per_unit > 1 && ws.htokens) {
+    if (lanes_per_unit > 1 && ws.htokens && !count_only) {
       sc.hplane = ws.htokens + (oo >> SPEC_HSHIFT);
       sc.hcap = (uint32_t)(((oo + cap) >> SPEC_HSHIFT) - (oo >> SPEC_HSHIFT));
     }
     uint8_t *us = ws.uscratch + (size_t)unit * USCRATCH_BYTES;
     sc.bm = reinterpret_cast<uint32_t *>(us);
-    sc.pieces = ws.pieces + (size_t)unit * PIECE_WORDS;
+    sc.pieces = count_only ? nullptr : ws.pieces + (size_t)unit * PIECE_WORDS;
   }
   const UnitResult r = inflate_decode_unit(active, active ? in_base + in_off[unit] : nullptr, active ? in_len[unit] : 0u,
                                            active ? out_cap[unit] : 0u, tok, lut_l, lut_d, s_len_tab, s_dist_tab, s_xtab, sc);
@@ -279,6 +280,24 @@ k_inflate_expand(InflateWs ws, const uint8_t *__restrict__ in_base, const uint64
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Flush points: positions right after every byte-aligned 00 00 FF FF (the empty stored block Z_SYNC_FLUSH / Z_FULL_FLUSH
+// leave behind).  Candidates only: the caller proves them by decoding (b200z_api.cu, zip members).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_find_flush_markers(const uint8_t *__restrict__ in, unsigned long long n, unsigned long long *__restrict__ list,
+                     uint32_t *__restrict__ count, uint32_t cap) {
+  const unsigned long long i0 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) * 16ull;
+  if (i0 >= n) return;
+  uint8_t b[19];
+  for (int k = 0; k < 19; ++k) b[k] = (i0 + k < n) ? in[i0 + k] : (uint8_t)0x55;
+  for (int k = 0; k < 16; ++k)
+    if (b[k] == 0 && b[k + 1] == 0 && b[k + 2] == 0xff && b[k + 3] == 0xff && i0 + k + 4 <= n) {
+      uint32_t slot = atomicAdd(count, 1u);
+      if (slot < cap) list[slot] = i0 + k + 4;
+    }
+}
+
 #ifndef B200Z_EMU
 // ---------------------------------------------------------------------------------------------
 // host launchers
@@ -342,6 +361,16 @@ InflateWs inflate_ws_slice(const InflateWs &w, size_t first_unit, size_t first_o
   return s;
 }
 
+cudaError_t launch_find_markers(const uint8_t *d_in, size_t n, unsigned long long *d_list, uint32_t *d_count, uint32_t cap,
+                                cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(d_count, 0, 4, stream);
+  if (e != cudaSuccess || n == 0) return e;
+  const unsigned long long threads = (n + 15) / 16;
+  k_find_flush_markers<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(d_in, n, d_list, d_count, cap);
+  count_launch();
+  return cudaGetLastError();
+}
+
 cudaError_t launch_inflate(const InflateBatch &b, cudaStream_t stream) {
   if (b.n_units == 0) return cudaSuccess;
   if (!g_num_sms) {
@@ -397,11 +426,18 @@ cudaError_t launch_inflate(const InflateBatch &b, cudaStream_t stream) {
   }
   k_inflate_decode<<<blocks, B200Z_DECODE_THREADS, smem, stream>>>(b.in_base, b.in_off, b.in_len, b.out_off, b.out_cap, b.ws,
                                                                    b.out_len, b.status, b.in_used, (uint32_t)b.n_units, upw,
-                                                                   lpu);
+                                                                   b.count_only ? 1 : lpu, b.count_only ? 1 : 0);
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (g_prof) cudaEventRecord(pt.b, stream);
+  if (b.count_only) {
+    if (g_prof) {
+      cudaEventRecord(pt.c, stream);
+      g_prof_events.push_back(pt);
+    }
+    return cudaSuccess;
+  }
   const int ewarps = B200Z_EXPAND_THREADS / 32;
   uint64_t eblocks = (b.n_units + ewarps - 1) / ewarps;
   // resident expand warps x 32 KiB of LZ77 window each should stay inside the 126 MB L2

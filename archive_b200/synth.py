@@ -162,3 +162,32 @@ def gzip_workload(n_units: int, unit: int = 65536, seed: int = SEED, stream0: in
         except Exception:
             pass
     return dict(blob=blob, member_off=member_off, unit=unit, n_units=n_units, text=txt)
+
+
+def deflate_raw_flushed(chunk: bytes, every: int = 65536, level: int = 6, flush=zlib.Z_FULL_FLUSH) -> bytes:
+    """Raw DEFLATE with a flush point every `every` input bytes (still one valid stream, it decodes
+    identically in the reference, but exposes sub-member parallelism)."""
+    co = zlib.compressobj(level, zlib.DEFLATED, -15, 9)
+    out = []
+    for i in range(0, len(chunk), every):
+        out.append(co.compress(chunk[i:i + every]))
+        if i + every < len(chunk):
+            out.append(co.flush(flush))
+    out.append(co.flush())
+    return b"".join(out)
+
+
+def zip_from_deflated(members) -> bytes:
+    """A .zip whose members are already-compressed raw DEFLATE streams: members = [(name, deflated, crc32, size)]."""
+    import struct
+    out, cd = bytearray(), bytearray()
+    for name, z, crc, size in members:
+        nb = name.encode()
+        off = len(out)
+        out += struct.pack("<IHHHHHIIIHH", 0x04034b50, 20, 0, 8, 0, 0x21, crc, len(z), size, len(nb), 0) + nb + z
+        cd += struct.pack("<IHHHHHHIIIHHHHHII", 0x02014b50, 0x031e, 20, 0, 8, 0, 0x21, crc, len(z), size, len(nb), 0, 0, 0, 0,
+                          0o100644 << 16, off) + nb
+    cd_off = len(out)
+    out += cd
+    out += struct.pack("<IHHHHIIH", 0x06054b50, 0, 0, len(members), len(members), len(cd), cd_off, 0)
+    return bytes(out)

@@ -68,10 +68,10 @@ class Archive:
 
 
 class ZipDecoder:
-    def __init__(self, web_eos: bool = False):
+    def __init__(self, web_eos: bool = False, split_flush_points: bool = True):
         # web_eos: the pure-Dart Inflate's end-of-stream behaviour; default is what the Dart VM's ZipDecoder
         # gives (dart:io zlib): a member's last symbols are always decoded
-        self.flags = 1 if web_eos else 0
+        self.flags = (1 if web_eos else 0) | (0 if split_flush_points else 2)
         self.entries = []
 
     def list(self, data):

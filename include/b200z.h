@@ -143,6 +143,7 @@ typedef struct {
 } b200z_zip_entry;
 int b200z_zip_list(const uint8_t *zip, size_t zip_len, b200z_zip_entry *entries, size_t cap, size_t *n_entries);
 #define B200Z_ZIP_WEB_EOS 1u      /* flags: pure-Dart Inflate end-of-stream behaviour instead of dart:io's  */
+#define B200Z_ZIP_NO_SPLIT 2u     /* flags: do not look for full-flush points inside members                        */
 #define B200Z_ZIP_ENCRYPTED (-20)  /* status: encrypted member, not decoded                                      */
 #define B200Z_ZIP_TOO_LARGE (-21)  /* status: member of 4 GiB or more                                            */
 /* Member i is written to out[out_off[i] .. +out_room[i]); out_len[i] = bytes it produced (may exceed the room:

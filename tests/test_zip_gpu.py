@@ -79,8 +79,8 @@ def _synthetic(n_members=40, seed=3, force64=False):
                 zi, kw = zipfile.ZipInfo(name), dict(compress_type=zipfile.ZIP_DEFLATED, compresslevel=int(rng.choice([1, 6, 9])))
             zi.external_attr = (0o100644 | (i & 0o111)) << 16
             if i % 7 == 3:  # streamed member: sizes and CRC in a data descriptor after the data
+                zi.compress_type = kw["compress_type"]
                 with z.open(zi, "w", force_zip64=force64) as f:
-                    zi.compress_type = kw["compress_type"]
                     f.write(body)
             else:
                 zi.compress_type = kw["compress_type"]
@@ -148,3 +148,26 @@ def test_large_members_one_batch(a):
     arc = a.ZipDecoder().decode_bytes(buf.getvalue())
     for i, f in enumerate(arc.files):
         assert zlib.crc32(f.content) == zlib.crc32(txt[i * size:(i + 1) * size].tobytes())
+
+
+def test_flush_points_split_members(a):
+    """Members written with Z_FULL_FLUSH points are decoded piece by piece (proven by a sizing pass); Z_SYNC_FLUSH points
+    look the same but keep the window, so those members must come out right as well (decoded whole), and a flush-point
+    pattern inside stored data must not fool the splitter."""
+    import zipfile
+    from archive_b200 import synth
+    txt = synth.text(6 * (3 << 20), stream=960).tobytes()
+    parts, members = [], []
+    for i in range(6):
+        body = txt[i * (3 << 20):(i + 1) * (3 << 20)]
+        if i == 4:
+            body = (b"\x00\x00\xff\xff" * 1000 + body[:200000]) * 3  # marker bytes in the data itself
+        z = synth.deflate_raw_flushed(body, every=65536 if i % 2 == 0 else 100_000,
+                                      flush=zlib.Z_SYNC_FLUSH if i == 3 else zlib.Z_FULL_FLUSH, level=0 if i == 4 else 6)
+        members.append((f"m{i}", z, zlib.crc32(body), len(body)))
+        parts.append(body)
+    data = synth.zip_from_deflated(members)
+    assert zipfile.ZipFile(io.BytesIO(data)).read("m1") == parts[1]
+    for split in (True, False):
+        arc = a.ZipDecoder(split_flush_points=split).decode_bytes(data)
+        assert [f.content for f in arc.files] == parts, split
