@@ -32,7 +32,8 @@ with open(out, "w") as f:
                              capture_output=True, text=True).stdout
         srows = list(csv.reader(io.StringIO(src)))
         if len(srows) > 2:
-            sh, sd = srows[1], srows[2:]
+            sh = srows[1]
+            sd = [x for x in srows[2:] if len(x) == len(sh) and x[0].startswith('0x')]
             ia, isrc, ismp = sh.index("Instructions Executed"), sh.index("Source"), sh.index("# Samples")
             tot = sum(int(x[ismp]) for x in sd) or 1
             f.write("Hottest SASS (warp-stall samples):\n\n| samples | share | executed | SASS |\n|---|---|---|---|\n")
