@@ -194,13 +194,12 @@ k_inflate_expand(InflateWs ws, const uint8_t *__restrict__ in_base, const uint64
         for (uint32_t w = 0; w < total; w += 32) {
           const uint32_t p = w + lane;
           const bool active = p < total;
-          // first j with incl_j > p
-          int j = 0;
-#pragma unroll
-          for (int s = 16; s >= 1; s >>= 1) {
-            uint32_t v = __shfl_sync(FULL, incl, j + s - 1);
-            if (v <= p) j += s;
-          }
+          // The token of byte q of this window = (tokens that start before the window) + (tokens that start inside it at
+          // or before q) - 1: one vote and one OR-reduction per window instead of a binary search per byte.  (Tokens of
+          // length 0 only trail the real ones in a group that takes this path, so rank == lane.)
+          const uint32_t before = (uint32_t)__popc(__ballot_sync(FULL, len != 0u && start < w));
+          const uint32_t starts = __reduce_or_sync(FULL, (len != 0u && start >= w && start < w + 32u) ? (1u << (start - w)) : 0u);
+          int j = (int)(before + (uint32_t)__popc(starts & ((2u << lane) - 1u))) - 1;
           j &= 31;
           uint32_t tj = __shfl_sync(FULL, t, j);
           uint32_t sj = __shfl_sync(FULL, start, j);
@@ -218,13 +217,8 @@ k_inflate_expand(InflateWs ws, const uint8_t *__restrict__ in_base, const uint64
           // chase sources that are still inside this (unwritten) window
           while (__any_sync(FULL, !have && src2 >= (int)w)) {
             const bool need = !have && src2 >= (int)w;
-            uint32_t q = need ? (uint32_t)src2 : 0u;
-            int j2 = 0;
-#pragma unroll
-            for (int s = 16; s >= 1; s >>= 1) {
-              uint32_t v = __shfl_sync(FULL, incl, j2 + s - 1);
-              if (v <= q) j2 += s;
-            }
+            uint32_t q = need ? (uint32_t)src2 : w;
+            int j2 = (int)(before + (uint32_t)__popc(starts & ((2u << (q - w)) - 1u))) - 1;  // w <= q < w + 32
             j2 &= 31;
             uint32_t t2 = __shfl_sync(FULL, t, j2);
             uint32_t s2 = __shfl_sync(FULL, start, j2);

@@ -89,7 +89,7 @@ def bz2_walk_chain(reports, in_len: int, verify: bool):
     return kind, kept, n_out
 
 
-def bzip2_decode_sharded(data, verify: bool = False, group=None, rank=None, world=None, reports_in=None):
+def bzip2_decode_sharded(data, verify: bool = False, group=None, rank=None, world=None, reports_in=None, out_buf=None):
     """Every rank passes the same BZip2 stream; rank r decodes its share of the blocks on its GPU
     (b200z_bzip2_decode_shard), the per-block reports are exchanged (a few dozen bytes per block -- the only collective on
     this path; the decoded bytes stay where they were produced), and every rank derives the same chain.
@@ -107,13 +107,14 @@ def bzip2_decode_sharded(data, verify: bool = False, group=None, rank=None, worl
     addr, n, keep = _ffi.as_buffer(data)
     cap_blocks = n // 4096 + 64
     blocks = (_ffi.Bz2Block * cap_blocks)()
-    out_cap = n * 8 // world + (2 << 20)
+    # out_buf = (address, capacity) of a caller-owned (ideally pinned: b200z_host_alloc) buffer that is reused across calls
+    out_cap = out_buf[1] if out_buf else n * 8 // world + (2 << 20)
     while True:
-        out = (C.c_uint8 * out_cap)()
+        out = (C.c_uint8 * out_cap).from_address(out_buf[0]) if out_buf else (C.c_uint8 * out_cap)()
         out_len, nb = C.c_size_t(0), C.c_size_t(0)
         rc = L.b200z_bzip2_decode_shard(addr, n, rank, world, C.addressof(out), out_cap, C.byref(out_len), blocks,
                                         cap_blocks, C.byref(nb))
-        if rc == _ffi.E_NOSPC and out_len.value > out_cap:
+        if rc == _ffi.E_NOSPC and out_len.value > out_cap and not out_buf:
             out_cap = out_len.value + 64
             continue
         _ffi.check(rc)

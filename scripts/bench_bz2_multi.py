@@ -18,10 +18,12 @@ src = synth.text(m, stream=200)
 cap = L.b200z_bzip2_bound(m); zbuf = (C.c_uint8 * cap)(); zl = C.c_size_t(0)
 rc = L.b200z_bzip2_encode(src.ctypes.data, m, C.addressof(zbuf), cap, C.byref(zl)); assert rc == 0, _ffi.last_error()
 z = bytes(zbuf[:zl.value])
+h_z = L.b200z_host_alloc(len(z)); C.memmove(h_z, z, len(z)); zv = (C.c_uint8 * len(z)).from_address(h_z)
+ocap = m // world + (64 << 20); h_o = L.b200z_host_alloc(ocap)
 def run():
     if world > 1: dist.barrier()
     torch.cuda.synchronize(); t0 = time.perf_counter()
-    r = shard.bzip2_decode_sharded(z, verify=True, group=gloo)
+    r = shard.bzip2_decode_sharded(zv, verify=True, group=gloo, out_buf=(h_o, ocap))
     torch.cuda.synchronize()
     if world > 1: dist.barrier()
     return time.perf_counter() - t0, r

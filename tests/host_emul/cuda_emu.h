@@ -304,6 +304,14 @@ static inline unsigned __reduce_add_sync(unsigned mask, unsigned v) {
     return r & 0xffffffffull;
   });
 }
+static inline unsigned __reduce_or_sync(unsigned mask, unsigned v) {
+  return (unsigned)cuemu::collective(mask, v, [](unsigned, const unsigned long long *val, unsigned m) {
+    unsigned long long r = 0;
+    for (int k = 0; k < 32; ++k)
+      if (m >> k & 1) r |= (unsigned)val[k];
+    return r;
+  });
+}
 static inline unsigned __reduce_max_sync(unsigned mask, unsigned v) {
   return (unsigned)cuemu::collective(mask, v, [](unsigned, const unsigned long long *val, unsigned m) {
     unsigned long long r = 0;
