@@ -244,7 +244,7 @@ int encode_device(const uint8_t *d_in, size_t n, uint8_t *d_out, size_t out_cap,
       const uint32_t ntl = (max_n + TS - 1) / TS;
       B200Z_LAUNCH(k_m_lsym, dim3(ntl, nb), 256, 0, s, b.blockbuf, b.SA, b.nblk, b.inuse, b.lsym, b.lastocc);
       B200Z_LAUNCH(k_m_scan_last, nb, 256, 0, s, b.lastocc, b.nblk);
-      B200Z_LAUNCH(k_m_mtf, dim3(ntl, nb), 64, 0, s, b.lsym, b.lastocc, b.nblk, b.mtfpos, b.tile_nzlast);
+      B200Z_LAUNCH(k_m_mtf, dim3((ntl + MTF_CPB - 1) / MTF_CPB, nb), MTF_CPB, 0, s, b.lsym, b.lastocc, b.nblk, b.inuse, b.mtfpos, b.tile_nzlast);
       B200Z_LAUNCH(k_m_zr<false>, dim3(ntl, nb), 256, 0, s, b.mtfpos, b.tile_nzlast, b.nblk, b.tile_cnt,
                    (const uint32_t *)nullptr, (const uint32_t *)nullptr, (const uint32_t *)nullptr, (uint16_t *)nullptr,
                    (uint32_t *)nullptr);

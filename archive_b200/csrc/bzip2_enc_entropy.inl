@@ -65,52 +65,83 @@ k_m_scan_last(int *__restrict__ lastocc, const uint32_t *__restrict__ nblk) {
   }
 }
 
-// C3: move-to-front positions of one chunk; the start list is the symbols by decreasing recency key
-__global__ void __launch_bounds__(64)
+// C3: move-to-front positions.  One THREAD per 2048-symbol chunk (the walk is serial per chunk; a warp walks 32 chunks).
+// The start list of a chunk is the symbols by decreasing recency key, built cooperatively, one chunk after the other.  The
+// walk keeps the first 8 list entries in registers (a BWT block's MTF positions are almost always that small): the common
+// symbol costs a handful of selects and no memory access; deeper positions continue in the thread's shared-memory list.
+constexpr uint32_t MTF_CPB = 64;  // chunks per CTA
+__global__ void __launch_bounds__(MTF_CPB)
 k_m_mtf(const uint8_t *__restrict__ lsym, const int *__restrict__ lastocc, const uint32_t *__restrict__ nblk,
-        uint8_t *__restrict__ mtfpos, int *__restrict__ tile_nzlast) {
+        const uint32_t *__restrict__ inuse, uint8_t *__restrict__ mtfpos, int *__restrict__ tile_nzlast) {
   __shared__ int s_key[256];
-  __shared__ uint8_t s_list[256];
-  __shared__ uint8_t s_buf[TS];
-  const uint32_t bl = blockIdx.y, tile = blockIdx.x, t = threadIdx.x;
-  const uint32_t n = nblk[bl], base = tile * TS;
-  if (base >= n) return;
-  const uint32_t len = umin(TS, n - base);
+  __shared__ uint8_t s_list[256][MTF_CPB];  // [position][chunk of this CTA]
+  const uint32_t bl = blockIdx.y, t = threadIdx.x;
+  const uint32_t n = nblk[bl];
+  const uint32_t ntl = (n + TS - 1) / TS;
+  const uint32_t tile0 = blockIdx.x * MTF_CPB;
+  if (tile0 >= ntl) return;
   const size_t eb = (size_t)bl * BZ2E_BSTRIDE;
-  for (uint32_t i = t; i < 256; i += 64) s_key[i] = lastocc[((size_t)bl * NT + tile) * 256 + i];
-  for (uint32_t i = t; i < len; i += 64) s_buf[i] = lsym[eb + base + i];
-  __syncthreads();
-  for (uint32_t c = t; c < 256; c += 64) {
-    int kc = s_key[c];
-    uint32_t r = 0;
-    for (uint32_t o = 0; o < 256; ++o) r += (s_key[o] > kc) ? 1u : 0u;
-    s_list[r] = (uint8_t)c;
-  }
-  __syncthreads();
-  if (t == 0) {
-    int nz = -1;
-    for (uint32_t i = 0; i < len; ++i) {
-      uint8_t c = s_buf[i];
-      uint8_t prev = s_list[0];
-      uint32_t j = 0;
-      if (prev != c) {
-        j = 1;
-        uint8_t cur;
-        while ((cur = s_list[j]) != c) {
-          s_list[j] = prev;
-          prev = cur;
-          j++;
-        }
-        s_list[j] = prev;
-        s_list[0] = c;
-        nz = (int)(base + i);
-      }
-      s_buf[i] = (uint8_t)j;
+  uint32_t niu = 0;
+  for (int w = 0; w < 8; ++w) niu += (uint32_t)__popc(inuse[(size_t)bl * 8 + w]);
+  for (uint32_t q = 0; q < MTF_CPB && tile0 + q < ntl; ++q) {
+    for (uint32_t i = t; i < 256; i += MTF_CPB) {
+      s_key[i] = lastocc[((size_t)bl * NT + tile0 + q) * 256 + i];
+      s_list[i][q] = (uint8_t)i;  // symbols >= niu never occur: they keep the tail, in index order
     }
-    tile_nzlast[(size_t)bl * NT + tile] = nz;
+    __syncthreads();
+    for (uint32_t c = t; c < niu; c += MTF_CPB) {
+      const int kc = s_key[c];
+      uint32_t r = 0;
+      for (uint32_t o = 0; o < niu; ++o) r += (s_key[o] > kc) ? 1u : 0u;
+      s_list[r][q] = (uint8_t)c;
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  for (uint32_t i = t; i < len; i += 64) mtfpos[eb + base + i] = s_buf[i];
+  const uint32_t tile = tile0 + t;
+  if (tile >= ntl) return;
+  const uint32_t base = tile * TS, len = umin(TS, n - base);
+  const uint32_t *src = reinterpret_cast<const uint32_t *>(lsym + eb + base);  // eb and base are multiples of 4
+  uint32_t *dst = reinterpret_cast<uint32_t *>(mtfpos + eb + base);
+  int nz = -1;
+  uint32_t r0 = s_list[0][t], r1 = s_list[1][t], r2 = s_list[2][t], r3 = s_list[3][t], r4 = s_list[4][t], r5 = s_list[5][t],
+           r6 = s_list[6][t], r7 = s_list[7][t];
+  for (uint32_t i4 = 0; i4 < len; i4 += 4) {
+    const uint32_t word = src[i4 >> 2];
+    uint32_t outw = 0;
+    for (uint32_t k = 0; k < 4 && i4 + k < len; ++k) {
+      const uint32_t c = (word >> (8 * k)) & 0xffu;
+      uint32_t j;
+      if (c == r0) {
+        j = 0;
+      } else {
+        const uint32_t m = (c == r1 ? 2u : 0u) | (c == r2 ? 4u : 0u) | (c == r3 ? 8u : 0u) | (c == r4 ? 16u : 0u) |
+                           (c == r5 ? 32u : 0u) | (c == r6 ? 64u : 0u) | (c == r7 ? 128u : 0u);
+        j = m ? (uint32_t)(__ffs((int)m) - 1) : 8u;
+        const uint32_t last = r7;  // falls off the register window when the symbol sits deeper
+        r7 = j >= 7 ? r6 : r7;
+        r6 = j >= 6 ? r5 : r6;
+        r5 = j >= 5 ? r4 : r5;
+        r4 = j >= 4 ? r3 : r4;
+        r3 = j >= 3 ? r2 : r3;
+        r2 = j >= 2 ? r1 : r2;
+        r1 = r0;
+        r0 = c;
+        if (j == 8u) {
+          uint8_t prev = (uint8_t)last, cur;
+          while ((cur = s_list[j][t]) != (uint8_t)c) {
+            s_list[j][t] = prev;
+            prev = cur;
+            j++;
+          }
+          s_list[j][t] = prev;
+        }
+        nz = (int)(base + i4 + k);
+      }
+      outw |= j << (8 * k);
+    }
+    dst[i4 >> 2] = outw;
+  }
+  tile_nzlast[(size_t)bl * NT + tile] = nz;
 }
 
 // digits of a zero run of length r in the bijective base-2 RUNA/RUNB code
@@ -384,32 +415,65 @@ k_h_tables(const uint16_t *__restrict__ mtfv, const uint32_t *__restrict__ nmtf_
         }
       }
       sel[g] = (uint8_t)bt;
-      for (uint32_t i = gs; i < ge; ++i) atomicAdd(&s_rfreq[bt][mv[i]], 1);
+      // RUNA / RUNB are a large part of a BWT block: count them in registers, one shared-memory atomic per group
+      uint32_t c0 = 0, c1 = 0;
+      for (uint32_t i = gs; i < ge; ++i) {
+        const uint32_t icv = mv[i];
+        c0 += icv == 0u;
+        c1 += icv == 1u;
+        if (icv > 1u) atomicAdd(&s_rfreq[bt][icv], 1);
+      }
+      if (c0) atomicAdd(&s_rfreq[bt][0], (int)c0);
+      if (c1) atomicAdd(&s_rfreq[bt][1], (int)c1);
     }
     __syncthreads();
     if (t < n_groups) hb_make_code_lengths(s_len[t], s_rfreq[t], (int)alpha, 17, s_heap[t], s_weight[t], s_parent[t]);
     __syncthreads();
   }
-  // selector MTF :640-657 (thread 0), code assignment :866-878 (threads 32..), table sizes
-  if (t == 0) {
-    uint8_t pos[BZ_N_GROUPS];
-    for (uint32_t i = 0; i < n_groups; i++) pos[i] = (uint8_t)i;
-    uint32_t bits = 0;
-    for (uint32_t i = 0; i < n_sel; i++) {
-      uint8_t ll = sel[i];
-      uint32_t j = 0;
-      uint8_t tmp = pos[0];
-      while (ll != tmp) {
-        j++;
-        uint8_t tmp2 = tmp;
-        tmp = pos[j];
-        pos[j] = tmp2;
+  // selector MTF :640-657.  The list over <= 6 tables at any selector is the tables by recency (never-used ones keep
+  // their initial order at the end), so every thread rebuilds it for the start of its own run of selectors by looking
+  // back, then walks the run; selectors are staged in shared memory (the tree arrays are free by now).
+  uint8_t *s_sel = reinterpret_cast<uint8_t *>(&s_weight[0][0]);  // 6 * 516 * 4 = 12 384 B
+  uint8_t *s_sel2 = reinterpret_cast<uint8_t *>(&s_parent[0][0]); // the next 12 384 B
+  if (t == 0) s_misc[0] = 0;
+  for (uint32_t i = t; i < n_sel; i += 512) {
+    const uint8_t v = sel[i];
+    if (i < 12384u) s_sel[i] = v;
+    else s_sel2[i - 12384u] = v;
+  }
+  __syncthreads();
+  {
+    const uint32_t per = (n_sel + 511) / 512;
+    const uint32_t lo = umin(n_sel, t * per), hi = umin(n_sel, lo + per);
+    if (hi > lo) {
+      uint8_t pos[BZ_N_GROUPS];
+      uint32_t np_ = 0, seen = 0;
+      for (int i = (int)lo - 1; i >= 0 && np_ < n_groups; --i) {
+        const uint32_t v = (uint32_t)i < 12384u ? s_sel[i] : s_sel2[i - 12384];
+        if (!((seen >> v) & 1u)) {
+          seen |= 1u << v;
+          pos[np_++] = (uint8_t)v;
+        }
       }
-      pos[0] = tmp;
-      smtf[i] = (uint8_t)j;
-      bits += j + 1;
+      for (uint32_t v = 0; v < n_groups; ++v)
+        if (!((seen >> v) & 1u)) pos[np_++] = (uint8_t)v;
+      uint32_t bits = 0;
+      for (uint32_t i = lo; i < hi; ++i) {
+        const uint8_t ll = i < 12384u ? s_sel[i] : s_sel2[i - 12384u];
+        uint32_t j = 0;
+        uint8_t tmp = pos[0];
+        while (ll != tmp) {
+          j++;
+          const uint8_t tmp2 = tmp;
+          tmp = pos[j];
+          pos[j] = tmp2;
+        }
+        pos[0] = tmp;
+        smtf[i] = (uint8_t)j;
+        bits += j + 1;
+      }
+      atomicAdd(&s_misc[0], bits);
     }
-    s_misc[0] = bits;
   }
   if (t >= 32 && t < 32 + n_groups) {
     const uint32_t q = t - 32;
