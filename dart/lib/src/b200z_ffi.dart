@@ -40,6 +40,69 @@ typedef _Bz2DecodeC = Int32 Function(
 typedef _Bz2DecodeD = int Function(
     Pointer<Uint8> inp, int inLen, int verify, Pointer<Uint8> out, int outCap, Pointer<Size> outLen);
 
+typedef _DeflateRawC = Int32 Function(Pointer<Uint8> inp, Size inLen, Int32 level, Int32 windowBits, Pointer<Uint8> out,
+    Size outCap, Pointer<Size> outLen, Pointer<Uint32> crc32OfInput);
+typedef _DeflateRawD = int Function(Pointer<Uint8> inp, int inLen, int level, int windowBits, Pointer<Uint8> out,
+    int outCap, Pointer<Size> outLen, Pointer<Uint32> crc32OfInput);
+typedef _SizeOfC = Size Function(Size inLen);
+typedef _SizeOfD = int Function(int inLen);
+typedef _ZlibEncodeC = Int32 Function(Pointer<Uint8> inp, Size inLen, Int32 level, Int32 windowBits, Int32 raw,
+    Pointer<Uint8> out, Size outCap, Pointer<Size> outLen);
+typedef _ZlibEncodeD = int Function(Pointer<Uint8> inp, int inLen, int level, int windowBits, int raw,
+    Pointer<Uint8> out, int outCap, Pointer<Size> outLen);
+typedef _GzipEncodeC = Int32 Function(
+    Pointer<Uint8> inp, Size inLen, Int32 level, Uint32 mtime, Pointer<Uint8> out, Size outCap, Pointer<Size> outLen);
+typedef _GzipEncodeD = int Function(
+    Pointer<Uint8> inp, int inLen, int level, int mtime, Pointer<Uint8> out, int outCap, Pointer<Size> outLen);
+typedef _Bz2EncodeC = Int32 Function(Pointer<Uint8> inp, Size inLen, Pointer<Uint8> out, Size outCap, Pointer<Size> outLen);
+typedef _Bz2EncodeD = int Function(Pointer<Uint8> inp, int inLen, Pointer<Uint8> out, int outCap, Pointer<Size> outLen);
+
+/// b200z_zip_entry (include/b200z.h)
+final class ZipEntry extends Struct {
+  @Uint64()
+  external int localHeaderOff;
+  @Uint64()
+  external int dataOff;
+  @Uint64()
+  external int compSize;
+  @Uint64()
+  external int uncompSize;
+  @Uint64()
+  external int hintUncompSize;
+  @Uint64()
+  external int nameOff;
+  @Uint64()
+  external int cdNameOff;
+  @Uint32()
+  external int nameLen;
+  @Uint32()
+  external int cdNameLen;
+  @Uint32()
+  external int crc32;
+  @Uint32()
+  external int method;
+  @Uint32()
+  external int flags;
+  @Uint32()
+  external int modTime;
+  @Uint32()
+  external int modDate;
+  @Uint32()
+  external int extAttr;
+  @Uint32()
+  external int versionMadeBy;
+  @Uint32()
+  external int hasData;
+}
+
+typedef _ZipListC = Int32 Function(
+    Pointer<Uint8> zip, Size zipLen, Pointer<ZipEntry> entries, Size cap, Pointer<Size> nEntries);
+typedef _ZipListD = int Function(Pointer<Uint8> zip, int zipLen, Pointer<ZipEntry> entries, int cap, Pointer<Size> nEntries);
+typedef _ZipExtractC = Int32 Function(Pointer<Uint8> zip, Size zipLen, Pointer<ZipEntry> entries, Size n, Pointer<Uint8> out,
+    Size outCap, Pointer<Uint64> outOff, Pointer<Uint64> outRoom, Pointer<Uint64> outLen, Pointer<Int32> status, Uint32 flags);
+typedef _ZipExtractD = int Function(Pointer<Uint8> zip, int zipLen, Pointer<ZipEntry> entries, int n, Pointer<Uint8> out,
+    int outCap, Pointer<Uint64> outOff, Pointer<Uint64> outRoom, Pointer<Uint64> outLen, Pointer<Int32> status, int flags);
+
 class B200ZException implements Exception {
   final int code;
   final String message;
@@ -61,6 +124,14 @@ class B200Z {
   late final _ZlibDecodeD zlibDecode = _lib.lookupFunction<_ZlibDecodeC, _ZlibDecodeD>('b200z_zlib_decode');
   late final _BoundD gzipBound = _lib.lookupFunction<_BoundC, _BoundD>('b200z_gzip_bound');
   late final _Bz2DecodeD bzip2Decode = _lib.lookupFunction<_Bz2DecodeC, _Bz2DecodeD>('b200z_bzip2_decode');
+  late final _DeflateRawD deflateRaw = _lib.lookupFunction<_DeflateRawC, _DeflateRawD>('b200z_deflate_raw');
+  late final _SizeOfD deflateBound = _lib.lookupFunction<_SizeOfC, _SizeOfD>('b200z_deflate_bound');
+  late final _ZlibEncodeD zlibEncode = _lib.lookupFunction<_ZlibEncodeC, _ZlibEncodeD>('b200z_zlib_encode');
+  late final _GzipEncodeD gzipEncode = _lib.lookupFunction<_GzipEncodeC, _GzipEncodeD>('b200z_gzip_encode');
+  late final _Bz2EncodeD bzip2Encode = _lib.lookupFunction<_Bz2EncodeC, _Bz2EncodeD>('b200z_bzip2_encode');
+  late final _SizeOfD bzip2Bound = _lib.lookupFunction<_SizeOfC, _SizeOfD>('b200z_bzip2_bound');
+  late final _ZipListD zipList = _lib.lookupFunction<_ZipListC, _ZipListD>('b200z_zip_list');
+  late final _ZipExtractD zipExtract = _lib.lookupFunction<_ZipExtractC, _ZipExtractD>('b200z_zip_extract');
 
   B200Z._(this._lib);
 

@@ -147,3 +147,161 @@ class BZip2Decoder {
     }
   }
 }
+
+// ---- encoders: the `platformZLibEncoder` / `platformGZipEncoder` seam (_zlib_encoder.dart:1, _gzip_encoder.dart:1),
+// `Deflate` (deflate.dart:25-100) and `BZip2Encoder` (bzip2_encoder.dart:15-81) ----
+
+/// Same surface as the reference's `Deflate`: the stream is produced in the constructor.
+class Deflate {
+  final ar.OutputStream _output;
+  int crc32 = 0;
+
+  Deflate(List<int> bytes, {int level = 6, int windowBits = 15, ar.OutputStream? output})
+      : _output = output ?? ar.OutputMemoryStream() {
+    final z = B200Z.instance;
+    final inp = z.toNative(bytes);
+    final crc = calloc<Uint32>();
+    try {
+      final (out, _) = z.grow(z.deflateBound(bytes.length),
+          (o, cap, outLen) => z.deflateRaw(inp, bytes.length, level, windowBits, o, cap, outLen, crc));
+      crc32 = crc.value;
+      _output.writeBytes(out);
+    } finally {
+      calloc.free(crc);
+      z.hostFree(inp);
+    }
+  }
+
+  Uint8List getBytes() => _output.getBytes();
+}
+
+class _B200ZLibEncoder extends ar.ZLibEncoderBase {
+  const _B200ZLibEncoder();
+
+  @override
+  Uint8List encodeBytes(List<int> bytes, {int? level, int? windowBits, bool raw = false}) {
+    final z = B200Z.instance;
+    final inp = z.toNative(bytes);
+    try {
+      final (out, _) = z.grow(z.deflateBound(bytes.length) + 16,
+          (o, cap, outLen) => z.zlibEncode(inp, bytes.length, level ?? 6, windowBits ?? 15, raw ? 1 : 0, o, cap, outLen));
+      return out;
+    } finally {
+      z.hostFree(inp);
+    }
+  }
+
+  @override
+  void encodeStream(ar.InputStream input, ar.OutputStream output, {int? level, int? windowBits, bool raw = false}) {
+    output.writeBytes(encodeBytes(_drain(input), level: level, windowBits: windowBits, raw: raw));
+  }
+}
+
+class _B200GZipEncoder extends ar.ZLibEncoderBase {
+  const _B200GZipEncoder();
+
+  @override
+  Uint8List encodeBytes(List<int> bytes, {int? level, int? windowBits, bool raw = false}) {
+    final z = B200Z.instance;
+    final inp = z.toNative(bytes);
+    final mtime = DateTime.now().millisecondsSinceEpoch ~/ 1000; // _gzip_encoder_web.dart:82-90 writes "now"
+    try {
+      final (out, _) = z.grow(z.deflateBound(bytes.length) + 32,
+          (o, cap, outLen) => z.gzipEncode(inp, bytes.length, level ?? 6, mtime, o, cap, outLen));
+      return out;
+    } finally {
+      z.hostFree(inp);
+    }
+  }
+
+  @override
+  void encodeStream(ar.InputStream input, ar.OutputStream output, {int? level, int? windowBits, bool raw = false}) {
+    output.writeBytes(encodeBytes(_drain(input), level: level));
+  }
+}
+
+const platformZLibEncoder = _B200ZLibEncoder();
+const platformGZipEncoder = _B200GZipEncoder();
+
+class BZip2Encoder {
+  Uint8List encodeBytes(List<int> data) {
+    final z = B200Z.instance;
+    final inp = z.toNative(data);
+    try {
+      final (out, _) =
+          z.grow(z.bzip2Bound(data.length), (o, cap, outLen) => z.bzip2Encode(inp, data.length, o, cap, outLen));
+      return out;
+    } finally {
+      z.hostFree(inp);
+    }
+  }
+
+  Uint8List encode(List<int> data) => encodeBytes(data);
+
+  bool encodeStream(ar.InputStream input, ar.OutputStream output) {
+    output.writeBytes(encodeBytes(_drain(input)));
+    return true;
+  }
+}
+
+/// ZipDecoder (zip_decoder.dart:18-81) with all members decompressed by ONE b200z_zip_extract call.
+class ZipDecoder {
+  ar.Archive decodeBytes(List<int> bytes, {bool verify = false, String? password}) {
+    final z = B200Z.instance;
+    final inp = z.toNative(bytes);
+    final n = calloc<Size>();
+    try {
+      var rc = z.zipList(inp, bytes.length, nullptr, 0, n);
+      if (rc == b200zEThrow) throw RangeError(z.lastError);
+      final count = n.value;
+      final archive = ar.Archive();
+      if (count == 0) return archive;
+      final ents = calloc<ZipEntry>(count);
+      final off = calloc<Uint64>(count), room = calloc<Uint64>(count), len = calloc<Uint64>(count);
+      final st = calloc<Int32>(count);
+      try {
+        rc = z.zipList(inp, bytes.length, ents, count, n);
+        if (rc != b200zOk) throw B200ZException(rc, z.lastError);
+        var total = 0;
+        for (var i = 0; i < count; i++) {
+          final e = ents[i];
+          final r = e.hasData != 0 ? (e.hintUncompSize > e.uncompSize ? e.hintUncompSize : e.uncompSize) : 0;
+          off[i] = total;
+          room[i] = r;
+          total += (r + 63) & ~63;
+        }
+        final out = z.hostAlloc(total == 0 ? 64 : total);
+        try {
+          rc = z.zipExtract(inp, bytes.length, ents, count, out, total, off, room, len, st, 0);
+          if (rc != b200zOk) throw B200ZException(rc, z.lastError);
+          // (members whose size fields lied report B200Z_U_NOSPC: retry those with more room, as archive_b200/zip.py does)
+          final all = out.asTypedList(total == 0 ? 0 : total);
+          for (var i = 0; i < count; i++) {
+            final e = ents[i];
+            final name = e.hasData != 0 ? String.fromCharCodes(bytes.sublist(e.nameOff, e.nameOff + e.nameLen)) : '';
+            if (archive.find(name) != null) continue;
+            final isDir = name.endsWith('/') || name.endsWith('\\');
+            final content = Uint8List.fromList(all.sublist(off[i], off[i] + (len[i] < room[i] ? len[i] : room[i])));
+            final f = isDir ? ar.ArchiveFile.directory(name) : ar.ArchiveFile.bytes(name, content);
+            f.mode = e.extAttr >> 16;
+            f.crc32 = e.crc32;
+            f.lastModTime = e.modDate << 16 | e.modTime;
+            archive.add(f);
+          }
+        } finally {
+          z.hostFree(out);
+        }
+        return archive;
+      } finally {
+        calloc.free(ents);
+        calloc.free(off);
+        calloc.free(room);
+        calloc.free(len);
+        calloc.free(st);
+      }
+    } finally {
+      calloc.free(n);
+      z.hostFree(inp);
+    }
+  }
+}
