@@ -832,9 +832,9 @@ static int bzip2_decode_impl(const uint8_t *in, size_t in_len, int verify, uint8
   std::vector<uint32_t> chain_of(nb, 0xffffffffu);
   if (shard) {
     for (uint32_t k = k_lo; k < k_hi; ++k)
-      if (h_st[k] == 0 && !h_rnd[k]) {
+      if (h_st[k] == 0) {
         chain_of[k] = (uint32_t)chain.size();
-        chain.push_back({k - k_lo, h_nblock[k], h_nrec[k], h_optr[k]});
+        chain.push_back({k - k_lo, h_nblock[k], h_nrec[k], h_optr[k], h_rnd[k] ? 1u : 0u});
         stored_crc.push_back(blk_bits[k] + 80 <= total_bits ? be32_at_bit(in, in_len, blk_bits[k] + 48) : 0u);
       }
   }
@@ -873,14 +873,7 @@ static int bzip2_decode_impl(const uint8_t *in, size_t in_len, int verify, uint8
       final_rc = B200Z_E_DATA;
       break;
     }
-    if (h_rnd[k]) {
-      // randomised blocks (obsolete since bzip2 0.9.5; the reference's variant of that path also differs from
-      // libbzip2) are not implemented on the device
-      set_err("bzip2: randomised block at bit %llu is not supported", (unsigned long long)pos);
-      final_rc = B200Z_E_DATA;
-      break;
-    }
-    chain.push_back({k, h_nblock[k], h_nrec[k], h_optr[k]});
+    chain.push_back({k, h_nblock[k], h_nrec[k], h_optr[k], h_rnd[k] ? 1u : 0u});  // randomised blocks: serial walk in K8
     stored_crc.push_back(crc_field);
     pos = h_end[k];
   }
@@ -906,6 +899,7 @@ static int bzip2_decode_impl(const uint8_t *in, size_t in_len, int verify, uint8
     w.seg_len = A.seg_len; w.seg_next = A.seg_next; w.seg_off = A.seg_off; w.irregular = A.irregular; w.cycle_len = A.cycle_len; w.raw = A.raw;
     w.slice_state = A.slice_state; w.slice_out = A.slice_out; w.block_out = A.block_out; w.block_off = A.block_off;
     w.block_crc = A.block_crc; w.out = (uint8_t *)g.d_out.p; w.out_cap = out_cap;
+    for (const BzChainHost &ce : chain) w.any_randomised = w.any_randomised || (ce.flags & 1u);
     CU(bz2_launch_ibwt(w, g.stream));
     CU(cudaMemcpyAsync(h_off.data(), A.block_off, (size_t)(nc + 1) * 8, cudaMemcpyDeviceToHost, g.stream));
     CU(cudaMemcpyAsync(h_crc.data(), A.block_crc, (size_t)nc * 4, cudaMemcpyDeviceToHost, g.stream));
@@ -928,7 +922,7 @@ static int bzip2_decode_impl(const uint8_t *in, size_t in_len, int verify, uint8
       b.start_bit = blk_bits[k];
       b.end_bit = h_end[k];
       b.status = h_st[k];
-      b.flags = h_rnd[k] ? B200Z_BZ2_RANDOMISED : 0u;
+      b.flags = 0u;  // randomised blocks are decoded like the others (serial walk)
       b.crc_stored = blk_bits[k] + 80 <= total_bits ? be32_at_bit(in, in_len, blk_bits[k] + 48) : 0u;
       const uint32_t c = chain_of[k];
       if (c != 0xffffffffu) {
@@ -966,12 +960,18 @@ static int bzip2_decode_impl(const uint8_t *in, size_t in_len, int verify, uint8
   size_t n_out = 0;
   uint32_t combined = 0;
   for (uint32_t i = 0; i < nc; ++i) {
-    if (h_irr[i]) {
+    if (h_irr[i] == 1) {
       set_err("bzip2: block %u: corrupt BWT cycle", i);
       final_rc = B200Z_E_DATA;
       break;
     }
     n_out = (size_t)h_off[i + 1];
+    if (h_irr[i] == 2) {  // randomised block whose walk overran (:497-499): false, its bytes are already written
+      set_err("bzip2: block %u: randomised block overruns", i);
+      final_rc = B200Z_E_DATA;
+      have_eos = false;
+      break;
+    }
     if (verify && h_crc[i] != stored_crc[i]) {
       set_err("bzip2: block %u CRC mismatch", i);
       final_rc = B200Z_E_DATA;

@@ -77,9 +77,11 @@ struct Bz2Ibwt {  // K8 over the validated chain
   uint32_t *block_crc;                         // [n_chain]
   uint8_t *out;
   unsigned long long out_cap;
+  bool any_randomised = false;
 };
 struct BzChainHost {
   uint32_t cand, nblock, n_rec, orig_ptr;
+  uint32_t flags;  // bit 0: randomised block (serial path in K8)
 };
 size_t bz2_entropy_smem();
 cudaError_t bz2_launch_scan(const uint8_t *d_in, uint64_t n_bytes, unsigned long long *d_cand, uint32_t *d_ncand,

@@ -19,6 +19,7 @@
 #include <stdint.h>
 
 #include "b200z_internal.h"
+#include "bz2_rnums.h"
 
 namespace b200z {
 
@@ -419,6 +420,7 @@ struct BzChain {           // one entry per block that is on the validated chain
   uint32_t nblock;
   uint32_t n_rec;
   uint32_t orig_ptr;
+  uint32_t flags;          // bit 0: randomised block
 };
 
 __global__ void __launch_bounds__(256)
@@ -683,6 +685,7 @@ k_bz2_rle_count(const BzChain *__restrict__ chain, const uint8_t *__restrict__ r
   __shared__ uint32_t sm_map[BZ_RLE_THREADS];
   __shared__ uint32_t sm_cnt[BZ_RLE_THREADS];
   const BzChain c = chain[blockIdx.x];
+  if (c.flags & 1u) return;  // randomised: k_bz2_rand
   const uint8_t *src = raw + (size_t)blockIdx.x * nblock_max;
   const uint32_t t = threadIdx.x;
   const uint32_t per = (c.nblock + BZ_RLE_THREADS - 1) / BZ_RLE_THREADS;
@@ -761,6 +764,7 @@ k_bz2_rle_emit(const BzChain *__restrict__ chain, const uint8_t *__restrict__ ra
   __shared__ uint32_t sm_crc[BZ_RLE_THREADS];
   __shared__ uint32_t sm_len[BZ_RLE_THREADS];
   const BzChain c = chain[blockIdx.x];
+  if (c.flags & 1u) return;  // randomised: k_bz2_rand
   const uint32_t t = threadIdx.x;
   if (t < 256) {
     uint32_t v = t << 24;
@@ -815,6 +819,108 @@ k_bz2_rle_emit(const BzChain *__restrict__ chain, const uint8_t *__restrict__ ra
     // whole block with the real initial register 0xffffffff, then the final xor (bzip2.dart:9,16-18)
     uint32_t r = bzcrc_mulmod(0xffffffffu, bzcrc_xpow8(sm_len[t])) ^ sm_crc[t];
     block_crc[blockIdx.x] = r ^ 0xffffffffu;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Randomised blocks (bzip2_decoder.dart:492-608).  The byte read from the inverse BWT is XORed with 1 whenever a countdown
+// loaded from the 512-entry table stands at 1; in the reference only the FIRST read of every turn of the run-length
+// state machine decrements that countdown (the 2nd-5th reads reload it at 0 but do not count down -- SURVEY Q6, unlike
+// libbzip2), so the mask depends on the run structure of the already unmasked bytes: one serial walk per block.
+// EMIT = false: output size of the block; EMIT = true: bytes + CRC.  A walk that overruns the block (:497-499) reports
+// irregular = 2 after its bytes are written, as the reference's output stream has them by then.
+// ---------------------------------------------------------------------------------------------
+template <bool EMIT>
+__global__ void k_bz2_rand(const BzChain *__restrict__ chain, uint32_t n_chain, const uint8_t *__restrict__ raw,
+                           uint32_t nblock_max, unsigned long long *__restrict__ block_out,
+                           const unsigned long long *__restrict__ block_off, unsigned long long out_cap, uint8_t *__restrict__ out,
+                           uint32_t *__restrict__ block_crc, int32_t *__restrict__ irregular) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_chain) return;
+  const BzChain c = chain[i];
+  if (!(c.flags & 1u) || c.nblock == 0) return;
+  const uint8_t *src = raw + (size_t)i * nblock_max;
+  const uint32_t nb = c.nblock;
+  unsigned long long o = EMIT ? block_off[i] : 0ull, o0 = o;
+  uint32_t crc = 0xffffffffu;
+  int r_n_to_go = 0, r_t_pos = 0;
+  uint32_t rd = 0;  // reads so far; read number q returns byte q of the cycle (which closes after nblock bytes)
+#define BZ_READ(dst)                              \
+  do {                                            \
+    (dst) = src[rd < nb ? rd : rd % nb];          \
+    rd++;                                         \
+    if (r_n_to_go == 0) {                         \
+      r_n_to_go = c_bz2_rnums[r_t_pos];           \
+      r_t_pos = (r_t_pos + 1) & 511;              \
+    }                                             \
+  } while (0)
+  int k0, k1;
+  BZ_READ(k0);
+  r_n_to_go--;
+  k0 ^= (r_n_to_go == 1) ? 1 : 0;
+  const uint32_t save = nb + 1;
+  uint32_t n_used = 1;
+  int out_len = 0, out_ch = 0;
+  bool fail = false;
+  for (;;) {
+    for (; out_len > 0; --out_len) {
+      if (EMIT) {
+        if (o < out_cap) out[o] = (uint8_t)out_ch;
+        uint32_t v = (crc >> 24) ^ (uint32_t)out_ch;
+        uint32_t tv = v << 24;
+        for (int b = 0; b < 8; ++b) tv = (tv & 0x80000000u) ? (tv << 1) ^ 0x04c11db7u : tv << 1;
+        crc = (crc << 8) ^ tv;
+      }
+      o++;
+    }
+    if (n_used == save) break;
+    if (n_used > save) {
+      fail = true;
+      break;
+    }
+    out_len = 1;
+    out_ch = k0;
+    BZ_READ(k1);
+    r_n_to_go--;
+    k1 ^= (r_n_to_go == 1) ? 1 : 0;
+    n_used++;
+    if (n_used == save) continue;
+    if (k1 != k0) {
+      k0 = k1;
+      continue;
+    }
+    out_len = 2;
+    BZ_READ(k1);
+    k1 ^= (r_n_to_go == 1) ? 1 : 0;
+    n_used++;
+    if (n_used == save) continue;
+    if (k1 != k0) {
+      k0 = k1;
+      continue;
+    }
+    out_len = 3;
+    BZ_READ(k1);
+    k1 ^= (r_n_to_go == 1) ? 1 : 0;
+    n_used++;
+    if (n_used == save) continue;
+    if (k1 != k0) {
+      k0 = k1;
+      continue;
+    }
+    BZ_READ(k1);
+    k1 ^= (r_n_to_go == 1) ? 1 : 0;
+    n_used++;
+    out_len = k1 + 4;
+    BZ_READ(k0);
+    k0 ^= (r_n_to_go == 1) ? 1 : 0;
+    n_used++;
+  }
+#undef BZ_READ
+  if (!EMIT) {
+    block_out[i] = o - o0;
+  } else {
+    block_crc[i] = crc ^ 0xffffffffu;
+    if (fail) irregular[i] = 2;
   }
 }
 
@@ -876,11 +982,21 @@ cudaError_t bz2_launch_ibwt(const Bz2Ibwt &a, cudaStream_t s) {
   count_launch();
   k_bz2_rle_count<<<a.n_chain, BZ_RLE_THREADS, 0, s>>>(chain, a.raw, a.nblock_max, a.slice_state, a.slice_out, a.block_out);
   count_launch();
+  if (a.any_randomised) {
+    k_bz2_rand<false><<<(a.n_chain + 31) / 32, 32, 0, s>>>(chain, a.n_chain, a.raw, a.nblock_max, a.block_out, a.block_off,
+                                                           a.out_cap, a.out, a.block_crc, a.irregular);
+    count_launch();
+  }
   k_bz2_offsets<<<1, 32, 0, s>>>(a.block_out, a.n_chain, a.block_off);
   count_launch();
   k_bz2_rle_emit<<<a.n_chain, BZ_RLE_THREADS, 0, s>>>(chain, a.raw, a.nblock_max, a.slice_state, a.slice_out, a.block_off,
                                                      a.out_cap, a.out, a.block_crc);
   count_launch();
+  if (a.any_randomised) {
+    k_bz2_rand<true><<<(a.n_chain + 31) / 32, 32, 0, s>>>(chain, a.n_chain, a.raw, a.nblock_max, a.block_out, a.block_off,
+                                                          a.out_cap, a.out, a.block_crc, a.irregular);
+    count_launch();
+  }
   return cudaGetLastError();
 }
 

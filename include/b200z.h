@@ -111,7 +111,7 @@ typedef struct {
   uint32_t flags;              /* B200Z_BZ2_*                                                           */
 } b200z_bz2_block;
 #define B200Z_BZ2_EOS 1u            /* an end-of-stream magic (crc_stored = the combined CRC) */
-#define B200Z_BZ2_RANDOMISED 2u     /* randomised block: not decoded                          */
+#define B200Z_BZ2_RANDOMISED 2u     /* (unused: randomised blocks are decoded)                */
 #define B200Z_BZ2_CORRUPT_CYCLE 4u  /* inverse BWT is not one cycle: not decoded              */
 int b200z_bzip2_decode_shard(const uint8_t *in, size_t in_len, uint32_t rank, uint32_t world, uint8_t *out,
                              size_t out_cap, size_t *out_len, b200z_bz2_block *blocks, size_t blocks_cap,

@@ -94,3 +94,25 @@ def test_scale_multiblock(a):
     z = bz2.compress(d, 9)
     out = a.BZip2Decoder().decode_bytes(z, verify=True)
     assert len(out) == len(d) and out == d
+
+
+def test_randomised_blocks(a):
+    """The obsolete randomised-block bit (no encoder has set it since bzip2 0.9.5): the reference decodes such blocks with its
+    own variant of the de-randomisation (bzip2_decoder.dart:492-608, SURVEY Q6 -- it differs from libbzip2, so libbz2 is no
+    witness here; the oracle restates it).  Setting the bit on a normal stream changes the decoded bytes (CRCs then mismatch,
+    which only `verify` looks at)."""
+    from archive_b200 import synth
+    rng = random.Random(8)
+    cases = [b"hello hello hello, randomised world! " * 40,
+             bytes(rng.randrange(256) for _ in range(5000)),
+             b"a" * 3000 + b"bcd" * 500 + bytes(range(256)) * 4,
+             synth.text(1_200_000, stream=970).tobytes()]  # two blocks: the first one randomised
+    for src in cases:
+        z = bytearray(bz2.compress(src, 9))
+        z[14] |= 0x80  # bit 112 = 32 (stream header) + 48 (block magic) + 32 (block CRC): the "randomised" flag
+        z = bytes(z)
+        st, want = orc.bzip2_decode(z, verify=False)
+        got = a.BZip2Decoder().decode_bytes(z, verify=False)
+        assert got == want and want != src
+        ok = a.BZip2Decoder().decode_stream(a.InputMemoryStream(z), a.OutputMemoryStream(), verify=True)
+        assert ok is False  # block CRC no longer matches
