@@ -32,6 +32,7 @@ typedef const void *b200z_saddr;
 #define B200Z_BREV(x) __brev(x)
 #define B200Z_POPC(x) __popc(x)
 #define B200Z_LDCG(p) (*(p))
+#define B200Z_STCS(p, v) (*(p) = (v))
 #define B200Z_REDOR(p, v) atomicOr((p), (v))
 #elif defined(__CUDA_ARCH__)
 // 32-bit shared-window addressing for the per-lane LUTs: keeps the hot loop free of 64-bit generic pointers
@@ -56,6 +57,7 @@ typedef uint32_t b200z_saddr;
 #define B200Z_SYNCWARP() __syncwarp()
 #define B200Z_POPC(x) __popc(x)
 #define B200Z_LDCG(p) __ldcg(p)
+#define B200Z_STCS(p, v) __stcs((p), (v))
 #define B200Z_REDOR(p, v) atomicOr((p), (v))
 __device__ __forceinline__ uint32_t b200z_opaque(uint32_t v) {
   uint32_t o;
@@ -77,6 +79,7 @@ typedef const void *b200z_saddr;
 #define B200Z_SYNCWARP() ((void)0)
 #define B200Z_POPC(x) __builtin_popcount(x)
 #define B200Z_LDCG(p) (*(p))
+#define B200Z_STCS(p, v) (*(p) = (v))
 #define B200Z_REDOR(p, v) (*(p) |= (v))
 #define B200Z_OPAQUE(x) (x)
 #define B200Z_LDG(p) (*(p))
@@ -390,7 +393,7 @@ B200Z_HD UnitResult inflate_decode_unit(bool active, const uint8_t *in, uint32_t
   const bool count_only = sc.count_only;
 #define B200Z_TOK(p, v)          \
   do {                          \
-    if (!count_only) (p)[nt] = (v); \
+    if (!count_only) B200Z_STCS((p) + nt, (v)); /* written once, read once by the expand kernel: evict first */ \
     nt++;                       \
   } while (0)
   const bool is_master = sc.sub == 0;

@@ -45,8 +45,10 @@ namespace b200z {
 // phase 1
 // ---------------------------------------------------------------------------------------------
 #ifdef B200Z_EMU
+#define B200Z_LDCS(p) (*(p))
 #define B200Z_DYN_SMEM(name) uint32_t *name = cuemu_dyn_smem
 #else
+#define B200Z_LDCS(p) __ldcs(p)
 #define B200Z_DYN_SMEM(name) extern __shared__ uint32_t name[]
 #endif
 
@@ -144,7 +146,7 @@ k_inflate_expand(InflateWs ws, const uint8_t *__restrict__ in_base, const uint64
       const uint32_t src = P[2 + 3 * pi], pstart = P[3 + 3 * pi], nt = P[4 + 3 * pi];
       const uint32_t *T = (src == 0 ? ws.tokens + oo : ws.htokens + (size_t)(src - 1) * ws.hstride + (oo >> SPEC_HSHIFT)) + pstart;
     for (uint32_t g = 0; g < nt && !stop; g += 32) {
-      uint32_t t = (g + lane < nt) ? T[g + lane] : 0u;
+      uint32_t t = (g + lane < nt) ? B200Z_LDCS(T + g + lane) : 0u;  // read once: do not keep it in L2
       uint32_t tprev = __shfl_up_sync(FULL, t, 1);
       const bool payload = lane > 0 && (tprev >> 30) == 1u;  // payload words have top bits 00: no chains
       uint32_t len = tok_len(t, payload);
