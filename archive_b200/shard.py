@@ -144,3 +144,35 @@ def bzip2_decode_sharded(data, verify: bool = False, group=None, rank=None, worl
                 pieces.append((pos, view[r[8]:r[8] + r[2]], r[8]))
         pos += r[2]
     return {"kind": kind, "total": n_out, "pieces": [(o, v) for o, v, _ in pieces], "n_chain": len(chain), "reports": mine}
+
+
+# ---------------------------------------------------------------------------------------------
+# ZIP members sharded over ranks: largest-first bin packing by compressed size
+# ---------------------------------------------------------------------------------------------
+def pack_members(comp_sizes, world: int):
+    """-> list (one per rank) of member indices; greedy largest-first onto the least loaded rank, ties to the lower rank,
+    every rank's list in archive order.  Deterministic, so every rank computes the same assignment without talking."""
+    order = sorted(range(len(comp_sizes)), key=lambda i: (-int(comp_sizes[i]), i))
+    load = [0] * world
+    bins = [[] for _ in range(world)]
+    for i in order:
+        r = min(range(world), key=lambda k: (load[k], k))
+        bins[r].append(i)
+        load[r] += int(comp_sizes[i]) + 1
+    return [sorted(b) for b in bins]
+
+
+def zip_extract_sharded(data, rank: int, world: int, web_eos: bool = False):
+    """Rank `rank` of `world` decodes its share of the archive's members with one b200z_zip_extract call.
+    -> (entries, {member index: bytes}) -- the directory is parsed by every rank (host work, no device)."""
+    from .zip import ZipDecoder
+    dec = ZipDecoder(web_eos=web_eos)
+    ents, n = dec.list(data)
+    mine = pack_members([ents[i].comp_size if ents[i].has_data else 0 for i in range(n)], world)[rank]
+    if not mine:
+        return ents, {}
+    import ctypes as C
+    from . import _ffi
+    sub = (_ffi.ZipEntry * len(mine))(*[ents[i] for i in mine])
+    contents, statuses = dec._extract(data, sub, len(mine))
+    return ents, {i: contents[k] for k, i in enumerate(mine)}

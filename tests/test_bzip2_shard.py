@@ -104,3 +104,37 @@ def test_shards_reassemble_on_one_gpu():
     parts = [shard.bzip2_decode_sharded(bytes(bad), rank=r, world=2) for r in range(2)]
     kind, chain, n_out = shard.bz2_walk_chain([x for p in parts for x in p["reports"]], len(bad), True)
     assert kind == "data" and n_out == len(ref_ok)
+
+
+def test_zip_member_packing():
+    sizes = [10, 500, 20, 499, 498, 1, 0, 300]
+    bins = shard.pack_members(sizes, 3)
+    assert sorted(i for b in bins for i in b) == list(range(len(sizes)))
+    loads = [sum(sizes[i] for i in b) for b in bins]
+    assert max(loads) - min(loads) <= max(sizes)  # largest-first greedy: within one member of each other
+    assert bins == shard.pack_members(sizes, 3)  # deterministic: every rank computes the same plan
+    assert shard.pack_members(sizes, 1) == [list(range(len(sizes)))]
+    assert shard.pack_members([], 4) == [[], [], [], []]
+
+
+@pytest.mark.gpu
+def test_zip_members_sharded_on_one_gpu():
+    import io
+    import zipfile
+    from archive_b200 import synth
+    txt = synth.text(40 * 200_000, stream=990).tobytes()
+    buf = io.BytesIO()
+    want = []
+    with zipfile.ZipFile(buf, "w") as z:
+        for i in range(40):
+            body = txt[i * 200_000:i * 200_000 + 1000 * (i % 7) * (i % 5) * 8 + i]
+            z.writestr(f"f{i}", body, compress_type=zipfile.ZIP_DEFLATED if i % 3 else zipfile.ZIP_STORED)
+            want.append(body)
+    data = buf.getvalue()
+    for world in (1, 3):
+        got = {}
+        for r in range(world):
+            ents, part = shard.zip_extract_sharded(data, r, world)
+            assert not set(part) & set(got)
+            got.update(part)
+        assert [got[i] for i in range(40)] == want
