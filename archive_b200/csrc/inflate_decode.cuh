@@ -78,6 +78,11 @@ typedef const void *b200z_saddr;
 #define B200Z_SHFL(v, src) (v)
 #define B200Z_SYNCWARP() ((void)0)
 #define B200Z_POPC(x) __builtin_popcount(x)
+#ifndef __CUDACC__
+struct alignas(16) uint4 {
+  uint32_t x, y, z, w;
+};
+#endif
 #define B200Z_LDCG(p) (*(p))
 #define B200Z_STCS(p, v) (*(p) = (v))
 #define B200Z_REDOR(p, v) (*(p) |= (v))
@@ -138,13 +143,14 @@ B200Z_CONST uint32_t c_dist_tab[32] = {
 
 constexpr int LBITS = B200Z_LBITS;  // primary literal/length LUT bits
 constexpr int DBITS = B200Z_DBITS;  // primary distance LUT bits
-constexpr int SUBN = 160;           // second-level entries shared by the codes longer than LBITS / DBITS of one block
+constexpr int SUBN = 128;           // second-level entries shared by the codes longer than LBITS / DBITS of one block
 constexpr int LUT_HALFWORDS = (1 << LBITS) + (1 << DBITS) + SUBN;
 constexpr int LANE_STRIDE_WORDS = LUT_HALFWORDS / 2 + 1;  // +1 word: same index -> different bank per lane
 constexpr int CONST_WORDS = 16 + 32 + 64;                  // len table (32 x u16) + dist table (32 x u32) + xtab (64 x u32)
+constexpr int STAGE_WORDS = 32 * 4;                        // per warp: 4 tokens per lane, so that tokens leave as 16-byte stores
 
 static inline size_t inflate_decode_smem_bytes(int warps_per_block, int units_per_warp) {
-  return (size_t)(CONST_WORDS + warps_per_block * units_per_warp * LANE_STRIDE_WORDS) * 4;
+  return (size_t)(CONST_WORDS + warps_per_block * (units_per_warp * LANE_STRIDE_WORDS + STAGE_WORDS)) * 4;
 }
 
 // Canonical-code side tables for codes longer than the LUT (rare): per lane, in local memory.
@@ -367,6 +373,7 @@ struct SpecCtx {
   int lane, sub, G;   // lane in the warp, index inside the stream's lane group (0 = master), lanes per stream
   bool spec;          // warp-uniform: helpers are in use in this launch
   bool count_only;    // warp-uniform: sizes only -- tokens are counted, not written (no expand follows)
+  uint32_t *stage;    // shared memory: this lane's 4-token staging slot (16-byte aligned)
   uint32_t *hplane;   // helper k's token region = hplane + (k - 1) * hstride  [hcap words]
   size_t hstride;
   uint32_t hcap;
@@ -576,6 +583,10 @@ B200Z_HD UnitResult inflate_decode_unit(bool active, const uint8_t *in, uint32_t
       uint32_t rel_bits = 32u * br.widx - (uint32_t)br.cnt - 8u * br.lead - sp_origin;
       uint32_t succ_rel = (sp_seg != 0u && succ < G) ? (succ - (uint32_t)sc.sub) * sp_seg : 0xffffffffu;
       bool mark = !is_master && spec_on;
+      // Tokens are staged four at a time in shared memory and leave as one 16-byte store: 32 lanes writing 4 bytes each to
+      // 32 different sectors per turn were almost half of this kernel's time.  q0 = first token not yet in memory.
+      const bool stage_ok = !count_only && (reinterpret_cast<uintptr_t>(tk) & 15u) == 0u;
+      uint32_t q0 = nt;
       for (;;) {
         const bool can = fast_ok && (mode_dist || br.widx + 2u <= br.nw);
         if (B200Z_BALLOT(can) != expect) break;
@@ -633,13 +644,31 @@ B200Z_HD UnitResult inflate_decode_unit(bool active, const uint8_t *in, uint32_t
           br.buf >>= tot;
           br.cnt -= (int)tot;
           rel_bits += tot;
-          if (islit || dm) B200Z_TOK(tk, islit ? (TOK_LIT | sym) : ((mlen_pending << 16) | val));
+          if (islit || dm) {
+            const uint32_t tv = islit ? (TOK_LIT | sym) : ((mlen_pending << 16) | val);
+            if (stage_ok) {
+              sc.stage[nt & 3u] = tv;
+              nt++;
+              if ((nt & 3u) == 0u) {
+                if (q0 + 4u <= nt) {
+                  B200Z_STCS(reinterpret_cast<uint4 *>(tk + nt - 4u), *reinterpret_cast<const uint4 *>(sc.stage));
+                } else {  // the group of four began before this bulk session
+                  for (uint32_t k = q0; k < nt; ++k) B200Z_STCS(tk + k, sc.stage[k & 3u]);
+                }
+                q0 = nt;
+              }
+            } else {
+              B200Z_TOK(tk, tv);
+            }
+          }
           olen = nolen;
           mlen_pending = islen ? val : mlen_pending;
           mode_dist = islen;
         }
         fast_ok = !special;
       }
+      if (stage_ok)
+        for (uint32_t k = q0; k < nt; ++k) B200Z_STCS(tk + k, sc.stage[k & 3u]);  // at most 3 left over
       if (!is_master) h_fast = fast_ok;
     }
     // ---- the master met a helper: close its own piece; the adoption runs at the top of the next turns ----

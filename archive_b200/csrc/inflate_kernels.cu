@@ -83,11 +83,13 @@ k_inflate_decode(const uint8_t *__restrict__ in_base, const uint64_t *__restrict
   uint16_t *lut_l = reinterpret_cast<uint16_t *>(smem + CONST_WORDS +
                                                  (warp_in_block * units_per_warp + (active ? sidx : 0)) * LANE_STRIDE_WORDS);
   uint16_t *lut_d = lut_l + (1 << LBITS);
+  uint32_t *s_stage = smem + CONST_WORDS + (blockDim.x >> 5) * units_per_warp * LANE_STRIDE_WORDS + warp_in_block * STAGE_WORDS;
 
   SpecCtx sc;
   sc.lane = lane;
   sc.sub = sub;
   sc.G = lanes_per_unit;
+  sc.stage = s_stage + lane * 4;
   sc.spec = lanes_per_unit > 1 && ws.htokens != nullptr && !count_only;
   sc.count_only = count_only != 0;
   sc.hplane = nullptr;

@@ -48,6 +48,8 @@ extern "C" int emul_inflate(const uint8_t *in, uint32_t in_len, uint8_t *out, ui
   sc.G = 1;
   sc.spec = false;
   sc.count_only = false;
+  alignas(16) static uint32_t stage[4];
+  sc.stage = stage;
   UnitResult r = inflate_decode_unit(true, p, in_len, cap, tok.data(), lut.data(), lut.data() + (1 << B200Z_LBITS),
                                      c_len_tab, c_dist_tab, xtab, sc);
   expand(tok.data(), r.ntok, p, out);
