@@ -150,7 +150,7 @@ constexpr int CONST_WORDS = 16 + 32 + 64;                  // len table (32 x u1
 constexpr int STAGE_WORDS = 32 * 4;                        // per warp: 4 tokens per lane, so that tokens leave as 16-byte stores
 
 static inline size_t inflate_decode_smem_bytes(int warps_per_block, int units_per_warp) {
-  return (size_t)(CONST_WORDS + warps_per_block * (units_per_warp * LANE_STRIDE_WORDS + STAGE_WORDS)) * 4;
+  return (size_t)(CONST_WORDS + warps_per_block * (units_per_warp * LANE_STRIDE_WORDS + STAGE_WORDS) + 4) * 4;
 }
 
 // Canonical-code side tables for codes longer than the LUT (rare): per lane, in local memory.

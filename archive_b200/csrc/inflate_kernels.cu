@@ -19,7 +19,7 @@
 //                     bytes of the same window that are not written yet).
 #ifdef B200Z_EMU  // CPU emulation build (tests/host_emul/inflate_emul.cpp): kernels only
 #include "cuda_emu.h"
-static uint32_t cuemu_dyn_smem[64 * 1024];
+alignas(16) static uint32_t cuemu_dyn_smem[64 * 1024];
 #define B200Z_DECODE_THREADS 32
 #define B200Z_EXPAND_THREADS 256
 namespace b200z {
@@ -49,7 +49,7 @@ namespace b200z {
 #define B200Z_DYN_SMEM(name) uint32_t *name = cuemu_dyn_smem
 #else
 #define B200Z_LDCS(p) __ldcs(p)
-#define B200Z_DYN_SMEM(name) extern __shared__ uint32_t name[]
+#define B200Z_DYN_SMEM(name) extern __shared__ __align__(16) uint32_t name[]
 #endif
 
 __global__ void __launch_bounds__(B200Z_DECODE_THREADS)
@@ -83,7 +83,8 @@ k_inflate_decode(const uint8_t *__restrict__ in_base, const uint64_t *__restrict
   uint16_t *lut_l = reinterpret_cast<uint16_t *>(smem + CONST_WORDS +
                                                  (warp_in_block * units_per_warp + (active ? sidx : 0)) * LANE_STRIDE_WORDS);
   uint16_t *lut_d = lut_l + (1 << LBITS);
-  uint32_t *s_stage = smem + CONST_WORDS + (blockDim.x >> 5) * units_per_warp * LANE_STRIDE_WORDS + warp_in_block * STAGE_WORDS;
+  // (16-byte aligned: the slots are read back with one 128-bit load)
+  uint32_t *s_stage = smem + ((CONST_WORDS + (blockDim.x >> 5) * units_per_warp * LANE_STRIDE_WORDS + 3) & ~3) + warp_in_block * STAGE_WORDS;
 
   SpecCtx sc;
   sc.lane = lane;
