@@ -126,6 +126,7 @@ int encode_device(const uint8_t *d_in, size_t n, uint8_t *d_out, size_t out_cap,
   BZ2E_CK(cudaMemcpyAsync(b.st, &st0, sizeof st0, cudaMemcpyHostToDevice, s));
   Stats stt{0, 0, 0, 0};
   uint32_t h_nb[2] = {0, 0};
+  std::vector<BlkInfo> h_blk_v;
   BlkInfo *h_blk = nullptr;
   if (n > 0) {
     const uint32_t n32 = (uint32_t)n;
@@ -139,15 +140,16 @@ int encode_device(const uint8_t *d_in, size_t n, uint8_t *d_out, size_t out_cap,
     BZ2E_CK(cudaMemcpyAsync(h_nb, b.n_blocks, 8, cudaMemcpyDeviceToHost, s));
     BZ2E_CK(cudaStreamSynchronize(s));
     if (h_nb[1] || h_nb[0] == 0) return -6;
-    h_blk = new BlkInfo[h_nb[0]];
+    h_blk_v.resize(h_nb[0]);
+    h_blk = h_blk_v.data();
     BZ2E_CK(cudaMemcpyAsync(h_blk, b.blk, sizeof(BlkInfo) * h_nb[0], cudaMemcpyDeviceToHost, s));
     BZ2E_CK(cudaStreamSynchronize(s));
   }
   const uint32_t nblocks = h_nb[0];
   stt.n_blocks = nblocks;
   int rc = 0;
-  uint32_t *h_n = new uint32_t[p.batch];
-  uint32_t *h_cnt = new uint32_t[p.batch];
+  std::vector<uint32_t> h_n_v(p.batch), h_cnt_v(p.batch);
+  uint32_t *h_n = h_n_v.data(), *h_cnt = h_cnt_v.data();
   for (uint32_t lo = 0; lo < nblocks && rc == 0; lo += p.batch) {
     const uint32_t nb = (nblocks - lo < p.batch) ? nblocks - lo : p.batch;
     const uint32_t hi = lo + nb;
@@ -268,9 +270,6 @@ int encode_device(const uint8_t *d_in, size_t n, uint8_t *d_out, size_t out_cap,
     B200Z_LAUNCH(k_h_emit_data, dim3(NET, nb), 256, 0, s, b.mtfv, b.nmtf, b.hinfo, b.bit_off, b.tile_bitoff, b.selector,
                  b.lens, b.codes, out32);
   }
-  delete[] h_blk;
-  delete[] h_n;
-  delete[] h_cnt;
   if (rc == -3) {
     *out_len = bound(n);
     return -3;

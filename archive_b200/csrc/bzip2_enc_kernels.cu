@@ -36,6 +36,8 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include <vector>
+
 #include "bzip2_enc.h"
 
 namespace b200z {

@@ -510,7 +510,8 @@ static int serial_sort_blocks(const uint8_t *blockbuf, const uint32_t *nblk, con
                               uint32_t nb, uint32_t *SA, uint32_t *origptr, void *scratchA, void *scratchB, void *scratchC,
                               cudaStream_t s) {
   (void)h_n;
-  uint32_t *h_list = new uint32_t[nb + 1];
+  std::vector<uint32_t> h_list_v(nb + 1);
+  uint32_t *h_list = h_list_v.data();
   uint32_t n_list = 0;
   for (uint32_t i = 0; i < nb; ++i)
     if (h_cnt[i]) h_list[n_list++] = i;
@@ -525,7 +526,6 @@ static int serial_sort_blocks(const uint8_t *blockbuf, const uint32_t *nblk, con
   int h_fail = 0;
   cudaMemcpyAsync(&h_fail, d_fail, 4, cudaMemcpyDeviceToHost, s);
   cudaError_t e = cudaStreamSynchronize(s);
-  delete[] h_list;
   if (e != cudaSuccess || h_fail) return -6;
   return 0;
 }
