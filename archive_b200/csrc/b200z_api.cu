@@ -1481,6 +1481,17 @@ int b200z_bzip2_decode(const uint8_t *in, size_t in_len, int verify, uint8_t *ou
   return rc;
 }
 void b200z_profile_enable(int on) { profile_enable(on != 0); }
+int b200z_crc32(const uint8_t *in, size_t in_len, uint32_t *crc) {
+  int rc = require_init();
+  if (rc) return rc;
+  if (!crc) return B200Z_E_ARG;
+  std::lock_guard<std::mutex> lk(g.mu);
+  CU(cudaSetDevice(g.device));
+  rc = stage_input(in, in_len);
+  if (rc) return rc;
+  return device_crc32((const uint8_t *)g.d_in.p, in_len, crc);
+}
+
 int b200z_bzip2_decode_shard(const uint8_t *in, size_t in_len, uint32_t rank, uint32_t world, uint8_t *out, size_t out_cap,
                              size_t *out_len, b200z_bz2_block *blocks, size_t blocks_cap, size_t *n_blocks) {
   int rc = require_init();

@@ -140,3 +140,108 @@ class ZipDecoder:
                 contents[i] = C.string_at(C.addressof(out) + off[k], min(int(out_len[k]), room[i]))
             todo = again
         return contents, statuses
+
+
+# ---------------------------------------------------------------------------------------------
+# ZipEncoder (lib/src/codecs/zip_encoder.dart:66-583)
+# ---------------------------------------------------------------------------------------------
+def _dos_time(t):  # _getTime :33-40
+    t1 = ((t.tm_min & 0x7) << 5) | (t.tm_sec // 2)
+    t2 = (t.tm_hour << 3) | (t.tm_min >> 3)
+    return ((t2 & 0xFF) << 8) | (t1 & 0xFF)
+
+
+def _dos_date(t):  # _getDate :42-49
+    d1 = ((t.tm_mon & 0x7) << 5) | t.tm_mday
+    d2 = (((t.tm_year - 1980) & 0x7F) << 1) | (t.tm_mon >> 3)
+    return ((d2 & 0xFF) << 8) | (d1 & 0xFF)
+
+
+def _b200_compress(content: bytes, method: str, level: int):
+    """-> (payload, crc32 of content): the member's data as the reference produces it -- raw DEFLATE through
+    platformZLibEncoder.encodeStream(raw: true) (:244-249), BZip2Encoder (:250-255) or the bytes themselves -- on the device."""
+    L = _ffi.ensure_init()
+    addr, n, keep = _ffi.as_buffer(content)
+    crc = C.c_uint32(0)
+    if method == "deflate":
+        cap = L.b200z_deflate_bound(n)
+        out = (C.c_uint8 * cap)()
+        out_len = C.c_size_t(0)
+        _ffi.check(L.b200z_deflate_raw(addr, n, level, 15, C.addressof(out), cap, C.byref(out_len), C.byref(crc)))
+        return C.string_at(out, out_len.value), crc.value
+    _ffi.check(L.b200z_crc32(addr, n, C.byref(crc)))
+    if method == "bzip2":
+        cap = L.b200z_bzip2_bound(n)
+        out = (C.c_uint8 * cap)()
+        out_len = C.c_size_t(0)
+        _ffi.check(L.b200z_bzip2_encode(addr, n, C.addressof(out), cap, C.byref(out_len)))
+        return C.string_at(out, out_len.value), crc.value
+    return bytes(content), crc.value
+
+
+class ZipEncoder:
+    """`ZipEncoder().encode_bytes(archive, level: 1, modified:)` (zip_encoder.dart:66-121): local headers + data, central
+    directory, (zip64) end records, written field by field as `_writeFile` :309-372 and `_writeCentralDirectory` :391-497 do.
+    Members are compressed on the device (`compress` exists so that the CPU test tier can check the container logic with a
+    stand-in).  Not mirrored: encryption, and passing already-compressed members through (`file.isCompressed`, :214-235) --
+    the ArchiveFile of this package holds content, not the source archive's bytes."""
+
+    VERSION = 20
+
+    def __init__(self, compress=None):
+        self._compress = compress or _b200_compress
+
+    def encode_bytes(self, archive, level: int = 1, modified=None, comment: str = "") -> bytes:
+        import struct
+        import time
+        out = bytearray()
+        files = []
+        for entry in archive:
+            lm = time.localtime(modified if modified is not None else entry.last_mod_time)  # DateTime.fromMillisecondsSinceEpoch
+            name = entry.name.replace("\\", "/")
+            if not entry.is_file and not name.endswith("/"):
+                name += "/"
+            method = (entry.compression or "deflate") if entry.is_file else "deflate"
+            payload, crc = b"", 0
+            if entry.is_file:
+                payload, crc = self._compress(entry.content or b"", method, level if level is not None else 6)
+            fd = dict(name=name, time=_dos_time(lm), date=_dos_date(lm), crc=crc, csize=len(payload),
+                      usize=entry.size if entry.is_file else 0, method=method, mode=entry.mode, pos=len(out),
+                      comment=getattr(entry, "comment", None) or "")
+            files.append(fd)
+            # _writeFile
+            z64 = fd["csize"] > 0xFFFFFFFF or fd["usize"] > 0xFFFFFFFF
+            extra = struct.pack("<BBBBQQ", 1, 0, 0x10, 0, fd["usize"], fd["csize"]) if z64 else b""
+            m = {"deflate": 8, "bzip2": 12}.get(method, 0)
+            nb = name.encode("utf-8")
+            out += struct.pack("<IHHHHHIIIHH", 0x04034B50, self.VERSION, 0x800, m, fd["time"], fd["date"], crc,
+                               0xFFFFFFFF if z64 else fd["csize"], 0xFFFFFFFF if z64 else fd["usize"], len(nb), len(extra))
+            out += nb + extra + payload
+        # _writeCentralDirectory
+        cd_pos = len(out)
+        any64 = False
+        for fd in files:
+            z64 = fd["csize"] > 0xFFFFFFFF or fd["usize"] > 0xFFFFFFFF or fd["pos"] > 0xFFFFFFFF
+            any64 |= z64
+            extra = struct.pack("<BBBBQQQ", 1, 0, 0x18, 0, fd["usize"], fd["csize"], fd["pos"]) if z64 else b""
+            m = {"deflate": 8, "bzip2": 12}.get(fd["method"], 0)
+            nb, cb = fd["name"].encode("utf-8"), fd["comment"].encode("utf-8")
+            out += struct.pack("<IHHHHHHIIIHHHHHII", 0x02014B50, (0 << 8) | self.VERSION, self.VERSION, 0x800, m, fd["time"],
+                               fd["date"], fd["crc"], 0xFFFFFFFF if z64 else fd["csize"], 0xFFFFFFFF if z64 else fd["usize"],
+                               len(nb), len(extra), len(cb), 0, 0, (fd["mode"] << 16) & 0xFFFFFFFF,
+                               0xFFFFFFFF if z64 else fd["pos"])
+            out += nb + extra + cb
+        cd_size = len(out) - cd_pos
+        n = len(files)
+        need64 = any64 or n > 0xFFFF or cd_size > 0xFFFFFFFF or cd_pos > 0xFFFFFFFF
+        if need64:
+            eocd64 = len(out)
+            out += struct.pack("<IQHHIIQQQQ", 0x06064B50, 0x2C, 0x2D, 0x2D, 0, 0, n, n, cd_size, cd_pos)
+            out += struct.pack("<IIQI", 0x07064B50, 0, eocd64, 1)
+        cb = (comment or "").encode("utf-8")
+        out += struct.pack("<IHHHHIIH", 0x06054B50, 0, 0xFFFF if need64 else 0, 0xFFFF if need64 else n,
+                           0xFFFF if need64 else n, 0xFFFFFFFF if need64 else cd_size, 0xFFFFFFFF if need64 else cd_pos, len(cb))
+        out += cb
+        return bytes(out)
+
+    encode = encode_bytes

@@ -122,6 +122,10 @@ int b200z_bzip2_decode_shard(const uint8_t *in, size_t in_len, uint32_t rank, ui
 int b200z_bzip2_encode(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_cap, size_t *out_len);
 size_t b200z_bzip2_bound(size_t in_len); /* output capacity that always suffices */
 
+/* getCrc32(bytes) -- crc32.dart:6-27 (CRC-32, reflected 0xEDB88320) of a host buffer, computed on the device (tile CRCs
+ * folded with x^(8n) mod P): what ZipEncoder stores for members it does not deflate (zip_encoder.dart:113-134).   */
+int b200z_crc32(const uint8_t *in, size_t in_len, uint32_t *crc);
+
 /* ---- ZIP container: ZipDecoder / ZipDirectory / ZipFileHeader / ZipFile ------------------------------------
  * b200z_zip_list   = ZipDirectory.read (zip_directory.dart:25-183) + ZipFileHeader.read (zip_file_header.dart:28-111)
  *                    + ZipFile.read (zip_file.dart:73-149), host only: no device is needed.

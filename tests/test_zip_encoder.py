@@ -1,0 +1,95 @@
+"""ZipEncoder mirror (archive_b200/zip.py; zip_encoder.dart:66-583).  CPU tier: the container logic (headers, central
+directory, zip64 end records, DOS times, name normalisation) with a stand-in compressor, read back by CPython's zipfile and by
+b200z_zip_list.  GPU tier: members compressed on the device, byte-identical payloads to the oracle's Deflate / BZip2Encoder, and a
+ZipDecoder round trip (test/zip_test.dart:400-470 does the same round trip)."""
+import bz2
+import io
+import struct
+import time
+import zipfile
+import zlib
+
+import pytest
+
+from archive_b200.zip import Archive, ArchiveFile, ZipDecoder, ZipEncoder
+
+
+def standin(content, method, level):  # test infrastructure: CPython codecs instead of the device
+    crc = zlib.crc32(content)
+    if method == "deflate":
+        co = zlib.compressobj(level, zlib.DEFLATED, -15)
+        return co.compress(content) + co.flush(), crc
+    if method == "bzip2":
+        return bz2.compress(content, 9), crc
+    return bytes(content), crc
+
+
+def make_archive():
+    arc = Archive()
+    t0 = int(time.mktime((2024, 5, 17, 13, 37, 42, 0, 0, -1)))
+    for i, (name, body, comp) in enumerate([("a.txt", b"hello zip " * 100, None), ("dir\\b.bin", bytes(range(256)) * 9, "none"),
+                                            ("c.bz2src", b"bzip me " * 500, "bzip2"), ("empty", b"", None)]):
+        f = ArchiveFile(name, len(body))
+        f.content, f.compression, f.last_mod_time, f.mode = body, comp, t0 + 2 * i, 0o100644 if i % 2 == 0 else 0o100600
+        arc.add(f)
+    d = ArchiveFile("folder", 0, is_file=False)
+    d.last_mod_time, d.mode = t0, 0o40755
+    arc.add(d)
+    return arc, t0
+
+
+def test_container_layout_with_standin():
+    arc, t0 = make_archive()
+    data = ZipEncoder(compress=standin).encode_bytes(arc, level=6, comment="made by a test")
+    z = zipfile.ZipFile(io.BytesIO(data))
+    assert z.comment == b"made by a test"
+    infos = z.infolist()
+    assert [i.filename for i in infos] == ["a.txt", "dir/b.bin", "c.bz2src", "empty", "folder/"]
+    assert [i.compress_type for i in infos] == [8, 0, 12, 8, 8]
+    for i, f in zip(infos, arc.files):
+        assert i.flag_bits == 0x800 and i.create_version == 20 and i.extract_version == 20 and i.create_system == 0
+        assert i.external_attr == (f.mode << 16) & 0xFFFFFFFF
+        if f.is_file:
+            assert z.read(i) == f.content and i.CRC == zlib.crc32(f.content) and i.file_size == len(f.content)
+    assert infos[0].date_time == (2024, 5, 17, 13, 37, 42) and infos[1].date_time == (2024, 5, 17, 13, 37, 44)
+    # `modified` overrides every member's time (zip_encoder.dart:188-191)
+    data2 = ZipEncoder(compress=standin).encode_bytes(arc, level=1, modified=t0 + 3600)
+    assert all(i.date_time == (2024, 5, 17, 14, 37, 42) for i in zipfile.ZipFile(io.BytesIO(data2)).infolist())
+    # the package's own directory reader agrees with zipfile
+    dec = ZipDecoder()
+    ents, n = dec.list(data)
+    assert n == 5 and [e.method for e in dec.entries] == [8, 0, 12, 8, 8]
+
+
+def test_zip64_end_records_when_there_are_too_many_entries():
+    arc = Archive()
+    for i in range(0x10000 + 3):
+        f = ArchiveFile(f"f{i}", 0)
+        f.compression = "none"
+        arc.add(f)
+    data = ZipEncoder(compress=standin).encode_bytes(arc)
+    eocd = data.rfind(b"PK\x05\x06")
+    assert struct.unpack_from("<HHHHII", data, eocd + 4) == (0, 0xFFFF, 0xFFFF, 0xFFFF, 0xFFFFFFFF, 0xFFFFFFFF)
+    assert data[eocd - 20:eocd - 16] == b"PK\x06\x07" and data[eocd - 76:eocd - 72] == b"PK\x06\x06"
+    assert len(zipfile.ZipFile(io.BytesIO(data)).infolist()) == 0x10003
+    ents, n = ZipDecoder().list(data)
+    assert n == 0x10003
+
+
+@pytest.mark.gpu
+def test_members_compressed_on_the_device():
+    import oracle_lib as orc
+    from archive_b200 import synth
+    arc, t0 = make_archive()
+    big = ArchiveFile("big.txt", 700_000)
+    big.content, big.last_mod_time = synth.text(700_000, stream=995).tobytes(), t0
+    arc.add(big)
+    for level in (1, 6):
+        data = ZipEncoder().encode_bytes(arc, level=level)
+        ref = ZipEncoder(compress=lambda c, m, l: ((orc.deflate(c, l)[1] if m == "deflate" else orc.bzip2_encode(c)[1] if m == "bzip2"
+                                                   else bytes(c)), zlib.crc32(c))).encode_bytes(arc, level=level)
+        assert data == ref  # payloads are the reference's Deflate / BZip2Encoder output, CRCs from the device
+        back = ZipDecoder().decode_bytes(data)
+        assert [(f.name, f.content) for f in back.files if f.is_file] == \
+               [(f.name.replace("\\", "/"), f.content) for f in arc.files if f.is_file]
+        assert zipfile.ZipFile(io.BytesIO(data)).read("big.txt") == big.content
