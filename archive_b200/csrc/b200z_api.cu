@@ -1274,6 +1274,26 @@ extern "C" int b200z_zip_list(const uint8_t *z, size_t len, b200z_zip_entry *ent
   return B200Z_OK;
 }
 
+// ZipDirectory.zipFileComment (zip_directory.dart:41-44): byte range of the archive comment, or length 0
+extern "C" int b200z_zip_comment(const uint8_t *z, size_t len, uint64_t *off, uint32_t *clen) {
+  if (off) *off = 0;
+  if (clen) *clen = 0;
+  const long long fp = zip_find_eocd(z, len);
+  if (fp < 0) return B200Z_OK;
+  if ((unsigned long long)fp + 22 > len) {
+    set_err("zip: read past the end at %lld (Dart: RangeError)", fp);
+    return B200Z_E_THROW;
+  }
+  const uint32_t n = le16(z + fp + 20);
+  if ((unsigned long long)fp + 22 + n > len) {
+    set_err("zip: comment overruns the archive (Dart: RangeError)");
+    return B200Z_E_THROW;
+  }
+  if (off) *off = (uint64_t)fp + 22;
+  if (clen) *clen = n;
+  return B200Z_OK;
+}
+
 extern "C" int b200z_zip_extract(const uint8_t *z, size_t len, const b200z_zip_entry *entries, size_t n, uint8_t *out,
                                  size_t out_cap, const uint64_t *out_off, const uint64_t *out_room, uint64_t *out_len,
                                  int32_t *status, uint32_t flags) {

@@ -73,6 +73,7 @@ class ZipDecoder:
         # gives (dart:io zlib): a member's last symbols are always decoded
         self.flags = (1 if web_eos else 0) | (0 if split_flush_points else 2)
         self.entries = []
+        self.zip_file_comment = ""
 
     def list(self, data):
         L = _ffi.lib()
@@ -82,6 +83,10 @@ class ZipDecoder:
         ents = (_ffi.ZipEntry * max(1, cnt.value))()
         _ffi.check(L.b200z_zip_list(addr, n, ents, cnt.value, C.byref(cnt)))
         self.entries = [ents[i] for i in range(cnt.value)]
+        off, clen = C.c_uint64(0), C.c_uint32(0)
+        _ffi.check(L.b200z_zip_comment(addr, n, C.byref(off), C.byref(clen)))
+        raw = bytes(memoryview(data)[off.value:off.value + clen.value]) if clen.value else b""
+        self.zip_file_comment = raw.decode("latin-1")  # readString(utf8: false) (zip_directory.dart:43)
         return ents, cnt.value
 
     def decode_bytes(self, data, verify: bool = False, password=None) -> Archive:

@@ -146,6 +146,8 @@ typedef struct {
   uint32_t has_data;         /* 0: no local header signature at local_header_off -> empty content              */
 } b200z_zip_entry;
 int b200z_zip_list(const uint8_t *zip, size_t zip_len, b200z_zip_entry *entries, size_t cap, size_t *n_entries);
+/* ZipDirectory.zipFileComment: byte range of the archive comment inside `zip` (host only). */
+int b200z_zip_comment(const uint8_t *zip, size_t zip_len, uint64_t *off, uint32_t *len);
 #define B200Z_ZIP_WEB_EOS 1u      /* flags: pure-Dart Inflate end-of-stream behaviour instead of dart:io's  */
 #define B200Z_ZIP_NO_SPLIT 2u     /* flags: do not look for full-flush points inside members                        */
 #define B200Z_ZIP_ENCRYPTED (-20)  /* status: encrypted member, not decoded                                      */

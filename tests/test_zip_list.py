@@ -83,3 +83,23 @@ def test_eocd_search_quirks():
     same_as_oracle(b"", "empty")
     same_as_oracle(b"PK\x05\x06", "only-sig")
     same_as_oracle(b"PK\x05\x06" + bytes(18), "empty-archive")
+
+
+TABLE = json.load(open(os.path.join(Z, "reference_table.json")))
+
+
+@pytest.mark.parametrize("name", [k for k in TABLE if not k.startswith("_")])
+def test_reference_table_directory(name):
+    """What the reference's own 'unzip' tests expect of the directory (test/zip_test.dart:731-775): the archive comment, the
+    number of file headers and their names."""
+    from archive_b200.zip import ZipDecoder
+    data = open(os.path.join(Z, name), "rb").read()
+    dec = ZipDecoder()
+    ents, n = dec.list(data)
+    want = TABLE[name]
+    if "Comment" in want:
+        assert dec.zip_file_comment == want["Comment"]
+    if "File" in want:
+        assert n == len(want["File"])
+        for e, h in zip(dec.entries, want["File"]):
+            assert data[e.name_off:e.name_off + e.name_len].decode() == h["Name"]
