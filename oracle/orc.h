@@ -93,4 +93,17 @@ typedef struct {
 int orc_zip_list(const uint8_t *b, size_t blen, orc_zip_entry *out, size_t cap, size_t *n_out);
 int orc_zip_member(const uint8_t *b, size_t blen, const orc_zip_entry *e, int web_eos, uint8_t **out, size_t *out_len);
 
+/* ZipEncoder container (zip_enc.c). */
+typedef struct {
+  const char *name;      /* UTF-8, zero terminated                                    */
+  const uint8_t *content;
+  size_t content_len;
+  int method;            /* 0 none, 1 deflate, 2 bzip2 (CompressionType)             */
+  int is_file;
+  uint32_t mode;
+  uint32_t dos_time, dos_date;
+  const char *comment;   /* may be NULL                                               */
+} orc_zip_member_in;
+int orc_zip_encode(const orc_zip_member_in *m, size_t n, int level, const char *comment, uint8_t **out, size_t *out_len);
+
 #endif

@@ -142,3 +142,21 @@ def zip_member(data: bytes, entry, web_eos=False):
     out, n = C.POINTER(C.c_uint8)(), C.c_size_t()
     st = L().orc_zip_member(data, C.c_size_t(len(data)), C.byref(entry), int(web_eos), C.byref(out), C.byref(n))
     return st, _take(out, n)
+
+
+class ZipMemberIn(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("content", C.c_char_p), ("content_len", C.c_size_t), ("method", C.c_int), ("is_file", C.c_int),
+                ("mode", C.c_uint32), ("dos_time", C.c_uint32), ("dos_date", C.c_uint32), ("comment", C.c_char_p)]
+
+
+def zip_encode(members, level=1, comment=""):
+    """members: [(name, content, method 'none'|'deflate'|'bzip2', is_file, mode, dos_time, dos_date, comment)] -> (status, bytes)"""
+    arr = (ZipMemberIn * max(1, len(members)))()
+    keep = []
+    for i, (name, content, method, is_file, mode, t, d, cm) in enumerate(members):
+        nb, cb = name.encode(), (cm.encode() if cm else None)
+        keep += [nb, cb, content]
+        arr[i] = ZipMemberIn(nb, content, len(content), {"none": 0, "deflate": 1, "bzip2": 2}[method], int(is_file), mode, t, d, cb)
+    out, n = C.POINTER(C.c_uint8)(), C.c_size_t()
+    st = L().orc_zip_encode(arr, C.c_size_t(len(members)), level, comment.encode(), C.byref(out), C.byref(n))
+    return st, _take(out, n)

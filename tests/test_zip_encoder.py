@@ -93,3 +93,28 @@ def test_members_compressed_on_the_device():
         assert [(f.name, f.content) for f in back.files if f.is_file] == \
                [(f.name.replace("\\", "/"), f.content) for f in arc.files if f.is_file]
         assert zipfile.ZipFile(io.BytesIO(data)).read("big.txt") == big.content
+
+
+def test_container_equals_the_oracle_restatement():
+    """The Python mirror's container bytes against oracle/zip_enc.c (a second, independent restatement of
+    zip_encoder.dart:158-497), members compressed by the oracle's Deflate / BZip2Encoder in both."""
+    import time as _t
+
+    import oracle_lib as orc
+    from archive_b200.zip import _dos_date, _dos_time
+    arc, t0 = make_archive()
+    for f in arc.files:
+        if f.name == "a.txt":
+            f.comment = "a comment"
+    comp = lambda c, m, l: ((orc.deflate(c, l)[1] if m == "deflate" else orc.bzip2_encode(c)[1] if m == "bzip2" else bytes(c)),
+                            zlib.crc32(c))
+    for level in (1, 6):
+        mine = ZipEncoder(compress=comp).encode_bytes(arc, level=level, comment="zc")
+        members = []
+        for f in arc.files:
+            lm = _t.localtime(f.last_mod_time)
+            name = f.name.replace("\\", "/") + ("/" if not f.is_file and not f.name.endswith("/") else "")
+            members.append((name, f.content or b"", (f.compression or "deflate") if f.is_file else "deflate", f.is_file, f.mode,
+                            _dos_time(lm), _dos_date(lm), getattr(f, "comment", None)))
+        st, ref = orc.zip_encode(members, level=level, comment="zc")
+        assert st == orc.OK and mine == ref
