@@ -199,6 +199,17 @@ class Deflate:
         self.crc32 = crc.value
         self._output.write_bytes(C.string_at(out, out_len.value))
 
+    @classmethod
+    def stream(cls, input: InputMemoryStream, level: int = 6, window_bits: int = 15, output: OutputMemoryStream | None = None):
+        """`Deflate.stream(input, level:, windowBits:, output:)` (deflate.dart:59-67): consumes the rest of `input`."""
+        data = input.buffer[input.position:]
+        d = cls(data, level=level, window_bits=window_bits, output=output)
+        input.position = len(input.buffer)
+        return d
+
+    def finish(self):  # deflate.dart:69 -- everything is already flushed when the constructor returns
+        return None
+
     def get_bytes(self) -> bytes:
         return self._output.get_bytes()
 
@@ -222,6 +233,12 @@ class ZLibEncoderWeb:
         _ffi.check(rc)
         return C.string_at(out, out_len.value)
 
+    def encode_stream(self, input: InputMemoryStream, output: OutputMemoryStream, level: int | None = None,
+                      window_bits: int | None = None, raw: bool = False) -> None:
+        """_zlib_encoder_web.dart:30-73: the rest of `input` is consumed."""
+        output.write_bytes(self.encode_bytes(input.buffer[input.position:], level=level, window_bits=window_bits, raw=raw))
+        input.position = len(input.buffer)
+
 
 class GZipEncoderWeb:
     """GZipEncoderWeb().encodeBytes(bytes, level:) -- _gzip_encoder_web.dart:17-100.  The reference stamps MTIME with the
@@ -238,6 +255,12 @@ class GZipEncoderWeb:
                                  C.addressof(out), cap, C.byref(out_len))
         _ffi.check(rc)
         return C.string_at(out, out_len.value)
+
+    def encode_stream(self, input: InputMemoryStream, output: OutputMemoryStream, level: int | None = None,
+                      mtime: int | None = None) -> None:
+        """_gzip_encoder_web.dart:30-100: the rest of `input` is consumed."""
+        output.write_bytes(self.encode_bytes(input.buffer[input.position:], level=level, mtime=mtime))
+        input.position = len(input.buffer)
 
 
 ZLibEncoder = ZLibEncoderWeb
