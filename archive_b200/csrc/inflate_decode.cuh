@@ -382,7 +382,7 @@ struct SpecCtx {
 };
 
 B200Z_HD void piece_add(uint32_t *pieces, uint32_t &np, uint32_t src, uint32_t start, uint32_t count) {
-  if (count == 0 || !pieces) return;
+  if (count == 0 || !pieces || np >= (uint32_t)PIECE_MAX) return;  // (the table cannot fill up: see where helpers are started)
   pieces[2 + 3 * np] = src;
   pieces[3 + 3 * np] = start;
   pieces[4 + 3 * np] = count;
@@ -909,7 +909,9 @@ B200Z_HD UnitResult inflate_decode_unit(bool active, const uint8_t *in, uint32_t
       maxl = sl.maxlen;
       maxd = sd.maxlen;
       in_block = true;
-      if (spec_on && np + G + 2u <= (uint32_t)PIECE_MAX) {  // start the helpers on the rest of the input
+      // a block can add 2G pieces (own, helper 1, own, helper 2 ... when every link of the chain breaks) and one more
+      // closes the unit: only start helpers while the piece table has room for that
+      if (spec_on && np + 2u * G + 2u <= (uint32_t)PIECE_MAX) {  // start the helpers on the rest of the input
         br.refill();
         const uint32_t p0 = 32u * br.widx - (uint32_t)br.cnt - 8u * br.lead, eb = 8u * br.in_len;
         if (eb > p0 && (eb - p0) / G >= 2u * (uint32_t)SPEC_W) {
