@@ -812,13 +812,30 @@ static int bzip2_decode_impl(const uint8_t *in, size_t in_len, int verify, uint8
     e.randomised = A.rnd; e.end_bit = A.end_bit; e.status = A.status;
     CU(bz2_launch_entropy(e, g.stream));
     const uint32_t m = k_hi - k_lo;
-    CU(cudaMemcpyAsync(h_nrec.data() + k_lo, A.n_rec, m * 4, cudaMemcpyDeviceToHost, g.stream));
-    CU(cudaMemcpyAsync(h_nblock.data() + k_lo, A.nblock, m * 4, cudaMemcpyDeviceToHost, g.stream));
-    CU(cudaMemcpyAsync(h_optr.data() + k_lo, A.orig_ptr, m * 4, cudaMemcpyDeviceToHost, g.stream));
-    CU(cudaMemcpyAsync(h_rnd.data() + k_lo, A.rnd, m * 4, cudaMemcpyDeviceToHost, g.stream));
-    CU(cudaMemcpyAsync(h_end.data() + k_lo, A.end_bit, (size_t)m * 8, cudaMemcpyDeviceToHost, g.stream));
-    CU(cudaMemcpyAsync(h_st.data() + k_lo, A.status, m * 4, cudaMemcpyDeviceToHost, g.stream));
-    CU(cudaStreamSynchronize(g.stream));
+    auto fetch = [&]() -> int {
+      CU(cudaMemcpyAsync(h_nrec.data() + k_lo, A.n_rec, m * 4, cudaMemcpyDeviceToHost, g.stream));
+      CU(cudaMemcpyAsync(h_nblock.data() + k_lo, A.nblock, m * 4, cudaMemcpyDeviceToHost, g.stream));
+      CU(cudaMemcpyAsync(h_optr.data() + k_lo, A.orig_ptr, m * 4, cudaMemcpyDeviceToHost, g.stream));
+      CU(cudaMemcpyAsync(h_rnd.data() + k_lo, A.rnd, m * 4, cudaMemcpyDeviceToHost, g.stream));
+      CU(cudaMemcpyAsync(h_end.data() + k_lo, A.end_bit, (size_t)m * 8, cudaMemcpyDeviceToHost, g.stream));
+      CU(cudaMemcpyAsync(h_st.data() + k_lo, A.status, m * 4, cudaMemcpyDeviceToHost, g.stream));
+      CU(cudaStreamSynchronize(g.stream));
+      return B200Z_OK;
+    };
+    rc = fetch();
+    if (rc) return rc;
+    // damaged blocks that the reference keeps decoding past a bad Huffman code (K7 status -3): decoded again the reference's
+    // way, one thread each (bzip2_kernels.cu: k_bz2_entropy_literal); intact streams have none
+    std::vector<uint32_t> quirk;
+    for (uint32_t k = k_lo; k < k_hi; ++k)
+      if (h_st[k] == -3) quirk.push_back(k - k_lo);
+    if (!quirk.empty()) {
+      uint32_t *d_list = (uint32_t *)((uint8_t *)g.d_small.p + 256);  // the candidate list is on the host by now
+      CU(cudaMemcpyAsync(d_list, quirk.data(), quirk.size() * 4, cudaMemcpyHostToDevice, g.stream));
+      CU(bz2_launch_entropy_literal(e, d_list, (uint32_t)quirk.size(), g.stream));
+      rc = fetch();
+      if (rc) return rc;
+    }
   }
 
   // ---- walk the chain exactly as decodeStream's loop does (:46-87) ----
@@ -840,9 +857,27 @@ static int bzip2_decode_impl(const uint8_t *in, size_t in_len, int verify, uint8
   }
   for (; !shard;) {
     if ((pos + 7) / 8 >= in_len) break;  // input.isEOS: every byte has been pulled into the bit reader
-    if (pos + 48 > total_bits) {          // _readBlockType reads 6 bytes
-      set_err("bzip2: truncated block header (Dart: RangeError)");
-      final_rc = B200Z_E_THROW;
+    if (pos + 48 > total_bits) {
+      // _readBlockType (:90-111) reads its 6 bytes one at a time: the first one that fits neither magic returns -1 before
+      // the missing bytes are asked for (RangeError)
+      static const uint8_t blk_magic[6] = {0x31, 0x41, 0x59, 0x26, 0x53, 0x59}, eos_magic[6] = {0x17, 0x72, 0x45, 0x38, 0x50, 0x90};
+      bool blk = true, eos = true, mismatch = false;
+      for (int i = 0; i < 6 && pos + 8 * (uint64_t)(i + 1) <= total_bits; ++i) {
+        const uint8_t b = (uint8_t)(be32_at_bit(in, in_len, pos + 8 * (uint64_t)i) >> 24);
+        blk = blk && b == blk_magic[i];
+        eos = eos && b == eos_magic[i];
+        if (!blk && !eos) {
+          mismatch = true;
+          break;
+        }
+      }
+      if (mismatch) {
+        set_err("bzip2: no block signature at bit %llu", (unsigned long long)pos);
+        final_rc = B200Z_E_DATA;
+      } else {
+        set_err("bzip2: truncated block header (Dart: RangeError)");
+        final_rc = B200Z_E_THROW;
+      }
       break;
     }
     while (ci < ncand && (cand[ci] & ~(1ull << 63)) < pos) ++ci;
@@ -928,7 +963,8 @@ static int bzip2_decode_impl(const uint8_t *in, size_t in_len, int verify, uint8
       if (c != 0xffffffffu) {
         b.out_bytes = h_off[c + 1] - h_off[c];
         b.crc_calc = h_crc[c];
-        if (h_irr[c]) b.flags |= B200Z_BZ2_CORRUPT_CYCLE;
+        if (h_irr[c] == 2) b.flags |= B200Z_BZ2_OVERRUN;
+        else if (h_irr[c]) b.flags |= B200Z_BZ2_CORRUPT_CYCLE;
       }
       push(b);
     }
@@ -966,8 +1002,8 @@ static int bzip2_decode_impl(const uint8_t *in, size_t in_len, int verify, uint8
       break;
     }
     n_out = (size_t)h_off[i + 1];
-    if (h_irr[i] == 2) {  // randomised block whose walk overran (:497-499): false, its bytes are already written
-      set_err("bzip2: block %u: randomised block overruns", i);
+    if (h_irr[i] == 2) {  // the run-length walk overran the block (:497-499, :628-631): false, its bytes are already written
+      set_err("bzip2: block %u: run overruns the block", i);
       final_rc = B200Z_E_DATA;
       have_eos = false;
       break;

@@ -87,6 +87,8 @@ size_t bz2_entropy_smem();
 cudaError_t bz2_launch_scan(const uint8_t *d_in, uint64_t n_bytes, unsigned long long *d_cand, uint32_t *d_ncand,
                             uint32_t cap, cudaStream_t s);
 cudaError_t bz2_launch_entropy(const Bz2Entropy &a, cudaStream_t s);
+// blocks K7 left with status -3 (a damaged block that the reference keeps decoding): d_list = their indices into a's arrays
+cudaError_t bz2_launch_entropy_literal(const Bz2Entropy &a, const uint32_t *d_list, uint32_t n_list, cudaStream_t s);
 cudaError_t bz2_launch_ibwt(const Bz2Ibwt &a, cudaStream_t s);
 void count_launch();
 void profile_enable(bool on);

@@ -116,6 +116,8 @@ struct BzSmem {
 #define BZ_OK 0
 #define BZ_DATA (-1)    // _readCompressed returned -1 -> decodeStream returns false
 #define BZ_THROW (-2)   // the Dart code would have thrown (read past the end / selector overrun)
+#define BZ_QUIRK (-3)   // _getMtfVal returned -1 after the first symbol: the reference does not look at that value and goes
+                        // on with it (:387, :306) -- k_bz2_entropy_literal decodes such a block the reference's way
 
 __global__ void __launch_bounds__(32)
 k_bz2_entropy(const uint32_t *__restrict__ words, uint64_t n_bytes, const unsigned long long *__restrict__ blk_bit,
@@ -393,7 +395,7 @@ k_bz2_entropy(const uint32_t *__restrict__ words, uint64_t n_bytes, const unsign
         }
       }
       if (derr) {
-        err = derr;
+        err = BZ_QUIRK;
         break;
       }
       sym = nsym;
@@ -408,6 +410,244 @@ k_bz2_entropy(const uint32_t *__restrict__ words, uint64_t n_bytes, const unsign
   orig_ptr[b] = optr;
   randomised[b] = rnd;
   end_bit[b] = endp;
+  status[b] = err;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K7 for damaged blocks.  _getMtfVal (:732-772) returns -1 for a code that fits no table entry, for a 21-bit code and when
+// the selectors run out; only its FIRST call is checked (:273-275).  Later on the -1 is used as a symbol: nn = -2 picks the
+// byte two places in front of the MTF list's first block (:331-347) and decoding goes on -- until the block fills up (-1),
+// the input ends (RangeError) or, often enough, an end-of-block code turns up and the block decodes to SOMETHING.  What
+// that byte is depends on the reference's own list layout (4096 bytes, 16 blocks of 16 that creep downwards and are
+// re-packed when the first reaches 0), so this path keeps exactly that layout.  One thread per block; damaged data only.
+// ---------------------------------------------------------------------------------------------
+struct BzLitSmem {
+  int32_t limit[6][24];
+  int32_t base[6][24];
+  uint16_t perm[6][258];
+  uint8_t len[6][258];
+  uint8_t minlen[6];
+  uint8_t selector[BZ_MAX_SEL + 2];
+  uint8_t seq2unseq[256];
+  uint8_t mtfa[4096];
+  int32_t mtfbase[16];
+};
+
+__global__ void __launch_bounds__(32)
+k_bz2_entropy_literal(const uint32_t *__restrict__ words, uint64_t n_bytes, const unsigned long long *__restrict__ blk_bit,
+                      const uint32_t *__restrict__ list, uint32_t n_list, uint32_t nblock_max, uint32_t *__restrict__ rec_val,
+                      uint32_t *__restrict__ rec_pos, uint32_t *__restrict__ n_rec, uint32_t *__restrict__ nblock_out,
+                      unsigned long long *__restrict__ end_bit, int32_t *__restrict__ status) {
+  __shared__ BzLitSmem S;
+  if (blockIdx.x >= n_list || threadIdx.x != 0) return;
+  const uint32_t b = list[blockIdx.x];
+  const uint64_t total_bits = n_bytes * 8;
+  BzBits br;
+  br.w = words;
+  br.n_words = (n_bytes + 3) >> 2;
+  br.seek(blk_bit[b] + 48 + 32 + 1);  // the randomised bit is K7's to report
+  uint32_t optr = br.get(8);
+  optr = (optr << 8) | br.get(8);
+  optr = (optr << 8) | br.get(8);
+  int err = 0, n_in_use = 0;
+  for (int i = 0; i < 256; ++i) S.seq2unseq[i] = 0;  // Uint8List(256): entries past numInUse read 0
+  {
+    const uint32_t used16 = br.get(16);
+    for (int i = 0; i < 16; ++i)
+      if (used16 & (0x8000u >> i)) {
+        const uint32_t m = br.get(16);
+        for (int j = 0; j < 16; ++j)
+          if (m & (0x8000u >> j)) S.seq2unseq[n_in_use++] = (uint8_t)(i * 16 + j);
+      }
+  }
+  if (n_in_use == 0) err = BZ_DATA;
+  const int alpha = n_in_use + 2;
+  int n_groups = 0, n_sel = 0;
+  if (!err) {
+    n_groups = (int)br.get(3);
+    if (n_groups < 2 || n_groups > 6) err = BZ_DATA;
+  }
+  if (!err) {
+    n_sel = (int)br.get(15);
+    if (n_sel < 1) err = BZ_DATA;
+  }
+  if (!err) {  // selectors (:160-186)
+    uint8_t pos[6];
+    for (int i = 0; i < n_groups; ++i) pos[i] = (uint8_t)i;
+    for (int i = 0; i < n_sel && !err; ++i) {
+      int j = 0;
+      while (br.get(1)) {
+        if (++j >= n_groups) {
+          err = BZ_DATA;
+          break;
+        }
+      }
+      if (err) break;
+      if (i >= BZ_MAX_SEL) {
+        err = BZ_THROW;
+        break;
+      }
+      const uint8_t tmp = pos[j];
+      for (int v = j; v > 0; --v) pos[v] = pos[v - 1];
+      pos[0] = tmp;
+      S.selector[i] = tmp;
+      if (br.bitpos() > total_bits) err = BZ_THROW;
+    }
+  }
+  for (int t = 0; t < n_groups && !err; ++t) {  // code lengths (:189-212)
+    int c = (int)br.get(5);
+    for (int i = 0; i < alpha && !err; ++i) {
+      for (;;) {
+        if (c < 1 || c > 20) {
+          err = BZ_DATA;
+          break;
+        }
+        if (br.get(1) == 0) break;
+        c += br.get(1) == 0 ? 1 : -1;
+      }
+      S.len[t][i] = (uint8_t)c;
+    }
+    if (!err && br.bitpos() > total_bits) err = BZ_THROW;
+  }
+  for (int t = 0; t < n_groups && !err; ++t) {  // _hbCreateDecodeTables (:774-813)
+    int mn = 32, mx = 0;
+    for (int i = 0; i < alpha; ++i) {
+      const int l = S.len[t][i];
+      mx = l > mx ? l : mx;
+      mn = l < mn ? l : mn;
+    }
+    S.minlen[t] = (uint8_t)mn;
+    for (int i = 0; i < 258; ++i) S.perm[t][i] = 0;
+    int pp = 0;
+    for (int l = mn; l <= mx; ++l)
+      for (int j = 0; j < alpha; ++j)
+        if (S.len[t][j] == l) S.perm[t][pp++] = (uint16_t)j;
+    int32_t *base = S.base[t], *limit = S.limit[t];
+    for (int i = 0; i < 24; ++i) base[i] = limit[i] = 0;
+    for (int i = 0; i < alpha; ++i) base[S.len[t][i] + 1]++;
+    for (int i = 1; i < 23; ++i) base[i] += base[i - 1];
+    int32_t vec = 0;
+    for (int l = mn; l <= mx; ++l) {
+      vec += base[l + 1] - base[l];
+      limit[l] = vec - 1;
+      vec <<= 1;
+    }
+    for (int l = mn + 1; l <= mx; ++l) base[l] = ((limit[l - 1] + 1) << 1) - base[l];
+  }
+
+  uint32_t nrec = 0, nblock = 0;
+  if (!err) {
+    for (int i = 0; i < 4096; ++i) S.mtfa[i] = 0;  // Uint8List(4096)
+    {
+      int kk = 4095;
+      for (int ii = 15; ii >= 0; --ii) {
+        for (int jj = 15; jj >= 0; --jj) S.mtfa[kk--] = (uint8_t)(ii * 16 + jj);
+        S.mtfbase[ii] = kk + 1;
+      }
+    }
+    const int eob = n_in_use + 1;
+    uint32_t *rv = rec_val + (size_t)b * nblock_max;
+    uint32_t *rp = rec_pos + (size_t)b * nblock_max;
+    int gpos = 0, gno = -1, gsel = 0;
+    auto get_mtf_val = [&]() -> int {  // (:732-772), -1 and all
+      if (gpos == 0) {
+        gno++;
+        if (gno >= n_sel) return -1;
+        gpos = 50;
+        gsel = S.selector[gno];
+      }
+      gpos--;
+      int zn = S.minlen[gsel];
+      int32_t zvec = (int32_t)br.get(zn);
+      for (;;) {
+        if (zn > 20) return -1;
+        if (zvec <= S.limit[gsel][zn]) break;
+        zn++;
+        zvec = (zvec << 1) | (int32_t)br.get(1);
+      }
+      const int32_t idx = zvec - S.base[gsel][zn];
+      if (idx < 0 || idx >= 258) return -1;
+      return (int)S.perm[gsel][idx];
+    };
+    int next = get_mtf_val();
+    if (next < 0) err = BZ_DATA;
+    while (!err) {
+      if (br.bitpos() > total_bits) {  // the read that produced `next` went past the end: RangeError there and then
+        err = BZ_THROW;
+        break;
+      }
+      if (next == eob) break;
+      if (next == 0 || next == 1) {
+        long long es = -1, n = 1;
+        do {
+          if (n >= 2 * 1024 * 1024) {
+            err = BZ_DATA;
+            break;
+          }
+          es += next == 0 ? n : 2 * n;
+          n *= 2;
+          next = get_mtf_val();
+        } while ((next == 0 || next == 1) && br.bitpos() <= total_bits);
+        if (err) break;
+        if (br.bitpos() > total_bits) continue;  // -> BZ_THROW at the top
+        es++;
+        if ((long long)nblock + es > (long long)nblock_max) {  // (:313-316): fills up to the limit, then -1
+          err = BZ_DATA;
+          break;
+        }
+        rv[nrec] = ((uint32_t)es << 8) | S.seq2unseq[S.mtfa[S.mtfbase[0]]];
+        rp[nrec] = nblock;
+        nrec++;
+        nblock += (uint32_t)es;
+        continue;
+      }
+      if (nblock >= nblock_max) {
+        err = BZ_DATA;
+        break;
+      }
+      int nn = next - 1;  // next == -1: nn = -2
+      uint32_t uc;
+      if (nn < 16) {
+        const int pp = S.mtfbase[0];
+        if (pp + nn < 0) {  // _mtfa[-1]: RangeError
+          err = BZ_THROW;
+          break;
+        }
+        uc = S.mtfa[pp + nn];
+        for (; nn > 0; --nn) S.mtfa[pp + nn] = S.mtfa[pp + nn - 1];
+        S.mtfa[pp] = (uint8_t)uc;  // nn = -2: the stale byte simply becomes the list's front entry
+      } else {
+        int lno = nn >> 4;
+        int pp = S.mtfbase[lno] + (nn & 15);
+        uc = S.mtfa[pp];
+        for (; pp > S.mtfbase[lno]; --pp) S.mtfa[pp] = S.mtfa[pp - 1];
+        S.mtfbase[lno]++;
+        for (; lno > 0; --lno) {
+          S.mtfbase[lno]--;
+          S.mtfa[S.mtfbase[lno]] = S.mtfa[S.mtfbase[lno - 1] + 15];
+        }
+        S.mtfbase[0]--;
+        S.mtfa[S.mtfbase[0]] = (uint8_t)uc;
+        if (S.mtfbase[0] == 0) {  // re-pack at the top (:364-377)
+          int kk = 4095;
+          for (int ii = 15; ii >= 0; --ii) {
+            for (int jj = 15; jj >= 0; --jj) S.mtfa[kk--] = S.mtfa[S.mtfbase[ii] + jj];
+            S.mtfbase[ii] = kk + 1;
+          }
+        }
+      }
+      rv[nrec] = (1u << 8) | S.seq2unseq[uc];
+      rp[nrec] = nblock;
+      nrec++;
+      nblock++;
+      next = get_mtf_val();
+    }
+    if (!err && optr >= nblock) err = BZ_DATA;
+  }
+  if (br.bitpos() > total_bits) err = BZ_THROW;
+  n_rec[b] = nrec;
+  nblock_out[b] = nblock;
+  end_bit[b] = br.bitpos();
   status[b] = err;
 }
 
@@ -588,13 +828,17 @@ __global__ void k_bz2_walk_order(const BzChain *__restrict__ chain, uint32_t n_c
   for (uint32_t j = 0; j <= g.kb; ++j) so[j] = 0xffffffffu;
   uint32_t seg = g.start_id, off = 0, visited = 0;
   while (off < c.nblock) {
-    if (seg > g.kb || sl[seg] == 0 || ++visited > g.kb + 1) {
+    if (seg > g.kb) {
       irregular[bi] = 1;
       return;
     }
     if (so[seg] != 0xffffffffu) {  // back at the start: the cycle is shorter than the block
       if (seg != g.start_id) irregular[bi] = 1;
       cycle_len[bi] = off;
+      return;
+    }
+    if (sl[seg] == 0 || ++visited > g.kb + 1) {
+      irregular[bi] = 1;
       return;
     }
     so[seg] = off;
@@ -681,7 +925,8 @@ constexpr int BZ_RLE_THREADS = 1024;
 // pass 1: per-block decoded size
 __global__ void __launch_bounds__(BZ_RLE_THREADS)
 k_bz2_rle_count(const BzChain *__restrict__ chain, const uint8_t *__restrict__ raw, uint32_t nblock_max,
-                uint32_t *__restrict__ slice_state, uint32_t *__restrict__ slice_out, unsigned long long *__restrict__ block_out) {
+                uint32_t *__restrict__ slice_state, uint32_t *__restrict__ slice_out, unsigned long long *__restrict__ block_out,
+                const uint32_t *__restrict__ cycle_len, int32_t *__restrict__ irregular) {
   __shared__ uint32_t sm_map[BZ_RLE_THREADS];
   __shared__ uint32_t sm_cnt[BZ_RLE_THREADS];
   const BzChain c = chain[blockIdx.x];
@@ -738,7 +983,18 @@ k_bz2_rle_count(const BzChain *__restrict__ chain, const uint8_t *__restrict__ r
     __syncthreads();
   }
   slice_out[(size_t)blockIdx.x * BZ_RLE_THREADS + t] = sm_cnt[t] - outn;  // exclusive
-  if (t == BZ_RLE_THREADS - 1) block_out[blockIdx.x] = sm_cnt[t];
+  if (t == BZ_RLE_THREADS - 1) {
+    // The block ends on 4 equal bytes with no count behind them (no encoder writes that; damaged data does): the reference
+    // reads the count without looking at cNBlockUsed (:708-716) -- one step further round the cycle -- writes the run
+    // and only then returns -1 (:628-631).  Same verdict as an overrunning randomised block: irregular = 2.
+    unsigned long long total = sm_cnt[t];
+    if (s == 4) {
+      const uint32_t cl = cycle_len[blockIdx.x];
+      total += src[cl ? c.nblock % cl : 0u];
+      if (irregular[blockIdx.x] == 0) irregular[blockIdx.x] = 2;
+    }
+    block_out[blockIdx.x] = total;
+  }
 }
 
 // exclusive scan of the block sizes (a few hundred values)
@@ -759,7 +1015,7 @@ __global__ void __launch_bounds__(BZ_RLE_THREADS)
 k_bz2_rle_emit(const BzChain *__restrict__ chain, const uint8_t *__restrict__ raw, uint32_t nblock_max,
                const uint32_t *__restrict__ slice_state, const uint32_t *__restrict__ slice_out,
                const unsigned long long *__restrict__ block_off, unsigned long long out_cap, uint8_t *__restrict__ out,
-               uint32_t *__restrict__ block_crc) {
+               uint32_t *__restrict__ block_crc, const uint32_t *__restrict__ cycle_len) {
   __shared__ uint32_t crc_tab[256];
   __shared__ uint32_t sm_crc[BZ_RLE_THREADS];
   __shared__ uint32_t sm_len[BZ_RLE_THREADS];
@@ -796,6 +1052,15 @@ k_bz2_rle_emit(const BzChain *__restrict__ chain, const uint8_t *__restrict__ ra
     }
     s = rle_step(s, eq);
     prev = x;
+  }
+  if (t == BZ_RLE_THREADS - 1 && s == 4) {  // a run of 4 ends the block: its count is read past the end (k_bz2_rle_count)
+    const uint32_t cl = cycle_len[blockIdx.x];
+    const uint32_t extra = src[cl ? c.nblock % cl : 0u];
+    for (uint32_t k = 0; k < extra; ++k) {
+      if (o < out_cap) out[o] = prev;
+      o++;
+      crc = (crc << 8) ^ crc_tab[(crc >> 24) ^ prev];
+    }
   }
   // combine: R(init, A||B) = R(init, A) * x^(8|B|) ^ R(0, B)
   sm_crc[t] = crc;
@@ -834,20 +1099,22 @@ template <bool EMIT>
 __global__ void k_bz2_rand(const BzChain *__restrict__ chain, uint32_t n_chain, const uint8_t *__restrict__ raw,
                            uint32_t nblock_max, unsigned long long *__restrict__ block_out,
                            const unsigned long long *__restrict__ block_off, unsigned long long out_cap, uint8_t *__restrict__ out,
-                           uint32_t *__restrict__ block_crc, int32_t *__restrict__ irregular) {
+                           uint32_t *__restrict__ block_crc, int32_t *__restrict__ irregular,
+                           const uint32_t *__restrict__ cycle_len) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_chain) return;
   const BzChain c = chain[i];
   if (!(c.flags & 1u) || c.nblock == 0) return;
   const uint8_t *src = raw + (size_t)i * nblock_max;
   const uint32_t nb = c.nblock;
+  const uint32_t cl = cycle_len[i] ? cycle_len[i] : nb;  // the walk goes round a cycle of cl <= nblock bytes (k_bz2_walk_order)
   unsigned long long o = EMIT ? block_off[i] : 0ull, o0 = o;
   uint32_t crc = 0xffffffffu;
   int r_n_to_go = 0, r_t_pos = 0;
-  uint32_t rd = 0;  // reads so far; read number q returns byte q of the cycle (which closes after nblock bytes)
+  uint32_t rd = 0;  // reads so far; read number q returns byte q of the cycle: raw[q] = raw[q mod cl] below nblock, and beyond
 #define BZ_READ(dst)                              \
   do {                                            \
-    (dst) = src[rd < nb ? rd : rd % nb];          \
+    (dst) = src[rd < nb ? rd : rd % cl];          \
     rd++;                                         \
     if (r_n_to_go == 0) {                         \
       r_n_to_go = c_bz2_rnums[r_t_pos];           \
@@ -956,6 +1223,14 @@ cudaError_t bz2_launch_entropy(const Bz2Entropy &a, cudaStream_t s) {
   return cudaGetLastError();
 }
 
+cudaError_t bz2_launch_entropy_literal(const Bz2Entropy &a, const uint32_t *d_list, uint32_t n_list, cudaStream_t s) {
+  if (n_list == 0) return cudaSuccess;
+  k_bz2_entropy_literal<<<n_list, 32, 0, s>>>(a.words, a.n_bytes, a.blk_bit, d_list, n_list, a.nblock_max, a.rec_val, a.rec_pos,
+                                              a.n_rec, a.nblock, a.end_bit, a.status);
+  count_launch();
+  return cudaGetLastError();
+}
+
 cudaError_t bz2_launch_ibwt(const Bz2Ibwt &a, cudaStream_t s) {
   if (a.n_chain == 0) return cudaSuccess;
   const BzChain *chain = reinterpret_cast<const BzChain *>(a.chain);
@@ -980,21 +1255,22 @@ cudaError_t bz2_launch_ibwt(const Bz2Ibwt &a, cudaStream_t s) {
   count_launch();
   k_bz2_periodic_fill<<<dim3(64, a.n_chain), 256, 0, s>>>(chain, a.cycle_len, a.nblock_max, a.raw);
   count_launch();
-  k_bz2_rle_count<<<a.n_chain, BZ_RLE_THREADS, 0, s>>>(chain, a.raw, a.nblock_max, a.slice_state, a.slice_out, a.block_out);
+  k_bz2_rle_count<<<a.n_chain, BZ_RLE_THREADS, 0, s>>>(chain, a.raw, a.nblock_max, a.slice_state, a.slice_out, a.block_out,
+                                                           a.cycle_len, a.irregular);
   count_launch();
   if (a.any_randomised) {
     k_bz2_rand<false><<<(a.n_chain + 31) / 32, 32, 0, s>>>(chain, a.n_chain, a.raw, a.nblock_max, a.block_out, a.block_off,
-                                                           a.out_cap, a.out, a.block_crc, a.irregular);
+                                                           a.out_cap, a.out, a.block_crc, a.irregular, a.cycle_len);
     count_launch();
   }
   k_bz2_offsets<<<1, 32, 0, s>>>(a.block_out, a.n_chain, a.block_off);
   count_launch();
   k_bz2_rle_emit<<<a.n_chain, BZ_RLE_THREADS, 0, s>>>(chain, a.raw, a.nblock_max, a.slice_state, a.slice_out, a.block_off,
-                                                     a.out_cap, a.out, a.block_crc);
+                                                     a.out_cap, a.out, a.block_crc, a.cycle_len);
   count_launch();
   if (a.any_randomised) {
     k_bz2_rand<true><<<(a.n_chain + 31) / 32, 32, 0, s>>>(chain, a.n_chain, a.raw, a.nblock_max, a.block_out, a.block_off,
-                                                          a.out_cap, a.out, a.block_crc, a.irregular);
+                                                          a.out_cap, a.out, a.block_crc, a.irregular, a.cycle_len);
     count_launch();
   }
   return cudaGetLastError();

@@ -34,14 +34,36 @@ def out_slices(out_len, ranges):
 # ---------------------------------------------------------------------------------------------
 # BZip2: blocks sharded over ranks
 # ---------------------------------------------------------------------------------------------
-BZ2_EOS, BZ2_RANDOMISED, BZ2_CORRUPT_CYCLE = 1, 2, 4
+BZ2_EOS, BZ2_RANDOMISED, BZ2_CORRUPT_CYCLE, BZ2_OVERRUN = 1, 2, 4, 8
 
 
-def bz2_walk_chain(reports, in_len: int, verify: bool):
+_BZ2_MAGIC_BLOCK, _BZ2_MAGIC_EOS = bytes.fromhex("314159265359"), bytes.fromhex("177245385090")
+
+
+def _bz2_short_magic(data, in_len: int, pos: int) -> str:
+    """_readBlockType with fewer than 48 bits left (bzip2_decoder.dart:90-111): the six bytes are read one at a time and the
+    first one that fits neither magic returns -1 (decodeStream false) BEFORE the missing bytes are asked for (RangeError)."""
+    total = in_len * 8
+    blk = eos = True
+    for i in range(6):
+        p = pos + 8 * i
+        if p + 8 > total:
+            return "throw"
+        hi, lo = data[p >> 3], (data[(p >> 3) + 1] if (p >> 3) + 1 < in_len else 0)
+        b = (((hi << 8) | lo) >> (8 - (p & 7))) & 0xFF
+        blk = blk and b == _BZ2_MAGIC_BLOCK[i]
+        eos = eos and b == _BZ2_MAGIC_EOS[i]
+        if not blk and not eos:
+            return "data"
+    return "throw"
+
+
+def bz2_walk_chain(reports, in_len: int, verify: bool, data=None):
     """Merge the block reports of all ranks and walk them exactly as BZip2Decoder.decodeStream does
     (bzip2_decoder.dart:46-87): the stream is the chain of blocks in which every block starts on the bit where the
     previous one ended, up to the first end-of-stream magic; CRCs are compared only when `verify`.
-    reports: iterable of (start_bit, end_bit, out_bytes, crc_calc, crc_stored, status, flags, rank, local_off).
+    reports: iterable of (start_bit, end_bit, out_bytes, crc_calc, crc_stored, status, flags, rank, local_off);
+    data: the stream (anything indexable to ints), looked at only when it ends inside a block signature.
     -> (kind, chain, n_out): kind 'ok' | 'data' (decodeStream returns false) | 'throw' (RangeError); chain = the
     reports that make up the output, in order; n_out = bytes of output that are kept."""
     by_start = {}
@@ -53,7 +75,7 @@ def bz2_walk_chain(reports, in_len: int, verify: bool):
         if (pos + 7) // 8 >= in_len:
             break
         if pos + 48 > total_bits:
-            kind = "throw"
+            kind = _bz2_short_magic(data, in_len, pos) if data is not None else "throw"
             break
         r = by_start.get(pos)
         if r is None:
@@ -80,6 +102,9 @@ def bz2_walk_chain(reports, in_len: int, verify: bool):
             break
         kept.append(r)
         n_out += r[2]
+        if r[6] & BZ2_OVERRUN:  # the bytes are written before the reference notices (bzip2_decoder.dart:628-631)
+            kind, eos = "data", None
+            break
         if verify and r[3] != r[4]:
             kind, eos = "data", None
             break
@@ -132,7 +157,7 @@ def bzip2_decode_sharded(data, verify: bool = False, group=None, rank=None, worl
         reports = [r for part in gathered for r in part]
     else:
         reports = mine
-    kind, chain, n_out = bz2_walk_chain(reports, n, verify)
+    kind, chain, n_out = bz2_walk_chain(reports, n, verify, data=(C.c_uint8 * n).from_address(addr) if n else b"")
     pieces, pos = [], 0
     view = memoryview(out)
     for r in chain:

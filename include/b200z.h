@@ -113,6 +113,8 @@ typedef struct {
 #define B200Z_BZ2_EOS 1u            /* an end-of-stream magic (crc_stored = the combined CRC) */
 #define B200Z_BZ2_RANDOMISED 2u     /* (unused: randomised blocks are decoded)                */
 #define B200Z_BZ2_CORRUPT_CYCLE 4u  /* inverse BWT is not one cycle: not decoded              */
+#define B200Z_BZ2_OVERRUN 8u        /* the run-length walk overran the block (bzip2_decoder.dart:497-499, 628-631):
+                                     * its bytes ARE written, then decodeStream returns false */
 int b200z_bzip2_decode_shard(const uint8_t *in, size_t in_len, uint32_t rank, uint32_t world, uint8_t *out,
                              size_t out_cap, size_t *out_len, b200z_bz2_block *blocks, size_t blocks_cap,
                              size_t *n_blocks);

@@ -40,6 +40,19 @@ def pytest_configure(config):
                        check=True)
 
 
+    # the BZip2 decode kernels on the emulation, from a generated copy of the product source (gen_bz2dec.py)
+    sys.path.insert(0, emul)
+    import gen_bz2dec
+    inc = gen_bz2dec.generate(ROOT)
+    src = os.path.join(emul, "bz2dec_emul.cpp")
+    so = os.path.join(emul, "libbz2dec_emul.so")
+    deps = [src, inc, os.path.join(emul, "cuda_emu.h"), os.path.join(csrc, "b200z_internal.h"), os.path.join(csrc, "bz2_rnums.h"),
+            os.path.join(ROOT, "include", "b200z.h")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
+        subprocess.run(["g++", "-O2", "-g", "-fPIC", "-shared", "-std=c++17", "-I", os.path.join(emul, "shim"), "-I", emul, "-I",
+                        csrc, src, "-o", so], check=True)
+
+
 def pytest_collection_modifyitems(config, items):
     try:
         import torch

@@ -398,6 +398,13 @@ template <class T>
 static inline T __ldg(const T *p) {
   return *p;
 }
+// CUDA's global-namespace min / max overloads (device code calls them unqualified)
+static inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
+static inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }
+static inline int min(int a, int b) { return a < b ? a : b; }
+static inline int max(int a, int b) { return a > b ? a : b; }
+static inline unsigned long long min(unsigned long long a, unsigned long long b) { return a < b ? a : b; }
+static inline unsigned long long max(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
 static inline unsigned umin(unsigned a, unsigned b) { return a < b ? a : b; }
 static inline unsigned umax(unsigned a, unsigned b) { return a > b ? a : b; }
 static inline unsigned long long ullmin(unsigned long long a, unsigned long long b) { return a < b ? a : b; }

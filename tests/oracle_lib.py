@@ -160,3 +160,51 @@ def zip_encode(members, level=1, comment=""):
     out, n = C.POINTER(C.c_uint8)(), C.c_size_t()
     st = L().orc_zip_encode(arr, C.c_size_t(len(members)), level, comment.encode(), C.byref(out), C.byref(n))
     return st, _take(out, n)
+
+
+_BD = None
+
+
+def emul_bzip2_decode(data: bytes, verify: bool = True, cap: int | None = None):
+    """The device BZip2 decoder's kernels (magic scan, entropy decode, inverse BWT, RLE, CRC) run on the CUDA emulation
+    (tests/host_emul/bz2dec_emul.cpp); the block chain is walked by the product's host logic (archive_b200/shard.py).
+    -> (status, output, n_block_reports): status OK, FALSE (decodeStream returns false) or THROW (RangeError)."""
+    global _BD
+    import sys
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    from archive_b200._ffi import Bz2Block
+    from archive_b200.shard import bz2_walk_chain
+    if _BD is None:
+        _BD = C.CDLL(os.path.join(ROOT, "tests", "host_emul", "libbz2dec_emul.so"))
+    n = len(data)
+    cap = cap or max(1 << 20, n * 8)
+    cap_blocks = n // 8 + 64
+    blocks = (Bz2Block * cap_blocks)()
+    while True:
+        out = (C.c_uint8 * cap)()
+        out_len, nb, empty = C.c_size_t(), C.c_size_t(), C.c_int()
+        rc = _BD.emu_bzip2_blocks(data, C.c_size_t(n), out, C.c_size_t(cap), C.byref(out_len), blocks,
+                                  C.c_size_t(cap_blocks), C.byref(nb), C.byref(empty))
+        if rc == -3 and out_len.value > cap:
+            cap = out_len.value + 64
+            continue
+        break
+    if rc:
+        return {-1: FALSE, -2: THROW}[rc], b"", 0
+    if empty.value:
+        return 0, b"", 0
+    reports, off = [], 0
+    for i in range(nb.value):
+        b = blocks[i]
+        reports.append((b.start_bit, b.end_bit, b.out_bytes, b.crc_calc, b.crc_stored, b.status, b.flags, 0, off))
+        off += b.out_bytes
+    kind, chain, n_out = bz2_walk_chain(reports, n, verify, data=data)
+    body = b"".join(bytes(out[r[8]:r[8] + r[2]]) for r in chain)
+    assert len(body) == n_out
+    return {"ok": OK, "data": FALSE, "throw": THROW}[kind], body, nb.value
+
+
+def emul_bzip2_last_quirk() -> int:
+    """Blocks of the last emul_bzip2_decode call that took the literal path (k_bz2_entropy_literal)."""
+    return int(_BD.emu_bzip2_last_quirk()) if _BD is not None else 0

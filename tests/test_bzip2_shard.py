@@ -106,6 +106,61 @@ def test_shards_reassemble_on_one_gpu():
     assert kind == "data" and n_out == len(ref_ok)
 
 
+def test_chain_walk_overrun_and_short_signature():
+    # a block whose run-length walk overran: its bytes count, then the stream is false -- whatever `verify` says
+    n = 1000
+    blocks = [rep(32, 3000, 100, 11), rep(3000, 6000, 250, 22, flags=shard.BZ2_OVERRUN), rep(6000, 7000, 50, 33)]
+    for verify in (False, True):
+        kind, chain, n_out = shard.bz2_walk_chain(blocks, n, verify)
+        assert (kind, n_out, len(chain)) == ("data", 350, 2)
+    # the stream ends inside the next block signature (bzip2_decoder.dart:90-111): a byte that fits neither magic -> false,
+    # a proper prefix of either magic -> RangeError; without the stream at hand the walk can only say RangeError
+    head = [rep(32, 7968, 10, 5)]
+    for tail, want in ((b"\x31\x41\x59", "throw"), (b"\x17\x72", "throw"), (b"\x31\x42", "data"), (b"\x00", "data"),
+                       (b"\x17\x72\x45\x38\x50", "throw"), (b"\x31\x41\x59\x26\x53\x58"[:5], "throw")):
+        data = bytes(996) + tail
+        assert shard.bz2_walk_chain(head, len(data), False, data=data)[0] == want, tail
+        assert shard.bz2_walk_chain(head, len(data), False)[0] == "throw"
+    # not byte aligned: the signature starts 3 bits into a byte
+    bits = "0" * (8 * 996 + 3) + "".join(f"{b:08b}" for b in b"\x31\x41") + "00000"
+    data = int(bits, 2).to_bytes(len(bits) // 8, "big")
+    assert shard.bz2_walk_chain([rep(32, 8 * 996 + 3, 10, 5)], len(data), False, data=data)[0] == "throw"
+    bits = "0" * (8 * 996 + 3) + "".join(f"{b:08b}" for b in b"\x31\x40") + "00000"
+    data = int(bits, 2).to_bytes(len(bits) // 8, "big")
+    assert shard.bz2_walk_chain([rep(32, 8 * 996 + 3, 10, 5)], len(data), False, data=data)[0] == "data"
+
+
+@pytest.mark.gpu
+def test_shards_agree_on_damaged_streams():
+    """The damaged-stream fixtures (tests/golden/manifest.json) through the sharded path: bytes a block has written before the
+    reference notices an overrun are kept (B200Z_BZ2_OVERRUN), a block decoded by the literal entropy kernel is reported
+    like any other."""
+    import hashlib
+    import json
+    import os
+    import oracle_lib as orc
+    G = os.path.join(os.path.dirname(__file__), "golden")
+    man = json.load(open(os.path.join(G, "manifest.json")))
+    for name in ("bz2_mtfval_quirk_a.bz2", "bz2_short_cycle.bz2", "bz2_rand_overrun_a.bz2", "bz2_run_at_block_end_a.bz2"):
+        z = open(os.path.join(G, name), "rb").read()
+        for world in (1, 2):
+            parts = [shard.bzip2_decode_sharded(z, rank=r, world=world) for r in range(world)]
+            reports = [x for p in parts for x in p["reports"]]
+            out = bytearray()
+            total = None
+            for r, p in enumerate(parts):
+                others = [x for q, pp in enumerate(parts) if q != r for x in pp["reports"]]
+                mine = shard.bzip2_decode_sharded(z, verify=False, rank=r, world=world, reports_in=others)
+                total = mine["total"]
+                out.extend(b"\0" * max(0, total - len(out)))
+                for off, v in mine["pieces"]:
+                    out[off:off + len(v)] = v
+                kind = mine["kind"]
+            st = {"ok": orc.OK, "data": orc.FALSE, "throw": orc.THROW}[kind]
+            assert st == man[name]["status"] and total == man[name]["size"], (name, world, kind, total)
+            assert hashlib.sha256(bytes(out)).hexdigest() == man[name]["sha256"], (name, world)
+
+
 def test_zip_member_packing():
     sizes = [10, 500, 20, 499, 498, 1, 0, 300]
     bins = shard.pack_members(sizes, 3)
