@@ -40,14 +40,23 @@ def pytest_configure(config):
                        check=True)
 
 
-    # the BZip2 decode kernels on the emulation, from a generated copy of the product source (gen_bz2dec.py)
+    # the BZip2 decode kernels on the emulation, from a generated copy of the product source (gen_emul.py)
     sys.path.insert(0, emul)
-    import gen_bz2dec
-    inc = gen_bz2dec.generate(ROOT)
+    import gen_emul
+    inc = gen_emul.generate(ROOT, "bzip2_kernels.cu")
     src = os.path.join(emul, "bz2dec_emul.cpp")
     so = os.path.join(emul, "libbz2dec_emul.so")
     deps = [src, inc, os.path.join(emul, "cuda_emu.h"), os.path.join(csrc, "b200z_internal.h"), os.path.join(csrc, "bz2_rnums.h"),
             os.path.join(ROOT, "include", "b200z.h")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
+        subprocess.run(["g++", "-O2", "-g", "-fPIC", "-shared", "-std=c++17", "-I", os.path.join(emul, "shim"), "-I", emul, "-I",
+                        csrc, src, "-o", so], check=True)
+
+    # the Deflate encoder kernels + their host driver on the emulation (gen_emul.py)
+    inc = gen_emul.generate(ROOT, "deflate_kernels.cu")
+    src = os.path.join(emul, "deflate_emul.cpp")
+    so = os.path.join(emul, "libdeflate_emul.so")
+    deps = [src, inc, os.path.join(emul, "cuda_emu.h"), os.path.join(csrc, "b200z_internal.h"), os.path.join(ROOT, "include", "b200z.h")]
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
         subprocess.run(["g++", "-O2", "-g", "-fPIC", "-shared", "-std=c++17", "-I", os.path.join(emul, "shim"), "-I", emul, "-I",
                         csrc, src, "-o", so], check=True)

@@ -1,7 +1,7 @@
 // bz2dec_emul.cpp -- TEST INFRASTRUCTURE: the BZip2 decode kernels (K6 magic scan, K7 entropy decode, K8 inverse BWT /
 // RLE / CRC) of archive_b200/csrc/bzip2_kernels.cu executed on the CUDA execution-model emulation, so that the CPU test
 // tier covers them.  The kernels and their launch order are compiled from a generated copy of the product file
-// (gen_bz2dec.py: only the <<<>>> syntax, the dynamic shared memory declaration and a prefetch hint differ).
+// (gen_emul.py: only the <<<>>> syntax, the dynamic shared memory declaration and a prefetch hint differ).
 //
 // The entry point has the shape of b200z_bzip2_decode_shard with world = 1: every block candidate is decoded and
 // reported; the caller walks the chain with archive_b200/shard.py (bz2_walk_chain), the same host logic the multi-GPU

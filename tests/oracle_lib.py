@@ -208,3 +208,21 @@ def emul_bzip2_decode(data: bytes, verify: bool = True, cap: int | None = None):
 def emul_bzip2_last_quirk() -> int:
     """Blocks of the last emul_bzip2_decode call that took the literal path (k_bz2_entropy_literal)."""
     return int(_BD.emu_bzip2_last_quirk()) if _BD is not None else 0
+
+
+_DE = None
+
+
+def emul_deflate_raw(data: bytes, level: int = 6, window_bits: int = 15):
+    """The device Deflate encoder (kernels + host driver of deflate_kernels.cu, levels 1..9) run on the CUDA emulation
+    (tests/host_emul/deflate_emul.cpp).  -> (rc, raw stream, stats[tokens, blocks, re-speculated chunks])"""
+    global _DE
+    if _DE is None:
+        _DE = C.CDLL(os.path.join(ROOT, "tests", "host_emul", "libdeflate_emul.so"))
+        _DE.emu_deflate_bound.restype = C.c_size_t
+    cap = _DE.emu_deflate_bound(C.c_size_t(len(data)))
+    out = (C.c_uint8 * cap)()
+    n = C.c_size_t()
+    st = (C.c_uint32 * 3)()
+    rc = _DE.emu_deflate_raw(data, C.c_size_t(len(data)), level, window_bits, out, C.c_size_t(cap), C.byref(n), st)
+    return rc, bytes(out[:n.value]), list(st)
