@@ -98,6 +98,9 @@ def lib():
     global _lib
     with _lock:
         if _lib is None:
+            if "_emu" in os.path.basename(LIB_PATH) and os.environ.get("B200Z_EMU_TESTS") != "1":
+                # tests/host_emul/libb200z_emu.so is the test tier's host build of these sources: never a codec backend
+                raise B200ZError(E_NODEVICE, f"{LIB_PATH} is the test suite's emulation build, not the product library")
             if not os.path.exists(LIB_PATH):
                 raise B200ZError(E_NODEVICE, f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; "
                                  "g.build()'` (there is no CPU fallback)")

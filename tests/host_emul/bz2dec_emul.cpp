@@ -7,11 +7,6 @@
 // reported; the caller walks the chain with archive_b200/shard.py (bz2_walk_chain), the same host logic the multi-GPU
 // path uses.
 #include "cuda_emu.h"
-enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
-template <typename K>
-static inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int) {
-  return cudaSuccess;
-}
 #include "b200z_internal.h"
 namespace b200z {
 void count_launch() {}

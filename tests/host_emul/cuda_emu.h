@@ -6,7 +6,8 @@
 // __syncthreads() and at warp collectives, CTAs run one after another in blockIdx order. `__shared__` becomes `static`
 // (valid because only one CTA is alive at a time). Nothing here is used by the product library.
 //
-// Include in exactly ONE translation unit.
+// Several translation units of one library may include it: each gets its own scheduler state (launches complete before they
+// return, so nothing is shared) and the context switch is a weak symbol.
 #pragma once
 #if !defined(__x86_64__)
 #error "cuda_emu.h needs x86-64"
@@ -52,6 +53,89 @@ static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSucce
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline const char *cudaGetErrorString(cudaError_t) { return "emulated"; }
 
+// ---- the rest of the runtime API the product's host layer uses: "device" memory is host memory, streams and events are
+// tokens (every launch and copy completes before it returns) ----
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+template <typename K>
+static inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int) {
+  return cudaSuccess;
+}
+enum { cudaHostAllocDefault = 0, cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2 };
+enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16 };
+typedef void *cudaEvent_t;
+static inline cudaError_t cudaMalloc(void **p, size_t n) {
+  *p = malloc(n ? n : 1);
+  if (!*p) return 2;
+  memset(*p, 0xCD, n);  // device memory is not zeroed: poison it so that reliance on zeros shows
+  return cudaSuccess;
+}
+template <typename T>
+static inline cudaError_t cudaMalloc(T **p, size_t n) {
+  return cudaMalloc((void **)p, n);
+}
+static inline cudaError_t cudaFree(void *p) {
+  free(p);
+  return cudaSuccess;
+}
+static inline cudaError_t cudaHostAlloc(void **p, size_t n, unsigned) {
+  *p = malloc(n ? n : 1);
+  return *p ? cudaSuccess : 2;
+}
+template <typename T>
+static inline cudaError_t cudaHostAlloc(T **p, size_t n, unsigned f) {
+  return cudaHostAlloc((void **)p, n, f);
+}
+static inline cudaError_t cudaFreeHost(void *p) {
+  free(p);
+  return cudaSuccess;
+}
+static inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) {
+  memmove(d, s, n);
+  return cudaSuccess;
+}
+static inline cudaError_t cudaMemGetInfo(size_t *free_b, size_t *total_b) {
+  *free_b = (size_t)6 << 30;
+  *total_b = (size_t)8 << 30;
+  return cudaSuccess;
+}
+static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+static inline cudaError_t cudaGetDevice(int *d) {
+  *d = 0;
+  return cudaSuccess;
+}
+static inline cudaError_t cudaGetDeviceCount(int *n) {
+  *n = 1;
+  return cudaSuccess;
+}
+static inline cudaError_t cudaDeviceGetAttribute(int *v, cudaDeviceAttr, int) {
+  *v = 148;
+  return cudaSuccess;
+}
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) {
+  *s = malloc(1);
+  return cudaSuccess;
+}
+static inline cudaError_t cudaStreamDestroy(cudaStream_t s) {
+  free(s);
+  return cudaSuccess;
+}
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
+static inline cudaError_t cudaEventCreate(cudaEvent_t *e) {
+  *e = malloc(1);
+  return cudaSuccess;
+}
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { return cudaEventCreate(e); }
+static inline cudaError_t cudaEventDestroy(cudaEvent_t e) {
+  free(e);
+  return cudaSuccess;
+}
+static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) { return cudaSuccess; }
+static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) {
+  *ms = 0.f;
+  return cudaSuccess;
+}
+
 #define __global__
 #define __device__
 #define __host__
@@ -64,7 +148,7 @@ static inline const char *cudaGetErrorString(cudaError_t) { return "emulated"; }
 extern "C" void cuemu_switch(void **save_sp, void *new_sp);
 asm(R"(
 .text
-.globl cuemu_switch
+.weak cuemu_switch
 .type cuemu_switch,@function
 cuemu_switch:
   pushq %rbp
@@ -403,6 +487,8 @@ static inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
 static inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
+static inline unsigned long min(unsigned long a, unsigned long b) { return a < b ? a : b; }
+static inline unsigned long max(unsigned long a, unsigned long b) { return a > b ? a : b; }
 static inline unsigned long long min(unsigned long long a, unsigned long long b) { return a < b ? a : b; }
 static inline unsigned long long max(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
 static inline unsigned umin(unsigned a, unsigned b) { return a < b ? a : b; }

@@ -4,11 +4,6 @@
 // against the oracle's line-by-line Deflate.  Compiled from a generated copy of the product file (gen_emul.py: only the
 // <<<>>> syntax and the dynamic shared memory declarations differ).
 #include "cuda_emu.h"
-enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
-template <typename K>
-static inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int) {
-  return cudaSuccess;
-}
 #include "b200z_internal.h"
 namespace b200z {
 void count_launch() {}
