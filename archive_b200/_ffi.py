@@ -15,6 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B200Z_LIB") or os.path.join(_HERE, "libb200z.so")
 
 OK, E_NODEVICE, E_ARG, E_NOSPC, E_DATA, E_THROW, E_INTERNAL = 0, -1, -2, -3, -4, -5, -6
+FILE_GZIP_DECODE, FILE_ZLIB_DECODE, FILE_BZIP2_DECODE, FILE_ZLIB_ENCODE, FILE_GZIP_ENCODE, FILE_BZIP2_ENCODE = 1, 2, 3, 4, 5, 6
 U_DONE, U_EOS, U_STOP, U_NOSPC, U_RANGE, U_BADCODE, U_THROW, U_TOKCAP = 0, 1, -1, -2, -3, -4, -5, -6
 
 
@@ -81,6 +82,9 @@ _SIGS = {
                                            C.POINTER(C.c_size_t), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "b200z_bzip2_encode": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "b200z_bzip2_bound": (C.c_size_t, [C.c_size_t]),
+    "b200z_file_codec": (C.c_int, [C.c_int, C.c_char_p, C.c_uint64, C.c_uint64, C.c_char_p, C.c_uint64, C.c_int32, C.c_int32,
+                                   C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "b200z_file_last_stats": (None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "b200z_inflate_batch": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "b200z_inflate_workspace_bytes": (C.c_size_t, [C.c_size_t, C.c_size_t, C.c_size_t]),

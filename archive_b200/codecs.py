@@ -13,9 +13,50 @@ no Dart SDK exists in the build image, so the parity tests drive this Python mir
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 from . import _ffi
-from .streams import BIG_ENDIAN, InputMemoryStream, OutputMemoryStream
+from .streams import BIG_ENDIAN, InputFileStream, InputMemoryStream, OutputFileStream, OutputMemoryStream
+
+
+def _rest(input):
+    """The rest of an input stream as one bytes-like object (InputStream.toUint8List)."""
+    if isinstance(input, InputFileStream):
+        return input.to_uint8_list()
+    return input.buffer[input.position:]
+
+
+def _consume(input):
+    """decodeStream / encodeStream read their input to its end."""
+    if isinstance(input, InputFileStream):
+        input.skip(max(0, input.length))
+    else:
+        input.position = len(input.buffer)
+
+
+def _both_files(input, output) -> bool:
+    return isinstance(input, InputFileStream) and isinstance(output, OutputFileStream)
+
+
+def _file_codec(op: int, input: InputFileStream, output: OutputFileStream, a0: int = 0, a1: int = 0, a2: int = 0) -> int:
+    """InputFileStream -> codec -> OutputFileStream without the bytes passing through the host language: the library gets
+    the two paths and byte ranges (b200z_file_codec, include/b200z.h; csrc/b200z_file.cu)."""
+    L = _ffi.ensure_init()
+    path, off, n = input.file_range()
+    opath, ooff = output.file_tail()
+    used, got = C.c_uint64(0), C.c_uint64(0)
+    rc = L.b200z_file_codec(op, os.fsencode(path), off, n, os.fsencode(opath), ooff, a0, a1, a2 & 0xFFFFFFFF,
+                            C.byref(used), C.byref(got))
+    output.advanced(got.value)
+    input.skip(n)
+    return rc
+
+
+def _stream_result(rc: int) -> bool:
+    if rc == _ffi.E_DATA:
+        return False
+    _ffi.check(rc)
+    return True
 
 
 def _grow_call(fn, in_addr, in_len, first_cap):
@@ -50,7 +91,7 @@ class Inflate:
 
     def _inflate(self, size_hint):
         L = _ffi.ensure_init()
-        view = self._input.buffer[self._input.position:]
+        view = _rest(self._input)
         if len(view) == 0:
             return
         addr, n, keep = _ffi.as_buffer(view)
@@ -64,7 +105,7 @@ class Inflate:
         self.status = ust.value
         if got:
             self._output.write_bytes(C.string_at(out, got))
-        self._input.position += used.value
+        self._input.position += used.value  # (a file stream's setter skips forward)
         _ffi.check(rc)
 
     def get_bytes(self) -> bytes:
@@ -88,22 +129,23 @@ class _FramedDecoder:
 
     def decode_stream(self, input: InputMemoryStream, output: OutputMemoryStream, verify: bool = False,
                       raw: bool = False) -> bool:
+        if _both_files(input, output):
+            return _stream_result(_file_codec(self._file_op, input, output, int(verify), int(raw)))
         L = _ffi.ensure_init()
-        view = input.buffer[input.position:]
+        view = _rest(input)
         addr, n, keep = _ffi.as_buffer(view)
         out_len = C.c_size_t(0)
         rc, out, got = _grow_call(lambda oa, cap: self._call(L, addr, n, verify, raw, oa, cap, out_len),
                                   addr, n, self._first_cap(L, addr, n))
         if got:
             output.write_bytes(C.string_at(out, got))
-        input.position = len(input.buffer)
-        if rc == _ffi.E_DATA:
-            return False
-        _ffi.check(rc)
-        return True
+        _consume(input)
+        return _stream_result(rc)
 
 
 class ZLibDecoderWeb(_FramedDecoder):
+    _file_op = _ffi.FILE_ZLIB_DECODE
+
     def _first_cap(self, L, addr, n):
         return 4 * n + 1024
 
@@ -113,6 +155,8 @@ class ZLibDecoderWeb(_FramedDecoder):
 
 
 class GZipDecoderWeb(_FramedDecoder):
+    _file_op = _ffi.FILE_GZIP_DECODE
+
     def _first_cap(self, L, addr, n):
         return L.b200z_gzip_bound(addr, n) or 4 * n + 1024
 
@@ -137,8 +181,10 @@ class BZip2Decoder:
         return out.get_bytes()
 
     def decode_stream(self, input: InputMemoryStream, output: OutputMemoryStream, verify: bool = False) -> bool:
+        if _both_files(input, output):
+            return _stream_result(_file_codec(_ffi.FILE_BZIP2_DECODE, input, output, int(verify)))
         L = _ffi.ensure_init()
-        view = input.buffer[input.position:]
+        view = _rest(input)
         addr, n, keep = _ffi.as_buffer(view)
         out_len = C.c_size_t(0)
 
@@ -149,11 +195,8 @@ class BZip2Decoder:
         rc, out, got = _grow_call(call, addr, n, 6 * n + 4096)
         if got:
             output.write_bytes(C.string_at(out, got))
-        input.position = len(input.buffer)
-        if rc == _ffi.E_DATA:
-            return False
-        _ffi.check(rc)
-        return True
+        _consume(input)
+        return _stream_result(rc)
 
 
 class BZip2Encoder:
@@ -168,15 +211,18 @@ class BZip2Encoder:
     encode = encode_bytes
 
     def encode_stream(self, input: InputMemoryStream, output: OutputMemoryStream) -> bool:
+        if _both_files(input, output):
+            _ffi.check(_file_codec(_ffi.FILE_BZIP2_ENCODE, input, output))
+            return True
         L = _ffi.ensure_init()
-        view = input.buffer[input.position:]
+        view = _rest(input)
         addr, n, keep = _ffi.as_buffer(view)
         cap = L.b200z_bzip2_bound(n)
         out = (C.c_uint8 * cap)()
         out_len = C.c_size_t(0)
         _ffi.check(L.b200z_bzip2_encode(addr, n, C.addressof(out), cap, C.byref(out_len)))
         output.write_bytes(C.string_at(out, out_len.value))
-        input.position = len(input.buffer)
+        _consume(input)
         return True
 
 
@@ -202,9 +248,8 @@ class Deflate:
     @classmethod
     def stream(cls, input: InputMemoryStream, level: int = 6, window_bits: int = 15, output: OutputMemoryStream | None = None):
         """`Deflate.stream(input, level:, windowBits:, output:)` (deflate.dart:59-67): consumes the rest of `input`."""
-        data = input.buffer[input.position:]
-        d = cls(data, level=level, window_bits=window_bits, output=output)
-        input.position = len(input.buffer)
+        d = cls(_rest(input), level=level, window_bits=window_bits, output=output)
+        _consume(input)
         return d
 
     def finish(self):  # deflate.dart:69 -- everything is already flushed when the constructor returns
@@ -236,8 +281,12 @@ class ZLibEncoderWeb:
     def encode_stream(self, input: InputMemoryStream, output: OutputMemoryStream, level: int | None = None,
                       window_bits: int | None = None, raw: bool = False) -> None:
         """_zlib_encoder_web.dart:30-73: the rest of `input` is consumed."""
-        output.write_bytes(self.encode_bytes(input.buffer[input.position:], level=level, window_bits=window_bits, raw=raw))
-        input.position = len(input.buffer)
+        if _both_files(input, output):
+            _ffi.check(_file_codec(_ffi.FILE_ZLIB_ENCODE, input, output, 6 if level is None else level,
+                                   15 if window_bits is None else window_bits, int(raw)))
+            return
+        output.write_bytes(self.encode_bytes(_rest(input), level=level, window_bits=window_bits, raw=raw))
+        _consume(input)
 
 
 class GZipEncoderWeb:
@@ -259,8 +308,13 @@ class GZipEncoderWeb:
     def encode_stream(self, input: InputMemoryStream, output: OutputMemoryStream, level: int | None = None,
                       mtime: int | None = None) -> None:
         """_gzip_encoder_web.dart:30-100: the rest of `input` is consumed."""
-        output.write_bytes(self.encode_bytes(input.buffer[input.position:], level=level, mtime=mtime))
-        input.position = len(input.buffer)
+        if _both_files(input, output):
+            import time
+            _ffi.check(_file_codec(_ffi.FILE_GZIP_ENCODE, input, output, 6 if level is None else level, 0,
+                                   int(time.time()) if mtime is None else mtime))
+            return
+        output.write_bytes(self.encode_bytes(_rest(input), level=level, mtime=mtime))
+        _consume(input)
 
 
 ZLibEncoder = ZLibEncoderWeb

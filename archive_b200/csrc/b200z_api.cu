@@ -563,6 +563,39 @@ static int gzip_fast_path(const uint8_t *in, size_t in_len, uint8_t *out, size_t
   return B200Z_OK;
 }
 
+// ---- hooks for the file-stream layer (b200z_file.cu) ----
+void set_error_text(const char *msg) { set_err("%s", msg); }
+
+// Bytes of `in` covered by whole members that carry a size hint, from offset 0 (the run gzip_fast_path would take), and the
+// output bytes their ISIZE fields promise.
+size_t gzip_hinted_prefix(const uint8_t *in, size_t n, size_t *out_bytes) {
+  size_t p = 0, o = 0;
+  while (p < n) {
+    size_t hdr_end, bsize;
+    if (gzip_header(in, n, p, &hdr_end, &bsize) != 1 || bsize == 0) break;
+    const size_t next = p + bsize;
+    if (next > n || next < hdr_end + 8) break;
+    o += le32(in + next - 4);
+    p = next;
+  }
+  if (out_bytes) *out_bytes = o;
+  return p;
+}
+
+// The hinted run at the front of `in`, decoded through the chunk pipeline: *in_used = end of the last member whose hint
+// was exact (== the whole run unless a hint lied), *out_len = the bytes those members produced.
+int gzip_decode_hinted(const uint8_t *in, size_t n, uint8_t *out, size_t out_cap, size_t *in_used, size_t *out_len) {
+  int rc = require_init();
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(g.mu);
+  CU(cudaSetDevice(g.device));
+  size_t pos = 0, out_pos = 0, needed = 0;
+  rc = gzip_fast_path(in, n, out, out_cap, &pos, &out_pos, &needed);
+  *in_used = pos;
+  *out_len = rc == B200Z_E_NOSPC ? needed : out_pos;
+  return rc;
+}
+
 // _zlib_decoder_web.dart:31-107 on staged input.
 static int zlib_decode_staged(const uint8_t *in, size_t in_len, size_t pos, int verify, int raw, int big_endian,
                               size_t out_pos, size_t out_cap, size_t *out_len_total) {
@@ -1649,6 +1682,7 @@ void b200z_shutdown(void) {
   cudaStreamSynchronize(g.stream);
   g.d_in.release(); g.d_out.release(); g.d_ws.release(); g.d_meta.release(); g.d_small.release(); g.d_bz.release();
   g.h_meta.release();
+  file_release();
   cudaStreamDestroy(g.stream);
   cudaStreamDestroy(g.s_h2d);
   cudaStreamDestroy(g.s_d2h);

@@ -94,6 +94,12 @@ void count_launch();
 void profile_enable(bool on);
 int profile_read(double *decode_ms, double *expand_ms, uint64_t *n);
 
+// ---- file streams (b200z_file.cu) and the hooks it uses (b200z_api.cu) ----
+void set_error_text(const char *msg);  // b200z_last_error() text of the calling thread
+size_t gzip_hinted_prefix(const uint8_t *in, size_t n, size_t *out_bytes);
+int gzip_decode_hinted(const uint8_t *in, size_t n, uint8_t *out, size_t out_cap, size_t *in_used, size_t *out_len);
+void file_release();  // frees the pinned segment buffers (b200z_shutdown)
+
 // ---- Deflate (deflate_kernels.cu) ----
 struct DeflStoredBlock {
   uint32_t start, len, eof;

@@ -160,6 +160,38 @@ int b200z_zip_extract(const uint8_t *zip, size_t zip_len, const b200z_zip_entry 
                       size_t out_cap, const uint64_t *out_off, const uint64_t *out_room, uint64_t *out_len,
                       int32_t *status, uint32_t flags);
 
+/* ---- file streams: InputFileStream -> codec -> OutputFileStream -------------------------------------------------
+ * decodeStream / encodeStream with an InputFileStream and an OutputFileStream (input_file_stream.dart:11-221,
+ * output_file_stream.dart:11-235; callers: extractFileToDisk, io/extract_archive_to_disk.dart:160-267, and the *_test.dart
+ * stream tests).  The reference pulls the file through a FileBuffer cache (file_buffer.dart:10, 1 KiB by default) one
+ * readByte() at a time; here the binding passes the PATHS and byte ranges and the library moves the data itself: page-locked
+ * segment buffers kept for the life of the library, filled and drained by threads with large pread()/pwrite() calls, so
+ * that reading segment k+1, decoding segment k and writing segment k-1 overlap.  GZip members with size hints are cut into
+ * segments at member boundaries (B200Z_FILE_SEG_KB, default 256 MiB of compressed bytes); every other case is one segment.
+ *
+ * Reads in_path[in_off .. in_off+in_len) (clamped to the file, as readBytes does) and writes the result to out_path from
+ * byte out_off on (the file is created if needed and NOT truncated: OutputFileStream has done that when it opened it).
+ * *in_used = bytes consumed (the streams are read to their end), *out_len = bytes written.  Return codes as for the memory
+ * entry points; on B200Z_E_DATA / B200Z_E_THROW the bytes produced before the error are in the file, as in the reference.
+ *   op                        a0       a1           a2
+ *   B200Z_FILE_GZIP_DECODE    verify   -            -        GZipDecoderWeb.decodeStream  (_gzip_decoder_web.dart:27-58)
+ *   B200Z_FILE_ZLIB_DECODE    verify   raw          -        ZLibDecoderWeb.decodeStream  (_zlib_decoder_web.dart:31-107)
+ *   B200Z_FILE_BZIP2_DECODE   verify   -            -        BZip2Decoder.decodeStream    (bzip2_decoder.dart:21-88)
+ *   B200Z_FILE_ZLIB_ENCODE    level    window_bits  raw      ZLibEncoderWeb.encodeStream  (_zlib_encoder_web.dart:30-73)
+ *   B200Z_FILE_GZIP_ENCODE    level    -            mtime    GZipEncoderWeb.encodeStream  (_gzip_encoder_web.dart:30-100)
+ *   B200Z_FILE_BZIP2_ENCODE   -        -            -        BZip2Encoder.encodeStream    (bzip2_encoder.dart:25-81)     */
+#define B200Z_FILE_GZIP_DECODE 1
+#define B200Z_FILE_ZLIB_DECODE 2
+#define B200Z_FILE_BZIP2_DECODE 3
+#define B200Z_FILE_ZLIB_ENCODE 4
+#define B200Z_FILE_GZIP_ENCODE 5
+#define B200Z_FILE_BZIP2_ENCODE 6
+int b200z_file_codec(int op, const char *in_path, uint64_t in_off, uint64_t in_len, const char *out_path, uint64_t out_off,
+                     int32_t a0, int32_t a1, uint32_t a2, uint64_t *in_used, uint64_t *out_len);
+/* How the last b200z_file_codec call of this process went: segments decoded through the member-boundary pipeline, and
+ * ranges handed to a memory entry point in one piece (tests, tuning of B200Z_FILE_SEG_KB).                          */
+void b200z_file_last_stats(uint32_t *n_segments, uint32_t *n_whole);
+
 /* ---- batched independent units (what the kernels run) --------------------------------- */
 /* n_units raw DEFLATE streams: unit u reads in_base[in_off[u] .. +in_len[u]) and writes
  * out_base[out_off[u] .. +out_cap[u]).  Per unit: out_len, status (B200Z_U_*), in_used.
