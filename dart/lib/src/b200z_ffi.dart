@@ -57,6 +57,18 @@ typedef _GzipEncodeD = int Function(
 typedef _Bz2EncodeC = Int32 Function(Pointer<Uint8> inp, Size inLen, Pointer<Uint8> out, Size outCap, Pointer<Size> outLen);
 typedef _Bz2EncodeD = int Function(Pointer<Uint8> inp, int inLen, Pointer<Uint8> out, int outCap, Pointer<Size> outLen);
 
+// b200z_file_codec (include/b200z.h): paths and byte ranges instead of bytes
+const b200zFileGzipDecode = 1;
+const b200zFileZlibDecode = 2;
+const b200zFileBzip2Decode = 3;
+const b200zFileZlibEncode = 4;
+const b200zFileGzipEncode = 5;
+const b200zFileBzip2Encode = 6;
+typedef _FileCodecC = Int32 Function(Int32 op, Pointer<Utf8> inPath, Uint64 inOff, Uint64 inLen, Pointer<Utf8> outPath,
+    Uint64 outOff, Int32 a0, Int32 a1, Uint32 a2, Pointer<Uint64> inUsed, Pointer<Uint64> outLen);
+typedef _FileCodecD = int Function(int op, Pointer<Utf8> inPath, int inOff, int inLen, Pointer<Utf8> outPath, int outOff,
+    int a0, int a1, int a2, Pointer<Uint64> inUsed, Pointer<Uint64> outLen);
+
 /// b200z_zip_entry (include/b200z.h)
 final class ZipEntry extends Struct {
   @Uint64()
@@ -130,6 +142,7 @@ class B200Z {
   late final _GzipEncodeD gzipEncode = _lib.lookupFunction<_GzipEncodeC, _GzipEncodeD>('b200z_gzip_encode');
   late final _Bz2EncodeD bzip2Encode = _lib.lookupFunction<_Bz2EncodeC, _Bz2EncodeD>('b200z_bzip2_encode');
   late final _SizeOfD bzip2Bound = _lib.lookupFunction<_SizeOfC, _SizeOfD>('b200z_bzip2_bound');
+  late final _FileCodecD fileCodec = _lib.lookupFunction<_FileCodecC, _FileCodecD>('b200z_file_codec');
   late final _ZipListD zipList = _lib.lookupFunction<_ZipListC, _ZipListD>('b200z_zip_list');
   late final _ZipExtractD zipExtract = _lib.lookupFunction<_ZipExtractC, _ZipExtractD>('b200z_zip_extract');
 
@@ -157,6 +170,27 @@ class B200Z {
     if (p == nullptr) throw B200ZException(b200zENoDevice, lastError);
     p.asTypedList(bytes.length).setAll(0, bytes);
     return p;
+  }
+
+  /// InputFileStream -> codec -> OutputFileStream without the bytes entering the Dart heap: the library reads
+  /// [inPath] from [inOff] for [inLen] bytes and writes the result into [outPath] from [outOff] on (pinned segment
+  /// buffers, threaded pread/pwrite; csrc/b200z_file.cu).  Returns (bytes written, ok); ok == false is the
+  /// reference's `decodeStream` returning false -- what was produced before the error is in the file.
+  (int, bool) fileCodecCall(int op, String inPath, int inOff, int inLen, String outPath, int outOff,
+      {int a0 = 0, int a1 = 0, int a2 = 0}) {
+    final ip = inPath.toNativeUtf8(), op_ = outPath.toNativeUtf8();
+    final used = calloc<Uint64>(), got = calloc<Uint64>();
+    try {
+      final rc = fileCodec(op, ip, inOff, inLen, op_, outOff, a0, a1, a2, used, got);
+      if (rc == b200zEThrow) throw RangeError(lastError);
+      if (rc != b200zOk && rc != b200zEData) throw B200ZException(rc, lastError);
+      return (got.value, rc == b200zOk);
+    } finally {
+      calloc.free(ip);
+      calloc.free(op_);
+      calloc.free(used);
+      calloc.free(got);
+    }
   }
 
   /// Runs [call](out, cap, outLen) growing the output buffer on B200Z_E_NOSPC; returns a Dart-owned copy.

@@ -53,6 +53,26 @@ class Inflate {
   Uint8List getBytes() => _output.getBytes();
 }
 
+/// decodeStream / encodeStream with an InputFileStream and an OutputFileStream: hand the library the two files.
+/// InputFileStream exposes its FileBuffer (`file`, input_file_stream.dart:218) but neither its path nor its offset
+/// into the file; the one-line getters INTEGRATION.md lists (`InputFileStream.path` / `.fileOffset`,
+/// `OutputFileStream.path` / `.advanced(n)`) are the only change to the reference's own classes this path needs.
+/// Returns null when the pair is not file/file (the caller then takes the in-memory route).
+bool? _fileToFile(int op, ar.InputStream input, ar.OutputStream output, {int a0 = 0, int a1 = 0, int a2 = 0}) {
+  if (input is! ar.InputFileStream || output is! ar.OutputFileStream) return null;
+  final inPath = (input as dynamic).path as String?;
+  final outPath = (output as dynamic).path as String?;
+  if (inPath == null || outPath == null) return null; // RAM file handles have no path: in-memory route
+  output.flush();
+  final start = ((input as dynamic).fileOffset as int) + input.position;
+  final n = input.length;
+  final (written, ok) =
+      B200Z.instance.fileCodecCall(op, inPath, start, n, outPath, output.length, a0: a0, a1: a1, a2: a2);
+  (output as dynamic).advanced(written); // _length += written; _fileHandle.position += written
+  input.skip(n);
+  return ok;
+}
+
 class _B200ZLibDecoder extends ar.ZLibDecoderBase {
   const _B200ZLibDecoder();
 
@@ -71,6 +91,8 @@ class _B200ZLibDecoder extends ar.ZLibDecoderBase {
 
   @override
   bool decodeStream(ar.InputStream input, ar.OutputStream output, {bool verify = false, bool raw = false}) {
+    final viaFiles = _fileToFile(b200zFileZlibDecode, input, output, a0: verify ? 1 : 0, a1: raw ? 1 : 0);
+    if (viaFiles != null) return viaFiles;
     final z = B200Z.instance;
     final data = _drain(input);
     final inp = z.toNative(data);
@@ -98,6 +120,8 @@ class _B200GZipDecoder extends ar.ZLibDecoderBase {
 
   @override
   bool decodeStream(ar.InputStream input, ar.OutputStream output, {bool verify = false, bool raw = false}) {
+    final viaFiles = _fileToFile(b200zFileGzipDecode, input, output, a0: verify ? 1 : 0);
+    if (viaFiles != null) return viaFiles;
     final z = B200Z.instance;
     final data = _drain(input);
     final inp = z.toNative(data);
@@ -133,6 +157,8 @@ class BZip2Decoder {
   }
 
   bool decodeStream(ar.InputStream input, ar.OutputStream output, {bool verify = false}) {
+    final viaFiles = _fileToFile(b200zFileBzip2Decode, input, output, a0: verify ? 1 : 0);
+    if (viaFiles != null) return viaFiles;
     final z = B200Z.instance;
     final data = _drain(input);
     final inp = z.toNative(data);
@@ -193,6 +219,7 @@ class _B200ZLibEncoder extends ar.ZLibEncoderBase {
 
   @override
   void encodeStream(ar.InputStream input, ar.OutputStream output, {int? level, int? windowBits, bool raw = false}) {
+    if (_fileToFile(b200zFileZlibEncode, input, output, a0: level ?? 6, a1: windowBits ?? 15, a2: raw ? 1 : 0) != null) return;
     output.writeBytes(encodeBytes(_drain(input), level: level, windowBits: windowBits, raw: raw));
   }
 }
@@ -216,6 +243,8 @@ class _B200GZipEncoder extends ar.ZLibEncoderBase {
 
   @override
   void encodeStream(ar.InputStream input, ar.OutputStream output, {int? level, int? windowBits, bool raw = false}) {
+    final now = DateTime.now().millisecondsSinceEpoch ~/ 1000; // _gzip_encoder_web.dart:82
+    if (_fileToFile(b200zFileGzipEncode, input, output, a0: level ?? 6, a2: now) != null) return;
     output.writeBytes(encodeBytes(_drain(input), level: level));
   }
 }
@@ -239,6 +268,7 @@ class BZip2Encoder {
   Uint8List encode(List<int> data) => encodeBytes(data);
 
   bool encodeStream(ar.InputStream input, ar.OutputStream output) {
+    if (_fileToFile(b200zFileBzip2Encode, input, output) != null) return true;
     output.writeBytes(encodeBytes(_drain(input)));
     return true;
   }
