@@ -201,3 +201,50 @@ def zip_extract_sharded(data, rank: int, world: int, web_eos: bool = False):
     sub = (_ffi.ZipEntry * len(mine))(*[ents[i] for i in mine])
     contents, statuses = dec._extract(data, sub, len(mine))
     return ents, {i: contents[k] for k, i in enumerate(mine)}
+
+
+# ---------------------------------------------------------------------------------------------
+# ZipEncoder members sharded over ranks: a member's payload depends on nothing but its own content
+# (zip_encoder.dart:185-259), so every rank compresses a share and ONE exchange of the payloads lets any rank write the
+# container -- byte for byte the archive a single rank produces.
+# ---------------------------------------------------------------------------------------------
+def zip_encode_sharded(archive, level: int = 1, modified=None, comment: str = "", group=None, rank=None, world=None,
+                       compress=None, payloads_in=None):
+    """ZipEncoder().encode_bytes(archive, ...) with the members' compression spread over the ranks of `group`.
+    Members are packed largest-first by content size (pack_members); every rank compresses its share on its own GPU, the
+    (payload, crc) pairs are exchanged with one all_gather_object, and every rank assembles the same container.
+    Without torch.distributed (`rank` / `world` given explicitly) the call returns this rank's {member index: (payload,
+    crc)} and accepts the other ranks' dictionaries as `payloads_in` -- the single-process form the tests drive.
+    `compress(content, method, level) -> (payload, crc32)` defaults to the device path (zip._b200_compress)."""
+    from .zip import ZipEncoder, _b200_compress
+    compress = compress or _b200_compress
+    entries = list(archive)
+    dist = None
+    if rank is None or world is None:
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+    sizes = [(e.size if e.is_file else 0) for e in entries]
+    mine = pack_members(sizes, world)[rank]
+    lv = level if level is not None else 6
+    done = {}
+    for i in mine:
+        e = entries[i]
+        if e.is_file:
+            method = e.compression or "deflate"
+            done[i] = compress(e.content or b"", method, lv)
+    if dist is not None:
+        parts = [None] * world
+        dist.all_gather_object(parts, done, group=group)
+    elif payloads_in is not None:
+        parts = [done] + list(payloads_in)
+    else:
+        return done
+    table = {}
+    for p in parts:
+        table.update(p)
+    order = iter(i for i, e in enumerate(entries) if e.is_file)
+
+    def lookup(content, method, level_):  # ZipEncoder asks for the members in archive order
+        return table[next(order)]
+
+    return ZipEncoder(compress=lookup).encode_bytes(entries, level=level, modified=modified, comment=comment)

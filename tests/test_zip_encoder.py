@@ -118,3 +118,79 @@ def test_container_equals_the_oracle_restatement():
                             _dos_time(lm), _dos_date(lm), getattr(f, "comment", None)))
         st, ref = orc.zip_encode(members, level=level, comment="zc")
         assert st == orc.OK and mine == ref
+
+
+def test_members_sharded_over_ranks_give_the_same_archive():
+    """the encoder's multi-GPU axis.  Ranks compress disjoint shares (largest first), exchange the payloads, and
+    any of them writes the container a single rank would have written."""
+    from archive_b200 import shard
+    arc, t0 = make_archive()
+    for k in range(9):
+        f = ArchiveFile(f"more/{k}.txt", 0)
+        f.content = (b"member %d " % k) * (50 + 37 * k)
+        f.size, f.last_mod_time, f.mode = len(f.content), t0 + k, 0o100644
+        arc.add(f)
+    want = ZipEncoder(compress=standin).encode_bytes(arc, level=6, comment="c")
+    for world in (1, 2, 3, 5):
+        shares = [shard.zip_encode_sharded(arc, level=6, rank=r, world=world, compress=standin) for r in range(world)]
+        assert sorted(i for s in shares for i in s) == [i for i, f in enumerate(arc.files) if f.is_file]
+        assert sum(len(s) for s in shares) == len({i for s in shares for i in s})  # disjoint
+        for r in range(world):
+            got = shard.zip_encode_sharded(arc, level=6, comment="c", rank=r, world=world, compress=standin,
+                                           payloads_in=[s for q, s in enumerate(shares) if q != r])
+            assert got == want, (world, r)
+
+
+def _zip_rank(rank, world, port, q):
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    sys.path.insert(0, os.path.join(root, "tests"))
+    import torch.distributed as dist
+    from archive_b200 import shard
+    import test_zip_encoder as t
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    arc, t0 = t.make_archive()
+    calls = []
+
+    def counting(content, method, level):
+        calls.append(len(content))
+        return t.standin(content, method, level)
+
+    data = shard.zip_encode_sharded(arc, level=6, compress=counting)
+    want = t.ZipEncoder(compress=t.standin).encode_bytes(arc, level=6)
+    q.put((rank, data == want, len(calls)))
+    dist.destroy_process_group()
+
+
+def test_two_gloo_ranks_encode_one_archive():
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_zip_rank, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    res = sorted(q.get(timeout=5) for _ in range(2))
+    assert [r[1] for r in res] == [True, True]
+    assert sum(r[2] for r in res) == 4 and all(r[2] > 0 for r in res)  # the four file members, split over the two ranks
+
+
+@pytest.mark.gpu
+def test_sharded_encode_on_the_device_equals_one_rank():
+    """The same, with the members compressed by the kernels (one process playing every rank in turn)."""
+    from archive_b200 import shard
+    arc, t0 = make_archive()
+    want = ZipEncoder().encode_bytes(arc, level=6)
+    shares = [shard.zip_encode_sharded(arc, level=6, rank=r, world=2) for r in range(2)]
+    assert shard.zip_encode_sharded(arc, level=6, rank=0, world=2, payloads_in=shares[1:]) == want
