@@ -13,6 +13,8 @@
 #include <algorithm>
 #include <atomic>
 #include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "b200z_internal.h"
@@ -1094,18 +1096,19 @@ static uint32_t crc_xpow8(uint64_t nbytes) {
   }
   return p;
 }
-static int device_crc32(const uint8_t *d, size_t n, uint32_t *out) {
-  const uint32_t TILE = 1u << 13;
+static const uint32_t kCrcTile = 1u << 13;
+// CRC-32 of d[0, n) on stream s: tile CRCs into d_part ((n / kCrcTile + 1) words of device memory), folded on the host
+static int device_crc32_on(const uint8_t *d, size_t n, uint32_t *d_part, cudaStream_t s, uint32_t *out) {
+  const uint32_t TILE = kCrcTile;
   if (n == 0) {
     *out = 0;
     return B200Z_OK;
   }
   size_t tiles = (n + TILE - 1) / TILE;
-  CU(g.d_small.reserve(tiles * 4 + 256));
-  CU(crc32_tiles_device(d, n, TILE, (uint32_t *)g.d_small.p, g.stream));
+  CU(crc32_tiles_device(d, n, TILE, d_part, s));
   std::vector<uint32_t> part(tiles);
-  CU(cudaMemcpyAsync(part.data(), g.d_small.p, tiles * 4, cudaMemcpyDeviceToHost, g.stream));
-  CU(cudaStreamSynchronize(g.stream));
+  CU(cudaMemcpyAsync(part.data(), d_part, tiles * 4, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
   uint32_t crc = part[0];
   const uint32_t xfull = crc_xpow8(TILE);
   for (size_t t = 1; t < tiles; ++t) {
@@ -1114,6 +1117,10 @@ static int device_crc32(const uint8_t *d, size_t n, uint32_t *out) {
   }
   *out = crc;
   return B200Z_OK;
+}
+static int device_crc32(const uint8_t *d, size_t n, uint32_t *out) {
+  CU(g.d_small.reserve((n / kCrcTile + 1) * 4 + 256));
+  return device_crc32_on(d, n, (uint32_t *)g.d_small.p, g.stream, out);
 }
 
 // the old deflate_stored (deflate.dart:691-737) touches no data: its block list follows from the length alone
@@ -1188,6 +1195,119 @@ static int deflate_staged(size_t n, int level, int window_bits, size_t *out_len)
   uint32_t stats[3];
   CU(deflate_slow_device((const uint8_t *)g.d_in.p, n, level, window_bits, (uint8_t *)g.d_out.p, cap, g.d_ws.p, g.d_ws.cap, out_len, stats,
                          g.stream));
+  return B200Z_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Many independent streams at once (ZipEncoder's members, zip_encoder.dart:185-259).  One stream's kernels are a chain
+// with three host round trips (token count, block count, bit count) and, at levels 1-3, a single serial thread: a lone
+// member leaves the device almost idle.  All inputs are staged with one burst of copies; `lanes` host threads then take
+// members off a counter, each with its own CUDA stream, workspace and output slot, so the chains of different members
+// overlap on the device.  Every member is compressed exactly as b200z_deflate_raw compresses it.
+// ---------------------------------------------------------------------------------------------
+static int deflate_member_on(const uint8_t *d_in, size_t n, int level, int window_bits, uint8_t *d_out, size_t cap, void *ws,
+                             size_t ws_bytes, cudaStream_t s, size_t *out_len, uint32_t *crc) {
+  if (level == 0) {
+    std::vector<DeflStoredBlock> bl;
+    stored_block_list(n, bl);
+    CU(deflate_stored_device(d_in, bl.data(), (uint32_t)bl.size(), d_out, cap, ws, ws_bytes, out_len, s));
+  } else {
+    uint32_t stats[3];
+    CU(deflate_slow_device(d_in, n, level, window_bits, d_out, cap, ws, ws_bytes, out_len, stats, s));
+  }
+  // the tile CRCs go to the front of the workspace: the encoder is done with it (both paths end synchronised)
+  return device_crc32_on(d_in, n, (uint32_t *)ws, s, crc);
+}
+
+static int deflate_batch_impl(const uint8_t *in_base, const uint64_t *in_off, const uint64_t *in_len, size_t n_units, int level,
+                              int window_bits, uint8_t *out_base, const uint64_t *out_off, const uint64_t *out_cap,
+                              uint64_t *out_len, uint32_t *crc32, int32_t *status) {
+  std::vector<size_t> din(n_units + 1), dout(n_units + 1);
+  size_t ws_lane = 4096, acc_in = 0, acc_out = 0;
+  for (size_t i = 0; i < n_units; ++i) {
+    const size_t n = (size_t)in_len[i];
+    if (n >= 0xffff0000ull) {
+      set_err("deflate_batch: unit %zu: inputs of 4 GiB and more are not supported", i);
+      return B200Z_E_ARG;
+    }
+    din[i] = acc_in;
+    dout[i] = acc_out;
+    acc_in += align_up(n + 64, 256);
+    acc_out += align_up(deflate_bound(n) + 16, 256);
+    size_t ws = (n / kCrcTile + 1) * 4 + 256;
+    if (level == 0) {
+      std::vector<DeflStoredBlock> bl;
+      stored_block_list(n, bl);
+      ws = std::max(ws, bl.size() * 64 + 1024);
+    } else {
+      ws = std::max(ws, deflate_workspace_bytes(n));
+    }
+    ws_lane = std::max(ws_lane, align_up(ws, 256));
+  }
+  din[n_units] = acc_in;
+  dout[n_units] = acc_out;
+  size_t lanes = Ctx::kCompStreams;
+  if (const char *e = getenv("B200Z_DEFLATE_LANES")) lanes = (size_t)atoi(e);
+  lanes = std::max<size_t>(1, std::min<size_t>(std::min<size_t>(lanes, Ctx::kCompStreams), n_units));
+  CU(g.d_in.reserve(acc_in + 64));
+  CU(g.d_out.reserve(acc_out + 64));
+  CU(g.d_ws.reserve(lanes * ws_lane));
+  cudaEvent_t staged;
+  CU(cudaEventCreateWithFlags(&staged, cudaEventDisableTiming));
+  CU(cudaMemsetAsync(g.d_in.p, 0, acc_in, g.s_h2d));  // the bytes behind every member read as zeros (as in deflate_raw)
+  for (size_t i = 0; i < n_units; ++i)
+    if (in_len[i])
+      CU(cudaMemcpyAsync((uint8_t *)g.d_in.p + din[i], in_base + in_off[i], (size_t)in_len[i], cudaMemcpyHostToDevice, g.s_h2d));
+  CU(cudaEventRecord(staged, g.s_h2d));
+  std::atomic<size_t> next{0};
+  std::vector<int> lane_rc(lanes, B200Z_OK);
+  std::vector<std::string> lane_err(lanes);
+  const int device = g.device;
+  auto lane = [&](size_t l) {
+    auto fail = [&](int rc) {
+      lane_rc[l] = rc;
+      lane_err[l] = t_err;
+      next.store(n_units);  // the other lanes stop taking members
+    };
+    if (cudaSetDevice(device) != cudaSuccess) return fail(B200Z_E_NODEVICE);  // a new thread starts on device 0
+    cudaStream_t s = g.s_comp[l];
+    if (cudaStreamWaitEvent(s, staged, 0) != cudaSuccess) return fail(B200Z_E_NODEVICE);
+    void *ws = (uint8_t *)g.d_ws.p + l * ws_lane;
+    for (;;) {
+      const size_t i = next.fetch_add(1);
+      if (i >= n_units) break;
+      size_t olen = 0;
+      uint32_t crc = 0;
+      const int rc = deflate_member_on((const uint8_t *)g.d_in.p + din[i], (size_t)in_len[i], level, window_bits,
+                                       (uint8_t *)g.d_out.p + dout[i], dout[i + 1] - dout[i], ws, ws_lane, s, &olen, &crc);
+      if (rc) return fail(rc);
+      out_len[i] = olen;
+      if (crc32) crc32[i] = crc;
+      if (olen > out_cap[i]) {
+        status[i] = B200Z_U_NOSPC;
+        continue;
+      }
+      status[i] = B200Z_OK;
+      if (olen && cudaMemcpyAsync(out_base + out_off[i], (uint8_t *)g.d_out.p + dout[i], olen, cudaMemcpyDeviceToHost, s) !=
+                      cudaSuccess)
+        return fail(B200Z_E_NODEVICE);
+    }
+    if (cudaStreamSynchronize(s) != cudaSuccess) fail(B200Z_E_NODEVICE);
+  };
+  if (lanes == 1) {
+    lane(0);
+  } else {
+    std::vector<std::thread> th;
+    for (size_t l = 1; l < lanes; ++l) th.emplace_back(lane, l);
+    lane(0);
+    for (auto &t : th) t.join();
+  }
+  cudaEventDestroy(staged);
+  for (size_t l = 0; l < lanes; ++l)
+    if (lane_rc[l]) {
+      set_err("deflate_batch: %s", lane_err[l].empty() ? "a lane failed" : lane_err[l].c_str());
+      return lane_rc[l];
+    }
   return B200Z_OK;
 }
 
@@ -1815,6 +1935,22 @@ int b200z_deflate_raw(const uint8_t *in, size_t in_len, int level, int window_bi
 }
 
 size_t b200z_deflate_bound(size_t in_len) { return deflate_bound(in_len) + 32; }
+
+int b200z_deflate_batch(const uint8_t *in_base, const uint64_t *in_off, const uint64_t *in_len, size_t n_units, int level,
+                        int window_bits, uint8_t *out_base, const uint64_t *out_off, const uint64_t *out_cap, uint64_t *out_len,
+                        uint32_t *crc32, int32_t *status) {
+  int rc = require_init();
+  if (rc) return rc;
+  if (window_bits < 9 || window_bits > 15 || level < 0 || level > 9) {
+    set_err("deflate: invalid level %d / windowBits %d (Dart: LateInitializationError)", level, window_bits);
+    return B200Z_E_ARG;
+  }
+  if (n_units == 0) return B200Z_OK;
+  std::lock_guard<std::mutex> lk(g.mu);
+  CU(cudaSetDevice(g.device));
+  return deflate_batch_impl(in_base, in_off, in_len, n_units, level, window_bits, out_base, out_off, out_cap, out_len, crc32,
+                            status);
+}
 
 int b200z_zlib_encode(const uint8_t *in, size_t in_len, int level, int window_bits, int raw, uint8_t *out, size_t out_cap,
                       size_t *out_len) {

@@ -184,6 +184,33 @@ def _b200_compress(content: bytes, method: str, level: int):
     return bytes(content), crc.value
 
 
+def deflate_batch(contents, level: int = 6, window_bits: int = 15):
+    """Raw DEFLATE of every item of `contents` with ONE b200z_deflate_batch call (all inputs staged at once, several members in
+    flight on the device) -> list of (payload, crc32).  Each payload equals Deflate(item, level:, windowBits:).getBytes()."""
+    import numpy as np
+    L = _ffi.ensure_init()
+    n = len(contents)
+    if n == 0:
+        return []
+    in_len = np.array([len(c) for c in contents], dtype=np.uint64)
+    in_off = np.zeros(n, dtype=np.uint64)
+    in_off[1:] = np.cumsum(in_len)[:-1]
+    blob = b"".join(bytes(c) for c in contents)
+    addr, nb, keep = _ffi.as_buffer(blob if blob else b"\0")
+    out_cap = np.array([L.b200z_deflate_bound(int(x)) for x in in_len], dtype=np.uint64)
+    out_off = np.zeros(n, dtype=np.uint64)
+    out_off[1:] = np.cumsum(out_cap)[:-1]
+    out = np.empty(int(out_cap.sum()), dtype=np.uint8)
+    out_len = np.zeros(n, dtype=np.uint64)
+    crc = np.zeros(n, dtype=np.uint32)
+    status = np.zeros(n, dtype=np.int32)
+    p = lambda a: a.ctypes.data
+    _ffi.check(L.b200z_deflate_batch(addr, p(in_off), p(in_len), n, level, window_bits, p(out), p(out_off), p(out_cap),
+                                     p(out_len), p(crc), p(status)))
+    assert not status.any(), "b200z_deflate_bound is an upper bound"
+    return [(out[int(out_off[i]):int(out_off[i] + out_len[i])].tobytes(), int(crc[i])) for i in range(n)]
+
+
 class ZipEncoder:
     """`ZipEncoder().encode_bytes(archive, level: 1, modified:)` (zip_encoder.dart:66-121): local headers + data, central
     directory, (zip64) end records, written field by field as `_writeFile` :309-372 and `_writeCentralDirectory` :391-497 do.
@@ -193,15 +220,30 @@ class ZipEncoder:
 
     VERSION = 20
 
-    def __init__(self, compress=None):
+    def __init__(self, compress=None, batch: bool = False):
+        """batch=True: all deflate members go to the device in one b200z_deflate_batch call (several members in flight)
+        instead of one b200z_deflate_raw call each; the archive bytes are the same."""
         self._compress = compress or _b200_compress
+        self._batch = batch and compress is None
 
     def encode_bytes(self, archive, level: int = 1, modified=None, comment: str = "") -> bytes:
         import struct
         import time
         out = bytearray()
         files = []
-        for entry in archive:
+        archive = list(archive)
+        compress = self._compress
+        if self._batch:
+            lv = level if level is not None else 6
+            idx = [i for i, e in enumerate(archive) if e.is_file and (e.compression or "deflate") == "deflate"]
+            table = dict(zip(idx, deflate_batch([archive[i].content or b"" for i in idx], lv)))
+            at = [None]
+
+            def compress(content, method, level_):
+                return table[at[0]] if method == "deflate" else self._compress(content, method, level_)
+        for pos_in_archive, entry in enumerate(archive):
+            if self._batch:
+                at[0] = pos_in_archive
             lm = time.localtime(modified if modified is not None else entry.last_mod_time)  # DateTime.fromMillisecondsSinceEpoch
             name = entry.name.replace("\\", "/")
             if not entry.is_file and not name.endswith("/"):
@@ -209,7 +251,7 @@ class ZipEncoder:
             method = (entry.compression or "deflate") if entry.is_file else "deflate"
             payload, crc = b"", 0
             if entry.is_file:
-                payload, crc = self._compress(entry.content or b"", method, level if level is not None else 6)
+                payload, crc = compress(entry.content or b"", method, level if level is not None else 6)
             fd = dict(name=name, time=_dos_time(lm), date=_dos_date(lm), crc=crc, csize=len(payload),
                       usize=entry.size if entry.is_file else 0, method=method, mode=entry.mode, pos=len(out),
                       comment=getattr(entry, "comment", None) or "")

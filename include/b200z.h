@@ -85,6 +85,15 @@ size_t b200z_gzip_bound(const uint8_t *in, size_t in_len);
 int b200z_deflate_raw(const uint8_t *in, size_t in_len, int level, int window_bits, uint8_t *out, size_t out_cap,
                       size_t *out_len, uint32_t *crc32_of_input);
 size_t b200z_deflate_bound(size_t in_len); /* output capacity that always suffices (+18 for gzip, +6 for zlib) */
+/* n_units independent Deflate(bytes, level:, windowBits:) streams in one call -- what ZipEncoder does member by member
+ * (zip_encoder.dart:185-259, platformZLibEncoder.encodeStream(raw: true) :244-249).  Unit u reads
+ * in_base[in_off[u] .. +in_len[u]) and writes out_base[out_off[u] .. +out_cap[u]); out_len[u] = its compressed size,
+ * crc32[u] (may be NULL) = CRC-32 of its input, status[u] = B200Z_OK or B200Z_U_NOSPC (out_len[u] = bytes needed).  All
+ * inputs are staged at once and up to 8 members (B200Z_DEFLATE_LANES) are in flight on separate CUDA streams; every
+ * stream is byte-identical to b200z_deflate_raw of the same input.                                                  */
+int b200z_deflate_batch(const uint8_t *in_base, const uint64_t *in_off, const uint64_t *in_len, size_t n_units, int level,
+                        int window_bits, uint8_t *out_base, const uint64_t *out_off, const uint64_t *out_cap,
+                        uint64_t *out_len, uint32_t *crc32, int32_t *status);
 /* ZLibEncoderWeb().encodeBytes -- _zlib_encoder_web.dart:17-73 (header 78 01 at every level, Adler-32 trailer)      */
 int b200z_zlib_encode(const uint8_t *in, size_t in_len, int level, int window_bits, int raw, uint8_t *out,
                       size_t out_cap, size_t *out_len);

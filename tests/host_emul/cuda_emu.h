@@ -12,6 +12,7 @@
 #if !defined(__x86_64__)
 #error "cuda_emu.h needs x86-64"
 #endif
+#include <mutex>
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
@@ -209,7 +210,14 @@ static inline void init_fiber(Fiber &f) {
 }
 
 static std::vector<Fiber> pool;
+// One launch at a time in the whole process (the scheduler state above is per translation unit and not re-entrant): host
+// code that drives the device from several threads (b200z_deflate_batch's lanes) runs here with its kernels serialised.
+inline std::mutex &launch_mutex() {
+  static std::mutex m;
+  return m;
+}
 static inline void launch(dim3 grid, dim3 block, const std::function<void()> &body) {
+  std::lock_guard<std::mutex> one_launch(launch_mutex());
   size_t nthr = (size_t)block.x * block.y * block.z;
   if (pool.size() < nthr) pool.resize(nthr);
   g_bdim = block;

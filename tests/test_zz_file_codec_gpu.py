@@ -222,3 +222,49 @@ def test_file_codec_argument_errors(a, tmp_path):
     assert L.b200z_file_codec(_ffi.FILE_GZIP_DECODE, os.fsencode(src), 0, 2**64 - 1, outp, 3, 0, 0, 0, C.byref(used), C.byref(got)) == 0
     assert used.value == os.path.getsize(src)
     assert open(str(tmp_path / "o"), "rb").read()[3:] == orc.gzip_decode(rd("a.txt.gz"))[1]
+
+
+# ---------------------------------------------------------------------------------------------
+# b200z_deflate_batch: ZipEncoder's members in one call, several in flight
+# ---------------------------------------------------------------------------------------------
+def test_deflate_batch_equals_one_by_one(a, monkeypatch):
+    import random
+    from archive_b200 import synth
+    from archive_b200.zip import deflate_batch
+    rng = random.Random(77)
+    text = synth.text(300000, stream=45).tobytes()
+    items = [b"", b"x", text[:70000], bytes(rng.randrange(256) for _ in range(3000)), text[70000:70000 + 33333],
+             b"ab" * 5000, text[110000:300000], bytes(1000), text[5:4000]]
+    for lanes in ("1", "8"):  # (on the CPU emulation the lanes' host threads run, their kernels one at a time)
+        monkeypatch.setenv("B200Z_DEFLATE_LANES", lanes)
+        for level in (6, 1, 0, 9):
+            got = deflate_batch(items, level)
+            for it, (payload, crc) in zip(items, got):
+                d = a.Deflate(it, level=level)
+                assert payload == d.get_bytes() and crc == d.crc32 == zlib.crc32(it), (lanes, level, len(it))
+            if level == 6:
+                for it, (payload, _) in zip(items, got):
+                    assert payload == orc.deflate(it, 6)[1]
+    assert deflate_batch([], 6) == []
+    with pytest.raises(a.B200ZError):
+        deflate_batch([b"abc"], 11)
+
+
+def test_zip_encoder_batch_mode(a):
+    import time
+    from archive_b200.zip import Archive, ArchiveFile, ZipDecoder, ZipEncoder
+    from archive_b200 import synth
+    arc = Archive()
+    t0 = int(time.mktime((2024, 5, 17, 13, 37, 42, 0, 0, -1)))
+    text = synth.text(200000, stream=46).tobytes()
+    for i, (name, body, comp) in enumerate([("a.txt", text[:90000], None), ("b.bin", bytes(range(256)) * 9, "none"),
+                                            ("c.src", b"bzip me " * 500, "bzip2"), ("empty", b"", None),
+                                            ("d.txt", text[90000:], "deflate")]):
+        f = ArchiveFile(name, len(body))
+        f.content, f.compression, f.last_mod_time, f.mode = body, comp, t0 + 2 * i, 0o100644
+        arc.add(f)
+    for level in (1, 6):
+        one = ZipEncoder().encode_bytes(arc, level=level)
+        assert ZipEncoder(batch=True).encode_bytes(arc, level=level) == one
+    back = ZipDecoder().decode_bytes(one)
+    assert [f.content for f in back.files] == [f.content for f in arc.files]
