@@ -464,16 +464,26 @@ static int gzip_fast_path(const uint8_t *in, size_t in_len, uint8_t *out, size_t
   const size_t in_lo = *pos_io, in_hi = p, out_lo = *out_pos_io;
   // chunks: ~8 per call (one compute stream each, so their kernels overlap: a stream's decode time is set by
   // its token count, not by how many streams run beside it), at least 4 MiB of compressed bytes each
+  size_t min_chunk = 4u << 20;  // (B200Z_GZIP_CHUNK_KB: smaller chunks for tests of the pipeline itself)
+  if (const char *e = getenv("B200Z_GZIP_CHUNK_KB")) min_chunk = std::max<size_t>(1, (size_t)atoll(e)) << 10;
   size_t target = (in_hi - in_lo) / Ctx::kCompStreams;
-  if (target < (4u << 20)) target = 4u << 20;
+  if (target < min_chunk) target = min_chunk;
+  // The device->host copy of the output bounds this path (it moves ~2.5x the bytes of the input copy over the same link),
+  // and it cannot start before the first chunk has been copied in and decoded: the first two chunks are a quarter and a
+  // half of a regular one, so that it starts early and is fed without a gap from then on.  (B200Z_GZIP_RAMP=0: equal chunks.)
+  const char *ramp_env = getenv("B200Z_GZIP_RAMP");
+  const bool ramp = !ramp_env || atoi(ramp_env) != 0;
   std::vector<size_t> cut{0};
   {
     size_t acc_start = in_lo;
-    for (size_t i = 0; i < nb; ++i)
-      if (ms[i].next - acc_start >= target && i + 1 < nb) {
+    for (size_t i = 0; i < nb; ++i) {
+      size_t want = target;
+      if (ramp && cut.size() <= 2) want = std::max<size_t>(target >> (3 - cut.size()), min_chunk);  // chunk 0: /4, chunk 1: /2
+      if (ms[i].next - acc_start >= want && i + 1 < nb) {
         cut.push_back(i + 1);
         acc_start = ms[i].next;
       }
+    }
     cut.push_back(nb);
   }
   const size_t nchunks = cut.size() - 1;
@@ -1796,13 +1806,13 @@ int b200z_init(int device, uint32_t flags) {
 }
 
 void b200z_shutdown(void) {
+  file_release();  // before g.mu: a file call holds its own lock while it takes g.mu, never the other way round
   std::lock_guard<std::mutex> lk(g.mu);
   if (!g.inited) return;
   cudaSetDevice(g.device);
   cudaStreamSynchronize(g.stream);
   g.d_in.release(); g.d_out.release(); g.d_ws.release(); g.d_meta.release(); g.d_small.release(); g.d_bz.release();
   g.h_meta.release();
-  file_release();
   cudaStreamDestroy(g.stream);
   cudaStreamDestroy(g.s_h2d);
   cudaStreamDestroy(g.s_d2h);

@@ -268,3 +268,19 @@ def test_zip_encoder_batch_mode(a):
         assert ZipEncoder(batch=True).encode_bytes(arc, level=level) == one
     back = ZipDecoder().decode_bytes(one)
     assert [f.content for f in back.files] == [f.content for f in arc.files]
+
+
+def test_gzip_chunk_pipeline_many_chunks(a, monkeypatch):
+    """The end-to-end chunk pipeline of b200z_gzip_decode (copy in / kernels / copy out on three streams, first chunks ramped)
+    with chunks small enough that a test-sized input makes a dozen of them: same bytes as the oracle, ramp on or off."""
+    from archive_b200 import synth
+    text = synth.text(64 * 16384, stream=47).tobytes()
+    blob = b"".join(_members(text, 16384))
+    assert orc.gzip_decode(blob) == (orc.OK, text)
+    monkeypatch.setenv("B200Z_GZIP_CHUNK_KB", "16")
+    assert a.GZipDecoder().decode_bytes(blob) == text
+    monkeypatch.setenv("B200Z_GZIP_RAMP", "0")
+    assert a.GZipDecoder().decode_bytes(blob) == text
+    monkeypatch.delenv("B200Z_GZIP_RAMP")
+    monkeypatch.setenv("B200Z_GZIP_CHUNK_KB", "200")
+    assert a.GZipDecoder().decode_bytes(blob + b"\x1f\x8b\x08\x00" + bytes(30)) == _mem_decode(a, a.GZipDecoder(), blob)[1]
