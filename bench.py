@@ -137,6 +137,29 @@ def oracle_gzip_throughput(blob: np.ndarray, member_off: np.ndarray, n_sample_un
     return total / best / 1e9, best, total
 
 
+def gpu_local_cpus(local_rank: int):
+    """CPUs on the NUMA node the GPU's PCIe link hangs off (/sys/bus/pci/devices/<bdf>/local_cpulist), restricted to the
+    CPUs this process may use; None when the box does not say.  One process per GPU bound to its GPU's node is how the
+    end-to-end path is meant to be deployed: the pinned staging buffers are then allocated on the memory the DMA reaches
+    without crossing the socket link."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        txt = open(f"/sys/bus/pci/devices/{bdf}/local_cpulist").read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        return cpus or None
+    except Exception:
+        return None
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path on this box's host cores.  The
     reference is pure Dart and cannot run here (no Dart SDK, no network): the arm times the C oracle, a
@@ -306,6 +329,10 @@ def main():
     # ---------------- end to end through the reference-facing call, host buffers ----------------
     e2e = None
     if not args.no_e2e:
+        all_cpus = os.sched_getaffinity(0)
+        near = gpu_local_cpus(local_rank)
+        if near and near != all_cpus:
+            os.sched_setaffinity(0, near)  # for the staging buffers' placement and the calling thread; undone below
         h_in = torch.empty(C_bytes, dtype=torch.uint8).pin_memory()
         h_in.numpy()[:] = blob
         h_out = torch.empty(U_bytes, dtype=torch.uint8).pin_memory()
@@ -337,7 +364,10 @@ def main():
             assert zlib.crc32(ho[i * UNIT:(i + 1) * UNIT].tobytes()) == crc
         e2e = {"value": world * U_bytes / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": C_bytes,
                "d2h_bytes_per_step": U_bytes, "ms_per_step": dt * 1e3,
-               "call": "b200z_gzip_decode(host in, host out) == GZipDecoderWeb.decodeBytes, pinned host buffers"}
+               "call": "b200z_gzip_decode(host in, host out) == GZipDecoderWeb.decodeBytes, pinned host buffers",
+               "cpu_binding": ("%d CPUs of the GPU's NUMA node" % len(near)) if near and near != all_cpus else "none"}
+        if near and near != all_cpus:
+            os.sched_setaffinity(0, all_cpus)
 
     clocks = sampler.stop() if rank == 0 else None
 
