@@ -283,4 +283,42 @@ def test_gzip_chunk_pipeline_many_chunks(a, monkeypatch):
     assert a.GZipDecoder().decode_bytes(blob) == text
     monkeypatch.delenv("B200Z_GZIP_RAMP")
     monkeypatch.setenv("B200Z_GZIP_CHUNK_KB", "200")
-    assert a.GZipDecoder().decode_bytes(blob + b"\x1f\x8b\x08\x00" + bytes(30)) == _mem_decode(a, a.GZipDecoder(), blob)[1]
+    tail = blob + b"\x1f\x8b\x08\x00" + bytes(30)  # garbage behind the last member: the verdict comes from the slow path
+    got = _mem_decode(a, a.GZipDecoder(), tail)
+    monkeypatch.delenv("B200Z_GZIP_CHUNK_KB")
+    assert got == _mem_decode(a, a.GZipDecoder(), tail) and got[1][:len(text)] == text
+
+
+def test_gzip_file_fuzz_vs_memory(a, tmp_path, monkeypatch):
+    """Seeded mixes of hinted / hint-free / lying / damaged members and segment sizes: the file always holds what the memory
+    entry point returns, with the same verdict."""
+    import random
+    from archive_b200 import synth
+    rng = random.Random(0xF11E)
+    text = synth.text(48 * 8192, stream=48).tobytes()
+    hinted = _members(text, 8192)
+    plain = _members(text, 8192, hint=False)
+    for trial in range(10):
+        ms = []
+        for i in range(rng.randrange(20, 48)):
+            r = rng.random()
+            if r < 0.80:
+                ms.append(hinted[i])
+            elif r < 0.90:
+                ms.append(plain[i])
+            elif r < 0.95:
+                m = bytearray(hinted[i])
+                m[-4:] = struct.pack("<I", rng.randrange(1, 9000))  # ISIZE lies
+                ms.append(bytes(m))
+            else:
+                m = bytearray(hinted[i])
+                m[rng.randrange(30, len(m) - 8)] ^= 1 << rng.randrange(8)  # damaged payload
+                ms.append(bytes(m))
+        blob = b"".join(ms)
+        if rng.random() < 0.3:
+            blob = blob[:rng.randrange(len(blob) // 2, len(blob))]
+        monkeypatch.setenv("B200Z_FILE_SEG_KB", str(rng.choice([64, 64, 96, 128])))
+        monkeypatch.setenv("B200Z_FILE_THREADS", str(rng.choice([1, 2, 8])))
+        mem = _mem_decode(a, a.GZipDecoder(), blob)
+        got = _file_decode(a, a.GZipDecoder(), tmp_path, blob, name=f"fuzz{trial}.gz", prefix=b"P" * rng.randrange(0, 5))
+        assert got[0] == mem[0] and got[1] == mem[1], (trial, got[0], mem[0], len(got[1]), len(mem[1]), _stats())
