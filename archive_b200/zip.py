@@ -89,6 +89,17 @@ class ZipDecoder:
         self.zip_file_comment = raw.decode("latin-1")  # readString(utf8: false) (zip_directory.dart:43)
         return ents, cnt.value
 
+    def decode_stream(self, input, verify: bool = False, password=None) -> Archive:
+        """ZipDecoder().decodeStream(input) (zip_decoder.dart:29-81): the rest of an InputMemoryStream or InputFileStream."""
+        from .streams import InputFileStream
+        if isinstance(input, InputFileStream):
+            data = input.to_uint8_list()
+            input.skip(len(data))
+        else:
+            data = bytes(input.buffer[input.position:])
+            input.position = len(input.buffer)
+        return self.decode_bytes(data, verify=verify, password=password)
+
     def decode_bytes(self, data, verify: bool = False, password=None) -> Archive:
         data = bytes(data) if not isinstance(data, (bytes, bytearray)) else data
         ents, n = self.list(data)

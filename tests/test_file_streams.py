@@ -122,3 +122,44 @@ def test_output_buffering_words_subset(tmp_path):  # output_file_stream.dart:96-
     be.write_uint32(0xA1B2C3D4)
     be.close_sync()
     assert open(p, "rb").read() == bytes.fromhex("1234a1b2c3d4")
+
+
+# ---------------------------------------------------------------------------------------------
+# extract_archive_to_disk (lib/src/io/extract_archive_to_disk.dart:19-103): host logic, no device
+# ---------------------------------------------------------------------------------------------
+def test_extract_archive_to_disk_layout_and_safety(tmp_path):
+    from archive_b200 import extract_archive_to_disk, get_input_extension
+    from archive_b200.zip import Archive, ArchiveFile
+    arc = Archive()
+
+    def add(name, body=None, link=None, mode=0o100644, is_file=True):
+        f = ArchiveFile(name, len(body or b""), is_file=is_file)
+        f.content, f.mode, f.symbolic_link = body, mode, link
+        arc.add(f)
+
+    add("a.txt", b"alpha")
+    add("dir/sub/b.bin", bytes(range(200)), mode=0o100600)
+    add("emptydir/", is_file=False, mode=0o40755)
+    add("dir/link", b"sub/b.bin", link="sub/b.bin", mode=0o120777)
+    add("../evil.txt", b"outside")                                # leaves the output directory: skipped (:19-22)
+    add("dir/../../evil2.txt", b"outside")
+    add("dir/badlink", b"/etc/passwd", link="/etc/passwd", mode=0o120777)       # absolute target: skipped (:27-30)
+    add("dir/badlink2", b"../../x", link="../../x", mode=0o120777)              # target outside: skipped (:32-35)
+    out = str(tmp_path / "out")
+    written = extract_archive_to_disk(arc, out, buffer_size=7)
+    assert sorted(os.path.relpath(p, out) for p in written) == ["a.txt", "dir/link", "dir/sub/b.bin"]
+    assert open(os.path.join(out, "a.txt"), "rb").read() == b"alpha"
+    assert open(os.path.join(out, "dir/sub/b.bin"), "rb").read() == bytes(range(200))
+    assert os.stat(os.path.join(out, "dir/sub/b.bin")).st_mode & 0o777 == 0o600
+    assert os.path.isdir(os.path.join(out, "emptydir"))
+    assert os.readlink(os.path.join(out, "dir/link")) == "sub/b.bin"
+    assert open(os.path.join(out, "dir/link"), "rb").read() == bytes(range(200))
+    assert not os.path.exists(str(tmp_path / "evil.txt")) and not os.path.exists(str(tmp_path / "evil2.txt"))
+    assert not os.path.lexists(os.path.join(out, "dir/badlink")) and not os.path.lexists(os.path.join(out, "dir/badlink2"))
+    for name, ext in (("x.tar.gz", ".tar.gz"), ("X.TAR.BZ2", ".tar.bz2"), ("a.b.tgz", ".tgz"), ("q.zip", ".zip"), ("noext", "")):
+        assert get_input_extension(name) == ext  # (:146-157)
+    from archive_b200 import extract_file_to_disk
+    with pytest.raises(ValueError):
+        extract_file_to_disk(str(tmp_path / "noext"), out)
+    with pytest.raises(ValueError):
+        extract_file_to_disk(str(tmp_path / "thing.rar"), out)

@@ -322,3 +322,51 @@ def test_gzip_file_fuzz_vs_memory(a, tmp_path, monkeypatch):
         mem = _mem_decode(a, a.GZipDecoder(), blob)
         got = _file_decode(a, a.GZipDecoder(), tmp_path, blob, name=f"fuzz{trial}.gz", prefix=b"P" * rng.randrange(0, 5))
         assert got[0] == mem[0] and got[1] == mem[1], (trial, got[0], mem[0], len(got[1]), len(mem[1]), _stats())
+
+
+def test_extract_file_to_disk(a, tmp_path):
+    """extractFileToDisk (io/extract_archive_to_disk.dart:160-267) for what this package decodes: .zip archives unpacked to
+    files, and the GZip / BZip2 stage of a compressed tar done file -> file by the library."""
+    import shutil
+    Z = os.path.join(G, "zip")
+    out = str(tmp_path / "unz")
+    written = a.extract_file_to_disk(os.path.join(Z, "test.zip"), out)
+    arc = a.ZipDecoder().decode_bytes(open(os.path.join(Z, "test.zip"), "rb").read())
+    files = [f for f in arc.files if f.is_file]
+    assert sorted(os.path.relpath(p, out) for p in written) == sorted(os.path.normpath(f.name) for f in files)
+    for f in files:
+        assert open(os.path.join(out, os.path.normpath(f.name)), "rb").read() == f.content
+    # symbolic links: the reference's fixture points OUTSIDE the output directory ("../target") and is skipped
+    # (_isValidSymLink :24-38); a link that stays inside becomes a link
+    out2 = str(tmp_path / "sym")
+    assert a.extract_file_to_disk(os.path.join(Z, "symlink.zip"), out2) == []
+    assert not os.path.lexists(os.path.join(out2, "symlink"))
+    import io
+    import zipfile
+    buf = io.BytesIO()
+    with zipfile.ZipFile(buf, "w", zipfile.ZIP_DEFLATED) as zf:
+        zf.writestr("data/real.txt", b"real " * 100)
+        zi = zipfile.ZipInfo("data/alias")
+        zi.create_system, zi.external_attr = 3, 0o120777 << 16
+        zf.writestr(zi, "real.txt")
+    p = str(tmp_path / "links.zip")
+    open(p, "wb").write(buf.getvalue())
+    out2b = str(tmp_path / "sym2")
+    a.extract_file_to_disk(p, out2b)
+    assert os.readlink(os.path.join(out2b, "data/alias")) == "real.txt"
+    assert open(os.path.join(out2b, "data/alias"), "rb").read() == b"real " * 100
+    # bzip2 members inside a zip
+    out3 = str(tmp_path / "bz")
+    a.extract_file_to_disk(os.path.join(G, "zip_bzip2.zip"), out3)
+    for f in a.ZipDecoder().decode_bytes(rd("zip_bzip2.zip")).files:
+        if f.is_file:
+            assert open(os.path.join(out3, os.path.normpath(f.name)), "rb").read() == f.content
+    # the decompression stage of .tar.gz / .tgz / .tar.bz2 / .tbz, file -> file
+    for src, name in (("test2.tar.gz", "test2.tar.gz"), ("test2.tar.gz", "other.TGZ"), ("test2.tar.bz2", "test2.tar.bz2"),
+                      ("test2.tar.bz2", "x.tbz")):
+        p = str(tmp_path / name)
+        shutil.copy(os.path.join(G, src), p)
+        d = str(tmp_path / ("out_" + name))
+        (tar_path,) = a.extract_file_to_disk(p, d)
+        assert os.path.dirname(tar_path) == d and tar_path.endswith(".tar")
+        assert open(tar_path, "rb").read() == rd("test2.tar")
