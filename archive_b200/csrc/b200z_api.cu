@@ -227,7 +227,7 @@ static size_t workspace_bytes(size_t n_units, size_t total_out_cap) { return inf
 // output goes to g.d_out.  Meta arrays are host arrays; results are copied back into them.
 static int run_batch_on_staged(const uint64_t *in_off, const uint32_t *in_len, const uint64_t *out_off,
                                const uint32_t *out_cap, uint32_t *out_len, int32_t *status, uint32_t *in_used,
-                               size_t n, size_t out_extent, bool count_only = false) {
+                               size_t n, size_t out_extent, bool count_only = false, uint32_t hist = 0) {
   MetaLayout ml(n);
   CU(g.h_meta.reserve(ml.bytes));
   CU(g.d_meta.reserve(ml.bytes));
@@ -252,6 +252,7 @@ static int run_batch_on_staged(const uint64_t *in_off, const uint32_t *in_len, c
   b.in_used = (uint32_t *)(dm + ml.off_in_used);
   b.n_units = n;
   b.ws = inflate_ws_carve(g.d_ws.p, n, out_extent);
+  b.ws.hist = hist;
   b.count_only = count_only;
   CU(launch_inflate(b, g.stream));
   CU(cudaMemcpyAsync(hm + ml.off_out_len, dm + ml.off_out_len, ml.bytes - ml.off_out_len, cudaMemcpyDeviceToHost,
@@ -281,7 +282,10 @@ struct OneResult {
   uint32_t out_len, in_used;
   int32_t status;
 };
-static int run_one_staged(size_t pos, size_t in_total, size_t out_pos, size_t out_cap_total, OneResult *r) {
+// `shared_output`: the stream is a gzip member -- everything already in g.d_out[0, out_pos) belongs to the same OutputStream
+// and is within reach of its back-references (InflateWs::hist)
+static int run_one_staged(size_t pos, size_t in_total, size_t out_pos, size_t out_cap_total, OneResult *r,
+                          bool shared_output = false) {
   uint64_t io = pos, oo = out_pos;
   size_t avail_in = in_total - pos;
   uint32_t il = (uint32_t)(avail_in > 0xfffffff0u ? 0xfffffff0u : avail_in);
@@ -290,7 +294,8 @@ static int run_one_staged(size_t pos, size_t in_total, size_t out_pos, size_t ou
   if (room > mx) room = mx;
   uint32_t oc = (uint32_t)(room > 0xfffffff0u ? 0xfffffff0u : room);
   CU(g.d_out.reserve_keep(out_pos + oc + 64, out_pos, g.stream));
-  return run_batch_on_staged(&io, &il, &oo, &oc, &r->out_len, &r->status, &r->in_used, 1, out_pos + oc);
+  const uint32_t hist = shared_output ? (uint32_t)(out_pos > 65535 ? 65535 : out_pos) : 0u;  // distances end at 32768
+  return run_batch_on_staged(&io, &il, &oo, &oc, &r->out_len, &r->status, &r->in_used, 1, out_pos + oc, false, hist);
 }
 
 static inline uint32_t le32(const uint8_t *p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }
@@ -404,7 +409,7 @@ static int gzip_decode_staged(const uint8_t *in, size_t in_len, int verify, size
     if (h == 0)  // no gzip header: fall back to zlib on the same little-endian stream (:31-37)
       return zlib_decode_staged(in, in_len, pos, verify, 0, /*big_endian=*/0, out_pos, out_cap, out_len_total);
     OneResult r;
-    int rc = run_one_staged(hdr_end, in_len, out_pos, out_cap, &r);
+    int rc = run_one_staged(hdr_end, in_len, out_pos, out_cap, &r, /*shared_output=*/true);
     if (rc) return rc;
     out_pos += r.out_len;
     *out_len_total = out_pos;
@@ -417,6 +422,13 @@ static int gzip_decode_staged(const uint8_t *in, size_t in_len, int verify, size
       return B200Z_E_THROW;
     }
     size_t after = hdr_end + r.in_used;
+    if (r.status == B200Z_U_STOP && after + 8 > in_len) {
+      // Inflate gave up because the input ran out inside a block (inflate.dart:166-168, 192-195): the byte-wise bit reader
+      // has pulled every byte by then, so the two readUint32 of the trailer (:40-41) start past the end -- RangeError.
+      // This is what a truncated file does.
+      set_err("gzip_decode: member at %zu: input ends inside the stream (Dart: RangeError)", pos);
+      return B200Z_E_THROW;
+    }
     if (r.status != B200Z_U_DONE && r.status != B200Z_U_EOS) {
       set_err("gzip_decode: member at %zu stopped with status %d", pos, r.status);
       return B200Z_E_DATA;  // DESIGN.md "Divergences": reference keeps parsing from an unspecified position
@@ -608,6 +620,30 @@ int gzip_decode_hinted(const uint8_t *in, size_t n, uint8_t *out, size_t out_cap
   return rc;
 }
 
+// The member loop over `in`, continuing a decodeStream call that has already produced output: its last `hist_len` bytes
+// (<= 65535; distances end at 32768) are placed in front, because the members share one OutputStream and may copy from it
+// (InflateWs::hist).  *out_len counts the new bytes only.
+int gzip_decode_after(const uint8_t *in, size_t n, int verify, const uint8_t *hist, size_t hist_len, uint8_t *out, size_t out_cap,
+                      size_t *out_len) {
+  int rc = require_init();
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(g.mu);
+  CU(cudaSetDevice(g.device));
+  rc = stage_input(in, n);
+  if (rc) return rc;
+  CU(g.d_out.reserve(hist_len + 64));
+  if (hist_len) CU(cudaMemcpyAsync(g.d_out.p, hist, hist_len, cudaMemcpyHostToDevice, g.stream));
+  size_t total = hist_len;
+  rc = gzip_decode_staged(in, n, verify, out_cap + hist_len, &total, 0, hist_len);
+  const size_t produced = total > hist_len ? total - hist_len : 0;
+  *out_len = produced;
+  if (rc == B200Z_E_NOSPC || rc == B200Z_E_NODEVICE) return rc;
+  const size_t hi = produced > out_cap ? out_cap : produced;
+  if (hi) CU(cudaMemcpyAsync(out, (const uint8_t *)g.d_out.p + hist_len, hi, cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  return rc;
+}
+
 // _zlib_decoder_web.dart:31-107 on staged input.
 static int zlib_decode_staged(const uint8_t *in, size_t in_len, size_t pos, int verify, int raw, int big_endian,
                               size_t out_pos, size_t out_cap, size_t *out_len_total) {
@@ -658,6 +694,12 @@ static int zlib_decode_staged(const uint8_t *in, size_t in_len, size_t pos, int 
       return B200Z_E_DATA;
     }
     pos += r.in_used;
+    if (r.status == B200Z_U_STOP && !raw && pos + 4 > in_len) {
+      // the input ran out inside a block: the Adler-32 read that follows (:86) starts past the end -- RangeError
+      *out_len_total = out_pos;  // (the stream's bytes were not committed yet, :82-84)
+      set_err("zlib_decode: input ends inside the stream (Dart: RangeError)");
+      return B200Z_E_THROW;
+    }
     if (r.status == B200Z_U_STOP) {
       // Inflate gave up: the reference's stream position is then wherever its byte-wise bit buffer had
       // got to (not rewound) -- unspecified; stop here with the partial output (DESIGN.md "Divergences").

@@ -144,9 +144,14 @@ size_t first_cap(const Args &a, const uint8_t *in, size_t n) {
   return 0;
 }
 
-int call_codec(const Args &a, const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *got) {
+// `hist`: the tail of what this decodeStream call has already written (gzip only: the members share one OutputStream and a
+// member may copy from the ones before it -- b200z_internal.h InflateWs::hist)
+int call_codec(const Args &a, const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *got,
+               const std::vector<uint8_t> *hist = nullptr) {
   switch (a.op) {
-    case B200Z_FILE_GZIP_DECODE: return b200z_gzip_decode(in, n, a.a0, out, cap, got);
+    case B200Z_FILE_GZIP_DECODE:
+      if (hist && !hist->empty()) return gzip_decode_after(in, n, a.a0, hist->data(), hist->size(), out, cap, got);
+      return b200z_gzip_decode(in, n, a.a0, out, cap, got);
     case B200Z_FILE_ZLIB_DECODE: return b200z_zlib_decode(in, n, a.a0, a.a1, out, cap, got);
     case B200Z_FILE_BZIP2_DECODE: return b200z_bzip2_decode(in, n, a.a0, out, cap, got);
     case B200Z_FILE_ZLIB_ENCODE: return b200z_zlib_encode(in, n, a.a0, a.a1, (int)a.a2, out, cap, got);
@@ -158,7 +163,8 @@ int call_codec(const Args &a, const uint8_t *in, size_t n, uint8_t *out, size_t 
 
 // One segment = the whole range [off, off + n): read, one codec call (grown on B200Z_E_NOSPC), write.  What a data error
 // leaves behind is written too -- the reference's streams have it by then (bzip2_decoder.dart:32-78, inflate.dart:150-151).
-int whole_range(const Args &a, int ifd, uint64_t off, size_t n, int ofd, uint64_t out_off, uint64_t *written) {
+int whole_range(const Args &a, int ifd, uint64_t off, size_t n, int ofd, uint64_t out_off, uint64_t *written,
+                const std::vector<uint8_t> *hist = nullptr) {
   *written = 0;
   F.n_whole++;
   if (!F.in[0].reserve(n + 8)) return B200Z_E_NODEVICE;
@@ -171,7 +177,7 @@ int whole_range(const Args &a, int ifd, uint64_t off, size_t n, int ofd, uint64_
   for (;;) {
     if (!F.out[0].reserve(cap)) return B200Z_E_NODEVICE;
     got = 0;
-    rc = call_codec(a, F.in[0].p, n, F.out[0].p, cap, &got);
+    rc = call_codec(a, F.in[0].p, n, F.out[0].p, cap, &got, hist);
     if (rc != B200Z_E_NOSPC || cap >= ((size_t)1 << 40)) break;
     cap = std::max(cap * 2, got + (got >> 3) + 64);
   }
@@ -199,6 +205,8 @@ int gzip_segments(const Args &a, int ifd, uint64_t off, uint64_t end, int ofd, u
   uint64_t wpos = out_off;
   int rc = B200Z_OK;
   bool rest = false;  // hand [off, end) to whole_range
+  std::vector<uint8_t> hist;  // the last 32 KiB written so far: within reach of the next member's back-references
+  const size_t kHist = 32768;
   while (off < end) {
     if (!rd.wait()) {
       set_error_text("b200z_file_codec: read failed (I/O error, or the file shrank)");
@@ -232,6 +240,12 @@ int gzip_segments(const Args &a, int ifd, uint64_t off, uint64_t end, int ofd, u
     }
     if (got) wr.start(true, ofd, F.out[s].p, got, wpos);
     wpos += got;
+    if (got >= kHist) {
+      hist.assign(F.out[s].p + got - kHist, F.out[s].p + got);
+    } else if (got) {
+      hist.insert(hist.end(), F.out[s].p, F.out[s].p + got);
+      if (hist.size() > kHist) hist.erase(hist.begin(), hist.end() - kHist);
+    }
     off += used;
     if (used < e) {  // a hint lied: the member at `off` is decoded the hint-free way, with the rest of the file behind it
       rest = true;
@@ -248,7 +262,7 @@ int gzip_segments(const Args &a, int ifd, uint64_t off, uint64_t end, int ofd, u
   *written = wpos - out_off;
   if (rc == B200Z_OK && rest && off < end) {
     uint64_t w2 = 0;
-    rc = whole_range(a, ifd, off, (size_t)(end - off), ofd, wpos, &w2);
+    rc = whole_range(a, ifd, off, (size_t)(end - off), ofd, wpos, &w2, &hist);
     *written += w2;
   }
   return rc;

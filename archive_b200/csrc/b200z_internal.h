@@ -24,6 +24,12 @@ struct InflateWs {
   size_t hstride = 0;
   uint32_t *pieces = nullptr;   // [n_units][PIECE_WORDS]: which token runs make up the unit, in order
   uint8_t *uscratch = nullptr;  // [n_units][USCRATCH_BYTES]: slow tables + helper boundary bitmaps
+  // Bytes of EARLIER output that lie directly in front of a unit's output slot and that its back-references may reach.
+  // 0 for independent streams (Inflate(bytes), zip members, zlib streams: each has an output stream of its own).  GZip
+  // members share ONE OutputStream in the reference (_gzip_decoder_web.dart:38: Inflate.stream(input, output: output)), so
+  // a member's distance may reach into the members before it (output_memory_stream.dart:79-98 checks against the whole
+  // stream): the member-by-member path sets this for its single-unit batches.
+  uint32_t hist = 0;
 };
 size_t inflate_ws_bytes(size_t n_units, size_t extent);
 size_t inflate_ws_extent_for(size_t n_units, size_t bytes);  // largest extent a workspace of `bytes` serves
@@ -98,6 +104,8 @@ int profile_read(double *decode_ms, double *expand_ms, uint64_t *n);
 void set_error_text(const char *msg);  // b200z_last_error() text of the calling thread
 size_t gzip_hinted_prefix(const uint8_t *in, size_t n, size_t *out_bytes);
 int gzip_decode_hinted(const uint8_t *in, size_t n, uint8_t *out, size_t out_cap, size_t *in_used, size_t *out_len);
+int gzip_decode_after(const uint8_t *in, size_t n, int verify, const uint8_t *hist, size_t hist_len, uint8_t *out, size_t out_cap,
+                      size_t *out_len);
 void file_release();  // frees the pinned segment buffers (b200z_shutdown)
 
 // ---- Deflate (deflate_kernels.cu) ----

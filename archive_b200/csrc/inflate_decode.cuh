@@ -379,6 +379,7 @@ struct SpecCtx {
   uint32_t hcap;
   uint32_t *bm;       // global: helper k's boundary bitmap = bm + (k - 1) * SPEC_BMW
   uint32_t *pieces;   // the unit's piece table (global)
+  uint32_t hist = 0;  // bytes of earlier output in front of the unit that a distance may reach (InflateWs::hist)
 };
 
 B200Z_HD void piece_add(uint32_t *pieces, uint32_t &np, uint32_t src, uint32_t start, uint32_t count) {
@@ -638,7 +639,7 @@ B200Z_HD UnitResult inflate_decode_unit(bool active, const uint8_t *in, uint32_t
         const bool islit = !dm && sym < 256u;
         const bool islen = !dm && sym > 256u;
         const uint32_t nolen = olen + (islit ? 1u : dm ? mlen_pending : 0u);
-        const bool special = odd || (dm && val > olen) || nolen > capx || nt >= nt_limit;
+        const bool special = odd || (dm && val > olen + sc.hist) || nolen > capx || nt >= nt_limit;
         if (!special) {
           const uint32_t tot = n + xb;
           br.buf >>= tot;
@@ -738,7 +739,7 @@ B200Z_HD UnitResult inflate_decode_unit(bool active, const uint8_t *in, uint32_t
           st = B200Z_U_STOP;
           done = true; break;
         }
-        if (val > olen) {  // writeBackReference before the start of the output (output_memory_stream.dart:83-86)
+        if (val > olen + sc.hist) {  // writeBackReference before the start of the output (output_memory_stream.dart:83-86)
           st = B200Z_U_RANGE;
           done = true; break;
         }
@@ -1007,7 +1008,7 @@ B200Z_HD UnitResult inflate_decode_unit(bool active, const uint8_t *in, uint32_t
       dist += x;
     }
     // writeBackReference (output_memory_stream.dart:79-98)
-    if (dist <= 0 || (uint32_t)dist > olen) {  // dist 0 only via a truncated extra-bits read
+    if (dist <= 0 || (uint32_t)dist > olen + sc.hist) {  // dist 0 only via a truncated extra-bits read
       st = B200Z_U_RANGE;
       done = true; break;
     }

@@ -28,6 +28,7 @@ struct InflateWs {
   size_t hstride = 0;
   uint32_t *pieces = nullptr;
   uint8_t *uscratch = nullptr;
+  uint32_t hist = 0;
 };
 }  // namespace b200z
 #else
@@ -52,6 +53,9 @@ namespace b200z {
 #define B200Z_DYN_SMEM(name) extern __shared__ __align__(16) uint32_t name[]
 #endif
 
+// HIST: the unit may reach InflateWs::hist bytes of earlier output (single gzip members decoded behind their predecessors).
+// The batch kernels are the HIST = false instantiations: the history term folds away and their code is what it was.
+template <bool HIST>
 __global__ void __launch_bounds__(B200Z_DECODE_THREADS)
 k_inflate_decode(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__ in_off,
                  const uint32_t *__restrict__ in_len, const uint64_t *__restrict__ out_off,
@@ -98,6 +102,7 @@ k_inflate_decode(const uint8_t *__restrict__ in_base, const uint64_t *__restrict
   sc.hcap = 0;
   sc.bm = nullptr;
   sc.pieces = nullptr;
+  sc.hist = HIST ? ws.hist : 0u;
   uint32_t *tok = nullptr;
   if (active) {
     const uint64_t oo = out_off[unit];
@@ -129,6 +134,7 @@ __device__ __forceinline__ uint32_t tok_len(uint32_t t, bool payload) {
   return t >> 16;
 }
 
+template <bool HIST>
 __global__ void __launch_bounds__(B200Z_EXPAND_THREADS)
 k_inflate_expand(InflateWs ws, const uint8_t *__restrict__ in_base, const uint64_t *__restrict__ in_off, uint8_t *out_base,
                  const uint64_t *__restrict__ out_off, const uint32_t *__restrict__ out_cap, uint32_t *__restrict__ out_len,
@@ -138,12 +144,16 @@ k_inflate_expand(InflateWs ws, const uint8_t *__restrict__ in_base, const uint64
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t unit = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; unit < n_units; unit += warps) {
     const uint64_t oo = out_off[unit];
-    const uint32_t cap = out_cap[unit];
+    // Positions below count from `hist` bytes in front of the unit (InflateWs::hist; 0 unless the unit is a gzip member
+    // decoded on its own behind its predecessors): the range check, the capacity check and the source reads then need
+    // nothing extra.
+    const uint32_t hist = HIST ? ws.hist : 0u;
+    const uint32_t cap = HIST ? (out_cap[unit] > 0xffffffffu - hist ? 0xffffffffu : out_cap[unit] + hist) : out_cap[unit];
     const uint32_t *P = ws.pieces + (size_t)unit * PIECE_WORDS;
     const uint32_t np = P[0];
-    uint8_t *out = out_base + oo;
+    uint8_t *out = out_base + oo - hist;
     const uint8_t *in = in_base + in_off[unit];
-    uint32_t pos0 = 0;
+    uint32_t pos0 = hist;
     bool stop = false;
     for (uint32_t pi = 0; pi < np && !stop; ++pi) {
       const uint32_t src = P[2 + 3 * pi], pstart = P[3 + 3 * pi], nt = P[4 + 3 * pi];
@@ -186,7 +196,7 @@ k_inflate_expand(InflateWs ws, const uint8_t *__restrict__ in_base, const uint64
           const uint32_t good = __shfl_sync(FULL, incl, 31);
           if (lane == 0) {
             status[unit] = r_range ? B200Z_U_RANGE : B200Z_U_NOSPC;
-            out_len[unit] = pos0 + good;
+            out_len[unit] = pos0 + good - hist;
           }
         }
       }
@@ -414,7 +424,9 @@ cudaError_t launch_inflate(const InflateBatch &b, cudaStream_t stream) {
   const size_t smem = inflate_decode_smem_bytes(warps_per_block, upw);
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(k_inflate_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_inflate_decode<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_inflate_decode<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr_smem = smem;
   }
@@ -423,9 +435,14 @@ cudaError_t launch_inflate(const InflateBatch &b, cudaStream_t stream) {
     cudaEventCreate(&pt.a); cudaEventCreate(&pt.b); cudaEventCreate(&pt.c);
     cudaEventRecord(pt.a, stream);
   }
-  k_inflate_decode<<<blocks, B200Z_DECODE_THREADS, smem, stream>>>(b.in_base, b.in_off, b.in_len, b.out_off, b.out_cap, b.ws,
-                                                                   b.out_len, b.status, b.in_used, (uint32_t)b.n_units, upw,
-                                                                   b.count_only ? 1 : lpu, b.count_only ? 1 : 0);
+  if (b.ws.hist)
+    k_inflate_decode<true><<<blocks, B200Z_DECODE_THREADS, smem, stream>>>(b.in_base, b.in_off, b.in_len, b.out_off, b.out_cap, b.ws,
+                                                                         b.out_len, b.status, b.in_used, (uint32_t)b.n_units, upw,
+                                                                         b.count_only ? 1 : lpu, b.count_only ? 1 : 0);
+  else
+    k_inflate_decode<false><<<blocks, B200Z_DECODE_THREADS, smem, stream>>>(b.in_base, b.in_off, b.in_len, b.out_off, b.out_cap, b.ws,
+                                                                          b.out_len, b.status, b.in_used, (uint32_t)b.n_units, upw,
+                                                                          b.count_only ? 1 : lpu, b.count_only ? 1 : 0);
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
@@ -448,8 +465,12 @@ cudaError_t launch_inflate(const InflateBatch &b, cudaStream_t stream) {
   }
   const uint64_t max_blocks = (uint64_t)g_num_sms * (uint64_t)bps;
   if (eblocks > max_blocks) eblocks = max_blocks;
-  k_inflate_expand<<<(unsigned)eblocks, B200Z_EXPAND_THREADS, 0, stream>>>(b.ws, b.in_base, b.in_off, b.out_base, b.out_off,
-                                                                           b.out_cap, b.out_len, b.status, (uint32_t)b.n_units);
+  if (b.ws.hist)
+    k_inflate_expand<true><<<(unsigned)eblocks, B200Z_EXPAND_THREADS, 0, stream>>>(b.ws, b.in_base, b.in_off, b.out_base, b.out_off,
+                                                                                 b.out_cap, b.out_len, b.status, (uint32_t)b.n_units);
+  else
+    k_inflate_expand<false><<<(unsigned)eblocks, B200Z_EXPAND_THREADS, 0, stream>>>(b.ws, b.in_base, b.in_off, b.out_base, b.out_off,
+                                                                                  b.out_cap, b.out_len, b.status, (uint32_t)b.n_units);
   count_launch();
   if (g_prof) {
     cudaEventRecord(pt.c, stream);

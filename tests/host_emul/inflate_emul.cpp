@@ -23,9 +23,9 @@ extern "C" int emu_inflate_batch(const uint8_t *in_base, const uint64_t *in_off,
   w.uscratch = us.data();
   // the kernel reads aligned 16-byte blocks around every unit: give the input a padded home
   const uint32_t n_warps = (n_units + upw - 1) / upw;
-  B200Z_LAUNCH(k_inflate_decode, n_warps, 32, 0, 0, in_base, in_off, in_len, out_off, out_cap, w, out_len, status, in_used,
+  B200Z_LAUNCH(k_inflate_decode<false>, n_warps, 32, 0, 0, in_base, in_off, in_len, out_off, out_cap, w, out_len, status, in_used,
                n_units, upw, lpu, 0);
-  B200Z_LAUNCH(k_inflate_expand, (n_units + 7) / 8, 256, 0, 0, w, in_base, in_off, out_base, out_off, out_cap, out_len, status,
+  B200Z_LAUNCH(k_inflate_expand<false>, (n_units + 7) / 8, 256, 0, 0, w, in_base, in_off, out_base, out_off, out_cap, out_len, status,
                n_units);
   g_last_pieces = pieces;
   if (pieces_out)
