@@ -59,3 +59,31 @@ def test_no_cpu_fallback_without_device():
     assert ei.value.code == _ffi.E_NODEVICE
     with pytest.raises(a.B200ZError):
         a.GZipDecoder().decode_bytes(b"\x1f\x8b\x08\x00" + bytes(20))
+
+
+def test_late_entry_points_fail_without_device(tmp_path):
+    """The file entry point and the member batch have no CPU path either: B200Z_E_NODEVICE before a file is touched."""
+    import ctypes as C
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("device present")
+    L = _ffi.lib()
+    src, dst = tmp_path / "in.gz", tmp_path / "out.bin"
+    src.write_bytes(b"\x1f\x8b\x08\x00" + bytes(20))
+    used, got = C.c_uint64(7), C.c_uint64(7)
+    rc = L.b200z_file_codec(_ffi.FILE_GZIP_DECODE, str(src).encode(), 0, 2**64 - 1, str(dst).encode(), 0, 0, 0, 0,
+                            C.byref(used), C.byref(got))
+    assert rc == _ffi.E_NODEVICE and (used.value, got.value) == (0, 0) and not dst.exists()
+    z = (C.c_uint64 * 1)(0)
+    n = (C.c_uint64 * 1)(3)
+    cap = (C.c_uint64 * 1)(64)
+    out = (C.c_uint8 * 64)()
+    ol, st = (C.c_uint64 * 1)(), (C.c_int32 * 1)()
+    data = (C.c_uint8 * 3)(1, 2, 3)
+    assert L.b200z_deflate_batch(data, z, n, 1, 6, 15, out, z, cap, ol, None, st) == _ffi.E_NODEVICE
+    import archive_b200 as a
+    tgz = tmp_path / "in.tgz"
+    tgz.write_bytes(src.read_bytes())
+    with pytest.raises(a.B200ZError) as ei:
+        a.extract_file_to_disk(str(tgz), str(tmp_path / "o"))
+    assert ei.value.code == _ffi.E_NODEVICE
