@@ -70,7 +70,8 @@ if EMU_TESTS:
     # B200 run stays the gate.  Tests that need real device memory / torch.cuda mark themselves `needs_device`.
     sys.path.insert(0, os.path.join(ROOT, "tests", "host_emul"))
     import build_emu_lib
-    os.environ["B200Z_LIB"] = build_emu_lib.build()
+    _emu_lib = build_emu_lib.build()
+    os.environ.setdefault("B200Z_LIB", _emu_lib)  # (a sanitizer build of the same sources may be named from outside)
 
 
 def pytest_collection_modifyitems(config, items):

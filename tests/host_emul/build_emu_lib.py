@@ -21,15 +21,26 @@ import gen_emul  # noqa: E402
 SO = os.path.join(HERE, "libb200z_emu.so")
 
 
-def build(force: bool = False) -> str:
+def build(force: bool = False, asan: bool = False) -> str:
+    """asan=True: the same sources with -fsanitize=address as libb200z_emu_asan.so -- out-of-bounds accesses of "device"
+    memory (what a GPU reports as an illegal address, or silently survives) stop the run.  Use:
+      B200Z_EMU_TESTS=1 B200Z_LIB=tests/host_emul/libb200z_emu_asan.so LD_PRELOAD=$(gcc -print-file-name=libasan.so) \
+      ASAN_OPTIONS=detect_leaks=0 python -m pytest tests -m gpu"""
+    if asan:
+        return _build(force, os.path.join(HERE, "libb200z_emu_asan.so"), ["-O1", "-fsanitize=address", "-fno-omit-frame-pointer"],
+                      ".asan.o")
+    return _build(force, SO, ["-O2"], ".emu.o")
+
+
+def _build(force: bool, so: str, opt: list, suffix: str) -> str:
     units = [gen_emul.generate(ROOT, n) for n in ("b200z_api.cu", "b200z_file.cu", "inflate_kernels.cu", "bzip2_kernels.cu", "deflate_kernels.cu")]
     units.append(os.path.join(CSRC, "bzip2_enc_kernels.cu"))  # carries its own B200Z_EMU switch
     deps = units + [os.path.join(HERE, "cuda_emu.h"), os.path.join(ROOT, "include", "b200z.h")] + [
         os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh", ".inl"))]
-    if not force and os.path.exists(SO) and os.path.getmtime(SO) >= max(os.path.getmtime(d) for d in deps):
-        return SO
-    flags = ["-O2", "-g", "-fPIC", "-std=c++17", "-DB200Z_EMU=1", "-w", "-I", os.path.join(HERE, "shim"), "-I", HERE, "-I", CSRC]
-    objs = [os.path.join(HERE, "_gen", os.path.basename(u).split(".")[0] + ".emu.o") for u in units]
+    if not force and os.path.exists(so) and os.path.getmtime(so) >= max(os.path.getmtime(d) for d in deps):
+        return so
+    flags = [*opt, "-g", "-fPIC", "-std=c++17", "-DB200Z_EMU=1", "-w", "-I", os.path.join(HERE, "shim"), "-I", HERE, "-I", CSRC]
+    objs = [os.path.join(HERE, "_gen", os.path.basename(u).split(".")[0] + suffix) for u in units]
 
     def cc(job):
         src, obj = job
@@ -37,9 +48,9 @@ def build(force: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=len(units)) as ex:
         list(ex.map(cc, zip(units, objs)))
-    subprocess.run(["g++", "-shared", "-o", SO, *objs, "-lpthread"], check=True)
-    return SO
+    subprocess.run(["g++", "-shared", *([f for f in opt if f.startswith("-fsanitize")]), "-o", so, *objs, "-lpthread"], check=True)
+    return so
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv))
+    print(build(force="--force" in sys.argv, asan="--asan" in sys.argv))
