@@ -346,6 +346,10 @@ static int gzip_header(const uint8_t *in, size_t n, size_t pos, size_t *hdr_end,
 static int zlib_decode_staged(const uint8_t *in, size_t in_len, size_t pos, int verify, int raw, int big_endian,
                               size_t out_pos, size_t out_cap, size_t *out_len_total);
 
+// An ISIZE that DEFLATE cannot reach from `comp` bytes (1032:1 at most: a 258-byte match costs two bits) is no size hint:
+// such a member is decoded the hint-free way instead of being believed (it would size buffers).
+static inline bool isize_possible(uint32_t isize, size_t comp) { return (uint64_t)isize <= (uint64_t)comp * 1040u + 1024u; }
+
 // GZip member loop on staged input.
 static int gzip_decode_staged(const uint8_t *in, size_t in_len, int verify, size_t out_cap, size_t *out_len_total,
                               size_t pos = 0, size_t out_pos = 0) {
@@ -364,6 +368,7 @@ static int gzip_decode_staged(const uint8_t *in, size_t in_len, int verify, size
       size_t next = p + bsize;
       if (next > in_len || next < hdr_end + 8) break;
       uint32_t isize = le32(in + next - 4);
+      if (!isize_possible(isize, next - hdr_end)) break;
       v_in_off.push_back(hdr_end);
       v_in_len.push_back((uint32_t)(next - hdr_end));
       v_out_off.push_back(o);
@@ -462,6 +467,7 @@ static int gzip_fast_path(const uint8_t *in, size_t in_len, uint8_t *out, size_t
     size_t next = p + bsize;
     if (next > in_len || next < hdr_end + 8) break;
     uint32_t isize = le32(in + next - 4);
+    if (!isize_possible(isize, next - hdr_end)) break;
     ms.push_back({hdr_end, next, isize});
     o += isize;
     p = next;
@@ -599,6 +605,7 @@ size_t gzip_hinted_prefix(const uint8_t *in, size_t n, size_t *out_bytes) {
     if (gzip_header(in, n, p, &hdr_end, &bsize) != 1 || bsize == 0) break;
     const size_t next = p + bsize;
     if (next > n || next < hdr_end + 8) break;
+    if (!isize_possible(le32(in + next - 4), next - hdr_end)) break;
     o += le32(in + next - 4);
     p = next;
   }
@@ -2088,6 +2095,7 @@ size_t b200z_gzip_bound(const uint8_t *in, size_t in_len) {
     if (h != 1 || bsize == 0) return 0;
     size_t next = pos + bsize;
     if (next > in_len || next < hdr_end + 8) return 0;
+    if (!isize_possible(le32(in + next - 4), next - hdr_end)) return 0;  // a size field that cannot be true: unknown
     total += le32(in + next - 4);
     pos = next;
   }

@@ -129,11 +129,15 @@ struct Args {
   uint32_t a2;
 };
 
+// DEFLATE cannot expand by more than 1032:1 (a 258-byte match costs at least two bits): ISIZE fields that promise more are
+// lying, and are not allowed to size a page-locked buffer
+const size_t kMaxExpansion = 1040;
+
 size_t first_cap(const Args &a, const uint8_t *in, size_t n) {
   switch (a.op) {
     case B200Z_FILE_GZIP_DECODE: {
       const size_t b = b200z_gzip_bound(in, n);
-      return b ? b + 64 : 4 * n + 4096;
+      return b && b <= kMaxExpansion * n + 1024 ? b + 64 : 4 * n + 4096;  // size fields that cannot be true are no bound
     }
     case B200Z_FILE_ZLIB_DECODE: return 4 * n + 4096;
     case B200Z_FILE_BZIP2_DECODE: return 6 * n + (1u << 20);
@@ -215,7 +219,7 @@ int gzip_segments(const Args &a, int ifd, uint64_t off, uint64_t end, int ofd, u
     }
     size_t promised = 0;
     const size_t e = gzip_hinted_prefix(F.in[s].p, have, &promised);
-    if (e == 0) {
+    if (e == 0 || promised > kMaxExpansion * e + 1024) {  // (hints that cannot be true: the hint-free path decides)
       rest = true;
       break;
     }

@@ -102,7 +102,10 @@ def test_gzip_mixed_members_and_bad_data(a, tmp_path, monkeypatch):
     lying[-4:] = struct.pack("<I", 16000)  # ISIZE says less than the member holds
     short = bytearray(hinted[12])
     short[16:18] = struct.pack("<H", len(short) - 40 - 1)  # the 'BC' size ends inside the member
+    huge = bytearray(hinted[9])
+    huge[-4:] = struct.pack("<I", 0xFFFFFFF0)  # an ISIZE no DEFLATE stream of this size can reach: not a hint at all
     cases = {
+        "huge_isize": b"".join(hinted[:9] + [bytes(huge)] + hinted[10:]),
         "nohint_middle": b"".join(hinted[:14] + plain[14:16] + hinted[16:]),
         "nohint_first": b"".join(plain[:1] + hinted[1:]),
         "all_plain": b"".join(plain[:6]),
