@@ -119,3 +119,21 @@ def test_truncated_streams_throw_like_the_reference(a):
             ost, oout = orc.zlib_decode(zb[:cut], verify=verify)
             st, got = run(a, a.ZLibDecoder(), zb[:cut], verify=verify)
             assert st == ost and (st == orc.THROW or got == oout), ("zlib", cut, verify, st, ost)
+
+
+def test_impossible_size_fields_are_not_hints(a):
+    """ISIZE is never looked at by the reference (_gzip_decoder_web.dart:40-41 reads and drops it).  Here it is a size hint
+    that is verified afterwards -- but a value DEFLATE cannot reach from the member's bytes (more than 1032:1) must not even
+    size a buffer: the member is decoded the hint-free way and the bytes are the reference's."""
+    from archive_b200 import _ffi, synth
+    text = synth.text(20 * 8192, stream=54).tobytes()
+    ms = [member(text[i:i + 8192], hint=True) for i in range(0, len(text), 8192)]
+    for k in (0, 7, 19):
+        bad = bytearray(ms[k])
+        bad[-4:] = struct.pack("<I", 0xFFFFFFF0)
+        blob = b"".join(ms[:k] + [bytes(bad)] + ms[k + 1:])
+        L = _ffi.ensure_init()
+        addr, n, keep = _ffi.as_buffer(blob)
+        assert L.b200z_gzip_bound(addr, n) == 0  # unknown, not 4 GiB
+        assert orc.gzip_decode(blob) == (orc.OK, text)
+        assert run(a, a.GZipDecoder(), blob) == (orc.OK, text), k
