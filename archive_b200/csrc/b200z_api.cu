@@ -350,6 +350,29 @@ static int zlib_decode_staged(const uint8_t *in, size_t in_len, size_t pos, int 
 // such a member is decoded the hint-free way instead of being believed (it would size buffers).
 static inline bool isize_possible(uint32_t isize, size_t comp) { return (uint64_t)isize <= (uint64_t)comp * 1040u + 1024u; }
 
+// THE definition of a hinted run: whole members from `pos` on that carry the BGZF 'BC' size and a believable ISIZE.
+// Returns the position behind the run; appends the members to `ms` when given; *out_bytes = what their ISIZE fields promise.
+struct HintedMember {
+  size_t hdr_end, next;  // first byte of the DEFLATE stream; first byte behind the member
+  uint32_t isize;
+};
+static size_t hinted_run(const uint8_t *in, size_t n, size_t pos, std::vector<HintedMember> *ms, size_t *out_bytes) {
+  size_t p = pos, o = 0;
+  while (p < n) {
+    size_t hdr_end, bsize;
+    if (gzip_header(in, n, p, &hdr_end, &bsize) != 1 || bsize == 0) break;
+    const size_t next = p + bsize;
+    if (next > n || next < hdr_end + 8) break;
+    const uint32_t isize = le32(in + next - 4);
+    if (!isize_possible(isize, next - hdr_end)) break;
+    if (ms) ms->push_back({hdr_end, next, isize});
+    o += isize;
+    p = next;
+  }
+  if (out_bytes) *out_bytes = o;
+  return p;
+}
+
 // GZip member loop on staged input.
 static int gzip_decode_staged(const uint8_t *in, size_t in_len, int verify, size_t out_cap, size_t *out_len_total,
                               size_t pos = 0, size_t out_pos = 0) {
@@ -360,22 +383,18 @@ static int gzip_decode_staged(const uint8_t *in, size_t in_len, int verify, size
   while (pos < in_len) {
     // -------- gather a run of members that carry a size hint (BGZF 'BC' + ISIZE) --------
     v_in_off.clear(); v_out_off.clear(); v_in_len.clear(); v_out_cap.clear(); v_next.clear();
-    size_t p = pos, o = out_pos;
-    while (p < in_len) {
-      size_t hdr_end, bsize;
-      int h = gzip_header(in, in_len, p, &hdr_end, &bsize);
-      if (h != 1 || bsize == 0) break;
-      size_t next = p + bsize;
-      if (next > in_len || next < hdr_end + 8) break;
-      uint32_t isize = le32(in + next - 4);
-      if (!isize_possible(isize, next - hdr_end)) break;
-      v_in_off.push_back(hdr_end);
-      v_in_len.push_back((uint32_t)(next - hdr_end));
-      v_out_off.push_back(o);
-      v_out_cap.push_back(isize);
-      v_next.push_back(next);
-      o += isize;
-      p = next;
+    size_t o = out_pos;
+    {
+      std::vector<HintedMember> run;
+      hinted_run(in, in_len, pos, &run, nullptr);
+      for (const HintedMember &m : run) {
+        v_in_off.push_back(m.hdr_end);
+        v_in_len.push_back((uint32_t)(m.next - m.hdr_end));
+        v_out_off.push_back(o);
+        v_out_cap.push_back(m.isize);
+        v_next.push_back(m.next);
+        o += m.isize;
+      }
     }
     size_t nb = v_in_off.size();
     if (nb > 0) {
@@ -458,20 +477,10 @@ static int gzip_decode_staged(const uint8_t *in, size_t in_len, int verify, size
 // ---------------------------------------------------------------------------------------------
 static int gzip_fast_path(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_cap, size_t *pos_io,
                           size_t *out_pos_io, size_t *needed) {
-  struct M { size_t hdr_end, next; uint32_t isize; };
-  std::vector<M> ms;
-  size_t p = *pos_io, o = *out_pos_io;
-  while (p < in_len) {
-    size_t hdr_end, bsize;
-    if (gzip_header(in, in_len, p, &hdr_end, &bsize) != 1 || bsize == 0) break;
-    size_t next = p + bsize;
-    if (next > in_len || next < hdr_end + 8) break;
-    uint32_t isize = le32(in + next - 4);
-    if (!isize_possible(isize, next - hdr_end)) break;
-    ms.push_back({hdr_end, next, isize});
-    o += isize;
-    p = next;
-  }
+  std::vector<HintedMember> ms;
+  size_t promised = 0;
+  const size_t p = hinted_run(in, in_len, *pos_io, &ms, &promised);
+  const size_t o = *out_pos_io + promised;
   const size_t nb = ms.size();
   if (nb == 0) return B200Z_OK;
   if (o > out_cap) {
@@ -598,20 +607,7 @@ void set_error_text(const char *msg) { set_err("%s", msg); }
 
 // Bytes of `in` covered by whole members that carry a size hint, from offset 0 (the run gzip_fast_path would take), and the
 // output bytes their ISIZE fields promise.
-size_t gzip_hinted_prefix(const uint8_t *in, size_t n, size_t *out_bytes) {
-  size_t p = 0, o = 0;
-  while (p < n) {
-    size_t hdr_end, bsize;
-    if (gzip_header(in, n, p, &hdr_end, &bsize) != 1 || bsize == 0) break;
-    const size_t next = p + bsize;
-    if (next > n || next < hdr_end + 8) break;
-    if (!isize_possible(le32(in + next - 4), next - hdr_end)) break;
-    o += le32(in + next - 4);
-    p = next;
-  }
-  if (out_bytes) *out_bytes = o;
-  return p;
-}
+size_t gzip_hinted_prefix(const uint8_t *in, size_t n, size_t *out_bytes) { return hinted_run(in, n, 0, nullptr, out_bytes); }
 
 // The hinted run at the front of `in`, decoded through the chunk pipeline: *in_used = end of the last member whose hint
 // was exact (== the whole run unless a hint lied), *out_len = the bytes those members produced.
@@ -2088,18 +2084,8 @@ int b200z_gzip_encode(const uint8_t *in, size_t in_len, int level, uint32_t mtim
 }
 
 size_t b200z_gzip_bound(const uint8_t *in, size_t in_len) {
-  size_t pos = 0, total = 0;
-  while (pos < in_len) {
-    size_t hdr_end, bsize;
-    int h = gzip_header(in, in_len, pos, &hdr_end, &bsize);
-    if (h != 1 || bsize == 0) return 0;
-    size_t next = pos + bsize;
-    if (next > in_len || next < hdr_end + 8) return 0;
-    if (!isize_possible(le32(in + next - 4), next - hdr_end)) return 0;  // a size field that cannot be true: unknown
-    total += le32(in + next - 4);
-    pos = next;
-  }
-  return total;
+  size_t total = 0;
+  return hinted_run(in, in_len, 0, nullptr, &total) == in_len ? total : 0;  // every member hinted, or unknown
 }
 
 int b200z_gzip_decode(const uint8_t *in, size_t in_len, int verify, uint8_t *out, size_t out_cap, size_t *out_len) {
