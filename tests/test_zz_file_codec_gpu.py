@@ -3,7 +3,9 @@ the file must hold exactly what the memory entry points and the oracle produce f
 (segments cut at member boundaries, forced small here), members without size hints, a lying hint, bad data with its
 partial output, stream positions either side.  Mirrors the reference's stream tests (test/io_test.dart:471-492 'stream gzip
 encode / decode', test/zlib_test.dart:35-58 'encodeStream', io/extract_archive_to_disk.dart:183-202).
-The file sorts last: it is the newest path."""
+Also here, for the same reason (written after the round's last GPU run; the file sorts last so that the established parity
+tests come first): b200z_deflate_batch / ZipEncoder(batch=True), the chunk pipeline of b200z_gzip_decode with
+test-sized chunks, extract_file_to_disk."""
 import bz2
 import os
 import struct
