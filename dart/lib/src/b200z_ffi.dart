@@ -115,6 +115,66 @@ typedef _ZipExtractC = Int32 Function(Pointer<Uint8> zip, Size zipLen, Pointer<Z
 typedef _ZipExtractD = int Function(Pointer<Uint8> zip, int zipLen, Pointer<ZipEntry> entries, int n, Pointer<Uint8> out,
     int outCap, Pointer<Uint64> outOff, Pointer<Uint64> outRoom, Pointer<Uint64> outLen, Pointer<Int32> status, int flags);
 
+
+// ---- the rest of include/b200z.h: batches, sharding, checksums, diagnostics ----
+/// b200z_bz2_block (include/b200z.h)
+final class Bz2Block extends Struct {
+  @Uint64()
+  external int startBit;
+  @Uint64()
+  external int endBit;
+  @Uint64()
+  external int outBytes;
+  @Uint32()
+  external int crcCalc;
+  @Uint32()
+  external int crcStored;
+  @Int32()
+  external int status;
+  @Uint32()
+  external int flags;
+}
+
+typedef _Bz2ShardC = Int32 Function(Pointer<Uint8> inp, Size inLen, Uint32 rank, Uint32 world, Pointer<Uint8> out, Size outCap,
+    Pointer<Size> outLen, Pointer<Bz2Block> blocks, Size blocksCap, Pointer<Size> nBlocks);
+typedef _Bz2ShardD = int Function(Pointer<Uint8> inp, int inLen, int rank, int world, Pointer<Uint8> out, int outCap,
+    Pointer<Size> outLen, Pointer<Bz2Block> blocks, int blocksCap, Pointer<Size> nBlocks);
+typedef _Crc32C = Int32 Function(Pointer<Uint8> inp, Size inLen, Pointer<Uint32> crc);
+typedef _Crc32D = int Function(Pointer<Uint8> inp, int inLen, Pointer<Uint32> crc);
+typedef _DeflateBatchC = Int32 Function(Pointer<Uint8> inBase, Pointer<Uint64> inOff, Pointer<Uint64> inLen, Size nUnits,
+    Int32 level, Int32 windowBits, Pointer<Uint8> outBase, Pointer<Uint64> outOff, Pointer<Uint64> outCap, Pointer<Uint64> outLen,
+    Pointer<Uint32> crc32, Pointer<Int32> status);
+typedef _DeflateBatchD = int Function(Pointer<Uint8> inBase, Pointer<Uint64> inOff, Pointer<Uint64> inLen, int nUnits, int level,
+    int windowBits, Pointer<Uint8> outBase, Pointer<Uint64> outOff, Pointer<Uint64> outCap, Pointer<Uint64> outLen,
+    Pointer<Uint32> crc32, Pointer<Int32> status);
+typedef _InflateBatchC = Int32 Function(Pointer<Uint8> inBase, Size inBytes, Pointer<Uint64> inOff, Pointer<Uint32> inLen,
+    Pointer<Uint8> outBase, Size outBytes, Pointer<Uint64> outOff, Pointer<Uint32> outCap, Pointer<Uint32> outLen,
+    Pointer<Int32> status, Pointer<Uint32> inUsed, Size nUnits);
+typedef _InflateBatchD = int Function(Pointer<Uint8> inBase, int inBytes, Pointer<Uint64> inOff, Pointer<Uint32> inLen,
+    Pointer<Uint8> outBase, int outBytes, Pointer<Uint64> outOff, Pointer<Uint32> outCap, Pointer<Uint32> outLen,
+    Pointer<Int32> status, Pointer<Uint32> inUsed, int nUnits);
+typedef _InflateBatchDeviceC = Int32 Function(Pointer<Uint8> dInBase, Pointer<Uint64> dInOff, Pointer<Uint32> dInLen,
+    Pointer<Uint8> dOutBase, Pointer<Uint64> dOutOff, Pointer<Uint32> dOutCap, Pointer<Uint32> dOutLen, Pointer<Int32> dStatus,
+    Pointer<Uint32> dInUsed, Size nUnits, Pointer<Void> dWorkspace, Size workspaceBytes, Pointer<Void> cudaStream);
+typedef _InflateBatchDeviceD = int Function(Pointer<Uint8> dInBase, Pointer<Uint64> dInOff, Pointer<Uint32> dInLen,
+    Pointer<Uint8> dOutBase, Pointer<Uint64> dOutOff, Pointer<Uint32> dOutCap, Pointer<Uint32> dOutLen, Pointer<Int32> dStatus,
+    Pointer<Uint32> dInUsed, int nUnits, Pointer<Void> dWorkspace, int workspaceBytes, Pointer<Void> cudaStream);
+typedef _WorkspaceBytesC = Size Function(Size nUnits, Size totalInBytes, Size totalOutCap);
+typedef _WorkspaceBytesD = int Function(int nUnits, int totalInBytes, int totalOutCap);
+typedef _FileStatsC = Void Function(Pointer<Uint32> nSegments, Pointer<Uint32> nWhole);
+typedef _FileStatsD = void Function(Pointer<Uint32> nSegments, Pointer<Uint32> nWhole);
+typedef _ZipCommentC = Int32 Function(Pointer<Uint8> zip, Size zipLen, Pointer<Uint64> off, Pointer<Uint32> len);
+typedef _ZipCommentD = int Function(Pointer<Uint8> zip, int zipLen, Pointer<Uint64> off, Pointer<Uint32> len);
+typedef _VoidC = Void Function();
+typedef _VoidD = void Function();
+typedef _IntC = Int32 Function();
+typedef _IntD = int Function();
+typedef _U64C = Uint64 Function();
+typedef _ProfileEnableC = Void Function(Int32 on);
+typedef _ProfileEnableD = void Function(int on);
+typedef _ProfileReadC = Int32 Function(Pointer<Double> decodeMs, Pointer<Double> expandMs, Pointer<Uint64> nBatches);
+typedef _ProfileReadD = int Function(Pointer<Double> decodeMs, Pointer<Double> expandMs, Pointer<Uint64> nBatches);
+
 class B200ZException implements Exception {
   final int code;
   final String message;
@@ -145,6 +205,22 @@ class B200Z {
   late final _FileCodecD fileCodec = _lib.lookupFunction<_FileCodecC, _FileCodecD>('b200z_file_codec');
   late final _ZipListD zipList = _lib.lookupFunction<_ZipListC, _ZipListD>('b200z_zip_list');
   late final _ZipExtractD zipExtract = _lib.lookupFunction<_ZipExtractC, _ZipExtractD>('b200z_zip_extract');
+  late final _ZipCommentD zipComment = _lib.lookupFunction<_ZipCommentC, _ZipCommentD>('b200z_zip_comment');
+  late final _Bz2ShardD bzip2DecodeShard = _lib.lookupFunction<_Bz2ShardC, _Bz2ShardD>('b200z_bzip2_decode_shard');
+  late final _Crc32D crc32 = _lib.lookupFunction<_Crc32C, _Crc32D>('b200z_crc32');
+  late final _DeflateBatchD deflateBatch = _lib.lookupFunction<_DeflateBatchC, _DeflateBatchD>('b200z_deflate_batch');
+  late final _InflateBatchD inflateBatch = _lib.lookupFunction<_InflateBatchC, _InflateBatchD>('b200z_inflate_batch');
+  late final _InflateBatchDeviceD inflateBatchDevice =
+      _lib.lookupFunction<_InflateBatchDeviceC, _InflateBatchDeviceD>('b200z_inflate_batch_device');
+  late final _WorkspaceBytesD inflateWorkspaceBytes =
+      _lib.lookupFunction<_WorkspaceBytesC, _WorkspaceBytesD>('b200z_inflate_workspace_bytes');
+  late final _FileStatsD fileLastStats = _lib.lookupFunction<_FileStatsC, _FileStatsD>('b200z_file_last_stats');
+  late final _VoidD shutdown = _lib.lookupFunction<_VoidC, _VoidD>('b200z_shutdown');
+  late final _IntD deviceCount = _lib.lookupFunction<_IntC, _IntD>('b200z_device_count');
+  late final _ErrC _version = _lib.lookupFunction<_ErrC, _ErrC>('b200z_version');
+  late final _IntD launchCount = _lib.lookupFunction<_U64C, _IntD>('b200z_launch_count');
+  late final _ProfileEnableD profileEnable = _lib.lookupFunction<_ProfileEnableC, _ProfileEnableD>('b200z_profile_enable');
+  late final _ProfileReadD profileRead = _lib.lookupFunction<_ProfileReadC, _ProfileReadD>('b200z_profile_read');
 
   B200Z._(this._lib);
 
@@ -163,6 +239,7 @@ class B200Z {
   }
 
   String get lastError => _lastError().toDartString();
+  String get version => _version().toDartString();
 
   /// Copies [bytes] into pinned native memory (full-speed PCIe); caller frees with [hostFree].
   Pointer<Uint8> toNative(List<int> bytes) {

@@ -87,3 +87,13 @@ def test_late_entry_points_fail_without_device(tmp_path):
     with pytest.raises(a.B200ZError) as ei:
         a.extract_file_to_disk(str(tgz), str(tmp_path / "o"))
     assert ei.value.code == _ffi.E_NODEVICE
+
+
+def test_dart_binding_names_every_symbol():
+    """dart/lib/src/b200z_ffi.dart cannot be compiled here (no Dart SDK); at least it must look up exactly the symbols the
+    header declares -- no more, no fewer."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    dart = open(os.path.join(root, "dart", "lib", "src", "b200z_ffi.dart")).read()
+    bound = set(re.findall(r"lookupFunction<[^>]+>\(\s*'(b200z_[a-z0-9_]+)'\)", dart))
+    assert bound == set(_ffi.declared_symbols())
