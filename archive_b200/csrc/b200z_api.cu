@@ -650,7 +650,12 @@ int gzip_decode_after(const uint8_t *in, size_t n, int verify, const uint8_t *hi
 // _zlib_decoder_web.dart:31-107 on staged input.
 static int zlib_decode_staged(const uint8_t *in, size_t in_len, size_t pos, int verify, int raw, int big_endian,
                               size_t out_pos, size_t out_cap, size_t *out_len_total) {
-  *out_len_total = out_pos;
+  // The reference inflates every stream into a buffer of its own and hands it to `output` only when the NEXT stream's
+  // header has been accepted, or at the end of the loop (:82-84, :101-103).  A stream whose successor's header is bad, or
+  // whose Adler-32 is wrong or missing, therefore never reaches the output.  Here the streams are decoded straight into
+  // their final position; `committed` is what `output` holds, `pending` the bytes of the stream that waits.
+  size_t committed = out_pos, pending = 0;
+  *out_len_total = committed;
   while (pos < in_len) {
     if (!raw) {
       if (pos + 2 > in_len) {
@@ -676,14 +681,14 @@ static int zlib_decode_staged(const uint8_t *in, size_t in_len, size_t pos, int 
         return B200Z_E_DATA;
       }
     }
-    // The reference commits stream k's bytes when stream k+1 starts or at the end (:82-84,:101-103);
-    // a failed Adler check drops only the failing stream.  Decoding straight into the final position
-    // and rolling the length back gives the same observable result.
+    committed += pending;  // output.writeBytes(buffer) (:82-84)
+    pending = 0;
+    *out_len_total = committed;
     OneResult r;
-    int rc = run_one_staged(pos, in_len, out_pos, out_cap, &r);
+    int rc = run_one_staged(pos, in_len, committed, out_cap, &r);
     if (rc) return rc;
     if (r.status == B200Z_U_NOSPC) {
-      *out_len_total = out_pos + r.out_len;
+      *out_len_total = committed + r.out_len;
       set_err("zlib_decode: out_cap %zu too small", out_cap);
       return B200Z_E_NOSPC;
     }
@@ -692,26 +697,21 @@ static int zlib_decode_staged(const uint8_t *in, size_t in_len, size_t pos, int 
       return B200Z_E_THROW;
     }
     if (r.status == B200Z_U_BADCODE) {
-      *out_len_total = out_pos + r.out_len;
+      *out_len_total = committed + r.out_len;
       set_err("zlib_decode: unusable Huffman code set");
       return B200Z_E_DATA;
     }
     pos += r.in_used;
-    if (r.status == B200Z_U_STOP && !raw && pos + 4 > in_len) {
-      // the input ran out inside a block: the Adler-32 read that follows (:86) starts past the end -- RangeError
-      *out_len_total = out_pos;  // (the stream's bytes were not committed yet, :82-84)
-      set_err("zlib_decode: input ends inside the stream (Dart: RangeError)");
-      return B200Z_E_THROW;
-    }
-    if (r.status == B200Z_U_STOP) {
-      // Inflate gave up: the reference's stream position is then wherever its byte-wise bit buffer had
+    if (r.status == B200Z_U_STOP && pos < in_len) {
+      // Inflate gave up with input left: the reference's stream position is then wherever its byte-wise bit buffer had
       // got to (not rewound) -- unspecified; stop here with the partial output (DESIGN.md "Divergences").
-      *out_len_total = out_pos + r.out_len;
+      *out_len_total = committed + r.out_len;
       set_err("zlib_decode: inflate stopped early");
       return B200Z_E_DATA;
     }
+    // (B200Z_U_STOP with the input used up == the stream ends inside a block: Inflate simply returns what it has, :85)
     if (!raw) {
-      if (pos + 4 > in_len) {
+      if (pos + 4 > in_len) {  // readUint32 past the end (:88); the stream's bytes were not handed over yet
         set_err("zlib_decode: truncated Adler-32 (Dart: RangeError)");
         return B200Z_E_THROW;
       }
@@ -720,7 +720,7 @@ static int zlib_decode_staged(const uint8_t *in, size_t in_len, size_t pos, int 
       pos += 4;
       if (verify) {
         uint32_t a;
-        rc = device_adler32((const uint8_t *)g.d_out.p + out_pos, r.out_len, &a);
+        rc = device_adler32((const uint8_t *)g.d_out.p + committed, r.out_len, &a);
         if (rc) return rc;
         if (a != stored) {
           set_err("zlib_decode: Adler-32 mismatch");
@@ -728,9 +728,9 @@ static int zlib_decode_staged(const uint8_t *in, size_t in_len, size_t pos, int 
         }
       }
     }
-    out_pos += r.out_len;
-    *out_len_total = out_pos;
+    pending = r.out_len;
   }
+  *out_len_total = committed + pending;  // (:101-103)
   return B200Z_OK;
 }
 

@@ -366,6 +366,7 @@ constexpr int SPEC_HSHIFT = 2;         // helper token region = unit capacity >>
 constexpr int PIECE_MAX = 30;
 constexpr int PIECE_WORDS = 2 + 3 * PIECE_MAX;  // [0] = count, then (src, start, count) from word 2: src 0 = own region, k = helper k
 constexpr int USCRATCH_BYTES = (SPEC_MAX_G - 1) * SPEC_BMW * 4;  // per unit: the helpers' boundary bitmaps
+constexpr int U_STOP_SHORT = -100;  // internal: B200Z_U_STOP because a read ran out of input (reported as B200Z_U_STOP)
 constexpr uint32_t SPEC_BIAS = 0x40000000u;  // helpers count output bytes from here, so "distance > produced" never fires
 constexpr uint32_t SPEC_NOLINK = 0xffffffffu;
 
@@ -834,15 +835,15 @@ B200Z_HD UnitResult inflate_decode_unit(bool active, const uint8_t *in, uint32_t
       } else if (type == 2) {
         // ---- dynamic (inflate.dart:239-298) ----
         int hlit = br.read_bits_checked(5);
-        if (hlit < 0) { st = B200Z_U_STOP; done = true; break; }
+        if (hlit < 0) { st = U_STOP_SHORT; done = true; break; }
         hlit += 257;
         if (hlit > 288) { st = B200Z_U_STOP; done = true; break; }
         int hdist = br.read_bits_checked(5);
-        if (hdist < 0) { st = B200Z_U_STOP; done = true; break; }
+        if (hdist < 0) { st = U_STOP_SHORT; done = true; break; }
         hdist += 1;
         if (hdist > 32) { st = B200Z_U_STOP; done = true; break; }
         int hclen = br.read_bits_checked(4);
-        if (hclen < 0) { st = B200Z_U_STOP; done = true; break; }
+        if (hclen < 0) { st = U_STOP_SHORT; done = true; break; }
         hclen += 4;
         if (hclen > 19) { st = B200Z_U_STOP; done = true; break; }
         for (int i = 0; i < 19; ++i) lens[i] = 0;
@@ -852,7 +853,7 @@ B200Z_HD UnitResult inflate_decode_unit(bool active, const uint8_t *in, uint32_t
           if (l < 0) { bad = true; break; }
           lens[c_order[i]] = (uint8_t)l;
         }
-        if (bad) { st = B200Z_U_STOP; done = true; break; }
+        if (bad) { st = U_STOP_SHORT; done = true; break; }
         // code-length alphabet: 7-bit LUT in the (not yet built) lit/len LUT area
         uint8_t clmax;
         {
@@ -866,7 +867,7 @@ B200Z_HD UnitResult inflate_decode_unit(bool active, const uint8_t *in, uint32_t
         int err = 0;
         while (i < num) {
           br.refill();
-          if (!br.fast() && br.rem_bits() < clmax) { err = B200Z_U_STOP; break; }
+          if (!br.fast() && br.rem_bits() < clmax) { err = U_STOP_SHORT; break; }
           uint32_t e = lut_l[br.peek(7)];
           int l = e & 15;
           int code = e >> 4;
@@ -880,16 +881,16 @@ B200Z_HD UnitResult inflate_decode_unit(bool active, const uint8_t *in, uint32_t
             continue;
           } else if (code == 16) {
             repeat = br.read_bits_checked(2);
-            if (repeat < 0) { err = B200Z_U_STOP; break; }
+            if (repeat < 0) { err = U_STOP_SHORT; break; }
             repeat += 3;
           } else if (code == 17) {
             repeat = br.read_bits_checked(3);
-            if (repeat < 0) { err = B200Z_U_STOP; break; }
+            if (repeat < 0) { err = U_STOP_SHORT; break; }
             repeat += 3;
             prev = 0;
           } else {
             repeat = br.read_bits_checked(7);
-            if (repeat < 0) { err = B200Z_U_STOP; break; }
+            if (repeat < 0) { err = U_STOP_SHORT; break; }
             repeat += 11;
             prev = 0;
           }
@@ -930,7 +931,7 @@ B200Z_HD UnitResult inflate_decode_unit(bool active, const uint8_t *in, uint32_t
     br.refill();
     const bool careful = !br.fast();
     if (careful && br.rem_bits() < maxl) {  // _readCodeByTable short read (quirk Q1)
-      st = B200Z_U_STOP;
+      st = U_STOP_SHORT;
       done = true; break;
     }
     uint32_t e = lut_l[br.peek(LBITS)];
@@ -978,7 +979,7 @@ B200Z_HD UnitResult inflate_decode_unit(bool active, const uint8_t *in, uint32_t
     br.refill();
     const bool careful2 = !br.fast();
     if (careful2 && br.rem_bits() < maxd) {
-      st = B200Z_U_STOP;
+      st = U_STOP_SHORT;
       done = true; break;
     }
     uint32_t de = lut_d[br.peek(DBITS)];
@@ -1043,11 +1044,14 @@ B200Z_HD UnitResult inflate_decode_unit(bool active, const uint8_t *in, uint32_t
   UnitResult r;
   r.ntok = nt;
   r.out_len = olen;
-  r.status = st;
+  r.status = st == U_STOP_SHORT ? B200Z_U_STOP : st;
   {
     long long rem = br.rem_bits();
     if (rem < 0) rem = 0;
     r.in_used = br.in_len - (uint32_t)(rem >> 3);  // whole unread bytes are given back (inflate.dart:337-340)
+    // A read that ran out of input has pulled every byte first (_readBits / _readCodeByTable loop on isEOS,
+    // inflate.dart:166-168,192-195) and nothing is given back on that path: the stream is left at its end.
+    if (st == U_STOP_SHORT) r.in_used = br.in_len;
   }
   return r;
 }

@@ -137,3 +137,90 @@ def test_impossible_size_fields_are_not_hints(a):
         assert L.b200z_gzip_bound(addr, n) == 0  # unknown, not 4 GiB
         assert orc.gzip_decode(blob) == (orc.OK, text)
         assert run(a, a.GZipDecoder(), blob) == (orc.OK, text), k
+
+
+def _gz(chunk, flags=0, extra=b"", name=b"", comment=b"", hcrc=False):
+    co = zlib.compressobj(6, zlib.DEFLATED, -15, 9)
+    body = co.compress(chunk) + co.flush()
+    f = flags | (4 if extra else 0) | (8 if name else 0) | (16 if comment else 0) | (2 if hcrc else 0)
+    h = b"\x1f\x8b\x08" + bytes([f]) + bytes(4) + b"\x00\xff"
+    if extra:
+        h += struct.pack("<H", len(extra)) + extra
+    if name:
+        h += name + b"\0"
+    if comment:
+        h += comment + b"\0"
+    if hcrc:
+        h += b"\xab\xcd"
+    return h + body + struct.pack("<II", zlib.crc32(chunk), len(chunk))
+
+
+def test_gzip_header_variants_and_zlib_fallback(a):
+    """_readHeader (_gzip_decoder_web.dart:60-138) with every optional field, size subfields that lie, reserved flag bits,
+    junk between members -- and the zlib fall-back (:31-37), whose streams reach the output one stream late
+    (_zlib_decoder_web.dart:82-84): a zlib stream followed by something that is not a zlib header is lost."""
+    from archive_b200 import synth
+    text = synth.text(40000, stream=55).tobytes()
+    t = [text[i * 5000:(i + 1) * 5000] for i in range(8)]
+    variants = [
+        _gz(t[0], name=b"file.txt") + _gz(t[1], comment=b"a comment") + _gz(t[2], hcrc=True),
+        _gz(t[0], extra=b"XY\x03\x00abc") + _gz(t[1], extra=b"BC\x02\x00\xff\xff") + _gz(t[2]),
+        _gz(t[0], extra=b"AB\x01\x00zBC\x02\x00\x10\x00") + _gz(t[1]),
+        _gz(t[0], flags=0xE0) + _gz(t[1], flags=0x20, name=b"n"),
+        _gz(t[0]) + b"\x00\x00\x00" + _gz(t[1]),
+        _gz(t[0]) + zlib.compress(t[1]) + _gz(t[2]),            # the zlib stream's bytes never reach the output
+        _gz(t[0]) + zlib.compress(t[1]) + zlib.compress(t[2]),  # ... here the first one does
+        _gz(t[0], extra=b"Q" * 300) + _gz(t[1], name=b"x" * 2000),
+        _gz(t[0])[:-8] + _gz(t[1]),
+        b"\x1f\x8b\x09\x00" + bytes(6) + _gz(t[0])[10:],
+        _gz(t[0], name=b"unterminated")[:22],
+        _gz(b""), _gz(b"") + _gz(t[3]), b"\x1f", b"\x1f\x8b", b"\x1f\x8b\x08",
+    ]
+    for i, z in enumerate(variants):
+        ost, oout = orc.gzip_decode(z)
+        st, got = run(a, a.GZipDecoder(), z)
+        assert st == ost and (st == orc.THROW or got == oout), (i, st, ost, len(got), len(oout))
+
+
+def test_zlib_streams_reach_the_output_one_stream_late(a):
+    from archive_b200 import synth
+    text = synth.text(30000, stream=56).tobytes()
+    s1, s2 = zlib.compress(text[:12000]), zlib.compress(text[12000:])
+    raw = []
+    for lvl, strat in ((6, zlib.Z_DEFAULT_STRATEGY), (6, zlib.Z_FIXED)):
+        co = zlib.compressobj(lvl, zlib.DEFLATED, -15, 8, strat)
+        raw.append(co.compress(text[:15000]) + co.flush())
+    cases = [(s1 + s2, {}), (s1 + b"\x78", {}), (s1 + b"\x00\x00", {}), (s1 + b"\x78\x9d" + s2[2:], {}),  # bad FCHECK behind s1
+             (s1 + s2[:-2], {}), (s1 + s2[:40], {}), (s1[:-1] + b"\x00" + s2, {"verify": True}),            # wrong Adler-32 in s1
+             (raw[0] + raw[1], {"raw": True}), (raw[0] + raw[1] + b"\x00", {"raw": True}), (raw[0] + b"junkjunk", {"raw": True}),
+             (raw[0][:-3], {"raw": True}), (b"", {"raw": True}), (b"", {})]
+    for i, (z, kw) in enumerate(cases):
+        for verify in (False, True):
+            k = dict(kw)
+            k.setdefault("verify", verify)
+            ost, oout = orc.zlib_decode(z, **k)
+            st, got = run(a, a.ZLibDecoder(), z, **k)
+            assert st == ost and (st == orc.THROW or got == oout), (i, k, st, ost, len(got), len(oout))
+
+
+def test_inflate_leaves_the_input_where_the_reference_does(a):
+    """Inflate.stream(input): output AND the position the input is left at (inflate.dart:337-340 gives whole unread bytes
+    back after a block; a read that runs out of input has pulled every byte, :166-168,192-195)."""
+    import random
+    from archive_b200 import synth
+    text = synth.text(15000, stream=57).tobytes()
+    rng = random.Random(11)
+    for lvl, strat in ((6, zlib.Z_DEFAULT_STRATEGY), (0, zlib.Z_DEFAULT_STRATEGY), (6, zlib.Z_FIXED), (9, zlib.Z_HUFFMAN_ONLY)):
+        co = zlib.compressobj(lvl, zlib.DEFLATED, -15, 8, strat)
+        z0 = co.compress(text) + co.flush()
+        cands = [z0 + b"TRAILER!", z0] + [z0[:k] for k in range(0, len(z0), max(1, len(z0) // 12))]
+        for z in cands:
+            ost, oout, ocons = orc.inflate(z)
+            ims = a.InputMemoryStream(z)
+            try:
+                got, st = a.Inflate.stream(ims).get_bytes(), orc.OK
+            except a.DartRangeError:
+                got, st = None, orc.THROW
+            assert (st == orc.THROW) == (ost == orc.THROW), (lvl, len(z))
+            if st != orc.THROW:
+                assert got == oout and ims.position == ocons, (lvl, strat, len(z), ims.position, ocons)
