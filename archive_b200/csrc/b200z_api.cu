@@ -1179,12 +1179,15 @@ static int device_crc32(const uint8_t *d, size_t n, uint32_t *out) {
 }
 
 // the old deflate_stored (deflate.dart:691-737) touches no data: its block list follows from the length alone
-static void stored_block_list(size_t n, std::vector<DeflStoredBlock> &out) {
-  const long long w_size = 32768, window_size = 65536, min_lookahead = 262;
+// windowBits sets the window (deflate.dart:132-134) and with it where the blocks are cut: 2^windowBits - 262 bytes at most
+static void stored_block_list(size_t n, int window_bits, std::vector<DeflStoredBlock> &out) {
+  const long long w_size = 1ll << window_bits, window_size = 2 * w_size, min_lookahead = 262;
   const long long max_block_size = 65536 - 5 < 0xffff ? 65536 - 5 : 0xffff;
   long long strstart = 0, block_start = 0, lookahead = 0, base = 0;  // base: absolute position of window index 0
   long long in_pos = 0;
   auto flush = [&](bool eof) {
+    // (block_start is never negative here: a block is flushed once it is w_size - min_lookahead long, and the window
+    // slides only when strstart has reached 2 * w_size - min_lookahead, so the data is always still there to be stored)
     out.push_back({(uint32_t)(base + block_start), (uint32_t)(strstart - block_start), eof ? 1u : 0u});
     block_start = strstart;
   };
@@ -1238,7 +1241,7 @@ static int deflate_staged(size_t n, int level, int window_bits, size_t *out_len)
   CU(g.d_out.reserve(cap));
   if (level == 0) {
     std::vector<DeflStoredBlock> bl;
-    stored_block_list(n, bl);
+    stored_block_list(n, window_bits, bl);
     const size_t ws = bl.size() * 64 + 1024;
     CU(g.d_ws.reserve(ws));
     CU(deflate_stored_device((const uint8_t *)g.d_in.p, bl.data(), (uint32_t)bl.size(), (uint8_t *)g.d_out.p, cap, g.d_ws.p,
@@ -1264,7 +1267,7 @@ static int deflate_member_on(const uint8_t *d_in, size_t n, int level, int windo
                              size_t ws_bytes, cudaStream_t s, size_t *out_len, uint32_t *crc) {
   if (level == 0) {
     std::vector<DeflStoredBlock> bl;
-    stored_block_list(n, bl);
+    stored_block_list(n, window_bits, bl);
     CU(deflate_stored_device(d_in, bl.data(), (uint32_t)bl.size(), d_out, cap, ws, ws_bytes, out_len, s));
   } else {
     uint32_t stats[3];
@@ -1292,7 +1295,7 @@ static int deflate_batch_impl(const uint8_t *in_base, const uint64_t *in_off, co
     size_t ws = (n / kCrcTile + 1) * 4 + 256;
     if (level == 0) {
       std::vector<DeflStoredBlock> bl;
-      stored_block_list(n, bl);
+      stored_block_list(n, window_bits, bl);
       ws = std::max(ws, bl.size() * 64 + 1024);
     } else {
       ws = std::max(ws, deflate_workspace_bytes(n));
