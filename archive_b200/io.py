@@ -111,3 +111,88 @@ def extract_file_to_disk(input_path: str, output_path: str, buffer_size: int | N
             out.close_sync()
         return [tar_path]
     raise ValueError(f"{input_path}: must end with {_EXTENSIONS}")
+
+
+class ZipFileEncoder:
+    """ZipFileEncoder (lib/src/io/zip_file_encoder.dart:11-225): build a .zip on disk from files and directories.  The
+    reference compresses every file as it is added (ZipEncoder.startEncode / add / endEncode); here the members are collected
+    and compressed when the archive is closed -- all deflate members of a level as ONE device batch when `batch` is set
+    (b200z_deflate_batch) -- and the container is written through an OutputFileStream.  The bytes are those of
+    ZipEncoder().encode_bytes over the same members in the same order.  Directory listings are taken in sorted order (the
+    reference takes whatever order Directory.listSync returns)."""
+    STORE, GZIP = 0, 1  # (:16-17) the reference's names for levels 0 and 1
+
+    def __init__(self, compress=None, batch: bool = False):
+        self._compress, self._batch = compress, batch
+        self._files, self._path, self._level, self._modified = None, None, None, None
+
+    @staticmethod
+    def _compose_zip_directory_path(dir_path: str, filename):  # (:56-74)
+        if filename is None:
+            return dir_path.rstrip("/\\") + ".zip"
+        a, b = os.path.abspath(dir_path), os.path.abspath(filename)
+        if b != a and os.path.commonpath([a, b]) == a:
+            raise ValueError(f"filename must not be within the directory being zipped: {filename}")  # FormatException
+        return filename
+
+    def create(self, zip_path: str, level=None, modified=None):  # (:78-91)
+        self._path, self._level, self._modified, self._files = zip_path, level, modified, []
+
+    open = create
+
+    def add_archive_file(self, f: ArchiveFile):  # (:212-214)
+        self._files.append(f)
+
+    def add_file(self, path: str, filename=None, level=None):  # addFileSync (:182-194)
+        name = (filename or os.path.basename(path)).replace(os.sep, "/")
+        st = os.stat(path)
+        with open(path, "rb") as fh:
+            body = fh.read()
+        f = ArchiveFile(name, len(body))
+        f.content, f.last_mod_time, f.mode = body, int(st.st_mtime), st.st_mode
+        f.compress_level = level  # add(file, level:) -- level 0 is still method 8, as stored DEFLATE blocks (zip_encoder.dart:248-252)
+        self._files.append(f)
+
+    def add_directory(self, dir_path: str, include_dir_name: bool = True, level=None, follow_links: bool = True, filter=None):
+        """addDirectorySync (:93-136).  filter(path, progress) -> "skip" | "cancel" | anything else."""
+        dir_name = os.path.basename(os.path.normpath(dir_path))
+        listing = []
+        for root, dirs, files in os.walk(dir_path, followlinks=follow_links):
+            dirs.sort()
+            listing += [(os.path.join(root, d), True) for d in dirs] + [(os.path.join(root, f), False) for f in sorted(files)]
+        listing.sort(key=lambda x: x[0])
+        for k, (p, is_dir) in enumerate(listing):
+            if filter is not None:
+                op = filter(p, (k + 1) / len(listing))
+                if op == "cancel":
+                    break
+                if op == "skip":
+                    continue
+            rel = os.path.relpath(p, dir_path).replace(os.sep, "/")
+            name = f"{dir_name}/{rel}" if include_dir_name else rel
+            if is_dir:
+                st = os.stat(p)
+                f = ArchiveFile(name, 0, is_file=False)
+                f.mode, f.last_mod_time = st.st_mode, int(st.st_mtime)
+                self._files.append(f)
+            else:
+                self.add_file(p, name, level)
+
+    def close(self):  # closeSync (:216-219): endEncode + close the stream
+        from .zip import ZipEncoder
+        data = ZipEncoder(compress=self._compress, batch=self._batch).encode_bytes(self._files, level=self._level,
+                                                                                 modified=self._modified)
+        out = OutputFileStream(self._path)
+        out.write_bytes(data)
+        out.close_sync()
+        self._files = None
+        return len(data)
+
+    close_sync = close
+
+    def zip_directory(self, dir_path: str, filename=None, level=None, follow_links: bool = True, modified=None, filter=None):
+        """zipDirectory (:22-43): level defaults to `gzip` (= 1)."""
+        level = self.GZIP if level is None else level
+        self.create(self._compose_zip_directory_path(dir_path, filename), level=level, modified=modified)
+        self.add_directory(dir_path, include_dir_name=False, level=level, follow_links=follow_links, filter=filter)
+        return self.close()

@@ -244,10 +244,16 @@ class ZipEncoder:
         files = []
         archive = list(archive)
         compress = self._compress
+        def level_of(e):  # add(file, level: ...) overrides the encoder's level for that member (zip_encoder.dart:137-183)
+            own = getattr(e, "compress_level", None)
+            return own if own is not None else (level if level is not None else 6)
+
         if self._batch:
-            lv = level if level is not None else 6
             idx = [i for i, e in enumerate(archive) if e.is_file and (e.compression or "deflate") == "deflate"]
-            table = dict(zip(idx, deflate_batch([archive[i].content or b"" for i in idx], lv)))
+            table = {}
+            for lv in sorted({level_of(archive[i]) for i in idx}):  # one device batch per level in use
+                grp = [i for i in idx if level_of(archive[i]) == lv]
+                table.update(zip(grp, deflate_batch([archive[i].content or b"" for i in grp], lv)))
             at = [None]
 
             def compress(content, method, level_):
@@ -262,7 +268,7 @@ class ZipEncoder:
             method = (entry.compression or "deflate") if entry.is_file else "deflate"
             payload, crc = b"", 0
             if entry.is_file:
-                payload, crc = compress(entry.content or b"", method, level if level is not None else 6)
+                payload, crc = compress(entry.content or b"", method, level_of(entry))
             fd = dict(name=name, time=_dos_time(lm), date=_dos_date(lm), crc=crc, csize=len(payload),
                       usize=entry.size if entry.is_file else 0, method=method, mode=entry.mode, pos=len(out),
                       comment=getattr(entry, "comment", None) or "")

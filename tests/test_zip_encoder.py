@@ -194,3 +194,60 @@ def test_sharded_encode_on_the_device_equals_one_rank():
     want = ZipEncoder().encode_bytes(arc, level=6)
     shares = [shard.zip_encode_sharded(arc, level=6, rank=r, world=2) for r in range(2)]
     assert shard.zip_encode_sharded(arc, level=6, rank=0, world=2, payloads_in=shares[1:]) == want
+
+
+def test_zip_file_encoder_on_a_directory_tree(tmp_path):
+    """ZipFileEncoder (io/zip_file_encoder.dart:11-225) with the stand-in compressor: directory walk, names relative to the
+    directory (with and without its own name in front), per-file level, modes and times from the file system, the archive
+    written through an OutputFileStream; zipDirectory's default name and its guard."""
+    import os
+    from archive_b200 import ZipFileEncoder
+    root = tmp_path / "tree"
+    (root / "sub" / "deep").mkdir(parents=True)
+    (root / "empty").mkdir()
+    files = {"a.txt": b"alpha " * 300, "sub/b.bin": bytes(range(256)) * 5, "sub/deep/c.txt": b"c" * 1000, "z.dat": b""}
+    for rel, body in files.items():
+        (root / rel).write_bytes(body)
+    os.chmod(root / "a.txt", 0o640)
+    levels = []
+
+    def counting(content, method, level):
+        levels.append(level)
+        return standin(content, method, level)
+
+    enc = ZipFileEncoder(compress=counting)
+    n = enc.zip_directory(str(root))  # default name: <dir>.zip, level 1 (:22-43)
+    zpath = str(root) + ".zip"
+    assert os.path.getsize(zpath) == n and set(levels) == {1}
+    z = zipfile.ZipFile(zpath)
+    names = z.namelist()
+    assert names == sorted(names) and set(names) == {"a.txt", "empty/", "sub/", "sub/b.bin", "sub/deep/", "sub/deep/c.txt", "z.dat"}
+    for rel, body in files.items():
+        assert z.read(rel) == body
+    assert (z.getinfo("a.txt").external_attr >> 16) & 0o777 == 0o640
+    with pytest.raises(ValueError):
+        ZipFileEncoder(compress=standin).zip_directory(str(root), filename=str(root / "inside.zip"))
+    # create / add_file / add_directory / add_archive_file / close, with the directory's name in front and per-file levels
+    del levels[:]
+    enc = ZipFileEncoder(compress=counting)
+    enc.create(str(tmp_path / "out" / "x.zip"), level=6)
+    enc.add_file(str(root / "a.txt"), level=9)
+    enc.add_file(str(root / "sub" / "b.bin"), "renamed/b.bin")
+    enc.add_directory(str(root), filter=lambda p, prog: "skip" if p.endswith("z.dat") else None)
+    extra = ArchiveFile("extra.txt", 5)
+    extra.content, extra.last_mod_time = b"extra", 86400 * 400
+    enc.add_archive_file(extra)
+    enc.close()
+    z = zipfile.ZipFile(str(tmp_path / "out" / "x.zip"))
+    assert z.namelist()[:2] == ["a.txt", "renamed/b.bin"] and "tree/sub/deep/c.txt" in z.namelist() and "tree/z.dat" not in z.namelist()
+    assert z.read("tree/sub/b.bin") == files["sub/b.bin"] and z.read("extra.txt") == b"extra"
+    assert levels[0] == 9 and set(levels[1:]) == {6}
+    # the same members through ZipEncoder give the same bytes
+    again = ZipFileEncoder(compress=standin)
+    again.create(str(tmp_path / "y.zip"), level=6)
+    again.add_file(str(root / "a.txt"))
+    again.close()
+    f = ArchiveFile("a.txt", len(files["a.txt"]))
+    st = os.stat(root / "a.txt")
+    f.content, f.last_mod_time, f.mode = files["a.txt"], int(st.st_mtime), st.st_mode
+    assert open(str(tmp_path / "y.zip"), "rb").read() == ZipEncoder(compress=standin).encode_bytes([f], level=6)

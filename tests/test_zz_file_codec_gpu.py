@@ -375,3 +375,25 @@ def test_extract_file_to_disk(a, tmp_path):
         (tar_path,) = a.extract_file_to_disk(p, d)
         assert os.path.dirname(tar_path) == d and tar_path.endswith(".tar")
         assert open(tar_path, "rb").read() == rd("test2.tar")
+
+
+def test_zip_file_encoder_on_the_device(tmp_path):
+    import os
+    from archive_b200 import ZipFileEncoder, extract_file_to_disk
+    from archive_b200 import synth
+    root = tmp_path / "tree"
+    (root / "d").mkdir(parents=True)
+    text = synth.text(120000, stream=64).tobytes()
+    files = {"one.txt": text[:50000], "d/two.txt": text[50000:], "d/three.bin": bytes(range(256)) * 20}
+    for rel, body in files.items():
+        (root / rel).write_bytes(body)
+    sizes = {}
+    for batch in (False, True):
+        zp = str(tmp_path / f"t{int(batch)}.zip")
+        ZipFileEncoder(batch=batch).zip_directory(str(root), filename=zp, level=6, modified=86400 * 365 * 30)
+        sizes[batch] = open(zp, "rb").read()
+    assert sizes[False] == sizes[True]
+    out = str(tmp_path / "back")
+    extract_file_to_disk(str(tmp_path / "t1.zip"), out)
+    for rel, body in files.items():
+        assert open(os.path.join(out, rel), "rb").read() == body
