@@ -67,11 +67,15 @@ int b200z_inflate_raw(const uint8_t *in, size_t in_len, uint8_t *out, size_t out
                       size_t *out_len, size_t *in_consumed, int32_t *unit_status);
 
 /* GZipDecoderWeb().decodeBytes -- _gzip_decoder_web.dart:19-58 (member loop, header skip,
- * CRC/ISIZE read and ignored, zlib fallback when there is no gzip header).                */
+ * CRC/ISIZE read and ignored, zlib fallback when there is no gzip header).  The members share
+ * one output stream, as in the reference (:38): a member's back-references may reach into the
+ * members decoded before it.  A stream that ends inside a block: B200Z_E_THROW (the reference's
+ * trailer read runs past the end), with the bytes decoded so far in `out`.                  */
 int b200z_gzip_decode(const uint8_t *in, size_t in_len, int verify, uint8_t *out, size_t out_cap,
                       size_t *out_len);
 /* ZLibDecoderWeb().decodeBytes -- _zlib_decoder_web.dart:21-107 (stream loop, Adler-32 when
- * verify, raw = no wrapper).                                                               */
+ * verify, raw = no wrapper).  Every stream has an output of its own and reaches `out` only once
+ * the next stream's header has been accepted, or at the end (:82-84, :101-103).            */
 int b200z_zlib_decode(const uint8_t *in, size_t in_len, int verify, int raw, uint8_t *out,
                       size_t out_cap, size_t *out_len);
 /* Upper bound for the output of b200z_gzip_decode / b200z_zlib_decode, from the framing's own
