@@ -58,7 +58,7 @@ _SIGS = {
     "b200z_host_free": (None, [C.c_void_p]),
     "b200z_launch_count": (C.c_uint64, []),
     "b200z_profile_enable": (None, [C.c_int]),
-    "b200z_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "b200z_profile_read": (C.c_int, [C.POINTER(C.c_double)] * 3 + [C.POINTER(C.c_uint64)]),
     "b200z_inflate_raw": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t),
                                     C.POINTER(C.c_size_t), C.POINTER(C.c_int32)]),
     "b200z_gzip_decode": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),

@@ -1403,11 +1403,14 @@ extern "C" int b200z_zip_list(const uint8_t *z, size_t len, b200z_zip_entry *ent
   if (!z && len) return B200Z_E_ARG;
   const long long fp = zip_find_eocd(z, len);
   if (fp < 0) return B200Z_OK;  // ZipDirectory.read returns with no headers (zip_directory.dart:26-29)
-#define ZNEED(pos, k)                                                              \
-  if ((unsigned long long)(pos) + (k) > len) {                                      \
+  // (overflow-safe: positions and sizes come from the archive as full 64-bit values)
+#define ZNEED_IN(pos, k, lim)                                                       \
+  if ((unsigned long long)(pos) > (unsigned long long)(lim) ||                      \
+      (unsigned long long)(k) > (unsigned long long)(lim) - (unsigned long long)(pos)) { \
     set_err("zip: read past the end at %llu (Dart: RangeError)", (unsigned long long)(pos)); \
     return B200Z_E_THROW;                                                          \
   }
+#define ZNEED(pos, k) ZNEED_IN(pos, k, len)
   ZNEED(fp, 22);
   uint64_t cd_size = le32(z + fp + 12), cd_off = le32(z + fp + 16);
   {
@@ -1428,11 +1431,20 @@ extern "C" int b200z_zip_list(const uint8_t *z, size_t len, b200z_zip_entry *ent
   // central directory :50-63
   size_t n = 0;
   uint64_t p = cd_off;
-  const uint64_t cd_end = cd_off + cd_size;  // dirContent = input.subset(position, length)
+  // dirContent = input.subset(position: offset, length: size) (input_memory_stream.dart:15-27,111-119): a length that
+  // reaches beyond the archive is cut to what is there; an offset beyond it, or a negative (>= 2^63) offset or size, makes
+  // Uint8List.view throw.  The headers are then read from that sub-stream: running over ITS end throws.
+  if (cd_off > len || (cd_size >> 63) != 0) {
+    set_err("zip: central directory at %llu (+%llu) lies outside the archive (Dart: RangeError)", (unsigned long long)cd_off,
+            (unsigned long long)cd_size);
+    return B200Z_E_THROW;
+  }
+  const uint64_t cd_end = cd_size > len - cd_off ? (uint64_t)len : cd_off + cd_size;
+#define DNEED(pos, k) ZNEED_IN(pos, k, cd_end)
   while (p < cd_end) {
-    ZNEED(p, 4);
+    DNEED(p, 4);
     if (le32(z + p) != 0x02014b50u) break;
-    ZNEED(p, 46);
+    DNEED(p, 46);
     // ZipFileHeader.read (zip_file_header.dart:28-111)
     const uint8_t *h = z + p;
     b200z_zip_entry e;
@@ -1442,7 +1454,7 @@ extern "C" int b200z_zip_list(const uint8_t *z, size_t len, b200z_zip_entry *ent
     const size_t fn_len = le16(h + 28), ex_len = le16(h + 30), cm_len = le16(h + 32);
     uint32_t disk = le16(h + 34);
     e.ext_attr = le32(h + 38);
-    ZNEED(p + 46, fn_len + ex_len + cm_len);
+    DNEED(p + 46, fn_len + ex_len + cm_len);
     e.cd_name_off = p + 46;
     e.cd_name_len = (uint32_t)fn_len;
     if (ex_len >= 4) {  // :48-98 -- shorter extra fields are ignored
@@ -1490,7 +1502,11 @@ extern "C" int b200z_zip_list(const uint8_t *z, size_t len, b200z_zip_entry *ent
       e.name_len = (uint32_t)lfn;
       e.data_off = lho + 30 + lfn + lex;
       e.has_data = 1;
-      if (e.data_off + comp > len) {  // readBytes hands out what is there
+      if ((comp >> 63) != 0) {  // readBytes(negative count): Uint8List.view throws
+        set_err("zip: compressed size %llu (Dart: RangeError)", (unsigned long long)comp);
+        return B200Z_E_THROW;
+      }
+      if (comp > len - e.data_off) {  // readBytes hands out what is there (data_off <= len: checked above)
         e.comp_size = len - e.data_off;
       }
       if (e.flags & 0x08) {  // data descriptor :137-148: CRC and the 32-bit sizes are replaced by what follows the data
@@ -1512,7 +1528,9 @@ extern "C" int b200z_zip_list(const uint8_t *z, size_t len, b200z_zip_entry *ent
     if (n < cap && entries) entries[n] = e;
     n++;
   }
+#undef DNEED
 #undef ZNEED
+#undef ZNEED_IN
   if (n_entries) *n_entries = n;
   if (n > cap && entries) {
     set_err("zip: %zu entries, capacity %zu", n, cap);
@@ -1565,7 +1583,7 @@ extern "C" int b200z_zip_extract(const uint8_t *z, size_t len, const b200z_zip_e
       status[i] = B200Z_ZIP_ENCRYPTED;
       continue;
     }
-    if (out_off[i] + out_room[i] > out_cap || e.data_off + e.comp_size > len) {
+    if (out_off[i] > out_cap || out_room[i] > out_cap - out_off[i] || e.data_off > len || e.comp_size > len - e.data_off) {
       set_err("zip_extract: entry %zu lies outside the buffers", i);
       return B200Z_E_ARG;
     }
@@ -1819,8 +1837,8 @@ int b200z_bzip2_encode(const uint8_t *in, size_t in_len, uint8_t *out, size_t ou
 }
 size_t b200z_bzip2_bound(size_t in_len) { return bz2e::bound(in_len); }
 
-int b200z_profile_read(double *decode_ms, double *expand_ms, uint64_t *n_batches) {
-  return profile_read(decode_ms, expand_ms, n_batches) ? B200Z_E_NODEVICE : B200Z_OK;
+int b200z_profile_read(double *fast_ms, double *decode_ms, double *expand_ms, uint64_t *n_batches) {
+  return profile_read(fast_ms, decode_ms, expand_ms, n_batches) ? B200Z_E_NODEVICE : B200Z_OK;
 }
 
 int b200z_device_count(void) {

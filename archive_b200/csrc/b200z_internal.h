@@ -98,7 +98,7 @@ cudaError_t bz2_launch_entropy_literal(const Bz2Entropy &a, const uint32_t *d_li
 cudaError_t bz2_launch_ibwt(const Bz2Ibwt &a, cudaStream_t s);
 void count_launch();
 void profile_enable(bool on);
-int profile_read(double *decode_ms, double *expand_ms, uint64_t *n);
+int profile_read(double *fast_ms, double *decode_ms, double *expand_ms, uint64_t *n);
 
 // ---- file streams (b200z_file.cu) and the hooks it uses (b200z_api.cu) ----
 void set_error_text(const char *msg);  // b200z_last_error() text of the calling thread

@@ -1,0 +1,996 @@
+// inflate_fast.cuh -- k_inflate_fast: one CTA decodes one DEFLATE unit entirely inside shared memory.
+//
+// Replaces, for units whose output fits the 64 KiB window (gzip members with size hints, flush pieces of zip members):
+//   lib/src/codecs/zlib/inflate.dart:104-343          _inflate / _parseBlock / _parseDynamicHuffmanBlock / _decodeHuffman
+//   lib/src/codecs/zlib/_huffman_table.dart:9-46      HuffmanTable
+//   lib/src/util/output_memory_stream.dart:41-98      writeByte / writeBackReference
+//
+// Shape (DESIGN.md "K1f"):
+//   * the compressed unit arrives by ONE bulk-async copy (cp.async.bulk + mbarrier) into shared memory; the copy of the
+//     NEXT unit is issued as soon as the last block of the current one is decoded, so it hides behind the LZ77 pass;
+//   * a block's symbols are one serial chain, so the CTA's 256 lanes start at 256 evenly spaced bit offsets with the
+//     block's tables.  Huffman streams self-synchronise: every lane marks the token boundaries of the first K bits of its
+//     segment in a bitmap, then runs on into its successor's segment until one of its own boundaries is one of the
+//     successor's -- from there the two parses are identical.  Lane 0 is exact, so the chain of meeting points is the
+//     true parse;
+//   * each lane's share of the output is counted, prefix-summed, and the lane decodes its share again straight into the
+//     64 KiB output window in shared memory: literals as bytes, a match as a 3-byte record (len-3, dist-1) at its own
+//     position plus one bit in a match-start bitmap (a match is >= 3 bytes long, so the record always fits);
+//   * LZ77 copies are resolved shared -> shared in 1 KiB chunks, one warp per chunk, lanes owning 32 output bytes each; a
+//     match waits only while bytes it reads are still owned by an unfinished match (per-warp vote inside the chunk, one
+//     counter of finished chunks across warps);
+//   * the finished unit leaves with one bulk-async store (shared -> global), ragged ends by byte stores.
+// Nothing but the compressed bytes is read from HBM and nothing but the output is written: no token round trip.
+//
+// Only CLEAN units finish here: anything the reference treats specially (a read that runs out of input, an invalid or
+// missing code, a distance before the start of the output, output beyond out_cap, over-subscribed code sets ...) leaves
+// the unit untouched and flagged, and the exact kernels of inflate_kernels.cu decode it (they restate every quirk).
+// A clean unit's result is what those kernels produce: the same bytes, out_len, in_used and status.
+#pragma once
+#include <stdint.h>
+
+namespace b200z {
+namespace fp {
+
+constexpr int NT = 256;          // threads (= lanes of the speculative decode) per CTA
+constexpr int NW = NT / 32;
+constexpr int LB = 10;           // literal/length root bits
+constexpr int DB = 8;            // distance root bits
+constexpr int SUBN = 384;        // second-level entries shared by the block's two alphabets
+constexpr uint32_t WIN = 65536u; // output window
+constexpr uint32_t IN_CAP = 30720u;  // staged compressed bytes (incl. the <= 15 bytes in front of an unaligned unit)
+constexpr uint32_t MIN_IN = 192u;    // shorter units stay with the lane-per-stream kernels (a CTA each would be waste)
+constexpr uint32_t MIN_SEG = 256u;   // bits per lane at least
+constexpr uint32_t END_EOB = 0xfffeu, END_BAD = 0xffffu, NONE = 0xffffffffu;
+constexpr uint32_t CHUNK_SHIFT = 10;  // LZ77 resolution chunk = 1024 output bytes = one warp x 32 bytes per lane
+constexpr uint32_t STEP = 16;         // bytes a lane copies per turn
+
+// table entry: bits 0-3 code length (0: link or hole), 4-7 extra bits, 8-9 kind, 16-31 value
+constexpr uint32_t K_LIT = 0u, K_BASE = 1u, K_EOB = 2u, K_INV = 3u;
+constexpr uint32_t E_PARK = 1u << 12;  // table build only: root slot holds the longest code length under it
+
+// shared memory map (bytes)
+constexpr uint32_t O_WIN = 0;
+constexpr uint32_t O_FLAGS = O_WIN + WIN + 16;   // u32[2048]: match starts, one bit per output byte
+constexpr uint32_t O_IN = O_FLAGS + 8192;
+constexpr uint32_t O_LUTL = O_IN + IN_CAP + 16;
+constexpr uint32_t O_LUTD = O_LUTL + (4u << LB);
+constexpr uint32_t O_SUB = O_LUTD + (4u << DB);
+constexpr uint32_t O_LENS = O_SUB + 4u * SUBN;   // u8[320]
+constexpr uint32_t O_GRP = O_LENS + 320;         // u32[10][16]
+constexpr uint32_t O_CNT = O_GRP + 640;          // u32 cnt_l[16], cnt_d[16], first_l[16], first_d[16]
+constexpr uint32_t O_LONG = O_CNT + 256;         // u32 long_l[288], long_d[32]
+constexpr uint32_t O_CTL = O_LONG + 1280;
+constexpr uint32_t O_MBAR = O_CTL + 256;
+constexpr uint32_t SMEM_BYTES = O_MBAR + 16;
+static_assert(SMEM_BYTES <= 115712, "two CTAs per SM");
+
+struct Ctl {
+  // the unit being fetched (written by fetch_next, read at the top of the loop)
+  uint32_t n_unit, n_in_len, n_lead, n_cap, n_wofs, n_elig;
+  // the unit being decoded
+  uint32_t end_bit, pos, olen, fb, done, status, cap;
+  uint32_t btype, bfinal, st_src, st_len;
+  uint32_t hlit, hdist, maxl, maxd, sub_used, nlong_l, nlong_d;
+  uint32_t nl, L, K, bm_stride, bm_off, p0;
+  uint32_t blk_end, blk_total;
+  uint32_t done_chunks;
+  uint32_t regmask[NW], validmask[NW], warp_tot[NW];
+};
+static_assert(sizeof(Ctl) <= 256, "Ctl");
+
+#if defined(B200Z_EMU)
+#define FP_DEV inline
+#define FP_SPIN()         \
+  do {                    \
+    cuemu::events++;      \
+    cuemu::yield();       \
+  } while (0)
+static inline void fp_mbar_init(uint64_t *, int) {}
+static inline void fp_load_bulk(void *dst, const void *src, uint32_t bytes, uint64_t *) { memcpy(dst, src, bytes); }
+static inline void fp_mbar_wait(uint64_t *, uint32_t) {}
+static inline void fp_store_bulk(void *gdst, const void *ssrc, uint32_t bytes) { memcpy(gdst, ssrc, bytes); }
+static inline void fp_store_wait_read() {}
+static inline void fp_fence_async() {}
+#define FP_VOL(x) (x)
+#else
+#define FP_DEV __device__ __forceinline__
+#define FP_SPIN() ((void)0)
+__device__ __forceinline__ uint32_t fp_saddr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void fp_mbar_init(uint64_t *mb, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(fp_saddr(mb)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// one bulk-async copy global -> shared, completion counted in bytes on the mbarrier
+__device__ __forceinline__ void fp_load_bulk(void *dst, const void *src, uint32_t bytes, uint64_t *mb) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fp_saddr(mb)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(fp_saddr(dst)),
+               "l"(src), "r"(bytes), "r"(fp_saddr(mb))
+               : "memory");
+}
+__device__ __forceinline__ void fp_mbar_wait(uint64_t *mb, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(fp_saddr(mb)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fp_store_bulk(void *gdst, const void *ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(fp_saddr(ssrc)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void fp_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fp_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#define FP_VOL(x) (*(volatile uint32_t *)&(x))
+#endif
+
+// ---- bit reader over the staged input (LSB first, inflate.dart:159-184); pos = bits consumed from word 0 ----
+struct BR {
+  uint64_t buf;
+  int cnt;
+  uint32_t wp;
+};
+FP_DEV void br_seek(BR &b, const uint32_t *in32, uint32_t bitpos) {
+  const uint32_t w = bitpos >> 5, sh = bitpos & 31u;
+  const uint64_t v = (uint64_t)in32[w] | ((uint64_t)in32[w + 1] << 32);
+  b.buf = v >> sh;
+  b.cnt = 64 - (int)sh;
+  b.wp = w + 2;
+}
+FP_DEV void br_refill(BR &b, const uint32_t *in32) {
+  if (b.cnt < 32) {
+    b.buf |= (uint64_t)in32[b.wp] << b.cnt;
+    b.cnt += 32;
+    b.wp++;
+  }
+}
+FP_DEV uint32_t br_pos(const BR &b) { return b.wp * 32u - (uint32_t)b.cnt; }
+
+FP_DEV uint32_t fp_lookup(uint32_t bits, bool dm, const uint32_t *lutl, const uint32_t *lutd, const uint32_t *sub) {
+  uint32_t e = dm ? lutd[bits & ((1u << DB) - 1u)] : lutl[bits & ((1u << LB) - 1u)];
+  if ((e & 15u) == 0u && e != 0u) {  // link to the second level
+    const uint32_t sb = (e >> 4) & 15u;
+    e = sub[(e >> 16) + ((bits >> (dm ? DB : LB)) & ((1u << sb) - 1u))];
+  }
+  return e;  // (e & 15) == 0: no code here
+}
+
+FP_DEV uint32_t fp_entry(uint32_t s, uint32_t l, bool dist) {
+  uint32_t kind, val, xb = 0;
+  if (dist) {
+    if (s < 30u) {
+      const uint32_t t = c_dist_tab[s];
+      kind = K_BASE;
+      val = t >> 4;
+      xb = t & 15u;
+    } else {
+      kind = K_INV;
+      val = 0;
+    }
+  } else if (s < 256u) {
+    kind = K_LIT;
+    val = s;
+  } else if (s == 256u) {
+    kind = K_EOB;
+    val = 0;
+  } else if (s <= 285u) {
+    const uint32_t t = c_len_tab[s - 257u];
+    kind = K_BASE;
+    val = t >> 4;
+    xb = t & 15u;
+  } else {
+    kind = K_INV;
+    val = 0;
+  }
+  return (val << 16) | (kind << 8) | (xb << 4) | l;
+}
+
+// thread 0: the CTA's next unit (units are dealt round-robin); a unit that can be decoded here gets its bulk load issued
+FP_DEV void fp_fetch_next(Ctl *ctl, uint8_t *s_in, uint64_t *mbar, const uint8_t *in_base, const uint64_t *in_off,
+                          const uint32_t *in_len, const uint8_t *out_base, const uint64_t *out_off, const uint32_t *out_cap,
+                          uint32_t n_units, uint32_t u) {
+  if (u >= n_units) {
+    ctl->n_unit = NONE;
+    return;
+  }
+  const uint8_t *src = in_base + in_off[u];
+  const uint32_t il = in_len[u], oc = out_cap[u];
+  const uint32_t lead = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15u);
+  const uint32_t bytes = (lead + il + 15u) & ~15u;
+  const bool elig = il >= MIN_IN && bytes <= IN_CAP && oc <= WIN && oc != 0u;
+  ctl->n_unit = u;
+  ctl->n_in_len = il;
+  ctl->n_lead = lead;
+  ctl->n_cap = oc;
+  ctl->n_wofs = (uint32_t)(reinterpret_cast<uintptr_t>(out_base + out_off[u]) & 15u);
+  ctl->n_elig = elig ? 1u : 0u;
+  if (elig) fp_load_bulk(s_in, src - lead, bytes, mbar);
+}
+
+// thread 0: _parseBlock header (inflate.dart:120-156, 213-298) -- clean cases only, anything else sets ctl->fb
+FP_DEV void fp_parse_header(Ctl *ctl, const uint8_t *s_in, uint8_t *lens, uint32_t *cl_lut) {
+  const uint32_t *in32 = reinterpret_cast<const uint32_t *>(s_in);
+  const uint32_t end_bit = ctl->end_bit;
+  uint32_t pos = ctl->pos;
+  if (end_bit - pos < 8u) {  // isEOS at a block boundary (inflate.dart:111): every byte already pulled
+    ctl->done = 1;
+    ctl->status = B200Z_U_EOS;
+    return;
+  }
+  BR br;
+  br_seek(br, in32, pos);
+#define FP_NEED(n)                       \
+  if (br_pos(br) + (n) > end_bit) {      \
+    ctl->fb = 1;                         \
+    return;                              \
+  }
+#define FP_GET(var, n)                                   \
+  br_refill(br, in32);                                   \
+  FP_NEED(n)                                             \
+  var = (uint32_t)br.buf & ((1u << (n)) - 1u);           \
+  br.buf >>= (n);                                        \
+  br.cnt -= (n);
+  uint32_t hdr;
+  FP_GET(hdr, 3)
+  ctl->bfinal = hdr & 1u;
+  const uint32_t type = hdr >> 1;
+  ctl->btype = type;
+  if (type == 0u) {
+    uint32_t p = (br_pos(br) + 7u) & ~7u;
+    if (p + 32u > end_bit) {  // the short reads of LEN / NLEN are the exact kernels' business
+      ctl->fb = 1;
+      return;
+    }
+    const uint32_t b = p >> 3;
+    const uint32_t len = s_in[b] | ((uint32_t)s_in[b + 1] << 8), nlen = (s_in[b + 2] | ((uint32_t)s_in[b + 3] << 8)) ^ 0xffffu;
+    if ((len != 0u && len != nlen) || len > ((end_bit - p) >> 3) - 4u || ctl->olen + len > ctl->cap) {
+      ctl->fb = 1;
+      return;
+    }
+    ctl->st_src = b + 4u;
+    ctl->st_len = len;
+    ctl->pos = p + 32u + 8u * len;
+    return;
+  }
+  if (type == 1u) {
+    ctl->hlit = 288;
+    ctl->hdist = 30;
+    ctl->p0 = br_pos(br);
+    return;
+  }
+  if (type != 2u) {
+    ctl->fb = 1;
+    return;
+  }
+  uint32_t hlit, hdist, hclen;
+  FP_GET(hlit, 5)
+  FP_GET(hdist, 5)
+  FP_GET(hclen, 4)
+  hlit += 257u;
+  hdist += 1u;
+  hclen += 4u;
+  if (hlit > 288u || hdist > 32u || hclen > 19u) {
+    ctl->fb = 1;
+    return;
+  }
+  // code-length alphabet: 7-bit table, entries (sym << 4) | len
+  for (uint32_t i = 0; i < hclen; ++i) {
+    uint32_t l;
+    FP_GET(l, 3)
+    lens[c_order[i]] = (uint8_t)l;  // scratch: the first 19 bytes of lens
+  }
+  for (uint32_t i = hclen; i < 19u; ++i) lens[c_order[i]] = 0;
+  {
+    uint32_t count[8], next[8];
+    for (int l = 0; l < 8; ++l) count[l] = 0;
+    for (int i = 0; i < 19; ++i) count[lens[i] & 7]++;
+    count[0] = 0;
+    int left = 1;
+    uint32_t code = 0;
+    next[0] = 0;
+    for (int l = 1; l < 8; ++l) {
+      left = (left << 1) - (int)count[l];
+      if (left < 0) {  // over-subscribed
+        ctl->fb = 1;
+        return;
+      }
+      code = (code + count[l - 1]) << 1;
+      next[l] = code;
+    }
+    for (int i = 0; i < 128; ++i) cl_lut[i] = 0;
+    for (uint32_t s = 0; s < 19u; ++s) {
+      const uint32_t l = lens[s];
+      if (l == 0u) continue;
+      const uint32_t c = next[l]++;
+      const uint32_t r = __brev(c) >> (32 - l);
+      for (uint32_t j = r; j < 128u; j += 1u << l) cl_lut[j] = (s << 4) | l;
+    }
+  }
+  // _decode (inflate.dart:345-401)
+  const uint32_t num = hlit + hdist;
+  uint32_t i = 0, prev = 0;
+  while (i < num) {
+    br_refill(br, in32);
+    const uint32_t e = cl_lut[(uint32_t)br.buf & 127u];
+    const uint32_t l = e & 15u, code = e >> 4;
+    if (l == 0u || br_pos(br) + 16u > end_bit) {  // hole, or close enough to the end for a short read to matter
+      ctl->fb = 1;
+      return;
+    }
+    br.buf >>= l;
+    br.cnt -= (int)l;
+    if (code < 16u) {
+      lens[i++] = (uint8_t)code;
+      prev = code;
+      continue;
+    }
+    uint32_t rep;
+    if (code == 16u) {
+      rep = ((uint32_t)br.buf & 3u) + 3u;
+      br.buf >>= 2;
+      br.cnt -= 2;
+    } else if (code == 17u) {
+      rep = ((uint32_t)br.buf & 7u) + 3u;
+      br.buf >>= 3;
+      br.cnt -= 3;
+      prev = 0;
+    } else {
+      rep = ((uint32_t)br.buf & 127u) + 11u;
+      br.buf >>= 7;
+      br.cnt -= 7;
+      prev = 0;
+    }
+    if (i + rep > num) {  // RangeError in the reference
+      ctl->fb = 1;
+      return;
+    }
+    for (uint32_t k = 0; k < rep; ++k) lens[i++] = (uint8_t)prev;
+  }
+  if (br_pos(br) > end_bit) {
+    ctl->fb = 1;
+    return;
+  }
+  ctl->hlit = hlit;
+  ctl->hdist = hdist;
+  ctl->p0 = br_pos(br);
+#undef FP_GET
+#undef FP_NEED
+}
+
+// thread 0: how many lanes decode the block, their segment length, sync window and where the boundary bitmaps live
+FP_DEV void fp_plan_lanes(Ctl *ctl, uint32_t wofs) {
+  const uint32_t R = ctl->end_bit - ctl->p0;
+  uint32_t nl = R / MIN_SEG;
+  if (nl > (uint32_t)NT) nl = NT;
+  const uint32_t used = wofs + ctl->olen;
+  const uint32_t room = (WIN + 16u - used) & ~3u;  // the part of the window this block has not reached yet
+  uint32_t L = 0, K = 0;
+  for (;;) {
+    if (nl < 2u) {
+      nl = 1;
+      break;
+    }
+    L = R / nl;
+    K = 1024;
+    while (K > L) K >>= 1;
+    while (K >= 128u && nl * (K / 32u + 1u) * 4u > room) K >>= 1;
+    if (K >= 128u) break;
+    nl = room / ((128u / 32u + 1u) * 4u);  // as many lanes as a 128-bit window each fits
+    if (nl > (uint32_t)NT) nl = NT;
+    if (nl >= 2u && R / nl < 128u) nl = R / 128u;
+  }
+  ctl->nl = nl;
+  ctl->L = nl > 1u ? L : 0u;
+  ctl->K = nl > 1u ? K : 0u;
+  ctl->bm_stride = nl > 1u ? K / 32u + 1u : 0u;
+  ctl->bm_off = nl > 1u ? ((WIN + 16u - nl * (K / 32u + 1u) * 4u) & ~3u) : 0u;
+}
+
+}  // namespace fp
+
+#ifdef B200Z_EMU
+#define FP_DYN_SMEM(name) uint8_t *name = reinterpret_cast<uint8_t *>(cuemu_dyn_smem)
+#else
+#define FP_DYN_SMEM(name) extern __shared__ __align__(16) uint8_t name[]
+#endif
+
+__global__ void __launch_bounds__(fp::NT, 2)
+k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__ in_off, const uint32_t *__restrict__ in_len,
+               uint8_t *__restrict__ out_base, const uint64_t *__restrict__ out_off, const uint32_t *__restrict__ out_cap,
+               uint32_t *__restrict__ out_len, int32_t *__restrict__ status, uint32_t *__restrict__ in_used, uint32_t n_units,
+               uint32_t *__restrict__ doneflag, uint32_t flag_stride) {
+  using namespace fp;
+  FP_DYN_SMEM(fsmem);
+  uint8_t *const smem = fsmem;
+  uint8_t *const win = smem + O_WIN;
+  uint32_t *const flags = reinterpret_cast<uint32_t *>(smem + O_FLAGS);
+  uint8_t *const s_in = smem + O_IN;
+  const uint32_t *const in32 = reinterpret_cast<const uint32_t *>(s_in);
+  uint32_t *const lutl = reinterpret_cast<uint32_t *>(smem + O_LUTL);
+  uint32_t *const lutd = reinterpret_cast<uint32_t *>(smem + O_LUTD);
+  uint32_t *const sub = reinterpret_cast<uint32_t *>(smem + O_SUB);
+  uint8_t *const lens = smem + O_LENS;
+  uint32_t *const grp = reinterpret_cast<uint32_t *>(smem + O_GRP);
+  uint32_t *const cnt_l = reinterpret_cast<uint32_t *>(smem + O_CNT);
+  uint32_t *const cnt_d = cnt_l + 16, *const first_l = cnt_l + 32, *const first_d = cnt_l + 48;
+  uint32_t *const long_l = reinterpret_cast<uint32_t *>(smem + O_LONG);
+  uint32_t *const long_d = long_l + 288;
+  Ctl *const ctl = reinterpret_cast<Ctl *>(smem + O_CTL);
+  uint64_t *const mbar = reinterpret_cast<uint64_t *>(smem + O_MBAR);
+
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const unsigned FULL = 0xffffffffu;
+
+  for (uint32_t i = tid; i < 2048u; i += NT) flags[i] = 0;
+  uint32_t next_u = blockIdx.x;  // (thread 0's copy is the one that counts)
+  if (tid == 0) {
+    fp_mbar_init(mbar, 1);
+    fp_fetch_next(ctl, s_in, mbar, in_base, in_off, in_len, out_base, out_off, out_cap, n_units, next_u);
+        next_u += gridDim.x;
+  }
+  uint32_t phase = 0;
+  for (;;) {
+    if (tid == 0) fp_store_wait_read();  // the previous unit's bulk store has read the window
+    __syncthreads();
+    const uint32_t unit = ctl->n_unit;
+    if (unit == NONE) break;
+    const uint32_t u_in_len = ctl->n_in_len, lead = ctl->n_lead, cap = ctl->n_cap, wofs = ctl->n_wofs;
+    const bool elig = ctl->n_elig != 0u;
+    uint8_t *const W = win + wofs;  // W[q] = output byte q; W is congruent to the global destination modulo 16
+    __syncthreads();
+    if (!elig) {
+      if (tid == 0) {
+        doneflag[(size_t)unit * flag_stride] = 0;
+        fp_fetch_next(ctl, s_in, mbar, in_base, in_off, in_len, out_base, out_off, out_cap, n_units, next_u);
+        next_u += gridDim.x;
+      }
+      continue;
+    }
+    fp_mbar_wait(mbar, phase);
+    phase ^= 1u;
+    if (tid == 0) {
+      ctl->end_bit = (lead + u_in_len) * 8u;
+      ctl->pos = lead * 8u;
+      ctl->olen = 0;
+      ctl->fb = 0;
+      ctl->done = 0;
+      ctl->status = B200Z_U_DONE;
+      ctl->bfinal = 0;
+      ctl->cap = cap;
+    }
+    __syncthreads();
+    const uint32_t end_bit = (lead + u_in_len) * 8u;
+
+    // ======================= blocks =======================
+    for (;;) {
+      if (tid == 0) {
+        if (ctl->bfinal) {
+          ctl->done = 1;
+          ctl->status = B200Z_U_DONE;
+        } else {
+          fp_parse_header(ctl, s_in, lens, sub);
+          if (!ctl->fb && !ctl->done && ctl->btype != 0u) fp_plan_lanes(ctl, wofs);
+        }
+      }
+      __syncthreads();
+      if (ctl->fb || ctl->done) break;
+      const uint32_t btype = ctl->btype;
+      if (btype == 0u) {  // stored (inflate.dart:213-235): input bytes -> window
+        const uint32_t src = ctl->st_src, n = ctl->st_len, o = ctl->olen;
+        for (uint32_t i = tid; i < n; i += NT) W[o + i] = s_in[src + i];
+        __syncthreads();
+        if (tid == 0) ctl->olen = o + n;
+        continue;
+      }
+      const uint32_t hlit = ctl->hlit, hdist = ctl->hdist;
+      // ---------------- tables (HuffmanTable, _huffman_table.dart:9-46, as root + second level) ----------------
+      if (btype == 1u) {
+        for (uint32_t i = tid; i < 320u; i += NT) lens[i] = i < 144u ? 8 : i < 256u ? 9 : i < 280u ? 7 : i < 288u ? 8 : 5;
+      }
+      for (uint32_t i = tid; i < (1u << LB); i += NT) lutl[i] = 0;
+      for (uint32_t i = tid; i < (1u << DB); i += NT) lutd[i] = 0;
+      for (uint32_t i = tid; i < (uint32_t)fp::SUBN; i += NT) sub[i] = 0;
+      for (uint32_t i = tid; i < 160u; i += NT) grp[i] = 0;
+      if (tid == 0) {
+        ctl->sub_used = 0;
+        ctl->nlong_l = 0;
+        ctl->nlong_d = 0;
+      }
+      __syncthreads();
+      // a symbol's canonical code = first[l] + (symbols of the same length before it): groups of 32 symbols, ranks by match_any
+      const uint32_t ngl = (hlit + 31u) >> 5;  // groups 0..ngl-1 literal/length, group 9 distance
+      uint32_t my_l[2] = {0, 0}, my_rank[2] = {0, 0}, my_s[2] = {0, 0}, my_g[2] = {NONE, NONE};
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {  // warp w: groups w and w + 8
+        const uint32_t g = warp + (uint32_t)k * NW;
+        if (g >= 10u || (g >= ngl && g != 9u)) continue;
+        const bool dist = g == 9u;
+        const uint32_t s = dist ? lane : g * 32u + lane;
+        const uint32_t l = dist ? (s < hdist ? lens[hlit + s] : 0u) : (s < hlit ? lens[s] : 0u);
+        const unsigned m = __match_any_sync(FULL, l);
+        if (l != 0u && (m & ((1u << lane) - 1u)) == 0u) grp[g * 16u + l] = (uint32_t)__popc(m);
+        my_l[k] = l;
+        my_rank[k] = (uint32_t)__popc(m & ((1u << lane) - 1u));
+        my_s[k] = s;
+        my_g[k] = g;
+      }
+      __syncthreads();
+      if (warp == 0) {
+        if (lane < 16u) {
+          uint32_t p = 0;
+          for (uint32_t g = 0; g < ngl; ++g) {
+            const uint32_t t = grp[g * 16u + lane];
+            grp[g * 16u + lane] = p;
+            p += t;
+          }
+          cnt_l[lane] = p;
+        } else {
+          const uint32_t l = lane - 16u;
+          cnt_d[l] = grp[9u * 16u + l];
+          grp[9u * 16u + l] = 0;
+        }
+        __syncwarp();
+        if (lane < 2u) {  // lane 0: literal/length, lane 1: distance -- Kraft sum, first codes, longest code
+          uint32_t *cnt = lane ? cnt_d : cnt_l, *first = lane ? first_d : first_l;
+          int left = 1;
+          uint32_t code = 0, mx = 0;
+          bool over = false;
+          first[0] = 0;
+          cnt[0] = 0;
+          for (uint32_t l = 1; l < 16u; ++l) {
+            left = (left << 1) - (int)cnt[l];
+            if (left < 0) over = true;
+            code = (code + cnt[l - 1]) << 1;
+            first[l] = code;
+            if (cnt[l]) mx = l;
+          }
+          if (over) ctl->fb = 1;  // over-subscribed: the reference's flat table decodes garbage (exact kernels: BADCODE)
+          if (lane) ctl->maxd = mx;
+          else ctl->maxl = mx;
+        }
+      }
+      __syncthreads();
+      if (ctl->fb) break;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const uint32_t l = my_l[k];
+        if (my_g[k] == NONE || l == 0u) continue;
+        const bool dist = my_g[k] == 9u;
+        const uint32_t code = (dist ? first_d : first_l)[l] + grp[my_g[k] * 16u + l] + my_rank[k];
+        const uint32_t r = __brev(code) >> (32u - l);
+        const uint32_t RB = dist ? DB : LB;
+        if (l <= RB) {
+          const uint32_t e = fp_entry(my_s[k], l, dist);
+          uint32_t *lut = dist ? lutd : lutl;
+          for (uint32_t j = r; j < (1u << RB); j += 1u << l) lut[j] = e;
+        } else {
+          const uint32_t slot = atomicAdd(dist ? &ctl->nlong_d : &ctl->nlong_l, 1u);
+          (dist ? long_d : long_l)[slot] = (r << 16) | (l << 10) | my_s[k];
+        }
+      }
+      __syncthreads();
+      if (tid == 0 || tid == 32) {  // codes longer than the root: one thread per alphabet places them
+        const bool dist = tid != 0;
+        const uint32_t RB = dist ? DB : LB, n = dist ? ctl->nlong_d : ctl->nlong_l;
+        const uint32_t *list = dist ? long_d : long_l;
+        uint32_t *lut = dist ? lutd : lutl;
+        for (uint32_t i = 0; i < n; ++i) {  // the longest code under every root prefix
+          const uint32_t it = list[i], r = it >> 16, l = (it >> 10) & 15u;
+          uint32_t &slot = lut[r & ((1u << RB) - 1u)];
+          if ((slot >> 16) < l) slot = (l << 16) | E_PARK;
+        }
+        for (uint32_t i = 0; i < n; ++i) {
+          const uint32_t it = list[i], r = it >> 16, l = (it >> 10) & 15u, s = it & 1023u;
+          uint32_t &slot = lut[r & ((1u << RB) - 1u)];
+          if (slot & E_PARK) {
+            const uint32_t sb = (slot >> 16) - RB;
+            const uint32_t base = atomicAdd(&ctl->sub_used, 1u << sb);
+            if (base + (1u << sb) > (uint32_t)fp::SUBN) {
+              ctl->fb = 1;  // pool exhausted (pathological code sets)
+              break;
+            }
+            slot = (base << 16) | (sb << 4) | (1u << 8);  // link: length nibble 0, not zero as a word
+          }
+          const uint32_t sb = (slot >> 4) & 15u, base = slot >> 16;
+          const uint32_t e = fp_entry(s, l, dist);
+          for (uint32_t j = r >> RB; j < (1u << sb); j += 1u << (l - RB)) sub[base + j] = e;
+        }
+      }
+      __syncthreads();
+      if (ctl->fb) break;
+
+      // ---------------- pass A: every lane decodes its segment, marking token boundaries ----------------
+      const uint32_t nl = ctl->nl, L = ctl->L, K = ctl->K, bms = ctl->bm_stride, p0 = ctl->p0;
+      const uint32_t maxl = ctl->maxl, maxd = ctl->maxd, olen0 = ctl->olen;
+      uint32_t *const bm = reinterpret_cast<uint32_t *>(win + ctl->bm_off);
+      // per-lane results of the block: they take over the bitmaps' place once those are dead (one lane: the group counters')
+      uint32_t *const tgt_arr = nl > 1u ? bm : grp, *const pos_arr = tgt_arr + nl, *const start_arr = tgt_arr + 2u * nl;
+      const bool lane_on = tid < nl;
+      const uint32_t myS = p0 + tid * L;
+      const uint32_t segEnd = (tid + 1u < nl) ? myS + L : NONE;
+      uint32_t sprime = myS, G = 0, pend = 0, tokpos = myS;
+      uint32_t tgt = END_BAD, endpos = 0;
+      bool dm = false;
+      int state = 2;  // 0 running, 1 at the end of the segment, 2 ended
+      BR br;
+      br.buf = 0;
+      br.cnt = 0;
+      br.wp = 0;
+      if (lane_on) {
+        if (nl > 1u)
+          for (uint32_t w = 0; w < bms; ++w) bm[tid * bms + w] = 0;
+        br_seek(br, in32, sprime);
+        state = 0;
+        while (state == 0) {
+          br_refill(br, in32);
+          const uint32_t pos = br_pos(br);
+          if (!dm) {
+            tokpos = pos;
+            if (pos >= segEnd) {
+              state = 1;
+              break;
+            }
+            const uint32_t rel = pos - myS;
+            if (rel < K) bm[tid * bms + (rel >> 5)] |= 1u << (rel & 31u);
+          }
+          const int rem = (int)(end_bit - pos);
+          const uint32_t bits = (uint32_t)br.buf;
+          const uint32_t e = fp_lookup(bits, dm, lutl, lutd, sub);
+          const uint32_t n = e & 15u, xb = (e >> 4) & 15u, kind = (e >> 8) & 3u;
+          bool bad = n == 0u || kind == K_INV;
+          if (rem < 32) bad = bad || rem < (int)(dm ? maxd : maxl) || (int)(n + xb) > rem;
+          if (bad || kind == K_EOB) {
+            // a lane that dies while it still decodes from its guessed offset has lost nothing: guess again one bit on
+            if (tid > 0u && tokpos + 1u - myS < K / 2u) {
+              for (uint32_t w = 0; w < bms; ++w) bm[tid * bms + w] = 0;
+              sprime = tokpos + 1u;
+              br_seek(br, in32, sprime);
+              G = 0;
+              dm = false;
+              continue;
+            }
+            if (!bad) {
+              tgt = END_EOB;
+              endpos = pos + n;
+            } else {
+              tgt = END_BAD;
+              endpos = tokpos;
+            }
+            state = 2;
+            break;
+          }
+          const uint32_t val = (e >> 16) + ((bits >> n) & ((1u << xb) - 1u));
+          const uint32_t tot = n + xb;
+          br.buf >>= tot;
+          br.cnt -= (int)tot;
+          if (dm) {
+            G += pend;
+            dm = false;
+          } else if (kind == K_LIT) {
+            G += 1u;
+          } else {
+            pend = val;
+            dm = true;
+          }
+        }
+      }
+      __syncthreads();
+      // ---------------- pass A2: run on until one of my boundaries is one of a successor's ----------------
+      if (state == 1) {
+        uint32_t succ = tid + 1u, succS = myS + L;
+        for (;;) {
+          br_refill(br, in32);
+          const uint32_t pos = br_pos(br);
+          if (!dm) {
+            tokpos = pos;
+            while (succ < nl && pos >= succS + K) {  // through that lane's window without meeting it: it is lost
+              succ++;
+              succS += L;
+            }
+            if (succ < nl && pos >= succS) {
+              const uint32_t off = pos - succS;
+              if ((bm[succ * bms + (off >> 5)] >> (off & 31u)) & 1u) {
+                tgt = succ;
+                endpos = pos;
+                break;
+              }
+            }
+          }
+          const int rem = (int)(end_bit - pos);
+          const uint32_t bits = (uint32_t)br.buf;
+          const uint32_t e = fp_lookup(bits, dm, lutl, lutd, sub);
+          const uint32_t n = e & 15u, xb = (e >> 4) & 15u, kind = (e >> 8) & 3u;
+          bool bad = n == 0u || kind == K_INV;
+          if (rem < 32) bad = bad || rem < (int)(dm ? maxd : maxl) || (int)(n + xb) > rem;
+          if (bad) {
+            tgt = END_BAD;
+            endpos = tokpos;
+            break;
+          }
+          if (kind == K_EOB) {
+            tgt = END_EOB;
+            endpos = pos + n;
+            break;
+          }
+          const uint32_t val = (e >> 16) + ((bits >> n) & ((1u << xb) - 1u));
+          const uint32_t tot = n + xb;
+          br.buf >>= tot;
+          br.cnt -= (int)tot;
+          if (dm) {
+            G += pend;
+            dm = false;
+          } else if (kind == K_LIT) {
+            G += 1u;
+          } else {
+            pend = val;
+            dm = true;
+          }
+        }
+      }
+      __syncthreads();  // every lane is through with the bitmaps (they share the window with nothing live, but the lane arrays follow)
+      // ---------------- the chain of meeting points from lane 0 is the true parse ----------------
+      if (lane_on) {
+        tgt_arr[tid] = tgt;
+        pos_arr[tid] = endpos;
+      }
+      {
+        const unsigned reg = __ballot_sync(FULL, lane_on && tgt == tid + 1u);
+        if (lane == 0) {
+          ctl->regmask[warp] = reg;
+          ctl->validmask[warp] = 0;
+        }
+      }
+      __syncthreads();
+      if (tid == 0) {
+        uint32_t cur = 0;
+        bool ok = false;
+        for (int it = 0; it < NT; ++it) {
+          uint32_t w = cur >> 5;
+          uint32_t m = ~ctl->regmask[w] & (0xffffffffu << (cur & 31u));
+          while (m == 0u && w + 1u < (uint32_t)NW) m = ~ctl->regmask[++w];
+          if (m == 0u) break;
+          const uint32_t E = w * 32u + (uint32_t)(__ffs((int)m) - 1);
+          for (uint32_t q = cur >> 5; q <= (E >> 5); ++q) {  // lanes cur..E are on the chain
+            uint32_t bits = 0xffffffffu;
+            if (q == (cur >> 5)) bits &= 0xffffffffu << (cur & 31u);
+            if (q == (E >> 5)) bits &= 0xffffffffu >> (31u - (E & 31u));
+            ctl->validmask[q] |= bits;
+          }
+          const uint32_t t = tgt_arr[E];
+          if (t == END_EOB) {
+            ok = true;
+            ctl->blk_end = pos_arr[E];
+            break;
+          }
+          if (t == END_BAD || t <= E || t >= nl) break;
+          cur = t;  // lanes in between never met the true parse: skipped
+        }
+        if (!ok) ctl->fb = 1;
+      }
+      __syncthreads();
+      if (ctl->fb) break;
+#ifdef FP_DEBUG
+      if (tid == 0) { int nv = 0; for (int w = 0; w < NW; ++w) nv += __popc(ctl->validmask[w]); fprintf(stderr, "unit %u: nl %u L %u K %u valid %d\n", unit, nl, L, K, nv); }
+#endif
+      const bool valid = ((ctl->validmask[warp] >> lane) & 1u) != 0u;
+      if (valid && tgt < END_EOB) start_arr[tgt] = endpos;
+      __syncthreads();
+      const uint32_t start = !valid ? 0u : tid == 0u ? p0 : start_arr[tid];
+      // ---------------- pass A3: bytes of my false start (my guessed offset .. where the true parse met me) ----------------
+      uint32_t nbytes = 0;
+      bool incons = false;
+      if (valid) {
+        uint32_t f = 0;
+        if (start != sprime) {
+          BR b3;
+          br_seek(b3, in32, sprime);
+          bool d3 = false;
+          uint32_t p3 = 0;
+          for (;;) {
+            br_refill(b3, in32);
+            const uint32_t pos = br_pos(b3);
+            if (!d3 && pos >= start) {
+              incons = pos != start;
+              break;
+            }
+            const uint32_t bits = (uint32_t)b3.buf;
+            const uint32_t e = fp_lookup(bits, d3, lutl, lutd, sub);
+            const uint32_t n = e & 15u, xb = (e >> 4) & 15u, kind = (e >> 8) & 3u;
+            if (n == 0u || kind >= K_EOB) {
+              incons = true;
+              break;
+            }
+            const uint32_t val = (e >> 16) + ((bits >> n) & ((1u << xb) - 1u));
+            const uint32_t tot = n + xb;
+            b3.buf >>= tot;
+            b3.cnt -= (int)tot;
+            if (d3) {
+              f += p3;
+              d3 = false;
+            } else if (kind == K_LIT) {
+              f += 1u;
+            } else {
+              p3 = val;
+              d3 = true;
+            }
+          }
+        }
+        nbytes = G - f;
+      }
+      // exclusive prefix sum of the lanes' byte counts
+      uint32_t incl = nbytes;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(FULL, incl, d);
+        if (lane >= (uint32_t)d) incl += v;
+      }
+      if (lane == 31u) ctl->warp_tot[warp] = incl;
+      if (incons) ctl->fb = 1;
+      __syncthreads();
+      uint32_t wbase = 0, total = 0;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) {
+        const uint32_t t = ctl->warp_tot[w];
+        if ((uint32_t)w < warp) wbase += t;
+        total += t;
+      }
+      if (ctl->fb || olen0 + total > cap) {  // beyond out_cap: B200Z_U_NOSPC is the exact kernels' to report
+        if (tid == 0) ctl->fb = 1;
+        __syncthreads();
+        break;
+      }
+      // ---------------- pass C: my share of the block again, into the window ----------------
+      if (valid) {
+        uint32_t o = olen0 + wbase + incl - nbytes;
+        BR bc;
+        br_seek(bc, in32, start);
+        bool dc = false;
+        uint32_t pc = 0;
+        bool trouble = false;
+        for (;;) {
+          br_refill(bc, in32);
+          const uint32_t pos = br_pos(bc);
+          if (!dc && tgt < END_EOB && pos >= endpos) {
+            trouble = pos != endpos;
+            break;
+          }
+          const uint32_t bits = (uint32_t)bc.buf;
+          const uint32_t e = fp_lookup(bits, dc, lutl, lutd, sub);
+          const uint32_t n = e & 15u, xb = (e >> 4) & 15u, kind = (e >> 8) & 3u;
+          if (kind == K_EOB && n != 0u) break;
+          if (n == 0u || kind == K_INV) {
+            trouble = true;
+            break;
+          }
+          const uint32_t val = (e >> 16) + ((bits >> n) & ((1u << xb) - 1u));
+          const uint32_t tot = n + xb;
+          bc.buf >>= tot;
+          bc.cnt -= (int)tot;
+          if (dc) {
+            if (val > o) {  // writeBackReference before the start of the output (output_memory_stream.dart:83-86)
+              trouble = true;
+              break;
+            }
+            W[o] = (uint8_t)(pc - 3u);
+            W[o + 1u] = (uint8_t)(val - 1u);
+            W[o + 2u] = (uint8_t)((val - 1u) >> 8);
+            atomicOr(&flags[o >> 5], 1u << (o & 31u));
+            o += pc;
+            dc = false;
+          } else if (kind == K_LIT) {
+            W[o++] = (uint8_t)val;
+          } else {
+            pc = val;
+            dc = true;
+          }
+        }
+        if (trouble) ctl->fb = 1;
+      }
+      __syncthreads();
+      if (ctl->fb) break;
+      if (tid == 0) {
+        ctl->olen = olen0 + total;
+        ctl->pos = ctl->blk_end;
+      }
+      // (the barrier at the top of the loop publishes olen / pos before anyone reads them)
+      __syncthreads();
+    }
+
+    // ======================= the unit's blocks are decoded (or the unit is given up) =======================
+    const bool fb = ctl->fb != 0u;
+    const uint32_t olen = ctl->olen, fin_status = ctl->status, fin_pos = ctl->pos;
+    __syncthreads();
+    if (tid == 0) {
+      ctl->done_chunks = 0;
+      // the staged input is dead: fetch the next unit behind the LZ77 pass
+      fp_fetch_next(ctl, s_in, mbar, in_base, in_off, in_len, out_base, out_off, out_cap, n_units, next_u);
+        next_u += gridDim.x;
+    }
+    if (fb) {
+      for (uint32_t i = tid; i < 2048u; i += NT) flags[i] = 0;
+      if (tid == 0) doneflag[(size_t)unit * flag_stride] = 0;
+      continue;
+    }
+    __syncthreads();
+    // ---------------- LZ77: matches copy shared -> shared, chunk by chunk ----------------
+    {
+      const uint32_t nchunks = (olen + (1u << CHUNK_SHIFT) - 1u) >> CHUNK_SHIFT;
+      for (uint32_t c = warp; c < nchunks; c += NW) {
+        uint32_t fwd = flags[c * 32u + lane];
+        flags[c * 32u + lane] = 0;
+        const uint32_t base = (c << CHUNK_SHIFT) + lane * 32u;
+        bool have = false, complete = fwd == 0u;
+        uint32_t p = 0, len = 0, dist = 0, k = 0;
+        for (;;) {
+          const unsigned inc = __ballot_sync(FULL, !complete);
+          if (inc == 0u) break;
+          const uint32_t F = (uint32_t)(__ffs((int)inc) - 1);
+          const uint32_t dch = FP_VOL(ctl->done_chunks);
+          __threadfence_block();
+          if (!complete) {
+            if (!have) {
+              const uint32_t b = (uint32_t)(__ffs((int)fwd) - 1);
+              fwd &= fwd - 1u;
+              p = base + b;
+              len = (uint32_t)W[p] + 3u;
+              dist = ((uint32_t)W[p + 1u] | ((uint32_t)W[p + 2u] << 8)) + 1u;
+              k = 0;
+              have = true;
+            }
+            const uint32_t src = p - dist;
+            const uint32_t need_end = min(src + len, p);  // bytes below this must be final before I copy
+            const uint32_t v = (need_end - 1u) >> CHUNK_SHIFT;
+            bool ready;
+            if (v < c) {
+              ready = dch > v;
+            } else {
+              const uint32_t lo = ((need_end - 1u) >> 5) & 31u;
+              ready = dch >= c && F >= min(lo + 1u, lane);
+            }
+            if (ready) {
+              const uint32_t m = min(len - k, STEP);
+              const uint8_t *sp = W + src + k;
+              uint8_t *dp = W + p + k;
+              for (uint32_t t = 0; t < m; ++t) dp[t] = sp[t];
+              k += m;
+              if (k == len) {
+                have = false;
+                complete = fwd == 0u;
+              }
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) {
+          while (FP_VOL(ctl->done_chunks) != c) FP_SPIN();
+          __threadfence_block();
+          FP_VOL(ctl->done_chunks) = c + 1u;
+        }
+        __syncwarp();
+      }
+    }
+    fp_fence_async();
+    __syncthreads();
+    // ---------------- output: one bulk store for the 16-byte aligned body, byte stores for the ragged ends ----------------
+    {
+      uint8_t *g = out_base + out_off[unit];
+      const uint32_t head = min((16u - wofs) & 15u, olen);
+      const uint32_t body = (olen - head) & ~15u;
+      if (tid < head) g[tid] = W[tid];
+      const uint32_t tail0 = head + body;
+      if (tail0 + tid < olen && tid < 16u) g[tail0 + tid] = W[tail0 + tid];
+      if (tid == 0) {
+        if (body) fp_store_bulk(g + head, W + head, body);
+        out_len[unit] = olen;
+        status[unit] = (int32_t)fin_status;
+        in_used[unit] = fin_status == (uint32_t)B200Z_U_EOS ? u_in_len : (fin_pos - lead * 8u + 7u) >> 3;
+        doneflag[(size_t)unit * flag_stride] = 1;
+      }
+    }
+  }
+}
+
+}  // namespace b200z

@@ -35,6 +35,7 @@ struct InflateWs {
 #include "b200z_internal.h"
 #endif
 #include "inflate_decode.cuh"
+#include "inflate_fast.cuh"
 
 #include <stdlib.h>
 
@@ -61,7 +62,7 @@ k_inflate_decode(const uint8_t *__restrict__ in_base, const uint64_t *__restrict
                  const uint32_t *__restrict__ in_len, const uint64_t *__restrict__ out_off,
                  const uint32_t *__restrict__ out_cap, InflateWs ws, uint32_t *__restrict__ out_len,
                  int32_t *__restrict__ status, uint32_t *__restrict__ in_used, uint32_t n_units, int units_per_warp,
-                 int lanes_per_unit, int count_only) {
+                 int lanes_per_unit, int count_only, int after_fast) {
   B200Z_DYN_SMEM(smem);
   uint16_t *s_len_tab = reinterpret_cast<uint16_t *>(smem);
   uint32_t *s_dist_tab = smem + 16;
@@ -82,7 +83,9 @@ k_inflate_decode(const uint8_t *__restrict__ in_base, const uint64_t *__restrict
   // reconverges); lanes without a stream are born finished.
   const int sidx = lane / lanes_per_unit, sub = lane % lanes_per_unit;
   const uint32_t unit = gwarp * units_per_warp + sidx;
-  const bool active = sidx < units_per_warp && unit < n_units;
+  // after_fast: k_inflate_fast has been over the batch; a unit it finished carries 1 in word 1 of its piece table
+  const bool active = sidx < units_per_warp && unit < n_units &&
+                      !(after_fast && ws.pieces[(size_t)unit * PIECE_WORDS + 1] == 1u);
 
   uint16_t *lut_l = reinterpret_cast<uint16_t *>(smem + CONST_WORDS +
                                                  (warp_in_block * units_per_warp + (active ? sidx : 0)) * LANE_STRIDE_WORDS);
@@ -138,11 +141,12 @@ template <bool HIST>
 __global__ void __launch_bounds__(B200Z_EXPAND_THREADS)
 k_inflate_expand(InflateWs ws, const uint8_t *__restrict__ in_base, const uint64_t *__restrict__ in_off, uint8_t *out_base,
                  const uint64_t *__restrict__ out_off, const uint32_t *__restrict__ out_cap, uint32_t *__restrict__ out_len,
-                 int32_t *__restrict__ status, uint32_t n_units) {
+                 int32_t *__restrict__ status, uint32_t n_units, int after_fast) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t unit = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; unit < n_units; unit += warps) {
+    if (after_fast && ws.pieces[(size_t)unit * PIECE_WORDS + 1] == 1u) continue;  // finished by k_inflate_fast
     const uint64_t oo = out_off[unit];
     // Positions below count from `hist` bytes in front of the unit (InflateWs::hist; 0 unless the unit is a gzip member
     // decoded on its own behind its predecessors): the range check, the capacity check and the source reads then need
@@ -314,22 +318,24 @@ k_find_flush_markers(const uint8_t *__restrict__ in, unsigned long long n, unsig
 static int g_num_sms = 0;
 
 // optional per-kernel timing (CUDA events on the launching stream; bench.py's roofline breakdown)
-struct ProfTriple { cudaEvent_t a, b, c; };
+struct ProfTriple { cudaEvent_t a, f, b, c; };  // start, after k_inflate_fast, after k_inflate_decode, after k_inflate_expand
 static bool g_prof = false;
 static std::vector<ProfTriple> g_prof_events;
 void profile_enable(bool on) { g_prof = on; }
-int profile_read(double *decode_ms, double *expand_ms, uint64_t *n) {
-  *decode_ms = *expand_ms = 0;
+int profile_read(double *fast_ms, double *decode_ms, double *expand_ms, uint64_t *n) {
+  *fast_ms = *decode_ms = *expand_ms = 0;
   *n = 0;
   for (auto &t : g_prof_events) {
     if (cudaEventSynchronize(t.c) != cudaSuccess) return -1;
-    float d = 0, e = 0;
-    cudaEventElapsedTime(&d, t.a, t.b);
+    float f = 0, d = 0, e = 0;
+    cudaEventElapsedTime(&f, t.a, t.f);
+    cudaEventElapsedTime(&d, t.f, t.b);
     cudaEventElapsedTime(&e, t.b, t.c);
+    *fast_ms += f;
     *decode_ms += d;
     *expand_ms += e;
     ++*n;
-    cudaEventDestroy(t.a); cudaEventDestroy(t.b); cudaEventDestroy(t.c);
+    cudaEventDestroy(t.a); cudaEventDestroy(t.f); cudaEventDestroy(t.b); cudaEventDestroy(t.c);
   }
   g_prof_events.clear();
   return 0;
@@ -432,17 +438,45 @@ cudaError_t launch_inflate(const InflateBatch &b, cudaStream_t stream) {
   }
   ProfTriple pt{};
   if (g_prof) {
-    cudaEventCreate(&pt.a); cudaEventCreate(&pt.b); cudaEventCreate(&pt.c);
+    cudaEventCreate(&pt.a); cudaEventCreate(&pt.f); cudaEventCreate(&pt.b); cudaEventCreate(&pt.c);
     cudaEventRecord(pt.a, stream);
   }
+  // k_inflate_fast first (inflate_fast.cuh): a CTA per unit, everything in shared memory.  It finishes the clean units
+  // whose output fits its window and flags them; the two exact kernels below then only see what is left.
+  int after_fast = 0;
+  {
+    static int fast_on = -1;
+    if (fast_on < 0) {
+      const char *e = getenv("B200Z_FAST");
+      fast_on = e ? atoi(e) : 0;  // (off until it beats the token path on the hardware)
+    }
+    if (fast_on && !b.count_only && b.ws.hist == 0 && b.ws.pieces != nullptr) {
+      static bool attr_done = false;
+      if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(k_inflate_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+      }
+      uint64_t fblocks = (uint64_t)g_num_sms * 2u;  // two resident CTAs per SM, each walks its share of the units
+      if (fblocks > b.n_units) fblocks = b.n_units;
+      k_inflate_fast<<<(unsigned)fblocks, fp::NT, fp::SMEM_BYTES, stream>>>(b.in_base, b.in_off, b.in_len, b.out_base, b.out_off, b.out_cap,
+                                                                        b.out_len, b.status, b.in_used, (uint32_t)b.n_units,
+                                                                        b.ws.pieces + 1, (uint32_t)PIECE_WORDS);
+      count_launch();
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) return e;
+      after_fast = 1;
+    }
+  }
+  if (g_prof) cudaEventRecord(pt.f, stream);
   if (b.ws.hist)
     k_inflate_decode<true><<<blocks, B200Z_DECODE_THREADS, smem, stream>>>(b.in_base, b.in_off, b.in_len, b.out_off, b.out_cap, b.ws,
                                                                          b.out_len, b.status, b.in_used, (uint32_t)b.n_units, upw,
-                                                                         b.count_only ? 1 : lpu, b.count_only ? 1 : 0);
+                                                                         b.count_only ? 1 : lpu, b.count_only ? 1 : 0, after_fast);
   else
     k_inflate_decode<false><<<blocks, B200Z_DECODE_THREADS, smem, stream>>>(b.in_base, b.in_off, b.in_len, b.out_off, b.out_cap, b.ws,
                                                                           b.out_len, b.status, b.in_used, (uint32_t)b.n_units, upw,
-                                                                          b.count_only ? 1 : lpu, b.count_only ? 1 : 0);
+                                                                          b.count_only ? 1 : lpu, b.count_only ? 1 : 0, after_fast);
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
@@ -467,10 +501,10 @@ cudaError_t launch_inflate(const InflateBatch &b, cudaStream_t stream) {
   if (eblocks > max_blocks) eblocks = max_blocks;
   if (b.ws.hist)
     k_inflate_expand<true><<<(unsigned)eblocks, B200Z_EXPAND_THREADS, 0, stream>>>(b.ws, b.in_base, b.in_off, b.out_base, b.out_off,
-                                                                                 b.out_cap, b.out_len, b.status, (uint32_t)b.n_units);
+                                                                                 b.out_cap, b.out_len, b.status, (uint32_t)b.n_units, after_fast);
   else
     k_inflate_expand<false><<<(unsigned)eblocks, B200Z_EXPAND_THREADS, 0, stream>>>(b.ws, b.in_base, b.in_off, b.out_base, b.out_off,
-                                                                                  b.out_cap, b.out_len, b.status, (uint32_t)b.n_units);
+                                                                                  b.out_cap, b.out_len, b.status, (uint32_t)b.n_units, after_fast);
   count_launch();
   if (g_prof) {
     cudaEventRecord(pt.c, stream);

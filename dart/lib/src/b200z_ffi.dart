@@ -172,8 +172,8 @@ typedef _IntD = int Function();
 typedef _U64C = Uint64 Function();
 typedef _ProfileEnableC = Void Function(Int32 on);
 typedef _ProfileEnableD = void Function(int on);
-typedef _ProfileReadC = Int32 Function(Pointer<Double> decodeMs, Pointer<Double> expandMs, Pointer<Uint64> nBatches);
-typedef _ProfileReadD = int Function(Pointer<Double> decodeMs, Pointer<Double> expandMs, Pointer<Uint64> nBatches);
+typedef _ProfileReadC = Int32 Function(Pointer<Double> fastMs, Pointer<Double> decodeMs, Pointer<Double> expandMs, Pointer<Uint64> nBatches);
+typedef _ProfileReadD = int Function(Pointer<Double> fastMs, Pointer<Double> decodeMs, Pointer<Double> expandMs, Pointer<Uint64> nBatches);
 
 class B200ZException implements Exception {
   final int code;

@@ -227,9 +227,10 @@ int b200z_inflate_batch_device(const uint8_t *d_in_base, const uint64_t *d_in_of
 /* Number of kernel launches issued by this library since b200z_init (bench.py gpu_launches). */
 uint64_t b200z_launch_count(void);
 /* Optional per-kernel timing with CUDA events on the launching stream: enable, run batches, then read
- * the summed durations (ms) of the decode and expand kernels and the number of batches timed.          */
+ * the summed durations (ms) of the three inflate kernels (k_inflate_fast, then the exact pair k_inflate_decode /
+ * k_inflate_expand over the units the first one left) and the number of batches timed.                        */
 void b200z_profile_enable(int on);
-int b200z_profile_read(double *decode_ms, double *expand_ms, uint64_t *n_batches);
+int b200z_profile_read(double *fast_ms, double *decode_ms, double *expand_ms, uint64_t *n_batches);
 
 #ifdef __cplusplus
 }

@@ -95,8 +95,11 @@ int orc_zip_list(const uint8_t *b, size_t blen, orc_zip_entry *out, size_t cap, 
     }
   }
   /* the central directory: a sub-stream [dir_offset, dir_offset + dir_size) */
-  cur d = {b, len, (int64_t)dir_offset, 0};
-  int64_t d_end = (int64_t)(dir_offset + dir_size);
+  /* subset(position, length) (input_memory_stream.dart:15-27,111-119): the length is cut to what the archive holds; an
+   * offset beyond it, or a negative offset / size, makes Uint8List.view throw; reads are bounded by the sub-stream */
+  if ((int64_t)dir_offset < 0 || (int64_t)dir_offset > len || (int64_t)dir_size < 0) return ORC_THROW;
+  int64_t d_end = (int64_t)dir_size > len - (int64_t)dir_offset ? len : (int64_t)(dir_offset + dir_size);
+  cur d = {b, d_end, (int64_t)dir_offset, 0};
   size_t n = 0;
   while (d.pos < d_end) {
     uint32_t fsig = rd(&d, 4);
@@ -162,6 +165,7 @@ int orc_zip_list(const uint8_t *b, size_t blen, orc_zip_entry *out, size_t cap, 
       e.data_off = (uint64_t)f.pos;
       e.has_data = 1;
       int64_t avail = len - f.pos;
+      if ((int64_t)comp < 0) return ORC_THROW; /* readBytes(negative count): Uint8List.view throws */
       if ((int64_t)comp > avail) e.comp_size = (uint64_t)avail; /* readBytes gives what is left */
       f.pos += (int64_t)e.comp_size;
       if (e.flags & 0x08) {

@@ -1,0 +1,207 @@
+"""k_inflate_fast (archive_b200/csrc/inflate_fast.cuh) executed on the CUDA execution-model emulation: one CTA per unit,
+everything in shared memory -- 256 speculative lanes per block, boundary bitmaps, the chain of meeting points, the in-place
+match records and the chunked LZ77 resolution.  A unit it FINISHES (flag 1) must be byte-for-byte what the oracle gives
+(bytes, out_len, status, in_used); a unit it leaves (flag 0) must be untouched, and it must leave everything the reference
+treats specially.  Clean units of the benchmark shape must all be finished here (otherwise the fast path is not the path)."""
+import ctypes as C
+import os
+import random
+import zlib
+
+import numpy as np
+import pytest
+
+import oracle_lib as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_E = None
+SENT_LEN, SENT_ST, SENT_USED = 0xDEADBEEF, -77, 0xFEEDF00D
+
+
+def run_fast(units, caps, blocks=3, misalign=True):
+    global _E
+    if _E is None:
+        _E = C.CDLL(os.path.join(ROOT, "tests", "host_emul", "libinflate_emul.so"))
+    n = len(units)
+    blob = bytearray(64)
+    in_off, in_len = [], []
+    for u in units:
+        in_off.append(len(blob))
+        in_len.append(len(u))
+        blob += u
+        if misalign:
+            blob += b"\xA5" * (3 + (len(blob) * 7) % 13)  # neighbours are never zero padding, offsets are unaligned
+        else:
+            blob += b"\xA5" * ((-len(blob)) % 16)
+    blob += bytes(64)
+    out_off, o = [], 5 if misalign else 0
+    for c in caps:
+        out_off.append(o)
+        o += c + (3 if misalign else 0)
+    inb = (C.c_uint8 * len(blob)).from_buffer(blob)
+    outb = (C.c_uint8 * (o + 64))()
+    C.memset(outb, 0x5A, o + 64)
+    arr = lambda t, l: (t * len(l))(*l)
+    ol, st, iu, fl = (C.c_uint32 * n)(), (C.c_int32 * n)(), (C.c_uint32 * n)(), (C.c_uint32 * n)()
+    for i in range(n):
+        ol[i], st[i], iu[i], fl[i] = SENT_LEN, SENT_ST, SENT_USED, 9
+    _E.emu_inflate_fast(inb, arr(C.c_uint64, in_off), arr(C.c_uint32, in_len), outb, arr(C.c_uint64, out_off),
+                        arr(C.c_uint32, caps), ol, st, iu, n, blocks, fl)
+    res = []
+    raw = bytes(outb)
+    for i in range(n):
+        assert fl[i] in (0, 1), "every unit is visited"
+        if fl[i] == 1:
+            res.append((raw[out_off[i]:out_off[i] + ol[i]], ol[i], st[i], iu[i]))
+        else:
+            assert (ol[i], st[i], iu[i]) == (SENT_LEN, SENT_ST, SENT_USED), "a unit that is left is not reported"
+            res.append(None)
+    # nothing outside the units' own slots is written
+    mask = bytearray(raw)
+    for i in range(n):
+        a = out_off[i]
+        b = a + (ol[i] if fl[i] == 1 else caps[i])
+        mask[a:b] = b"\x5A" * (b - a)
+    assert bytes(mask) == b"\x5A" * len(mask), "stray writes outside a unit's output slot"
+    return res
+
+
+def check_against_oracle(units, caps, must_finish=None, **kw):
+    got = run_fast(units, caps, **kw)
+    finished = 0
+    for i, (u, cap) in enumerate(zip(units, caps)):
+        if got[i] is None:
+            continue
+        # unit-level reference: the exact kernels' per-stream logic on the host (pinned to the oracle by
+        # tests/test_decode_logic_emul.py), and the oracle itself for the bytes
+        st, out, used, _ = orc.emul_inflate(u, cap)
+        finished += 1
+        assert st in (0, 1), f"unit {i}: finished here although the reference reports status {st}"
+        ost, oout, oused = orc.inflate(u)
+        assert ost == orc.OK and oout == out, f"unit {i}: reference disagreement"
+        assert got[i][0] == out, f"unit {i}: bytes"
+        assert got[i][1] == len(out), f"unit {i}: out_len"
+        assert got[i][2] == st, f"unit {i}: status"
+        assert got[i][3] == used, f"unit {i}: in_used"
+        if st == 0:
+            assert oused == used, f"unit {i}: consumed"
+    if must_finish is not None:
+        assert finished >= must_finish, f"only {finished} of {len(units)} units took the shared-memory path"
+    return got
+
+
+def text(rng, n):
+    words = [bytes(rng.choice(b"etaoinshrdlucmfwypvbgkqjxz") for _ in range(rng.randint(2, 10))) for _ in range(3000)]
+    b = bytearray()
+    while len(b) < n:
+        b += rng.choice(words) + rng.choice([b" ", b" ", b" ", b", ", b".\n"])
+    return bytes(b[:n])
+
+
+def deflate(data, level=6, mem=9, strategy=zlib.Z_DEFAULT_STRATEGY):
+    co = zlib.compressobj(level, zlib.DEFLATED, -15, mem, strategy)
+    return co.compress(data) + co.flush()
+
+
+def test_benchmark_shape_units_all_finish_here():
+    from archive_b200 import synth
+    t = synth.text(10 * 65536)
+    plain = [t[i * 65536:(i + 1) * 65536].tobytes() for i in range(10)]
+    units = [synth.deflate_raw(p) + bytes(8) for p in plain]  # + gzip trailer room, as the framing layer passes it
+    got = check_against_oracle(units, [65536] * 10, must_finish=10)
+    assert [g[0] for g in got] == plain
+    got = check_against_oracle(units, [65536] * 10, must_finish=10, misalign=False, blocks=1)
+    assert [g[0] for g in got] == plain
+
+
+def test_block_types_sizes_and_multi_block():
+    rng = random.Random(5)
+    units, caps = [], []
+    for n in (300, 1000, 4097, 20000, 65536, 50001):
+        p = text(rng, n)
+        for mem in (9, 8, 1):           # memLevel 1: a block every 127 symbols -- many blocks per unit
+            for strat in (zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE):
+                units.append(deflate(p, 6, mem, strat) + bytes(8))
+                caps.append(n)
+    # stored blocks, long runs (distance 1, length 258), binary noise with long codes, tiny alphabets
+    units.append(deflate(os.urandom(30000) if False else bytes(rng.randrange(256) for _ in range(20000)), 0) + bytes(8))
+    caps.append(20000)
+    units.append(deflate(b"\0" * 65536) + bytes(8)); caps.append(65536)
+    units.append(deflate(b"ab" * 30000) + bytes(8)); caps.append(60000)
+    noise = bytes(min(255, int(abs(rng.gauss(0, 40)))) for _ in range(60000))
+    units.append(deflate(noise, 9) + bytes(8)); caps.append(60000)
+    units.append(deflate(bytes(rng.choice(b"ab") for _ in range(40000))) + bytes(8)); caps.append(40000)
+    fits = sum(1 for u in units if 192 <= len(u) <= 30720 - 16)  # the staged-input window of the small variant
+    check_against_oracle(units, caps, must_finish=fits)
+
+
+def test_flush_pieces_end_of_stream_without_final_block():
+    from archive_b200 import synth
+    p = synth.text(3 * 65536, stream=2).tobytes()
+    co = zlib.compressobj(6, zlib.DEFLATED, -15, 8)
+    pieces = []
+    for i in range(3):
+        z = co.compress(p[i * 65536:(i + 1) * 65536]) + co.flush(zlib.Z_FULL_FLUSH)
+        pieces.append(z)
+    tail = co.flush()
+    got = check_against_oracle(pieces, [65536] * 3, must_finish=3)
+    assert all(g[2] == 1 for g in got)  # B200Z_U_EOS: the piece ends at a block boundary with the input used up
+    check_against_oracle([pieces[0] + tail + bytes(8)], [65536])
+
+
+def test_unusual_units_are_left_to_the_exact_kernels():
+    rng = random.Random(3)
+    p = text(rng, 40000)
+    z = deflate(p)
+    units, caps, must_leave = [], [], []
+    # output beyond out_cap
+    units.append(z + bytes(8)); caps.append(39999); must_leave.append(True)
+    # truncated inside a block, at every kind of place
+    for cut in (len(z) // 2, len(z) - 1, len(z) - 3, 40, 3):
+        units.append(z[:cut]); caps.append(40000); must_leave.append(True)
+    # stream that ends exactly with its last byte (zip member without lookahead): the short-read quirk may bite
+    units.append(z); caps.append(40000); must_leave.append(None)
+    # corrupted: flip bits all over
+    for k in range(24):
+        b = bytearray(z + bytes(8))
+        pos = rng.randrange(len(z) * 8)
+        b[pos >> 3] ^= 1 << (pos & 7)
+        units.append(bytes(b)); caps.append(40000); must_leave.append(None)
+    # reserved block type, bad stored length
+    units.append(b"\x07" + bytes(300)); caps.append(1000); must_leave.append(True)
+    units.append(b"\x01\x10\x00\x00\x00" + bytes(300)); caps.append(1000); must_leave.append(True)
+    got = check_against_oracle(units, caps)
+    for g, ml in zip(got, must_leave):
+        if ml:
+            assert g is None
+
+
+def test_distance_before_start_is_left():
+    # a block whose first token is a match: fixed Huffman, length 3 distance 1 at output position 0
+    # bits: BFINAL=1, BTYPE=01, then length code 257 (7 bits: 0000001), distance code 0 (5 bits), EOB (0000000)
+    bits = "1" + "10" + "0000001" + "00000" + "0000000"
+    v = int(bits[::-1], 2)
+    unit = v.to_bytes((len(bits) + 7) // 8, "little") + bytes(300)
+    got = check_against_oracle([unit], [1000])
+    assert got[0] is None
+
+
+def test_seeded_fuzz_small_windows_and_levels():
+    rng = random.Random(21)
+    units, caps = [], []
+    for k in range(40):
+        n = rng.randrange(200, 65537)
+        kind = rng.randrange(4)
+        if kind == 0:
+            p = text(rng, n)
+        elif kind == 1:
+            p = bytes(rng.randrange(256) for _ in range(n // 8)) * 8
+        elif kind == 2:
+            p = bytes(rng.choice(b"abc") for _ in range(n))
+        else:
+            p = text(rng, n // 2) + bytes(n - n // 2)
+        co = zlib.compressobj(rng.choice([1, 4, 6, 9]), zlib.DEFLATED, -rng.choice([9, 12, 15]), rng.choice([1, 5, 8, 9]))
+        z = co.compress(p) + co.flush()
+        units.append(z + bytes(rng.choice([0, 2, 8])))
+        caps.append(len(p) + rng.choice([0, 0, 100]))
+    check_against_oracle(units, caps, must_finish=20)

@@ -103,3 +103,55 @@ def test_reference_table_directory(name):
         assert n == len(want["File"])
         for e, h in zip(dec.entries, want["File"]):
             assert data[e.name_off:e.name_off + e.name_len].decode() == h["Name"]
+
+
+def _zip64_archive(comp64=None, cd_off64=None, cd_size64=None, lho64=None):
+    """One stored member 'a' holding b'hello', with a zip64 extra field in its central header and a zip64 end-of-central-
+    directory record + locator, so that every 64-bit field of the format can be set to anything."""
+    import struct
+    name, data = b"a", b"hello"
+    crc = orc.crc32(data)
+    local = struct.pack("<IHHHHHIIIHH", 0x04034b50, 45, 0, 0, 0, 0x21, crc, len(data), len(data), len(name), 0) + name + data
+    extra = b""
+    comp32, lho32 = len(data), 0
+    if comp64 is not None:
+        comp32 = 0xffffffff
+    if lho64 is not None:
+        lho32 = 0xffffffff
+    body = b""
+    if comp64 is not None:
+        body += struct.pack("<Q", comp64)
+    if lho64 is not None:
+        body += struct.pack("<Q", lho64)
+    if body:
+        extra = struct.pack("<HH", 1, len(body)) + body
+    cd = struct.pack("<IHHHHHHIIIHHHHHII", 0x02014b50, 0x031e, 45, 0, 0, 0, 0x21, crc, comp32, len(data), len(name), len(extra),
+                     0, 0, 0, 0o100644 << 16, lho32) + name + extra
+    cd_off = len(local)
+    z64 = struct.pack("<IQHHIIQQQQ", 0x06064b50, 44, 45, 45, 0, 0, 1, 1, len(cd) if cd_size64 is None else cd_size64,
+                      cd_off if cd_off64 is None else cd_off64)
+    z64_off = cd_off + len(cd)
+    loc = struct.pack("<IIQI", 0x07064b50, 0, z64_off, 1)
+    eocd = struct.pack("<IHHHHIIH", 0x06054b50, 0, 0, 1, 1, len(cd), cd_off, 0)
+    return local + cd + z64 + loc + eocd
+
+
+def test_zip64_fields_that_wrap_or_point_outside_the_archive():
+    """64-bit sizes and offsets are the archive's to choose: sums with them must not wrap, sizes are cut to
+    what the archive holds exactly as readBytes / subset do, and what makes Uint8List.view throw is B200Z_E_THROW."""
+    ok = _zip64_archive()
+    ref = same_as_oracle(ok, "plain zip64")
+    assert len(ref) == 1 and ref[0].comp_size == 5
+    arch = _zip64_archive(comp64=1 << 40)
+    big = same_as_oracle(arch, "compressed size beyond the archive")
+    assert big[0].comp_size == len(arch) - big[0].data_off  # clipped to what is there
+    for tag, kw in (("compressed size that wraps the sum", dict(comp64=0xffffffffffffffe2)),
+                    ("compressed size 2^63", dict(comp64=1 << 63)),
+                    ("directory offset near 2^64", dict(cd_off64=(1 << 64) - 4, cd_size64=2)),
+                    ("directory offset beyond the archive", dict(cd_off64=1 << 33)),
+                    ("directory size 2^64-1", dict(cd_size64=(1 << 64) - 1)),
+                    ("local header offset near 2^64", dict(lho64=(1 << 64) - 2))):
+        data = _zip64_archive(**kw)
+        assert same_as_oracle(data, tag) is None, tag  # the reference throws (RangeError)
+    # a directory size that merely reaches beyond the archive is cut to its end, and reading on from there throws
+    same_as_oracle(_zip64_archive(cd_size64=1 << 40), "directory size beyond the archive")
