@@ -91,6 +91,15 @@ _SIGS = {
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "b200z_inflate_workspace_bytes": (C.c_size_t, [C.c_size_t, C.c_size_t, C.c_size_t]),
     "b200z_inflate_batch_device": (C.c_int, [C.c_void_p] * 9 + [C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
+    # several GPUs driven by this one process
+    "b200z_multi_init": (C.c_int, [C.c_uint32, C.c_uint32]),
+    "b200z_multi_shutdown": (None, []),
+    "b200z_multi_device_count": (C.c_int, []),
+    "b200z_gzip_decode_multi": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t),
+                                          C.c_uint32]),
+    "b200z_inflate_batch_multi": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32]),
+    "b200z_multi_device_output": (C.c_void_p, [C.c_int, C.POINTER(C.c_size_t)]),
 }
 
 

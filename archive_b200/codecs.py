@@ -130,7 +130,8 @@ class _FramedDecoder:
     def decode_stream(self, input: InputMemoryStream, output: OutputMemoryStream, verify: bool = False,
                       raw: bool = False) -> bool:
         if _both_files(input, output):
-            return _stream_result(_file_codec(self._file_op, input, output, int(verify), int(raw)))
+            a0 = int(bool(verify)) | (2 if raw and self._file_op == _ffi.FILE_GZIP_DECODE else 0)  # B200Z_GZIP_RAW
+            return _stream_result(_file_codec(self._file_op, input, output, a0, int(raw)))
         L = _ffi.ensure_init()
         view = _rest(input)
         addr, n, keep = _ffi.as_buffer(view)
@@ -161,7 +162,7 @@ class GZipDecoderWeb(_FramedDecoder):
         return L.b200z_gzip_bound(addr, n) or 4 * n + 1024
 
     def _call(self, L, addr, n, verify, raw, oa, cap, out_len):
-        rc = L.b200z_gzip_decode(addr, n, int(verify), oa, cap, C.byref(out_len))
+        rc = L.b200z_gzip_decode(addr, n, int(bool(verify)) | (2 if raw else 0), oa, cap, C.byref(out_len))  # B200Z_GZIP_RAW
         return rc, out_len.value
 
 

@@ -352,10 +352,7 @@ static inline bool isize_possible(uint32_t isize, size_t comp) { return (uint64_
 
 // THE definition of a hinted run: whole members from `pos` on that carry the BGZF 'BC' size and a believable ISIZE.
 // Returns the position behind the run; appends the members to `ms` when given; *out_bytes = what their ISIZE fields promise.
-struct HintedMember {
-  size_t hdr_end, next;  // first byte of the DEFLATE stream; first byte behind the member
-  uint32_t isize;
-};
+// (struct HintedMember: b200z_internal.h)
 static size_t hinted_run(const uint8_t *in, size_t n, size_t pos, std::vector<HintedMember> *ms, size_t *out_bytes) {
   size_t p = pos, o = 0;
   while (p < n) {
@@ -431,7 +428,8 @@ static int gzip_decode_staged(const uint8_t *in, size_t in_len, int verify, size
       return B200Z_E_THROW;
     }
     if (h == 0)  // no gzip header: fall back to zlib on the same little-endian stream (:31-37)
-      return zlib_decode_staged(in, in_len, pos, verify, 0, /*big_endian=*/0, out_pos, out_cap, out_len_total);
+      return zlib_decode_staged(in, in_len, pos, verify & B200Z_GZIP_VERIFY, (verify & B200Z_GZIP_RAW) != 0, /*big_endian=*/0, out_pos,
+                                out_cap, out_len_total);  // decodeStream(input, output, verify: verify, raw: raw)
     OneResult r;
     int rc = run_one_staged(hdr_end, in_len, out_pos, out_cap, &r, /*shared_output=*/true);
     if (rc) return rc;
@@ -608,6 +606,9 @@ void set_error_text(const char *msg) { set_err("%s", msg); }
 // Bytes of `in` covered by whole members that carry a size hint, from offset 0 (the run gzip_fast_path would take), and the
 // output bytes their ISIZE fields promise.
 size_t gzip_hinted_prefix(const uint8_t *in, size_t n, size_t *out_bytes) { return hinted_run(in, n, 0, nullptr, out_bytes); }
+size_t gzip_hinted_members(const uint8_t *in, size_t n, size_t pos, std::vector<HintedMember> *ms, size_t *out_bytes) {
+  return hinted_run(in, n, pos, ms, out_bytes);
+}
 
 // The hinted run at the front of `in`, decoded through the chunk pipeline: *in_used = end of the last member whose hint
 // was exact (== the whole run unless a hint lied), *out_len = the bytes those members produced.

@@ -4,6 +4,8 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include <vector>
+
 #include "../../include/b200z.h"
 
 #ifndef B200Z_LBITS
@@ -103,6 +105,12 @@ int profile_read(double *fast_ms, double *decode_ms, double *expand_ms, uint64_t
 // ---- file streams (b200z_file.cu) and the hooks it uses (b200z_api.cu) ----
 void set_error_text(const char *msg);  // b200z_last_error() text of the calling thread
 size_t gzip_hinted_prefix(const uint8_t *in, size_t n, size_t *out_bytes);
+struct HintedMember {
+  size_t hdr_end, next;  // first byte of the DEFLATE stream; first byte behind the member
+  uint32_t isize;
+};
+// the run of members from `pos` on that carry the BGZF 'BC' size and a believable ISIZE (b200z_api.cu: hinted_run)
+size_t gzip_hinted_members(const uint8_t *in, size_t n, size_t pos, std::vector<HintedMember> *ms, size_t *out_bytes);
 int gzip_decode_hinted(const uint8_t *in, size_t n, uint8_t *out, size_t out_cap, size_t *in_used, size_t *out_len);
 int gzip_decode_after(const uint8_t *in, size_t n, int verify, const uint8_t *hist, size_t hist_len, uint8_t *out, size_t out_cap,
                       size_t *out_len);

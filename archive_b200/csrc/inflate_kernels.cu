@@ -388,10 +388,10 @@ cudaError_t launch_find_markers(const uint8_t *d_in, size_t n, unsigned long lon
 
 cudaError_t launch_inflate(const InflateBatch &b, cudaStream_t stream) {
   if (b.n_units == 0) return cudaSuccess;
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
   if (!g_num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, cur_dev);
     if (g_num_sms <= 0) g_num_sms = 148;
   }
   // Streams per warp.  Decode is latency-bound per stream, so what matters first is that every
@@ -428,7 +428,8 @@ cudaError_t launch_inflate(const InflateBatch &b, cudaStream_t stream) {
   const uint64_t n_warps = (b.n_units + upw - 1) / upw;
   const unsigned blocks = (unsigned)((n_warps + warps_per_block - 1) / warps_per_block);
   const size_t smem = inflate_decode_smem_bytes(warps_per_block, upw);
-  static size_t attr_smem = 0;
+  static size_t attr_smem_dev[64] = {};
+  size_t &attr_smem = attr_smem_dev[cur_dev & 63];
   if (smem > attr_smem) {
     cudaError_t e = cudaFuncSetAttribute(k_inflate_decode<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -451,11 +452,11 @@ cudaError_t launch_inflate(const InflateBatch &b, cudaStream_t stream) {
       fast_on = e ? atoi(e) : 0;  // (off until it beats the token path on the hardware)
     }
     if (fast_on && !b.count_only && b.ws.hist == 0 && b.ws.pieces != nullptr) {
-      static bool attr_done = false;
-      if (!attr_done) {
+      static uint64_t attr_done = 0;  // one bit per device: function attributes belong to the device's context
+      if (!((attr_done >> (cur_dev & 63)) & 1u)) {
         cudaError_t e = cudaFuncSetAttribute(k_inflate_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp::SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        attr_done |= 1ull << (cur_dev & 63);
       }
       uint64_t fblocks = (uint64_t)g_num_sms * 2u;  // two resident CTAs per SM, each walks its share of the units
       if (fblocks > b.n_units) fblocks = b.n_units;

@@ -139,6 +139,12 @@ def bzip2_decode_sharded(data, verify: bool = False, group=None, rank=None, worl
         out_len, nb = C.c_size_t(0), C.c_size_t(0)
         rc = L.b200z_bzip2_decode_shard(addr, n, rank, world, C.addressof(out), out_cap, C.byref(out_len), blocks,
                                         cap_blocks, C.byref(nb))
+        if rc == _ffi.E_NOSPC and nb.value > cap_blocks:
+            # more block reports than the array holds: highly compressible streams (a 900 kB block of one long run is
+            # ~40 bytes) and chance matches of the magic both add candidates
+            cap_blocks = nb.value + 64
+            blocks = (_ffi.Bz2Block * cap_blocks)()
+            continue
         if rc == _ffi.E_NOSPC and out_len.value > out_cap and not out_buf:
             out_cap = out_len.value + 64
             continue
@@ -225,13 +231,16 @@ def zip_encode_sharded(archive, level: int = 1, modified=None, comment: str = ""
         rank, world = dist.get_rank(group), dist.get_world_size(group)
     sizes = [(e.size if e.is_file else 0) for e in entries]
     mine = pack_members(sizes, world)[rank]
-    lv = level if level is not None else 6
+    def level_of(e):  # the member's own level wins (ZipEncoder.level_of, zip_encoder.dart:137-183)
+        own = getattr(e, "compress_level", None)
+        return own if own is not None else (level if level is not None else 6)
+
     done = {}
     for i in mine:
         e = entries[i]
         if e.is_file:
             method = e.compression or "deflate"
-            done[i] = compress(e.content or b"", method, lv)
+            done[i] = compress(e.content or b"", method, level_of(e))
     if dist is not None:
         parts = [None] * world
         dist.all_gather_object(parts, done, group=group)

@@ -159,6 +159,21 @@ typedef _InflateBatchDeviceC = Int32 Function(Pointer<Uint8> dInBase, Pointer<Ui
 typedef _InflateBatchDeviceD = int Function(Pointer<Uint8> dInBase, Pointer<Uint64> dInOff, Pointer<Uint32> dInLen,
     Pointer<Uint8> dOutBase, Pointer<Uint64> dOutOff, Pointer<Uint32> dOutCap, Pointer<Uint32> dOutLen, Pointer<Int32> dStatus,
     Pointer<Uint32> dInUsed, int nUnits, Pointer<Void> dWorkspace, int workspaceBytes, Pointer<Void> cudaStream);
+// several GPUs driven by this one isolate (include/b200z.h "several GPUs of one box")
+typedef _MultiInitC = Int32 Function(Uint32 deviceMask, Uint32 flags);
+typedef _MultiInitD = int Function(int deviceMask, int flags);
+typedef _GzipDecodeMultiC = Int32 Function(Pointer<Uint8> inp, Size inLen, Int32 verify, Pointer<Uint8> out, Size outCap,
+    Pointer<Size> outLen, Uint32 flags);
+typedef _GzipDecodeMultiD = int Function(Pointer<Uint8> inp, int inLen, int verify, Pointer<Uint8> out, int outCap,
+    Pointer<Size> outLen, int flags);
+typedef _InflateBatchMultiC = Int32 Function(Pointer<Uint8> inBase, Size inBytes, Pointer<Uint64> inOff, Pointer<Uint32> inLen,
+    Pointer<Uint8> outBase, Size outBytes, Pointer<Uint64> outOff, Pointer<Uint32> outCap, Pointer<Uint32> outLen,
+    Pointer<Int32> status, Pointer<Uint32> inUsed, Size nUnits, Uint32 flags);
+typedef _InflateBatchMultiD = int Function(Pointer<Uint8> inBase, int inBytes, Pointer<Uint64> inOff, Pointer<Uint32> inLen,
+    Pointer<Uint8> outBase, int outBytes, Pointer<Uint64> outOff, Pointer<Uint32> outCap, Pointer<Uint32> outLen,
+    Pointer<Int32> status, Pointer<Uint32> inUsed, int nUnits, int flags);
+typedef _MultiOutputC = Pointer<Void> Function(Int32 slot, Pointer<Size> bytes);
+typedef _MultiOutputD = Pointer<Void> Function(int slot, Pointer<Size> bytes);
 typedef _WorkspaceBytesC = Size Function(Size nUnits, Size totalInBytes, Size totalOutCap);
 typedef _WorkspaceBytesD = int Function(int nUnits, int totalInBytes, int totalOutCap);
 typedef _FileStatsC = Void Function(Pointer<Uint32> nSegments, Pointer<Uint32> nWhole);
@@ -215,6 +230,14 @@ class B200Z {
   late final _WorkspaceBytesD inflateWorkspaceBytes =
       _lib.lookupFunction<_WorkspaceBytesC, _WorkspaceBytesD>('b200z_inflate_workspace_bytes');
   late final _FileStatsD fileLastStats = _lib.lookupFunction<_FileStatsC, _FileStatsD>('b200z_file_last_stats');
+  late final _MultiInitD multiInit = _lib.lookupFunction<_MultiInitC, _MultiInitD>('b200z_multi_init');
+  late final _VoidD multiShutdown = _lib.lookupFunction<_VoidC, _VoidD>('b200z_multi_shutdown');
+  late final _IntD multiDeviceCount = _lib.lookupFunction<_IntC, _IntD>('b200z_multi_device_count');
+  late final _GzipDecodeMultiD gzipDecodeMulti =
+      _lib.lookupFunction<_GzipDecodeMultiC, _GzipDecodeMultiD>('b200z_gzip_decode_multi');
+  late final _InflateBatchMultiD inflateBatchMulti =
+      _lib.lookupFunction<_InflateBatchMultiC, _InflateBatchMultiD>('b200z_inflate_batch_multi');
+  late final _MultiOutputD multiDeviceOutput = _lib.lookupFunction<_MultiOutputC, _MultiOutputD>('b200z_multi_device_output');
   late final _VoidD shutdown = _lib.lookupFunction<_VoidC, _VoidD>('b200z_shutdown');
   late final _IntD deviceCount = _lib.lookupFunction<_IntC, _IntD>('b200z_device_count');
   late final _ErrC _version = _lib.lookupFunction<_ErrC, _ErrC>('b200z_version');

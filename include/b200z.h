@@ -71,6 +71,8 @@ int b200z_inflate_raw(const uint8_t *in, size_t in_len, uint8_t *out, size_t out
  * one output stream, as in the reference (:38): a member's back-references may reach into the
  * members decoded before it.  A stream that ends inside a block: B200Z_E_THROW (the reference's
  * trailer read runs past the end), with the bytes decoded so far in `out`.                  */
+#define B200Z_GZIP_VERIFY 1 /* bits of `verify`: verify, and the `raw` the reference hands on to the zlib decoder when */
+#define B200Z_GZIP_RAW 2    /* the input has no gzip header (_gzip_decoder_web.dart:31-37)                            */
 int b200z_gzip_decode(const uint8_t *in, size_t in_len, int verify, uint8_t *out, size_t out_cap,
                       size_t *out_len);
 /* ZLibDecoderWeb().decodeBytes -- _zlib_decoder_web.dart:21-107 (stream loop, Adler-32 when
@@ -223,6 +225,29 @@ int b200z_inflate_batch_device(const uint8_t *d_in_base, const uint64_t *d_in_of
                                uint32_t *d_out_len, int32_t *d_status, uint32_t *d_in_used,
                                size_t n_units, void *d_workspace, size_t workspace_bytes,
                                void *cuda_stream);
+
+/* ---- several GPUs of one box driven by ONE process (device_mask / n_gpus; 8e) ----------------
+ * The reference decodes the members of a gzip stream in one loop and returns one buffer
+ * (_gzip_decoder_web.dart:27-38).  Here the members -- or the units of a batch -- are cut into one contiguous range
+ * per GPU (balanced by compressed bytes); every GPU receives its range over its own link, decodes it, and its part of
+ * the output stream goes straight to its place in the caller's buffer.  B200Z_MULTI_GATHER: the shards are also
+ * exchanged over NVLink (NCCL, communicators owned by the library, looked up at run time) so that EVERY device then
+ * holds the whole stream in block order (b200z_multi_device_output) -- BASELINE north_star's all-gather.
+ * b200z_multi_init(mask): bit d = CUDA device d; also runs b200z_init on the first device of the mask, which serves
+ * whatever cannot be dealt (members without size hints, hints that lie, the zlib fall-back).                       */
+#define B200Z_MULTI_GATHER 1u
+int b200z_multi_init(uint32_t device_mask, uint32_t flags);
+void b200z_multi_shutdown(void);
+int b200z_multi_device_count(void);
+int b200z_gzip_decode_multi(const uint8_t *in, size_t in_len, int verify, uint8_t *out, size_t out_cap,
+                            size_t *out_len, uint32_t flags);
+int b200z_inflate_batch_multi(const uint8_t *in_base, size_t in_bytes, const uint64_t *in_off,
+                              const uint32_t *in_len, uint8_t *out_base, size_t out_bytes,
+                              const uint64_t *out_off, const uint32_t *out_cap, uint32_t *out_len,
+                              int32_t *status, uint32_t *in_used, size_t n_units, uint32_t flags);
+/* after a B200Z_MULTI_GATHER call: device `slot` (0 .. b200z_multi_device_count()-1) holds *bytes of output at the
+ * returned device pointer; NULL when the last call did not gather.                                             */
+const void *b200z_multi_device_output(int slot, size_t *bytes);
 
 /* Number of kernel launches issued by this library since b200z_init (bench.py gpu_launches). */
 uint64_t b200z_launch_count(void);

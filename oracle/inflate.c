@@ -570,6 +570,17 @@ int orc_gzip_decode_bytes(const uint8_t *in, size_t n, int verify, uint8_t **out
   *out_len = (size_t)o.len;
   return st;
 }
+/* GZipDecoderWeb().decodeBytes(bytes, verify:, raw:) -- `raw` only matters for input without a gzip header, which goes to
+ * the zlib decoder with it (_gzip_decoder_web.dart:31-37) */
+int orc_gzip_decode_bytes_raw(const uint8_t *in, size_t n, int verify, int raw, uint8_t **out, size_t *out_len) {
+  orc_ims s = {in, (int64_t)n, 0, 0};
+  orc_oms o;
+  orc_oms_init(&o, OMS_DEFAULT);
+  int st = orc_gzip_decode(&s, &o, verify, raw);
+  *out = o.buf;
+  *out_len = (size_t)o.len;
+  return st;
+}
 int orc_zlib_decode_bytes(const uint8_t *in, size_t n, int verify, int raw, uint8_t **out, size_t *out_len) {
   orc_ims s = {in, (int64_t)n, 0, 1}; /* _zlib_decoder_web.dart:21-28: big-endian */
   orc_oms o;

@@ -33,7 +33,7 @@ def build(force: bool = False, asan: bool = False) -> str:
 
 
 def _build(force: bool, so: str, opt: list, suffix: str) -> str:
-    units = [gen_emul.generate(ROOT, n) for n in ("b200z_api.cu", "b200z_file.cu", "inflate_kernels.cu", "bzip2_kernels.cu", "deflate_kernels.cu")]
+    units = [gen_emul.generate(ROOT, n) for n in ("b200z_api.cu", "b200z_file.cu", "b200z_multi.cu", "inflate_kernels.cu", "bzip2_kernels.cu", "deflate_kernels.cu")]
     units.append(os.path.join(CSRC, "bzip2_enc_kernels.cu"))  # carries its own B200Z_EMU switch
     deps = units + [os.path.join(HERE, "cuda_emu.h"), os.path.join(ROOT, "include", "b200z.h")] + [
         os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh", ".inl"))]

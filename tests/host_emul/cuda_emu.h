@@ -404,6 +404,14 @@ static inline unsigned __reduce_or_sync(unsigned mask, unsigned v) {
     return r;
   });
 }
+static inline unsigned __reduce_min_sync(unsigned mask, unsigned v) {
+  return (unsigned)cuemu::collective(mask, v, [](unsigned, const unsigned long long *val, unsigned m) {
+    unsigned long long r = 0xffffffffull;
+    for (int k = 0; k < 32; ++k)
+      if ((m >> k & 1) && (unsigned)val[k] < r) r = (unsigned)val[k];
+    return r;
+  });
+}
 static inline unsigned __reduce_max_sync(unsigned mask, unsigned v) {
   return (unsigned)cuemu::collective(mask, v, [](unsigned, const unsigned long long *val, unsigned m) {
     unsigned long long r = 0;

@@ -31,9 +31,9 @@ def inflate(data: bytes):
     return st, _take(out, n), c.value
 
 
-def gzip_decode(data: bytes, verify=False):
+def gzip_decode(data: bytes, verify=False, raw=False):
     out, n = C.POINTER(C.c_uint8)(), C.c_size_t()
-    st = L().orc_gzip_decode_bytes(data, C.c_size_t(len(data)), int(verify), C.byref(out), C.byref(n))
+    st = L().orc_gzip_decode_bytes_raw(data, C.c_size_t(len(data)), int(verify), int(raw), C.byref(out), C.byref(n))
     return st, _take(out, n)
 
 

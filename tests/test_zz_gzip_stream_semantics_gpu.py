@@ -180,6 +180,15 @@ def test_gzip_header_variants_and_zlib_fallback(a):
         ost, oout = orc.gzip_decode(z)
         st, got = run(a, a.GZipDecoder(), z)
         assert st == ost and (st == orc.THROW or got == oout), (i, st, ost, len(got), len(oout))
+    # `raw` is handed on to the zlib decoder (:31-37): raw DEFLATE without any header inflates through GZipDecoder(raw: true)
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    rawz = co.compress(t[4]) + co.flush()
+    for z in (rawz, rawz + rawz, rawz[:-2]):
+        for raw in (False, True):
+            ost, oout = orc.gzip_decode(z, raw=raw)
+            st, got = run(a, a.GZipDecoder(), z, raw=raw)
+            assert st == ost and (st == orc.THROW or got == oout), (raw, st, ost, len(got), len(oout))
+    assert orc.gzip_decode(rawz, raw=True)[1] == t[4]
 
 
 def test_zlib_streams_reach_the_output_one_stream_late(a):
