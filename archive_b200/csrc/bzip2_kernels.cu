@@ -130,7 +130,8 @@ k_bz2_entropy(const uint32_t *__restrict__ words, uint64_t n_bytes, const unsign
   if (b >= n_blocks) return;
   const int lane = threadIdx.x;
   const uint64_t total_bits = n_bytes * 8;
-  __shared__ int s_groups, s_alpha, s_err;
+  __shared__ int s_groups, s_alpha, s_err, s_nsel, s_inuse;
+  __shared__ uint32_t s_optr, s_rnd;
   __shared__ unsigned long long s_bitpos;
 
   BzBits br;
@@ -243,6 +244,10 @@ k_bz2_entropy(const uint32_t *__restrict__ words, uint64_t n_bytes, const unsign
     s_groups = n_groups;
     s_alpha = alpha;
     s_err = err;
+    s_nsel = n_sel;
+    s_inuse = n_in_use;
+    s_optr = optr;
+    s_rnd = rnd;
     s_bitpos = br.bitpos();
   }
   __syncwarp();
@@ -270,18 +275,31 @@ k_bz2_entropy(const uint32_t *__restrict__ words, uint64_t n_bytes, const unsign
     }
   }
   __syncwarp();
-  if (lane != 0) return;
-
+  // From here on EVERY lane walks the same bits with the same tables (shared-memory reads of one address are broadcasts),
+  // so the symbol is known to the whole warp without an exchange -- and the move-to-front list, the other serial chain of
+  // this stage, lives in the warp's registers: lane l holds entries 8l .. 8l+7 as one 64-bit word, a symbol's position is
+  // served by one shuffle and the shift of everything in front of it by another, whatever the position.  (With the list
+  // in shared memory a position of 20 cost five dependent read-modify-writes; text sits at 5-10 on average.)  The next
+  // symbol's Huffman look-up is issued before the list work of the current one, so the two chains overlap.
+  err = s_err;
+  n_sel = s_nsel;
+  n_in_use = s_inuse;
+  optr = s_optr;
+  rnd = s_rnd;
+  br.seek(s_bitpos);
+  const unsigned FULLW = 0xffffffffu;
   uint32_t nrec = 0, nblock = 0;
   if (!err) {
-    for (int i = 0; i < 64; ++i) S.mtfw[i] = (uint32_t)(4 * i) | ((uint32_t)(4 * i + 1) << 8) | ((uint32_t)(4 * i + 2) << 16) | ((uint32_t)(4 * i + 3) << 24);
+    uint64_t v = 0;  // my eight list entries
+    for (int k = 0; k < 8; ++k) v |= (uint64_t)(8 * lane + k) << (8 * k);
+    uint32_t front = 0;  // list entry 0 (every lane keeps it)
     const int eob = n_in_use + 1;
     uint32_t *rv = rec_val + (size_t)b * nblock_max;
     uint32_t *rp = rec_pos + (size_t)b * nblock_max;
+    uint32_t my_rv = 0, my_rp = 0;  // records leave 32 at a time, lane k carries record k of the group
     int gpos = 0, gno = -1, tsel = 0;
     int run_n = 0;       // number of RUNA/RUNB symbols in the open run
     uint32_t run_es = 0;  // value accumulated so far (es + 1 in the reference's terms)
-    uint32_t mtf0 = S.mtfw[0];  // entries 0..3 of the MTF list live in a register (most symbols land there)
     // ---- _getMtfVal (:732-772); sets derr instead of returning -1 ----
     int derr = 0;
     auto decode = [&]() -> int {
@@ -327,10 +345,21 @@ k_bz2_entropy(const uint32_t *__restrict__ words, uint64_t n_bytes, const unsign
       br.cnt -= zn;
       return sym;
     };
+    auto emit = [&](uint32_t val, uint32_t pos) {
+      if ((uint32_t)lane == (nrec & 31u)) {
+        my_rv = val;
+        my_rp = pos;
+      }
+      nrec++;
+      if ((nrec & 31u) == 0u) {
+        rv[nrec - 32u + lane] = my_rv;
+        rp[nrec - 32u + lane] = my_rp;
+      }
+    };
     int sym = decode();
     err = derr;
     while (!err) {
-      // the NEXT symbol's Huffman decode does not depend on the MTF work of this one: start it first so the two
+      // the NEXT symbol's Huffman decode does not depend on the list work of this one: start it first so the two
       // dependency chains overlap (a decode error is acted on after this symbol, as in the reference's order)
       const bool more = sym != eob;
       int nsym = 0;
@@ -349,9 +378,7 @@ k_bz2_entropy(const uint32_t *__restrict__ words, uint64_t n_bytes, const unsign
             err = BZ_DATA;
             break;
           }
-          rv[nrec] = (run_es << 8) | S.seq2unseq[mtf0 & 0xffu];
-          rp[nrec] = nblock;
-          nrec++;
+          emit((run_es << 8) | S.seq2unseq[front], nblock);
           nblock += run_es;
           run_n = 0;
           run_es = 0;
@@ -362,32 +389,21 @@ k_bz2_entropy(const uint32_t *__restrict__ words, uint64_t n_bytes, const unsign
           break;
         }
         // move entry nn to the front (:331-378 does the same job with its 16x16 blocks)
-        const int nn = sym - 1;
-        uint32_t uc;
-        if (nn < 4) {
-          const int sh = nn * 8;
-          uc = (mtf0 >> sh) & 0xffu;
-          const uint32_t below = mtf0 & ((1u << sh) - 1u);
-          const uint32_t upto = sh == 24 ? 0xffffffffu : ((1u << (sh + 8)) - 1u);
-          mtf0 = (mtf0 & ~upto) | (((below << 8) | uc) & upto);
-        } else {
-          const int wi = nn >> 2, sh = (nn & 3) * 8;
-          const uint32_t t = S.mtfw[wi];
-          uc = (t >> sh) & 0xffu;
-          uint32_t carry = mtf0 >> 24;
-          mtf0 = (mtf0 << 8) | uc;
-          for (int j = 1; j < wi; ++j) {
-            const uint32_t w = S.mtfw[j];
-            S.mtfw[j] = (w << 8) | carry;
-            carry = w >> 24;
-          }
-          const uint32_t below = sh ? (t & ((1u << sh) - 1u)) : 0u;
-          const uint32_t upto = sh == 24 ? 0xffffffffu : ((1u << (sh + 8)) - 1u);
-          S.mtfw[wi] = (t & ~upto) | (((below << 8) | carry) & upto);
+        const int nn = sym - 1, owner = nn >> 3;
+        const uint32_t half = (nn & 4) ? (uint32_t)(v >> 32) : (uint32_t)v;
+        const uint32_t uc = (__shfl_sync(FULLW, half, owner) >> ((nn & 3) * 8)) & 0xffu;
+        uint32_t carry = __shfl_up_sync(FULLW, (uint32_t)(v >> 56), 1);
+        if (lane == 0) carry = uc;
+        if (lane < owner) {
+          v = (v << 8) | carry;
+        } else if (lane == owner) {
+          const int sh = (nn & 7) * 8;
+          const uint64_t below = v & ((1ull << sh) - 1ull);
+          const uint64_t upto = sh == 56 ? ~0ull : ((1ull << (sh + 8)) - 1ull);
+          v = (v & ~upto) | (((below << 8) | carry) & upto);
         }
-        rv[nrec] = (1u << 8) | S.seq2unseq[uc];
-        rp[nrec] = nblock;
-        nrec++;
+        front = uc;
+        emit((1u << 8) | S.seq2unseq[uc], nblock);
         nblock++;
         if ((nrec & 1023u) == 0u && br.bitpos() > total_bits) {
           err = BZ_THROW;
@@ -400,8 +416,14 @@ k_bz2_entropy(const uint32_t *__restrict__ words, uint64_t n_bytes, const unsign
       }
       sym = nsym;
     }
+    // the records of the last, partial group
+    if ((nrec & 31u) != 0u && (uint32_t)lane < (nrec & 31u)) {
+      rv[(nrec & ~31u) + lane] = my_rv;
+      rp[(nrec & ~31u) + lane] = my_rp;
+    }
     if (!err && optr >= nblock) err = BZ_DATA;  // (:399-402) also covers nblock == 0
   }
+  if (lane != 0) return;
   uint64_t endp = err ? s_bitpos : br.bitpos();
   if (!err) endp = br.bitpos();
   if (br.bitpos() > total_bits) err = BZ_THROW;  // some read went past the end: InputStream.readByte throws
