@@ -168,6 +168,13 @@ FP_DEV void br_refill(BR &b, const uint32_t *in32) {
   }
 }
 FP_DEV uint32_t br_pos(const BR &b) { return b.wp * 32u - (uint32_t)b.cnt; }
+FP_DEV void br_seek_sa(BR &b, uint32_t s_in, uint32_t bitpos) {  // br_seek by shared address
+  const uint32_t w = bitpos >> 5, sh = bitpos & 31u;
+  const uint64_t v = (uint64_t)FP_LDS32(s_in + w * 4u) | ((uint64_t)FP_LDS32(s_in + w * 4u + 4u) << 32);
+  b.buf = v >> sh;
+  b.cnt = 64 - (int)sh;
+  b.wp = w + 2;
+}
 
 FP_DEV uint32_t fp_lookup(uint32_t bits, bool dm, const uint32_t *lutl, const uint32_t *lutd, const uint32_t *sub) {
   uint32_t e = dm ? lutd[bits & ((1u << DB) - 1u)] : lutl[bits & ((1u << LB) - 1u)];
@@ -200,24 +207,28 @@ struct FastCtx {
 };
 template <int MODE>
 FP_DEV bool fp_fast(BR &br, bool &dm_io, uint32_t &pend_io, uint32_t &acc_io, uint32_t &tokpos_io, const FastCtx &c) {
-  uint64_t buf = br.buf;
-  int cnt = br.cnt;
-  uint32_t wp = br.wp, pend = pend_io, acc = acc_io, tokpos = tokpos_io;
-  bool dm = dm_io, trouble = false;
-  uint32_t tb = dm ? c.s_lutd : c.s_lutl, tm = dm ? ((1u << DB) - 1u) << 2 : ((1u << LB) - 1u) << 2, rbits = dm ? DB : LB;
+  // the bit window: w0:w1 hold the 64 bits at word `posw / 32`, nx the word behind them (asked for one crossing ahead, so
+  // its latency is off the chain); sh = bits of w0 already consumed
+  uint32_t pos0 = br_pos(br);
+  uint32_t posw = pos0 & ~31u, sh = pos0 & 31u;
+  uint32_t pa = c.s_in + (posw >> 3);
+  uint32_t w0 = FP_LDS32(pa), w1 = FP_LDS32(pa + 4u), nx = FP_LDS32(pa + 8u);
+  pa += 8u;
+  uint32_t pend = pend_io, acc = acc_io, tokpos = tokpos_io;
+  bool trouble = false;
+  const uint32_t LM4 = ((1u << LB) - 1u) << 2, DM4 = ((1u << DB) - 1u) << 2;
+  uint32_t tb = dm_io ? c.s_lutd : c.s_lutl, tm = dm_io ? DM4 : LM4;
+  // a token that starts with 48 bits of input left needs no end-of-input test at all (15 + 5 + 15 + 13 bits at most)
+  const uint32_t stop2 = c.end_bit >= 48u ? min(c.stop, c.end_bit - 47u) : 0u;
   for (;;) {
-    if (cnt < 32) {
-      buf |= (uint64_t)FP_LDS32(c.s_in + wp * 4u) << cnt;
-      cnt += 32;
-      wp++;
-    }
+    const bool dm = tb != c.s_lutl;
+    const uint32_t pos = posw + sh;
 #ifdef FP_DEBUG
     fp_dbg_fastiters++;
 #endif
-    const uint32_t pos = wp * 32u - (uint32_t)cnt;
     if (!dm) {
       tokpos = pos;
-      if (pos >= c.stop) break;
+      if (pos >= stop2) break;
       if (MODE == 0) {
         const uint32_t rel = pos - c.org;
         if (rel < c.K) {
@@ -231,16 +242,13 @@ FP_DEV bool fp_fast(BR &br, bool &dm_io, uint32_t &pend_io, uint32_t &acc_io, ui
         if ((FP_LDS32(c.s_row + ((off >> 5) << 2)) >> (off & 31u)) & 1u) break;
       }
     }
-    if (pos + 32u > c.end_bit) break;
-    const uint32_t bits = (uint32_t)buf;
+    const uint32_t bits = __funnelshift_r(w0, w1, sh);
     uint32_t e = FP_LDS32(tb + ((bits << 2) & tm));
     if ((e & 15u) == 0u && e != 0u)  // a code longer than the root index: its entry is in the second level
-      e = FP_LDS32(c.s_sub + (((e >> 16) + ((bits >> rbits) & ~(0xffffffffu << ((e >> 4) & 15u)))) << 2));
-    const uint32_t n = e & 15u;
-    if (n == 0u || (e & 0x200u) != 0u) break;  // no code here, end of block, invalid
-    const uint32_t xb = (e >> 4) & 15u;
+      e = FP_LDS32(c.s_sub + (((e >> 16) + ((bits >> (tm == LM4 ? LB : DB)) & ~(0xffffffffu << ((e >> 4) & 15u)))) << 2));
+    if (((e & 0x20fu) - 1u) >= 15u) break;  // no code here, end of block, invalid
+    const uint32_t n = e & 15u, xb = (e >> 4) & 15u;
     const uint32_t val = (e >> 16) + ((bits >> n) & ~(0xffffffffu << xb));
-    const uint32_t tot = n + xb;
     const bool isbase = !dm && (e & 0x100u) != 0u;
     if (MODE == 3) {
       if (dm) {
@@ -248,27 +256,31 @@ FP_DEV bool fp_fast(BR &br, bool &dm_io, uint32_t &pend_io, uint32_t &acc_io, ui
           trouble = true;
           break;
         }
-        FP_STS8(c.s_W + acc, pend - 3u);
-        FP_STS8(c.s_W + acc + 1u, val - 1u);
-        FP_STS8(c.s_W + acc + 2u, (val - 1u) >> 8);
+        const uint32_t a = c.s_W + acc;
+        FP_STS8(a, pend - 3u);
+        FP_STS8(a + 1u, val - 1u);
+        FP_STS8(a + 2u, (val - 1u) >> 8);
         atomicOr(&c.flags[acc >> 5], 1u << (acc & 31u));
       } else if (!isbase) {
         FP_STS8(c.s_W + acc, val);
       }
     }
-    buf >>= tot;
-    cnt -= (int)tot;
+    sh += n + xb;
+    if (sh >= 32u) {
+      sh -= 32u;
+      posw += 32u;
+      w0 = w1;
+      w1 = nx;
+      pa += 4u;
+      nx = FP_LDS32(pa);
+    }
     acc += dm ? pend : (isbase ? 0u : 1u);
     pend = isbase ? val : pend;
-    dm = isbase;
     tb = isbase ? c.s_lutd : c.s_lutl;
-    tm = isbase ? ((1u << DB) - 1u) << 2 : ((1u << LB) - 1u) << 2;
-    rbits = isbase ? DB : LB;
+    tm = isbase ? DM4 : LM4;
   }
-  br.buf = buf;
-  br.cnt = cnt;
-  br.wp = wp;
-  dm_io = dm;
+  br_seek_sa(br, c.s_in, posw + sh);
+  dm_io = tb != c.s_lutl;
   pend_io = pend;
   acc_io = acc;
   tokpos_io = tokpos;
@@ -491,9 +503,8 @@ FP_DEV void fp_plan_lanes(Ctl *ctl, uint32_t wofs) {
       break;
     }
     L = R / nl;
-    K = 1024;
-    while (K > L) K >>= 1;
-    while (K >= 128u && nl * (K / 32u + 1u) * 4u > room) K >>= 1;
+    K = (L < 1024u ? L : 1024u) & ~31u;  // as wide as the segment (a wider window could place a lane's start behind its end)
+    while (K >= 128u && nl * (K / 32u + 1u) * 4u > room) K = (K >> 1) & ~31u;
     if (K >= 128u) break;
     nl = room / ((128u / 32u + 1u) * 4u);  // as many lanes as a 128-bit window each fits
     if (nl > (uint32_t)NT) nl = NT;
@@ -502,7 +513,7 @@ FP_DEV void fp_plan_lanes(Ctl *ctl, uint32_t wofs) {
   ctl->nl = nl;
   ctl->L = nl > 1u ? L : 0u;
   ctl->K = nl > 1u ? K : 0u;
-  ctl->bm_stride = nl > 1u ? K / 32u + 1u : 0u;
+  ctl->bm_stride = nl > 1u ? K / 32u + 1u : 0u;  // (+1: one spare word, and rows that do not all start in one bank)
   ctl->bm_off = nl > 1u ? ((WIN + 16u - nl * (K / 32u + 1u) * 4u) & ~3u) : 0u;
 }
 
@@ -923,7 +934,7 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
       __syncthreads();
       if (ctl->fb) break;
 #ifdef FP_DEBUG
-      if (tid == 0) { int nv = 0; for (int w = 0; w < NW; ++w) nv += __popc(ctl->validmask[w]); fprintf(stderr, "unit %u: nl %u L %u K %u valid %d restarts %lu fastiters %lu\n", unit, nl, L, K, nv, fp::fp_dbg_restarts, fp::fp_dbg_fastiters); }
+      if (tid == 0) { int nv = 0; for (int w = 0; w < NW; ++w) nv += __popc(ctl->validmask[w]); fprintf(stderr, "unit %u: nl %u L %u K %u valid %d restarts %lu fastiters %lu\n", unit, nl, L, K, nv, fp::fp_dbg_restarts, fp::fp_dbg_fastiters); for (uint32_t q = 0; q < nl; ++q) if (!((ctl->validmask[q >> 5] >> (q & 31)) & 1u)) fprintf(stderr, "   lane %u invalid: tgt %u endpos-rel %d ; pred tgt %u pred endrel %d\n", q, tgt_arr[q], (int)(pos_arr[q] - (p0 + q * L)), tgt_arr[q-1], (int)(pos_arr[q-1] - (p0 + q * L))); }
 #endif
       const bool valid = ((ctl->validmask[warp] >> lane) & 1u) != 0u;
       if (valid && tgt < END_EOB) start_arr[tgt] = endpos;
@@ -1117,13 +1128,14 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
         }
       }
       __syncthreads();
+      const uint32_t s_Wr = FP_SA(W), s_nf = FP_SA(nf);
       uint32_t w = tid;
       uint32_t f = w < nwords ? flags[w] : 0u, cand = f;
       bool has = false;  // a match of mine is ready and waits for the warp's next copy turn
       uint32_t rp = 0, rlen = 0, rdist = 0, rb = 0;
       for (;;) {
-        // ---- look for a ready match: up to two tries, fewer when most of the warp has one (copying with a few lanes
-        // costs the warp as much as copying with all of them) ----
+        // ---- look for a ready match (lanes that hold one wait for the warp's next copy turn: copying with a few lanes
+        // costs the warp as much as copying with all of them, so two looks are taken before every turn) ----
 #pragma unroll 1
         for (int tries = 0; tries < 2; ++tries) {
           if (!has && w < nwords) {
@@ -1138,16 +1150,19 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
               const uint32_t b = (uint32_t)(__ffs((int)cand) - 1);
               cand &= cand - 1u;
               const uint32_t p = w * 32u + b;
-              const uint32_t len = (uint32_t)W[p] + 3u;
-              const uint32_t dist = ((uint32_t)W[p + 1u] | ((uint32_t)W[p + 2u] << 8)) + 1u;
-              const uint32_t src = p - dist, need_end = min(src + len, p);  // [src, need_end) must be final
-              const uint32_t wa = src >> 5, wb = (need_end - 1u) >> 5;
-              uint32_t busy = FP_VOL(nf[wa]) & (0xffffffffu << (src & 31u));
+              // the 3-byte record, read as one unaligned word
+              const uint32_t ra = s_Wr + p;
+              const uint32_t rec = __funnelshift_r(FP_LDS32(ra & ~3u), FP_LDS32((ra & ~3u) + 4u), (ra & 3u) * 8u);
+              const uint32_t len = (rec & 0xffu) + 3u, dist = ((rec >> 8) & 0xffffu) + 1u;
+              const uint32_t src = p - dist, last = min(src + len, p) - 1u;  // [src, last] must be final
+              const uint32_t wa = src >> 5, wb = last >> 5;
+              const uint32_t mlo = 0xffffffffu << (src & 31u), mhi = 0xffffffffu >> (31u - (last & 31u));
+              uint32_t busy;
               if (wa == wb) {
-                busy &= 0xffffffffu >> (31u - ((need_end - 1u) & 31u));
+                busy = FP_LDS32(s_nf + wa * 4u) & mlo & mhi;
               } else {
-                for (uint32_t q = wa + 1u; q < wb; ++q) busy |= FP_VOL(nf[q]);
-                busy |= FP_VOL(nf[wb]) & (0xffffffffu >> (31u - ((need_end - 1u) & 31u)));
+                busy = (FP_LDS32(s_nf + wa * 4u) & mlo) | (FP_LDS32(s_nf + wb * 4u) & mhi);
+                for (uint32_t q = wa + 1u; q < wb; ++q) busy |= FP_LDS32(s_nf + q * 4u);
               }
               if (busy == 0u) {
                 has = true;
@@ -1158,7 +1173,7 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
               }
             }
           }
-          if (__popc(__ballot_sync(FULL, has)) >= 20) break;
+          if (tries == 0 && __popc(__ballot_sync(FULL, has)) >= 20) break;
         }
         if (__ballot_sync(FULL, has || w < nwords) == 0u) break;
         if (has) {
