@@ -383,17 +383,19 @@ def side_config4(L, cores, world=1, rank=0, dist=None):
     return res
 
 
-def _zip_member_job(b):
+def _zip_member_job(a):
+    """One member of the synthetic zip, made where it is compressed (nothing but the compressed bytes crosses a pipe)."""
+    i, size, stream = a
     from archive_b200 import synth
+    b = synth.text(size, stream=stream + i).tobytes()
     return synth.deflate_raw_flushed(b, 65536), zlib.crc32(b)
 
 
-def make_zip(n_members: int, size: int, stream: int = 700):
+def make_zip(n_members: int, size: int, stream: int = 7000):
     from concurrent.futures import ProcessPoolExecutor
     from archive_b200 import synth
-    txt = synth.text(n_members * size, stream=stream)
-    with ProcessPoolExecutor(max_workers=min(64, os.cpu_count() or 1)) as ex:
-        parts = list(ex.map(_zip_member_job, [txt[i * size:(i + 1) * size].tobytes() for i in range(n_members)], chunksize=4))
+    with ProcessPoolExecutor(max_workers=min(96, os.cpu_count() or 1)) as ex:
+        parts = list(ex.map(_zip_member_job, [(i, size, stream) for i in range(n_members)], chunksize=2))
     data = synth.zip_from_deflated([(f"member{i:04d}.txt", z, crc, size) for i, (z, crc) in enumerate(parts)])
     return data, [crc for _, crc in parts]
 
