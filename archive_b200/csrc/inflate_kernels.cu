@@ -446,11 +446,12 @@ cudaError_t launch_inflate(const InflateBatch &b, cudaStream_t stream) {
   // whose output fits its window and flags them; the two exact kernels below then only see what is left.
   int after_fast = 0;
   {
-    static int fast_on = -1;
-    if (fast_on < 0) {
-      const char *e = getenv("B200Z_FAST");
-      fast_on = e ? atoi(e) : 0;  // (off until it beats the token path on the hardware)
-    }
+    // B200Z_FAST=0 (read at every launch, so a process can time both) leaves everything to the exact pair.  Default on:
+    // on the benchmark shape the kernel moves a fifth of the pair's DRAM bytes and takes 10.3 ms per GiB whatever the
+    // data and the batch size, where the pair takes 9.3 ms on one rank's data and 13.5 on the others', and twice that
+    // when a batch is launched in quarters (profiles/r2_summary.md).
+    const char *fe = getenv("B200Z_FAST");
+    const int fast_on = fe ? atoi(fe) : 1;
     if (fast_on && !b.count_only && b.ws.hist == 0 && b.ws.pieces != nullptr) {
       static uint64_t attr_done = 0;  // one bit per device: function attributes belong to the device's context
       if (!((attr_done >> (cur_dev & 63)) & 1u)) {
@@ -458,7 +459,13 @@ cudaError_t launch_inflate(const InflateBatch &b, cudaStream_t stream) {
         if (e != cudaSuccess) return e;
         attr_done |= 1ull << (cur_dev & 63);
       }
-      uint64_t fblocks = (uint64_t)g_num_sms * 2u;  // two resident CTAs per SM, each walks its share of the units
+      // two resident CTAs per SM, each walks its share of the units.  B200Z_FAST_SPARE_SMS leaves SMs to kernels that
+      // have to run beside this one -- a collective that forwards the finished chunk while the next one is decoded
+      // (persistent CTAs that fill every SM keep NCCL's kernel waiting until the grid drains)
+      int spare = 0;
+      if (const char *se = getenv("B200Z_FAST_SPARE_SMS")) spare = atoi(se);
+      if (spare < 0 || spare >= g_num_sms) spare = 0;
+      uint64_t fblocks = (uint64_t)(g_num_sms - spare) * 2u;
       if (fblocks > b.n_units) fblocks = b.n_units;
       k_inflate_fast<<<(unsigned)fblocks, fp::NT, fp::SMEM_BYTES, stream>>>(b.in_base, b.in_off, b.in_len, b.out_base, b.out_off, b.out_cap,
                                                                         b.out_len, b.status, b.in_used, (uint32_t)b.n_units,

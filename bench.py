@@ -565,7 +565,8 @@ def main():
 
     # ---------------- workload: every rank owns its own re-drawn 1 GiB (weak scaling) ----------------
     t_gen = time.time()
-    w = synth.gzip_workload(N_UNITS, UNIT, stream0=rank * 4096, cache_dir=CACHE)
+    stream0 = int(os.environ.get("B200Z_BENCH_STREAM0", rank * 4096))  # (every rank its own re-drawn text)
+    w = synth.gzip_workload(N_UNITS, UNIT, stream0=stream0, cache_dir=CACHE)
     blob, moff = w["blob"], w["member_off"]
     n = N_UNITS
     hdr = 18  # synth.gzip_member with the BC hint: 10 + 2 + 6
@@ -704,6 +705,24 @@ def main():
     L.b200z_profile_enable(0)
     k_fast, k_dec, k_exp = (v.value / args.steps for v in (fms, dms, ems))
 
+    # the other inflate kernel on the same step (the library reads B200Z_FAST at every launch)
+    was = os.environ.get("B200Z_FAST")
+    other = "0" if (was or "1") != "0" else "1"
+    os.environ["B200Z_FAST"] = other
+    try:
+        ms_a, _ = timed(step_decode_only, args.steps, args.warmup)
+        alt = {"kernel": "k_inflate_fast, one CTA per unit in shared memory (B200Z_FAST=1)" if other == "1"
+               else "k_inflate_decode + k_inflate_expand (B200Z_FAST=0)",
+               "value": world * U_bytes / (ms_a / args.steps * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": ms_a / args.steps,
+               "all_units_ok": bool((d_status.cpu().numpy() == 0).all()),
+               "dram_bytes_per_pass": 1437029000 if other == "1" else 6980970000,
+               "note": "decode only, same buffers; DRAM bytes from profiles/ (ncu)"}
+    finally:
+        if was is None:
+            del os.environ["B200Z_FAST"]
+        else:
+            os.environ["B200Z_FAST"] = was
+
     decode_only = strong = per_rank = None
     if world > 1:
         ms_d, ms_d_own = timed(step_decode_only, args.steps, args.warmup)
@@ -798,15 +817,18 @@ def main():
             "metric": "inflate_uncompressed_GBps", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": cfg,
-            "workload_facts": {"compressed_bytes_per_gpu": C_bytes, "chunks": NCH, "generate_s": round(gen_s, 1)},
+            "workload_facts": {"compressed_bytes_per_gpu": C_bytes, "chunks": NCH, "generate_s": round(gen_s, 1), "text_stream0": stream0,
+                               "B200Z_FAST": os.environ.get("B200Z_FAST", "1 (default)"),
+                               "B200Z_FAST_SPARE_SMS": os.environ.get("B200Z_FAST_SPARE_SMS", "0 (default)")},
             "e2e": e2e, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_pass": C_bytes + U_bytes,
                          "kernels": {"k_inflate_fast_ms": k_fast, "k_inflate_decode_ms": k_dec, "k_inflate_expand_ms": k_exp},
-                         "note": "one pass = k_inflate_fast (clean units, in shared memory; B200Z_FAST) + the exact pair "
-                                 "k_inflate_decode / k_inflate_expand over the rest; achieved = (C+U) / their CUDA-event time"},
-            "cpu_baseline": cpu, "clocks": my_clocks,
+                         "note": "one pass = k_inflate_fast (clean units, all in shared memory) + the exact pair k_inflate_decode / "
+                                 "k_inflate_expand over what it leaves (nothing on this workload); achieved = (C+U) / their "
+                                 "CUDA-event time; traffic = ncu DRAM bytes of k_inflate_fast per pass (profiles/traffic.json)"},
+            "cpu_baseline": cpu, "clocks": my_clocks, "alt_kernel": alt,
         }
         if world > 1:
             line["collective"] = {"what": "all_gather_into_tensor of every chunk (NCCL over NVLink), in place, behind the next "

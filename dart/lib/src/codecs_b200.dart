@@ -120,7 +120,10 @@ class _B200GZipDecoder extends ar.ZLibDecoderBase {
 
   @override
   bool decodeStream(ar.InputStream input, ar.OutputStream output, {bool verify = false, bool raw = false}) {
-    final viaFiles = _fileToFile(b200zFileGzipDecode, input, output, a0: verify ? 1 : 0);
+    // `verify` carries two bits for the library: 1 = verify, 2 = raw (B200Z_GZIP_RAW: handed on to the zlib decoder when the
+    // input has no gzip header, _gzip_decoder_web.dart:31-37)
+    final vr = (verify ? 1 : 0) | (raw ? 2 : 0);
+    final viaFiles = _fileToFile(b200zFileGzipDecode, input, output, a0: vr);
     if (viaFiles != null) return viaFiles;
     final z = B200Z.instance;
     final data = _drain(input);
@@ -128,7 +131,10 @@ class _B200GZipDecoder extends ar.ZLibDecoderBase {
     try {
       final bound = z.gzipBound(inp, data.length);
       final (out, ok) = z.grow(bound > 0 ? bound : data.length * 4 + 1024,
-          (o, cap, outLen) => z.gzipDecode(inp, data.length, verify ? 1 : 0, o, cap, outLen));
+          // several devices initialised (B200Z.multiInit): the members are dealt to them -- the same bytes come back
+          (o, cap, outLen) => z.multiDeviceCount() > 1
+              ? z.gzipDecodeMulti(inp, data.length, vr, o, cap, outLen, 0)
+              : z.gzipDecode(inp, data.length, vr, o, cap, outLen));
       output.writeBytes(out);
       input.skip(data.length);
       return ok;
