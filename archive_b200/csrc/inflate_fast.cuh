@@ -32,8 +32,13 @@
 namespace b200z {
 namespace fp {
 
-constexpr int NT = 256;          // threads (= lanes of the speculative decode) per CTA
+constexpr int NT = 256;          // decode threads (= lanes of the speculative decode) per CTA
 constexpr int NW = NT / 32;
+#ifndef FP_XT
+#define FP_XT 0
+#endif
+constexpr int XT = FP_XT;        // extra threads that only take part in the LZ77 pass (latency hiding); 0 or a multiple of 32
+constexpr int NTT = NT + XT;     // threads the kernel is launched with
 constexpr int LB = 10;           // literal/length root bits
 constexpr int DB = 8;            // distance root bits
 constexpr int SUBN = 384;        // second-level entries shared by the block's two alphabets
@@ -43,7 +48,13 @@ constexpr uint32_t MIN_IN = 192u;    // shorter units stay with the lane-per-str
 constexpr uint32_t MIN_SEG = 256u;   // bits per lane at least
 constexpr uint32_t END_EOB = 0xfffeu, END_BAD = 0xffffu, NONE = 0xffffffffu;
 constexpr uint32_t CHUNK_SHIFT = 10;  // LZ77 resolution chunk = 1024 output bytes = one warp x 32 bytes per lane
-constexpr uint32_t STEP = 8;          // bytes a lane copies per batch
+#ifndef FP_STEP
+#define FP_STEP 8
+#endif
+#ifndef FP_TRIES
+#define FP_TRIES 2
+#endif
+constexpr uint32_t STEP = FP_STEP;    // bytes a lane copies per batch
 
 // table entry: bits 0-3 code length (0: link or hole), 4-7 extra bits, 8-9 kind, 16-31 value
 constexpr uint32_t K_LIT = 0u, K_BASE = 1u, K_EOB = 2u, K_INV = 3u;
@@ -74,7 +85,7 @@ struct Ctl {
   uint32_t hlit, hdist, maxl, maxd, sub_used, nlong_l, nlong_d;
   uint32_t nl, L, K, bm_stride, bm_off, p0;
   uint32_t blk_end, blk_total;
-  uint32_t done_chunks;
+  uint32_t x_state, x_olen, x_wofs;  // for the LZ77-only warps: 0 end, 1 nothing to do for this unit, 2 LZ77 over x_olen bytes
   uint32_t regmask[NW], validmask[NW], warp_tot[NW];
 };
 static_assert(sizeof(Ctl) <= 256, "Ctl");
@@ -145,6 +156,16 @@ __device__ __forceinline__ void fp_sts8(uint32_t a, uint32_t v) { asm volatile("
 #define FP_LDS32(a) fp_lds32(a)
 #define FP_STS32(a, v) fp_sts32((a), (v))
 #define FP_STS8(a, v) fp_sts8((a), (v))
+#endif
+
+// Two kinds of CTA barrier: FP_DSYNC among the NT decode threads (everything up to the LZ77 pass), FP_ASYNC among all NTT
+// threads (around the LZ77 pass).  Without extra warps they are the same barrier.
+#if defined(B200Z_EMU) || FP_XT == 0
+#define FP_DSYNC() __syncthreads()
+#define FP_ASYNC() __syncthreads()
+#else
+#define FP_DSYNC() asm volatile("bar.sync 1, 256;" ::: "memory")
+#define FP_ASYNC() __syncthreads()
 #endif
 
 // ---- bit reader over the staged input (LSB first, inflate.dart:159-184); pos = bits consumed from word 0 ----
@@ -517,6 +538,126 @@ FP_DEV void fp_plan_lanes(Ctl *ctl, uint32_t wofs) {
   ctl->bm_off = nl > 1u ? ((WIN + 16u - nl * (K / 32u + 1u) * 4u) & ~3u) : 0u;
 }
 
+// ---------------- LZ77: matches copy shared -> shared ----------------
+// A match may copy as soon as the bytes it reads are final -- nothing else orders the copies.  (Measured on the
+// benchmark text: 7.6 k matches per 64 KiB unit, longest chain of matches that feed each other 42.)  So finality is
+// tracked per BYTE: `nf` holds one bit per output byte that a match still has to write (literals are final from the
+// start); it lives where the block's code tables were, which are dead by now.  Every thread owns the bitmap words
+// t, t + nthr, ... (32 output bytes each) and keeps trying the pending matches of its current word: a match whose source
+// bits are all clear copies (up to STEP bytes per batch, loaded before they are stored) and then clears its own bits.
+// The earliest pending match of the unit is always ready, so the loop ends; threads never wait for each other otherwise.
+// Every thread of the CTA runs this, the decode lanes and -- when the kernel is built with some (FP_XT) -- the extra
+// warps that exist for this pass only: it is bound by latency, and more warps hide more of it.
+FP_DEV void fp_lz77(uint8_t *smem, uint32_t tid, uint32_t nthr, uint32_t olen, uint32_t wofs) {
+  const unsigned FULL = 0xffffffffu;
+  uint32_t *const flags = reinterpret_cast<uint32_t *>(smem + O_FLAGS);
+  uint8_t *const W = smem + O_WIN + wofs;
+    uint32_t *const nf = reinterpret_cast<uint32_t *>(smem + O_LUTL);
+    const uint32_t nwords = (olen + 31u) >> 5;
+    for (uint32_t i = tid; i < nwords + 9u && i < 2048u + 8u; i += nthr) nf[i] = 0;
+    FP_ASYNC();
+    for (uint32_t w = tid; w < nwords; w += nthr) {
+      uint32_t f = flags[w];
+      while (f) {
+        const uint32_t b = (uint32_t)(__ffs((int)f) - 1);
+        f &= f - 1u;
+        const uint32_t a = w * 32u + b, e = a + (uint32_t)W[a] + 3u;  // bytes [a, e) are this match's
+        const uint32_t wa = a >> 5, wb = (e - 1u) >> 5;
+        if (wa == wb) {
+          atomicOr(&nf[wa], (0xffffffffu << (a & 31u)) & (0xffffffffu >> (31u - ((e - 1u) & 31u))));
+        } else {
+          atomicOr(&nf[wa], 0xffffffffu << (a & 31u));
+          for (uint32_t q = wa + 1u; q < wb; ++q) atomicOr(&nf[q], 0xffffffffu);
+          atomicOr(&nf[wb], 0xffffffffu >> (31u - ((e - 1u) & 31u)));
+        }
+      }
+    }
+    FP_ASYNC();
+    const uint32_t s_Wr = FP_SA(W), s_nf = FP_SA(nf);
+    uint32_t w = tid;
+    uint32_t f = w < nwords ? flags[w] : 0u, cand = f;
+    bool has = false;  // a match of mine is ready and waits for the warp's next copy turn
+    uint32_t rp = 0, rlen = 0, rdist = 0, rb = 0;
+    for (;;) {
+      // ---- look for a ready match (lanes that hold one wait for the warp's next copy turn: copying with a few lanes
+      // costs the warp as much as copying with all of them, so two looks are taken before every turn) ----
+#pragma unroll 1
+      for (int tries = 0; tries < FP_TRIES; ++tries) {
+        if (!has && w < nwords) {
+          if (f == 0u) {  // this word's matches are done: next word of mine
+            flags[w] = 0;
+            w += nthr;
+            f = w < nwords ? flags[w] : 0u;
+            cand = f;
+          }
+          if (f != 0u) {
+            if (cand == 0u) cand = f;  // another sweep over what is still pending here
+            const uint32_t b = (uint32_t)(__ffs((int)cand) - 1);
+            cand &= cand - 1u;
+            const uint32_t p = w * 32u + b;
+            // the 3-byte record, read as one unaligned word
+            const uint32_t ra = s_Wr + p;
+            const uint32_t rec = __funnelshift_r(FP_LDS32(ra & ~3u), FP_LDS32((ra & ~3u) + 4u), (ra & 3u) * 8u);
+            const uint32_t len = (rec & 0xffu) + 3u, dist = ((rec >> 8) & 0xffffu) + 1u;
+            const uint32_t src = p - dist, last = min(src + len, p) - 1u;  // [src, last] must be final
+            const uint32_t wa = src >> 5, wb = last >> 5;
+            const uint32_t mlo = 0xffffffffu << (src & 31u), mhi = 0xffffffffu >> (31u - (last & 31u));
+            uint32_t busy;
+            if (wa == wb) {
+              busy = FP_LDS32(s_nf + wa * 4u) & mlo & mhi;
+            } else {
+              busy = (FP_LDS32(s_nf + wa * 4u) & mlo) | (FP_LDS32(s_nf + wb * 4u) & mhi);
+              for (uint32_t q = wa + 1u; q < wb; ++q) busy |= FP_LDS32(s_nf + q * 4u);
+            }
+            if (busy == 0u) {
+              has = true;
+              rp = p;
+              rlen = len;
+              rdist = dist;
+              rb = b;
+            }
+          }
+        }
+        if (tries == 0 && __popc(__ballot_sync(FULL, has)) >= 20) break;
+      }
+      if (__ballot_sync(FULL, has || w < nwords) == 0u) break;
+      if (has) {
+        __threadfence_block();  // the bytes behind the clear bits are visible
+        for (uint32_t k = 0; k < rlen;) {
+          uint32_t m = min(rlen - k, STEP), back = rdist;
+          if (rdist < STEP && rdist < rlen) {
+            // overlapping run: [p - dist, p + k) is final and periodic, so any multiple of dist that reaches back far
+            // enough serves as the distance; the run doubles until it moves STEP bytes a batch
+            m = min(m, ((k + rdist) / rdist) * rdist);
+            back = ((m + rdist - 1u) / rdist) * rdist;
+          }
+          const uint8_t *sp = W + rp + k - back;
+          uint8_t *dp = W + rp + k;
+          uint8_t r[STEP];
+#pragma unroll
+          for (uint32_t t = 0; t < STEP; ++t) r[t] = sp[t];  // (reading past the m-th byte is harmless)
+#pragma unroll
+          for (uint32_t t = 0; t < STEP; ++t)
+            if (t < m) dp[t] = r[t];
+          k += m;
+        }
+        __threadfence_block();  // ... before the bits say so
+        {
+          const uint32_t e = rp + rlen, wa = rp >> 5, wb = (e - 1u) >> 5;
+          if (wa == wb) {
+            atomicAnd(&nf[wa], ~((0xffffffffu << (rp & 31u)) & (0xffffffffu >> (31u - ((e - 1u) & 31u)))));
+          } else {
+            atomicAnd(&nf[wa], ~(0xffffffffu << (rp & 31u)));
+            for (uint32_t q = wa + 1u; q < wb; ++q) atomicAnd(&nf[q], 0u);
+            atomicAnd(&nf[wb], ~(0xffffffffu >> (31u - ((e - 1u) & 31u))));
+          }
+        }
+        f &= ~(1u << rb);
+        has = false;
+      }
+    }
+}
+
 }  // namespace fp
 
 #ifdef B200Z_EMU
@@ -525,7 +666,7 @@ FP_DEV void fp_plan_lanes(Ctl *ctl, uint32_t wofs) {
 #define FP_DYN_SMEM(name) extern __shared__ __align__(16) uint8_t name[]
 #endif
 
-__global__ void __launch_bounds__(fp::NT, 2)
+__global__ void __launch_bounds__(fp::NTT, 2)
 k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__ in_off, const uint32_t *__restrict__ in_len,
                uint8_t *__restrict__ out_base, const uint64_t *__restrict__ out_off, const uint32_t *__restrict__ out_cap,
                uint32_t *__restrict__ out_len, int32_t *__restrict__ status, uint32_t *__restrict__ in_used, uint32_t n_units,
@@ -559,6 +700,15 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
   fc.s_sub = FP_SA(sub);
   fc.flags = flags;
 
+  if (tid >= (uint32_t)NT) {  // the LZ77-only warps (FP_XT): two CTA-wide barriers per unit, the pass in between
+    for (;;) {
+      FP_ASYNC();  // (A) the unit's blocks are decoded, or there is nothing to do
+      const uint32_t xs = ctl->x_state, xo = ctl->x_olen, xw = ctl->x_wofs;
+      if (xs == 0u) return;
+      if (xs == 2u) fp_lz77(smem, tid, NTT, xo, xw);
+      FP_ASYNC();  // (B)
+    }
+  }
   for (uint32_t i = tid; i < 2048u; i += NT) flags[i] = 0;
   uint32_t next_u = blockIdx.x;  // (thread 0's copy is the one that counts)
   if (tid == 0) {
@@ -569,19 +719,26 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
   uint32_t phase = 0;
   for (;;) {
     if (tid == 0) fp_store_wait_read();  // the previous unit's bulk store has read the window
-    __syncthreads();
+    FP_DSYNC();
     const uint32_t unit = ctl->n_unit;
-    if (unit == NONE) break;
+    if (unit == NONE) {
+      if (tid == 0) ctl->x_state = 0;
+      FP_ASYNC();  // (A): releases the LZ77-only warps for good
+      break;
+    }
     const uint32_t u_in_len = ctl->n_in_len, lead = ctl->n_lead, cap = ctl->n_cap, wofs = ctl->n_wofs;
     const bool elig = ctl->n_elig != 0u;
     uint8_t *const W = win + wofs;  // W[q] = output byte q; W is congruent to the global destination modulo 16
-    __syncthreads();
+    FP_DSYNC();
     if (!elig) {
       if (tid == 0) {
         doneflag[(size_t)unit * flag_stride] = 0;
+        ctl->x_state = 1;
         fp_fetch_next(ctl, s_in, mbar, in_base, in_off, in_len, out_base, out_off, out_cap, n_units, next_u);
         next_u += gridDim.x;
       }
+      FP_ASYNC();  // (A)
+      FP_ASYNC();  // (B)
       continue;
     }
     fp_mbar_wait(mbar, phase);
@@ -596,7 +753,7 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
       ctl->bfinal = 0;
       ctl->cap = cap;
     }
-    __syncthreads();
+    FP_DSYNC();
     const uint32_t end_bit = (lead + u_in_len) * 8u;
 
     // ======================= blocks =======================
@@ -610,13 +767,13 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
           if (!ctl->fb && !ctl->done && ctl->btype != 0u) fp_plan_lanes(ctl, wofs);
         }
       }
-      __syncthreads();
+      FP_DSYNC();
       if (ctl->fb || ctl->done) break;
       const uint32_t btype = ctl->btype;
       if (btype == 0u) {  // stored (inflate.dart:213-235): input bytes -> window
         const uint32_t src = ctl->st_src, n = ctl->st_len, o = ctl->olen;
         for (uint32_t i = tid; i < n; i += NT) W[o + i] = s_in[src + i];
-        __syncthreads();
+        FP_DSYNC();
         if (tid == 0) ctl->olen = o + n;
         continue;
       }
@@ -634,7 +791,7 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
         ctl->nlong_l = 0;
         ctl->nlong_d = 0;
       }
-      __syncthreads();
+      FP_DSYNC();
       // a symbol's canonical code = first[l] + (symbols of the same length before it): groups of 32 symbols, ranks by match_any
       const uint32_t ngl = (hlit + 31u) >> 5;  // groups 0..ngl-1 literal/length, group 9 distance
       uint32_t my_l[2] = {0, 0}, my_rank[2] = {0, 0}, my_s[2] = {0, 0}, my_g[2] = {NONE, NONE};
@@ -652,7 +809,7 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
         my_s[k] = s;
         my_g[k] = g;
       }
-      __syncthreads();
+      FP_DSYNC();
       if (warp == 0) {
         if (lane < 16u) {
           uint32_t p = 0;
@@ -687,7 +844,7 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
           else ctl->maxl = mx;
         }
       }
-      __syncthreads();
+      FP_DSYNC();
       if (ctl->fb) break;
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
@@ -706,7 +863,7 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
           (dist ? long_d : long_l)[slot] = (r << 16) | (l << 10) | my_s[k];
         }
       }
-      __syncthreads();
+      FP_DSYNC();
       if (tid == 0 || tid == 32) {  // codes longer than the root: one thread per alphabet places them
         const bool dist = tid != 0;
         const uint32_t RB = dist ? DB : LB, n = dist ? ctl->nlong_d : ctl->nlong_l;
@@ -734,7 +891,7 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
           for (uint32_t j = r >> RB; j < (1u << sb); j += 1u << (l - RB)) sub[base + j] = e;
         }
       }
-      __syncthreads();
+      FP_DSYNC();
       if (ctl->fb) break;
 
       // ---------------- pass A: every lane decodes its segment, marking token boundaries ----------------
@@ -824,7 +981,7 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
           }
         } while (0);
       }
-      __syncthreads();
+      FP_DSYNC();
       // ---------------- pass A2: run on until one of my boundaries is one of a successor's ----------------
       {
         uint32_t succ = tid + 1u, succS = myS + L;
@@ -891,7 +1048,7 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
           } while (0);
         }
       }
-      __syncthreads();  // every lane is through with the bitmaps (they share the window with nothing live, but the lane arrays follow)
+      FP_DSYNC();  // every lane is through with the bitmaps (they share the window with nothing live, but the lane arrays follow)
       // ---------------- the chain of meeting points from lane 0 is the true parse ----------------
       if (lane_on) {
         tgt_arr[tid] = tgt;
@@ -904,7 +1061,7 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
           ctl->validmask[warp] = 0;
         }
       }
-      __syncthreads();
+      FP_DSYNC();
       if (tid == 0) {
         uint32_t cur = 0;
         bool ok = false;
@@ -931,14 +1088,14 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
         }
         if (!ok) ctl->fb = 1;
       }
-      __syncthreads();
+      FP_DSYNC();
       if (ctl->fb) break;
 #ifdef FP_DEBUG
       if (tid == 0) { int nv = 0; for (int w = 0; w < NW; ++w) nv += __popc(ctl->validmask[w]); fprintf(stderr, "unit %u: nl %u L %u K %u valid %d restarts %lu fastiters %lu\n", unit, nl, L, K, nv, fp::fp_dbg_restarts, fp::fp_dbg_fastiters); for (uint32_t q = 0; q < nl; ++q) if (!((ctl->validmask[q >> 5] >> (q & 31)) & 1u)) fprintf(stderr, "   lane %u invalid: tgt %u endpos-rel %d ; pred tgt %u pred endrel %d\n", q, tgt_arr[q], (int)(pos_arr[q] - (p0 + q * L)), tgt_arr[q-1], (int)(pos_arr[q-1] - (p0 + q * L))); }
 #endif
       const bool valid = ((ctl->validmask[warp] >> lane) & 1u) != 0u;
       if (valid && tgt < END_EOB) start_arr[tgt] = endpos;
-      __syncthreads();
+      FP_DSYNC();
       const uint32_t start = !valid ? 0u : tid == 0u ? p0 : start_arr[tid];
       // ---------------- pass A3: bytes of my false start (my guessed offset .. where the true parse met me) ----------------
       uint32_t nbytes = 0;
@@ -996,7 +1153,7 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
       }
       if (lane == 31u) ctl->warp_tot[warp] = incl;
       if (incons) ctl->fb = 1;
-      __syncthreads();
+      FP_DSYNC();
       uint32_t wbase = 0, total = 0;
 #pragma unroll
       for (int w = 0; w < NW; ++w) {
@@ -1006,7 +1163,7 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
       }
       if (ctl->fb || olen0 + total > cap) {  // beyond out_cap: B200Z_U_NOSPC is the exact kernels' to report
         if (tid == 0) ctl->fb = 1;
-        __syncthreads();
+        FP_DSYNC();
         break;
       }
       // ---------------- pass C: my share of the block again, into the window ----------------
@@ -1073,147 +1230,38 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
         }
         if (trouble) ctl->fb = 1;
       }
-      __syncthreads();
+      FP_DSYNC();
       if (ctl->fb) break;
       if (tid == 0) {
         ctl->olen = olen0 + total;
         ctl->pos = ctl->blk_end;
       }
       // (the barrier at the top of the loop publishes olen / pos before anyone reads them)
-      __syncthreads();
+      FP_DSYNC();
     }
 
     // ======================= the unit's blocks are decoded (or the unit is given up) =======================
     const bool fb = ctl->fb != 0u;
     const uint32_t olen = ctl->olen, fin_status = ctl->status, fin_pos = ctl->pos;
-    __syncthreads();
+    FP_DSYNC();
     if (tid == 0) {
+      ctl->x_state = fb ? 1u : 2u;
+      ctl->x_olen = olen;
+      ctl->x_wofs = wofs;
       // the staged input is dead: fetch the next unit behind the LZ77 pass
       fp_fetch_next(ctl, s_in, mbar, in_base, in_off, in_len, out_base, out_off, out_cap, n_units, next_u);
-        next_u += gridDim.x;
+      next_u += gridDim.x;
     }
+    FP_ASYNC();  // (A)
     if (fb) {
       for (uint32_t i = tid; i < 2048u; i += NT) flags[i] = 0;
       if (tid == 0) doneflag[(size_t)unit * flag_stride] = 0;
+      FP_ASYNC();  // (B)
       continue;
     }
-    __syncthreads();
-    // ---------------- LZ77: matches copy shared -> shared ----------------
-    // A match may copy as soon as the bytes it reads are final -- nothing else orders the copies.  (Measured on the
-    // benchmark text: 7.6 k matches per 64 KiB unit, longest chain of matches that feed each other 42.)  So finality is
-    // tracked per BYTE: `nf` holds one bit per output byte that a match still has to write (literals are final from the
-    // start); it lives where the block's code tables were, which are dead by now.  Every thread owns the bitmap words
-    // t, t + 256, ... (32 output bytes each) and keeps trying the pending matches of its current word: a match whose source
-    // bits are all clear copies (up to STEP bytes per batch, loaded before they are stored) and then clears its own bits.
-    // The earliest pending match of the unit is always ready, so the loop ends; threads never wait for each other otherwise.
-    {
-      uint32_t *const nf = reinterpret_cast<uint32_t *>(smem + O_LUTL);
-      const uint32_t nwords = (olen + 31u) >> 5;
-      for (uint32_t i = tid; i < nwords + 9u && i < 2048u + 8u; i += NT) nf[i] = 0;
-      __syncthreads();
-      for (uint32_t w = tid; w < nwords; w += NT) {
-        uint32_t f = flags[w];
-        while (f) {
-          const uint32_t b = (uint32_t)(__ffs((int)f) - 1);
-          f &= f - 1u;
-          const uint32_t a = w * 32u + b, e = a + (uint32_t)W[a] + 3u;  // bytes [a, e) are this match's
-          const uint32_t wa = a >> 5, wb = (e - 1u) >> 5;
-          if (wa == wb) {
-            atomicOr(&nf[wa], (0xffffffffu << (a & 31u)) & (0xffffffffu >> (31u - ((e - 1u) & 31u))));
-          } else {
-            atomicOr(&nf[wa], 0xffffffffu << (a & 31u));
-            for (uint32_t q = wa + 1u; q < wb; ++q) atomicOr(&nf[q], 0xffffffffu);
-            atomicOr(&nf[wb], 0xffffffffu >> (31u - ((e - 1u) & 31u)));
-          }
-        }
-      }
-      __syncthreads();
-      const uint32_t s_Wr = FP_SA(W), s_nf = FP_SA(nf);
-      uint32_t w = tid;
-      uint32_t f = w < nwords ? flags[w] : 0u, cand = f;
-      bool has = false;  // a match of mine is ready and waits for the warp's next copy turn
-      uint32_t rp = 0, rlen = 0, rdist = 0, rb = 0;
-      for (;;) {
-        // ---- look for a ready match (lanes that hold one wait for the warp's next copy turn: copying with a few lanes
-        // costs the warp as much as copying with all of them, so two looks are taken before every turn) ----
-#pragma unroll 1
-        for (int tries = 0; tries < 2; ++tries) {
-          if (!has && w < nwords) {
-            if (f == 0u) {  // this word's matches are done: next word of mine
-              flags[w] = 0;
-              w += NT;
-              f = w < nwords ? flags[w] : 0u;
-              cand = f;
-            }
-            if (f != 0u) {
-              if (cand == 0u) cand = f;  // another sweep over what is still pending here
-              const uint32_t b = (uint32_t)(__ffs((int)cand) - 1);
-              cand &= cand - 1u;
-              const uint32_t p = w * 32u + b;
-              // the 3-byte record, read as one unaligned word
-              const uint32_t ra = s_Wr + p;
-              const uint32_t rec = __funnelshift_r(FP_LDS32(ra & ~3u), FP_LDS32((ra & ~3u) + 4u), (ra & 3u) * 8u);
-              const uint32_t len = (rec & 0xffu) + 3u, dist = ((rec >> 8) & 0xffffu) + 1u;
-              const uint32_t src = p - dist, last = min(src + len, p) - 1u;  // [src, last] must be final
-              const uint32_t wa = src >> 5, wb = last >> 5;
-              const uint32_t mlo = 0xffffffffu << (src & 31u), mhi = 0xffffffffu >> (31u - (last & 31u));
-              uint32_t busy;
-              if (wa == wb) {
-                busy = FP_LDS32(s_nf + wa * 4u) & mlo & mhi;
-              } else {
-                busy = (FP_LDS32(s_nf + wa * 4u) & mlo) | (FP_LDS32(s_nf + wb * 4u) & mhi);
-                for (uint32_t q = wa + 1u; q < wb; ++q) busy |= FP_LDS32(s_nf + q * 4u);
-              }
-              if (busy == 0u) {
-                has = true;
-                rp = p;
-                rlen = len;
-                rdist = dist;
-                rb = b;
-              }
-            }
-          }
-          if (tries == 0 && __popc(__ballot_sync(FULL, has)) >= 20) break;
-        }
-        if (__ballot_sync(FULL, has || w < nwords) == 0u) break;
-        if (has) {
-          __threadfence_block();  // the bytes behind the clear bits are visible
-          for (uint32_t k = 0; k < rlen;) {
-            uint32_t m = min(rlen - k, STEP), back = rdist;
-            if (rdist < STEP && rdist < rlen) {
-              // overlapping run: [p - dist, p + k) is final and periodic, so any multiple of dist that reaches back far
-              // enough serves as the distance; the run doubles until it moves STEP bytes a batch
-              m = min(m, ((k + rdist) / rdist) * rdist);
-              back = ((m + rdist - 1u) / rdist) * rdist;
-            }
-            const uint8_t *sp = W + rp + k - back;
-            uint8_t *dp = W + rp + k;
-            uint8_t r[STEP];
-#pragma unroll
-            for (uint32_t t = 0; t < STEP; ++t) r[t] = sp[t];  // (reading past the m-th byte is harmless)
-#pragma unroll
-            for (uint32_t t = 0; t < STEP; ++t)
-              if (t < m) dp[t] = r[t];
-            k += m;
-          }
-          __threadfence_block();  // ... before the bits say so
-          {
-            const uint32_t e = rp + rlen, wa = rp >> 5, wb = (e - 1u) >> 5;
-            if (wa == wb) {
-              atomicAnd(&nf[wa], ~((0xffffffffu << (rp & 31u)) & (0xffffffffu >> (31u - ((e - 1u) & 31u)))));
-            } else {
-              atomicAnd(&nf[wa], ~(0xffffffffu << (rp & 31u)));
-              for (uint32_t q = wa + 1u; q < wb; ++q) atomicAnd(&nf[q], 0u);
-              atomicAnd(&nf[wb], ~(0xffffffffu >> (31u - ((e - 1u) & 31u))));
-            }
-          }
-          f &= ~(1u << rb);
-          has = false;
-        }
-      }
-    }
+    fp_lz77(smem, tid, NTT, olen, wofs);
     fp_fence_async();
-    __syncthreads();
+    FP_ASYNC();  // (B)
     // ---------------- output: one bulk store for the 16-byte aligned body, byte stores for the ragged ends ----------------
     {
       uint8_t *g = out_base + out_off[unit];

@@ -467,7 +467,7 @@ cudaError_t launch_inflate(const InflateBatch &b, cudaStream_t stream) {
       if (spare < 0 || spare >= g_num_sms) spare = 0;
       uint64_t fblocks = (uint64_t)(g_num_sms - spare) * 2u;
       if (fblocks > b.n_units) fblocks = b.n_units;
-      k_inflate_fast<<<(unsigned)fblocks, fp::NT, fp::SMEM_BYTES, stream>>>(b.in_base, b.in_off, b.in_len, b.out_base, b.out_off, b.out_cap,
+      k_inflate_fast<<<(unsigned)fblocks, fp::NTT, fp::SMEM_BYTES, stream>>>(b.in_base, b.in_off, b.in_len, b.out_base, b.out_off, b.out_cap,
                                                                         b.out_len, b.status, b.in_used, (uint32_t)b.n_units,
                                                                         b.ws.pieces + 1, (uint32_t)PIECE_WORDS);
       count_launch();
