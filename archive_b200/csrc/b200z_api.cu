@@ -477,10 +477,11 @@ static int gzip_fast_path_piped_fwd(const uint8_t *in, size_t in_len, uint8_t *o
                                     size_t *needed);
 static int gzip_fast_path(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_cap, size_t *pos_io,
                           size_t *out_pos_io, size_t *needed) {
-  // what the caller offers is a sane bound for the buffers (DEFLATE text sits near 3:1): walk inside the pipeline
+  // B200Z_GZIP_PIPED_WALK=1: the walk inside the pipeline (below).  Off by default: measured on a B200 (config 2, pinned
+  // buffers) it is SLOWER, 34.9 ms per call against 24.0 ms for walk-first -- see the comment on gzip_fast_path_piped.
   {
     const char *pe = getenv("B200Z_GZIP_PIPED_WALK");
-    const bool piped = !pe || atoi(pe) != 0;
+    const bool piped = pe && atoi(pe) != 0;
     const size_t span = in_len - *pos_io, room = out_cap >= *out_pos_io ? out_cap - *out_pos_io : 0;
     if (piped && *pos_io < in_len && room <= 32 * span + (64u << 20)) return gzip_fast_path_piped_fwd(in, in_len, out, out_cap, pos_io, out_pos_io, needed);
   }
@@ -613,10 +614,15 @@ static int gzip_fast_path(const uint8_t *in, size_t in_len, uint8_t *out, size_t
 // The same path with the HOST walk inside the pipeline.  Finding the members is a pointer chase through the compressed
 // bytes (a member's size is in its own header): 0.35 us per member, 5.7 ms for the 16 384 members of a GiB -- a fifth of
 // the whole call when it runs before anything else starts.  Here every chunk is sent and launched as soon as the walk
-// has covered its members, and the walk of the next chunk runs while the device works on this one.  Buffers are sized from what the caller offers
-// (out_cap) instead of from the walk's totals, so this form is taken when that is a sane bound; anything unexpected (a
-// hint that overflows out_cap, more members than the tables were sized for) ends the run early and the caller goes on
-// from the returned position exactly as before.
+// has covered its members, and the walk of the next chunk runs while the device works on this one.  Buffers are sized
+// from what the caller offers (out_cap) instead of from the walk's totals, so this form is taken when that is a sane
+// bound; anything unexpected (a hint that overflows out_cap, more members than the tables were sized for) ends the run
+// early and the caller goes on from the returned position exactly as before.
+// MEASURED (round 2, B200, config 2): 34.9 ms per call, against 24.0 ms with the walk in front -- in both forms tried
+// (whole input sent ahead in 16 MiB pieces; one copy per chunk as here).  The walk is a chain of dependent cache misses
+// into the caller's buffer, and it now runs while the copy engines move 100 GB/s through the same host memory; the
+// chunks reach the device later than the device could take them.  Kept as an option (B200Z_GZIP_PIPED_WALK=1) with its
+// tests; the default is walk-first.
 // ---------------------------------------------------------------------------------------------
 static int gzip_fast_path_piped(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_cap, size_t *pos_io, size_t *out_pos_io,
                                 size_t *needed) {

@@ -158,6 +158,23 @@ __device__ __forceinline__ void fp_sts8(uint32_t a, uint32_t v) { asm volatile("
 #define FP_STS8(a, v) fp_sts8((a), (v))
 #endif
 
+// FP_PROF builds (scripts/build_variant.sh prof -DFP_PROF): thread 0 adds the clocks between the barriers of a unit to
+// g_fp_prof[phase] -- where the WALL time of a unit goes, barrier waits included (the instruction counts of the ncu source
+// page do not show those).  Read and cleared by b200z_debug_fast_prof.
+#ifdef FP_PROF
+__device__ unsigned long long g_fp_prof[16];
+#define FP_TICK(k)                                                          \
+  do {                                                                      \
+    if (tid == 0) {                                                         \
+      const long long t_ = clock64();                                       \
+      atomicAdd(&g_fp_prof[k], (unsigned long long)(t_ - tl_));             \
+      tl_ = t_;                                                             \
+    }                                                                       \
+  } while (0)
+#else
+#define FP_TICK(k)
+#endif
+
 // Two kinds of CTA barrier: FP_DSYNC among the NT decode threads (everything up to the LZ77 pass), FP_ASYNC among all NTT
 // threads (around the LZ77 pass).  Without extra warps they are the same barrier.
 #if defined(B200Z_EMU) || FP_XT == 0
@@ -717,9 +734,13 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
         next_u += gridDim.x;
   }
   uint32_t phase = 0;
+#ifdef FP_PROF
+  long long tl_ = clock64();
+#endif
   for (;;) {
     if (tid == 0) fp_store_wait_read();  // the previous unit's bulk store has read the window
     FP_DSYNC();
+    FP_TICK(0);
     const uint32_t unit = ctl->n_unit;
     if (unit == NONE) {
       if (tid == 0) ctl->x_state = 0;
@@ -743,6 +764,7 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
     }
     fp_mbar_wait(mbar, phase);
     phase ^= 1u;
+    FP_TICK(1);
     if (tid == 0) {
       ctl->end_bit = (lead + u_in_len) * 8u;
       ctl->pos = lead * 8u;
@@ -768,6 +790,7 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
         }
       }
       FP_DSYNC();
+      FP_TICK(2);
       if (ctl->fb || ctl->done) break;
       const uint32_t btype = ctl->btype;
       if (btype == 0u) {  // stored (inflate.dart:213-235): input bytes -> window
@@ -892,6 +915,7 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
         }
       }
       FP_DSYNC();
+      FP_TICK(3);
       if (ctl->fb) break;
 
       // ---------------- pass A: every lane decodes its segment, marking token boundaries ----------------
@@ -982,6 +1006,7 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
         } while (0);
       }
       FP_DSYNC();
+      FP_TICK(4);
       // ---------------- pass A2: run on until one of my boundaries is one of a successor's ----------------
       {
         uint32_t succ = tid + 1u, succS = myS + L;
@@ -1049,6 +1074,7 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
         }
       }
       FP_DSYNC();  // every lane is through with the bitmaps (they share the window with nothing live, but the lane arrays follow)
+      FP_TICK(5);
       // ---------------- the chain of meeting points from lane 0 is the true parse ----------------
       if (lane_on) {
         tgt_arr[tid] = tgt;
@@ -1096,6 +1122,7 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
       const bool valid = ((ctl->validmask[warp] >> lane) & 1u) != 0u;
       if (valid && tgt < END_EOB) start_arr[tgt] = endpos;
       FP_DSYNC();
+      FP_TICK(6);
       const uint32_t start = !valid ? 0u : tid == 0u ? p0 : start_arr[tid];
       // ---------------- pass A3: bytes of my false start (my guessed offset .. where the true parse met me) ----------------
       uint32_t nbytes = 0;
@@ -1154,6 +1181,7 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
       if (lane == 31u) ctl->warp_tot[warp] = incl;
       if (incons) ctl->fb = 1;
       FP_DSYNC();
+      FP_TICK(7);
       uint32_t wbase = 0, total = 0;
 #pragma unroll
       for (int w = 0; w < NW; ++w) {
@@ -1164,6 +1192,7 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
       if (ctl->fb || olen0 + total > cap) {  // beyond out_cap: B200Z_U_NOSPC is the exact kernels' to report
         if (tid == 0) ctl->fb = 1;
         FP_DSYNC();
+        FP_TICK(7);
         break;
       }
       // ---------------- pass C: my share of the block again, into the window ----------------
@@ -1231,6 +1260,7 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
         if (trouble) ctl->fb = 1;
       }
       FP_DSYNC();
+      FP_TICK(8);
       if (ctl->fb) break;
       if (tid == 0) {
         ctl->olen = olen0 + total;
@@ -1253,6 +1283,7 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
       next_u += gridDim.x;
     }
     FP_ASYNC();  // (A)
+    FP_TICK(9);
     if (fb) {
       for (uint32_t i = tid; i < 2048u; i += NT) flags[i] = 0;
       if (tid == 0) doneflag[(size_t)unit * flag_stride] = 0;
@@ -1262,6 +1293,7 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
     fp_lz77(smem, tid, NTT, olen, wofs);
     fp_fence_async();
     FP_ASYNC();  // (B)
+    FP_TICK(10);
     // ---------------- output: one bulk store for the 16-byte aligned body, byte stores for the ragged ends ----------------
     {
       uint8_t *g = out_base + out_off[unit];
@@ -1278,6 +1310,7 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
         doneflag[(size_t)unit * flag_stride] = 1;
       }
     }
+    FP_TICK(11);
   }
 }
 

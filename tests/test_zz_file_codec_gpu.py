@@ -287,6 +287,11 @@ def test_gzip_chunk_pipeline_many_chunks(a, monkeypatch):
     monkeypatch.setenv("B200Z_GZIP_RAMP", "0")
     assert a.GZipDecoder().decode_bytes(blob) == text
     monkeypatch.delenv("B200Z_GZIP_RAMP")
+    monkeypatch.setenv("B200Z_GZIP_PIPED_WALK", "1")  # the optional form that walks the members between the launches
+    assert a.GZipDecoder().decode_bytes(blob) == text
+    cut_piped = _mem_decode(a, a.GZipDecoder(), blob[:-9])  # the last member ends short: same verdict, same bytes
+    monkeypatch.delenv("B200Z_GZIP_PIPED_WALK")
+    assert cut_piped == _mem_decode(a, a.GZipDecoder(), blob[:-9])
     monkeypatch.setenv("B200Z_GZIP_CHUNK_KB", "200")
     tail = blob + b"\x1f\x8b\x08\x00" + bytes(30)  # garbage behind the last member: the verdict comes from the slow path
     got = _mem_decode(a, a.GZipDecoder(), tail)
