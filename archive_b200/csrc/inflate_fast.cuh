@@ -55,6 +55,12 @@ constexpr uint32_t CHUNK_SHIFT = 10;  // LZ77 resolution chunk = 1024 output byt
 #define FP_TRIES 2
 #endif
 constexpr uint32_t STEP = FP_STEP;    // bytes a lane copies per batch
+#ifndef FP_DYNW
+#define FP_DYNW 1   // LZ77: threads take the next bitmap word off a counter (0: thread t owns words t, t + nthr, ...)
+#endif
+#ifndef FP_HDRAHEAD
+#define FP_HDRAHEAD 1  // thread 0 parses the NEXT unit's first block header while the other warps start the LZ77 pass
+#endif
 
 // table entry: bits 0-3 code length (0: link or hole), 4-7 extra bits, 8-9 kind, 16-31 value
 constexpr uint32_t K_LIT = 0u, K_BASE = 1u, K_EOB = 2u, K_INV = 3u;
@@ -71,6 +77,10 @@ constexpr uint32_t O_LENS = O_SUB + 4u * SUBN;   // u8[320]
 constexpr uint32_t O_GRP = O_LENS + 320;         // u32[10][16]
 constexpr uint32_t O_CNT = O_GRP + 640;          // u32 cnt_l[16], cnt_d[16], first_l[16], first_d[16]
 constexpr uint32_t O_LONG = O_CNT + 256;         // u32 long_l[288], long_d[32]
+// (during the LZ77 pass `nf` covers O_LUTL .. O_LONG + 356; the rest of O_LONG then holds the next unit's code lengths)
+constexpr uint32_t O_LENS2 = O_LONG + 368;       // u8[320]
+constexpr uint32_t O_CL2 = O_LONG + 688;         // u32[128]
+static_assert((2048u + 9u) * 4u <= O_LENS2 - O_LUTL && O_CL2 + 512u <= O_LONG + 1280u, "nf / header-ahead scratch");
 constexpr uint32_t O_CTL = O_LONG + 1280;
 constexpr uint32_t O_MBAR = O_CTL + 256;
 constexpr uint32_t SMEM_BYTES = O_MBAR + 16;
@@ -86,6 +96,8 @@ struct Ctl {
   uint32_t nl, L, K, bm_stride, bm_off, p0;
   uint32_t blk_end, blk_total;
   uint32_t x_state, x_olen, x_wofs;  // for the LZ77-only warps: 0 end, 1 nothing to do for this unit, 2 LZ77 over x_olen bytes
+  uint32_t lz_next;                  // LZ77: the next bitmap word nobody has taken yet
+  uint32_t ha_valid;                 // the unit being fetched already has its first block header parsed (lens in O_LENS2)
   uint32_t regmask[NW], validmask[NW], warp_tot[NW];
 };
 static_assert(sizeof(Ctl) <= 256, "Ctl");
@@ -377,6 +389,18 @@ FP_DEV void fp_fetch_next(Ctl *ctl, uint8_t *s_in, uint64_t *mbar, const uint8_t
   if (elig) fp_load_bulk(s_in, src - lead, bytes, mbar);
 }
 
+// thread 0: the unit fetch_next has announced becomes the unit being decoded
+FP_DEV void fp_unit_begin(Ctl *ctl) {
+  ctl->end_bit = (ctl->n_lead + ctl->n_in_len) * 8u;
+  ctl->pos = ctl->n_lead * 8u;
+  ctl->olen = 0;
+  ctl->fb = 0;
+  ctl->done = 0;
+  ctl->status = B200Z_U_DONE;
+  ctl->bfinal = 0;
+  ctl->cap = ctl->n_cap;
+}
+
 // thread 0: _parseBlock header (inflate.dart:120-156, 213-298) -- clean cases only, anything else sets ctl->fb
 FP_DEV void fp_parse_header(Ctl *ctl, const uint8_t *s_in, uint8_t *lens, uint32_t *cl_lut) {
   const uint32_t *in32 = reinterpret_cast<const uint32_t *>(s_in);
@@ -565,8 +589,7 @@ FP_DEV void fp_plan_lanes(Ctl *ctl, uint32_t wofs) {
 // The earliest pending match of the unit is always ready, so the loop ends; threads never wait for each other otherwise.
 // Every thread of the CTA runs this, the decode lanes and -- when the kernel is built with some (FP_XT) -- the extra
 // warps that exist for this pass only: it is bound by latency, and more warps hide more of it.
-FP_DEV void fp_lz77(uint8_t *smem, uint32_t tid, uint32_t nthr, uint32_t olen, uint32_t wofs) {
-  const unsigned FULL = 0xffffffffu;
+FP_DEV void fp_lz77_prep(uint8_t *smem, uint32_t tid, uint32_t nthr, uint32_t olen, uint32_t wofs) {
   uint32_t *const flags = reinterpret_cast<uint32_t *>(smem + O_FLAGS);
   uint8_t *const W = smem + O_WIN + wofs;
     uint32_t *const nf = reinterpret_cast<uint32_t *>(smem + O_LUTL);
@@ -590,8 +613,22 @@ FP_DEV void fp_lz77(uint8_t *smem, uint32_t tid, uint32_t nthr, uint32_t olen, u
       }
     }
     FP_ASYNC();
+}
+
+// (a thread may enter late: with FP_DYNW the words it would have owned are simply taken by the others)
+FP_DEV void fp_lz77_run(uint8_t *smem, uint32_t tid, uint32_t nthr, uint32_t olen, uint32_t wofs) {
+  const unsigned FULL = 0xffffffffu;
+  uint32_t *const flags = reinterpret_cast<uint32_t *>(smem + O_FLAGS);
+  uint8_t *const W = smem + O_WIN + wofs;
+    uint32_t *const nf = reinterpret_cast<uint32_t *>(smem + O_LUTL);
+    const uint32_t nwords = (olen + 31u) >> 5;
     const uint32_t s_Wr = FP_SA(W), s_nf = FP_SA(nf);
+#if FP_DYNW
+    uint32_t *const lz_next = &reinterpret_cast<Ctl *>(smem + O_CTL)->lz_next;
+    uint32_t w = atomicAdd(lz_next, 1u);
+#else
     uint32_t w = tid;
+#endif
     uint32_t f = w < nwords ? flags[w] : 0u, cand = f;
     bool has = false;  // a match of mine is ready and waits for the warp's next copy turn
     uint32_t rp = 0, rlen = 0, rdist = 0, rb = 0;
@@ -603,7 +640,11 @@ FP_DEV void fp_lz77(uint8_t *smem, uint32_t tid, uint32_t nthr, uint32_t olen, u
         if (!has && w < nwords) {
           if (f == 0u) {  // this word's matches are done: next word of mine
             flags[w] = 0;
+#if FP_DYNW
+            w = atomicAdd(lz_next, 1u);
+#else
             w += nthr;
+#endif
             f = w < nwords ? flags[w] : 0u;
             cand = f;
           }
@@ -619,13 +660,10 @@ FP_DEV void fp_lz77(uint8_t *smem, uint32_t tid, uint32_t nthr, uint32_t olen, u
             const uint32_t src = p - dist, last = min(src + len, p) - 1u;  // [src, last] must be final
             const uint32_t wa = src >> 5, wb = last >> 5;
             const uint32_t mlo = 0xffffffffu << (src & 31u), mhi = 0xffffffffu >> (31u - (last & 31u));
-            uint32_t busy;
-            if (wa == wb) {
-              busy = FP_LDS32(s_nf + wa * 4u) & mlo & mhi;
-            } else {
-              busy = (FP_LDS32(s_nf + wa * 4u) & mlo) | (FP_LDS32(s_nf + wb * 4u) & mhi);
+            // (the same instructions whether the source lies in one bitmap word or two; longer sources are rare)
+            uint32_t busy = (FP_LDS32(s_nf + wa * 4u) & mlo & (wa == wb ? mhi : 0xffffffffu)) | (FP_LDS32(s_nf + wb * 4u) & mhi);
+            if (wb > wa + 1u)
               for (uint32_t q = wa + 1u; q < wb; ++q) busy |= FP_LDS32(s_nf + q * 4u);
-            }
             if (busy == 0u) {
               has = true;
               rp = p;
@@ -640,14 +678,12 @@ FP_DEV void fp_lz77(uint8_t *smem, uint32_t tid, uint32_t nthr, uint32_t olen, u
       if (__ballot_sync(FULL, has || w < nwords) == 0u) break;
       if (has) {
         __threadfence_block();  // the bytes behind the clear bits are visible
+        // overlapping run (dist < len, dist < STEP): [p - dist, p + k) is final and periodic, so any multiple of dist that
+        // does not reach back beyond p - dist serves as the distance: it doubles until a batch moves STEP bytes
+        uint32_t back = rdist;
         for (uint32_t k = 0; k < rlen;) {
-          uint32_t m = min(rlen - k, STEP), back = rdist;
-          if (rdist < STEP && rdist < rlen) {
-            // overlapping run: [p - dist, p + k) is final and periodic, so any multiple of dist that reaches back far
-            // enough serves as the distance; the run doubles until it moves STEP bytes a batch
-            m = min(m, ((k + rdist) / rdist) * rdist);
-            back = ((m + rdist - 1u) / rdist) * rdist;
-          }
+          if (back < STEP && 2u * back <= k + rdist) back <<= 1;
+          const uint32_t m = min(rlen - k, min(STEP, back));
           const uint8_t *sp = W + rp + k - back;
           uint8_t *dp = W + rp + k;
           uint8_t r[STEP];
@@ -673,6 +709,11 @@ FP_DEV void fp_lz77(uint8_t *smem, uint32_t tid, uint32_t nthr, uint32_t olen, u
         has = false;
       }
     }
+}
+
+FP_DEV void fp_lz77(uint8_t *smem, uint32_t tid, uint32_t nthr, uint32_t olen, uint32_t wofs) {
+  fp_lz77_prep(smem, tid, nthr, olen, wofs);
+  fp_lz77_run(smem, tid, nthr, olen, wofs);
 }
 
 }  // namespace fp
@@ -730,6 +771,7 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
   uint32_t next_u = blockIdx.x;  // (thread 0's copy is the one that counts)
   if (tid == 0) {
     fp_mbar_init(mbar, 1);
+    ctl->ha_valid = 0;
     fp_fetch_next(ctl, s_in, mbar, in_base, in_off, in_len, out_base, out_off, out_cap, n_units, next_u);
         next_u += gridDim.x;
   }
@@ -749,6 +791,7 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
     }
     const uint32_t u_in_len = ctl->n_in_len, lead = ctl->n_lead, cap = ctl->n_cap, wofs = ctl->n_wofs;
     const bool elig = ctl->n_elig != 0u;
+    bool ahead = ctl->ha_valid != 0u;  // thread 0 has parsed the first block header already (behind the previous unit's LZ77 pass)
     uint8_t *const W = win + wofs;  // W[q] = output byte q; W is congruent to the global destination modulo 16
     FP_DSYNC();
     if (!elig) {
@@ -766,21 +809,19 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
     phase ^= 1u;
     FP_TICK(1);
     if (tid == 0) {
-      ctl->end_bit = (lead + u_in_len) * 8u;
-      ctl->pos = lead * 8u;
-      ctl->olen = 0;
-      ctl->fb = 0;
-      ctl->done = 0;
-      ctl->status = B200Z_U_DONE;
-      ctl->bfinal = 0;
-      ctl->cap = cap;
+      if (!ahead) fp_unit_begin(ctl);
+      ctl->ha_valid = 0;
     }
     FP_DSYNC();
     const uint32_t end_bit = (lead + u_in_len) * 8u;
 
     // ======================= blocks =======================
     for (;;) {
-      if (tid == 0) {
+      if (ahead) {  // the unit's first block: its code lengths wait in O_LENS2
+        for (uint32_t i = tid; i < 80u; i += NT)
+          reinterpret_cast<uint32_t *>(lens)[i] = reinterpret_cast<const uint32_t *>(smem + O_LENS2)[i];
+        ahead = false;
+      } else if (tid == 0) {
         if (ctl->bfinal) {
           ctl->done = 1;
           ctl->status = B200Z_U_DONE;
@@ -1278,6 +1319,7 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
       ctl->x_state = fb ? 1u : 2u;
       ctl->x_olen = olen;
       ctl->x_wofs = wofs;
+      ctl->lz_next = 0;
       // the staged input is dead: fetch the next unit behind the LZ77 pass
       fp_fetch_next(ctl, s_in, mbar, in_base, in_off, in_len, out_base, out_off, out_cap, n_units, next_u);
       next_u += gridDim.x;
@@ -1290,7 +1332,23 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
       FP_ASYNC();  // (B)
       continue;
     }
-    fp_lz77(smem, tid, NTT, olen, wofs);
+    fp_lz77_prep(smem, tid, NTT, olen, wofs);
+#if FP_HDRAHEAD
+    // The next unit's input is on its way (fetch_next above) and its first block header is a serial parse by one thread
+    // (measured: 36 k of a unit's 366 k clocks with everybody else at the barrier).  Warp 0 does it now, the other warps
+    // start on the matches, and warp 0 joins them afterwards.
+    if (warp == 0u && ctl->n_unit != NONE && ctl->n_elig != 0u) {
+      fp_mbar_wait(mbar, phase);  // (`phase` is the next load's parity by now; the wait at the top of the loop sees the same)
+      if (tid == 0) {
+        fp_unit_begin(ctl);
+        fp_parse_header(ctl, s_in, smem + O_LENS2, reinterpret_cast<uint32_t *>(smem + O_CL2));
+        if (!ctl->fb && !ctl->done && ctl->btype != 0u) fp_plan_lanes(ctl, ctl->n_wofs);
+        ctl->ha_valid = 1;
+      }
+      __syncwarp();
+    }
+#endif
+    fp_lz77_run(smem, tid, NTT, olen, wofs);
     fp_fence_async();
     FP_ASYNC();  // (B)
     FP_TICK(10);

@@ -26,7 +26,8 @@ def pytest_configure(config):
     # the inflate kernels (several lanes per stream) on the CUDA execution-model emulation
     src = os.path.join(emul, "inflate_emul.cpp")
     so = os.path.join(emul, "libinflate_emul.so")
-    deps = [src, os.path.join(emul, "cuda_emu.h"), hdr, os.path.join(ROOT, "archive_b200", "csrc", "inflate_kernels.cu")]
+    deps = [src, os.path.join(emul, "cuda_emu.h"), hdr, os.path.join(ROOT, "archive_b200", "csrc", "inflate_kernels.cu"),
+            os.path.join(ROOT, "archive_b200", "csrc", "inflate_fast.cuh")]
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
         subprocess.run(["g++", "-O2", "-g", "-fPIC", "-shared", "-std=c++17", "-I", emul, "-I",
                         os.path.join(ROOT, "archive_b200", "csrc"), src, "-o", so], check=True)
