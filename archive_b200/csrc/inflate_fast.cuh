@@ -32,7 +32,10 @@
 namespace b200z {
 namespace fp {
 
-constexpr int NT = 256;          // decode threads (= lanes of the speculative decode) per CTA
+#ifndef FP_NT
+#define FP_NT 256
+#endif
+constexpr int NT = FP_NT;        // decode threads (= lanes of the speculative decode) per CTA; a multiple of 32
 constexpr int NW = NT / 32;
 #ifndef FP_XT
 #define FP_XT 0
@@ -52,11 +55,17 @@ constexpr uint32_t CHUNK_SHIFT = 10;  // LZ77 resolution chunk = 1024 output byt
 #define FP_STEP 8
 #endif
 #ifndef FP_TRIES
-#define FP_TRIES 2
+#define FP_TRIES 1
 #endif
 constexpr uint32_t STEP = FP_STEP;    // bytes a lane copies per batch
 #ifndef FP_DYNW
 #define FP_DYNW 1   // LZ77: threads take the next bitmap word off a counter (0: thread t owns words t, t + nthr, ...)
+#endif
+#ifndef FP_GRAN
+#define FP_GRAN 1   // LZ77 with FP_DYNW: a work item is 32 >> FP_GRAN output bytes (smaller items keep the region in flight shorter)
+#endif
+#ifndef FP_LOOK2
+#define FP_LOOK2 0  // LZ77: a look-up examines two pending matches of the item at once
 #endif
 #ifndef FP_HDRAHEAD
 #define FP_HDRAHEAD 1  // thread 0 parses the NEXT unit's first block header while the other warps start the LZ77 pass
@@ -82,7 +91,7 @@ constexpr uint32_t O_LENS2 = O_LONG + 368;       // u8[320]
 constexpr uint32_t O_CL2 = O_LONG + 688;         // u32[128]
 static_assert((2048u + 9u) * 4u <= O_LENS2 - O_LUTL && O_CL2 + 512u <= O_LONG + 1280u, "nf / header-ahead scratch");
 constexpr uint32_t O_CTL = O_LONG + 1280;
-constexpr uint32_t O_MBAR = O_CTL + 256;
+constexpr uint32_t O_MBAR = O_CTL + 384;
 constexpr uint32_t SMEM_BYTES = O_MBAR + 16;
 static_assert(SMEM_BYTES <= 115712, "two CTAs per SM");
 
@@ -100,7 +109,7 @@ struct Ctl {
   uint32_t ha_valid;                 // the unit being fetched already has its first block header parsed (lens in O_LENS2)
   uint32_t regmask[NW], validmask[NW], warp_tot[NW];
 };
-static_assert(sizeof(Ctl) <= 256, "Ctl");
+static_assert(sizeof(Ctl) <= 384, "Ctl");
 
 #if defined(B200Z_EMU)
 #define FP_DEV inline
@@ -174,7 +183,7 @@ __device__ __forceinline__ void fp_sts8(uint32_t a, uint32_t v) { asm volatile("
 // g_fp_prof[phase] -- where the WALL time of a unit goes, barrier waits included (the instruction counts of the ncu source
 // page do not show those).  Read and cleared by b200z_debug_fast_prof.
 #ifdef FP_PROF
-__device__ unsigned long long g_fp_prof[16];
+__device__ unsigned long long g_fp_prof[20];
 #define FP_TICK(k)                                                          \
   do {                                                                      \
     if (tid == 0) {                                                         \
@@ -183,8 +192,17 @@ __device__ unsigned long long g_fp_prof[16];
       tl_ = t_;                                                             \
     }                                                                       \
   } while (0)
+// ... and every warp's lane 0 adds the clocks it WAITED at the barrier that ends pass A / A2 / A3 / C / LZ77 to
+// g_fp_prof[12 + k] (sum over the CTA's warps: 8 x the phase's clocks would mean everybody waited all the time)
+#define FP_ARR() ta_ = clock64()
+#define FP_TICKW(k)                                                                      \
+  do {                                                                                   \
+    if (lane == 0) atomicAdd(&g_fp_prof[12 + (k)], (unsigned long long)(clock64() - ta_)); \
+  } while (0)
 #else
 #define FP_TICK(k)
+#define FP_ARR()
+#define FP_TICKW(k)
 #endif
 
 // Two kinds of CTA barrier: FP_DSYNC among the NT decode threads (everything up to the LZ77 pass), FP_ASYNC among all NTT
@@ -193,7 +211,9 @@ __device__ unsigned long long g_fp_prof[16];
 #define FP_DSYNC() __syncthreads()
 #define FP_ASYNC() __syncthreads()
 #else
-#define FP_DSYNC() asm volatile("bar.sync 1, 256;" ::: "memory")
+#define FP_STR2(x) #x
+#define FP_STR(x) FP_STR2(x)
+#define FP_DSYNC() asm volatile("bar.sync 1, " FP_STR(FP_NT) ";" ::: "memory")
 #define FP_ASYNC() __syncthreads()
 #endif
 
@@ -624,12 +644,20 @@ FP_DEV void fp_lz77_run(uint8_t *smem, uint32_t tid, uint32_t nthr, uint32_t ole
     const uint32_t nwords = (olen + 31u) >> 5;
     const uint32_t s_Wr = FP_SA(W), s_nf = FP_SA(nf);
 #if FP_DYNW
+    // work items are handed out in position order off a counter: item q = output bytes [q * IB, (q + 1) * IB)
+    constexpr uint32_t G = FP_GRAN, IB = 32u >> G;
+    const uint32_t nitems = nwords << G;
     uint32_t *const lz_next = &reinterpret_cast<Ctl *>(smem + O_CTL)->lz_next;
+#define FP_ITEM_BITS(q) ((q) < nitems ? flags[(q) >> G] & ((0xffffffffu >> (32u - IB)) << (((q) & ((1u << G) - 1u)) * IB)) : 0u)
     uint32_t w = atomicAdd(lz_next, 1u);
+    uint32_t f = FP_ITEM_BITS(w), cand = f;
 #else
+    constexpr uint32_t G = 0;
+    const uint32_t nitems = nwords;
+#define FP_ITEM_BITS(q) ((q) < nitems ? flags[q] : 0u)
     uint32_t w = tid;
+    uint32_t f = FP_ITEM_BITS(w), cand = f;
 #endif
-    uint32_t f = w < nwords ? flags[w] : 0u, cand = f;
     bool has = false;  // a match of mine is ready and waits for the warp's next copy turn
     uint32_t rp = 0, rlen = 0, rdist = 0, rb = 0;
     for (;;) {
@@ -637,45 +665,66 @@ FP_DEV void fp_lz77_run(uint8_t *smem, uint32_t tid, uint32_t nthr, uint32_t ole
       // costs the warp as much as copying with all of them, so two looks are taken before every turn) ----
 #pragma unroll 1
       for (int tries = 0; tries < FP_TRIES; ++tries) {
-        if (!has && w < nwords) {
-          if (f == 0u) {  // this word's matches are done: next word of mine
-            flags[w] = 0;
+        if (!has && w < nitems) {
+          if (f == 0u) {  // this item's matches are done: the next one (the kernel clears the bitmap behind the pass)
 #if FP_DYNW
             w = atomicAdd(lz_next, 1u);
 #else
             w += nthr;
 #endif
-            f = w < nwords ? flags[w] : 0u;
+            f = FP_ITEM_BITS(w);
             cand = f;
           }
           if (f != 0u) {
             if (cand == 0u) cand = f;  // another sweep over what is still pending here
-            const uint32_t b = (uint32_t)(__ffs((int)cand) - 1);
+            // is the match at bit b of my word ready?  (its 3-byte record read as one unaligned word; [src, last] must be final)
+            auto probe = [&](uint32_t b, uint32_t &len, uint32_t &dist) -> bool {
+              const uint32_t p = (w >> G) * 32u + b;
+              const uint32_t ra = s_Wr + p;
+              const uint32_t rec = __funnelshift_r(FP_LDS32(ra & ~3u), FP_LDS32((ra & ~3u) + 4u), (ra & 3u) * 8u);
+              len = (rec & 0xffu) + 3u;
+              dist = ((rec >> 8) & 0xffffu) + 1u;
+              const uint32_t src = p - dist, last = min(src + len, p) - 1u;
+              const uint32_t wa = src >> 5, wb = last >> 5;
+              const uint32_t mlo = 0xffffffffu << (src & 31u), mhi = 0xffffffffu >> (31u - (last & 31u));
+              // (the same instructions whether the source lies in one bitmap word or two; longer sources are rare)
+              const uint32_t nfa = FP_LDS32(s_nf + wa * 4u), nfb = FP_LDS32(s_nf + wb * 4u);
+              uint32_t busy = wa == wb ? (nfa & mlo & mhi) : ((nfa & mlo) | (nfb & mhi));
+              if (wb > wa + 1u)
+                for (uint32_t q = wa + 1u; q < wb; ++q) busy |= FP_LDS32(s_nf + q * 4u);
+              return busy == 0u;
+            };
+            const uint32_t b0 = (uint32_t)(__ffs((int)cand) - 1);
             cand &= cand - 1u;
-            const uint32_t p = w * 32u + b;
-            // the 3-byte record, read as one unaligned word
-            const uint32_t ra = s_Wr + p;
-            const uint32_t rec = __funnelshift_r(FP_LDS32(ra & ~3u), FP_LDS32((ra & ~3u) + 4u), (ra & 3u) * 8u);
-            const uint32_t len = (rec & 0xffu) + 3u, dist = ((rec >> 8) & 0xffffu) + 1u;
-            const uint32_t src = p - dist, last = min(src + len, p) - 1u;  // [src, last] must be final
-            const uint32_t wa = src >> 5, wb = last >> 5;
-            const uint32_t mlo = 0xffffffffu << (src & 31u), mhi = 0xffffffffu >> (31u - (last & 31u));
-            // (the same instructions whether the source lies in one bitmap word or two; longer sources are rare)
-            uint32_t busy = (FP_LDS32(s_nf + wa * 4u) & mlo & (wa == wb ? mhi : 0xffffffffu)) | (FP_LDS32(s_nf + wb * 4u) & mhi);
-            if (wb > wa + 1u)
-              for (uint32_t q = wa + 1u; q < wb; ++q) busy |= FP_LDS32(s_nf + q * 4u);
-            if (busy == 0u) {
+            uint32_t len0, dist0;
+#if FP_LOOK2
+            // two candidates a look: their chains of loads overlap, and a look fails less often
+            const bool two = cand != 0u;
+            const uint32_t b1 = two ? (uint32_t)(__ffs((int)cand) - 1) : b0;
+            cand &= cand - 1u;
+            uint32_t len1, dist1;
+            const bool r0 = probe(b0, len0, dist0), r1 = probe(b1, len1, dist1);
+            if (r0 || r1) {
               has = true;
-              rp = p;
-              rlen = len;
-              rdist = dist;
-              rb = b;
+              rb = r0 ? b0 : b1;
+              rlen = r0 ? len0 : len1;
+              rdist = r0 ? dist0 : dist1;
+              rp = (w >> G) * 32u + rb;
             }
+#else
+            if (probe(b0, len0, dist0)) {
+              has = true;
+              rb = b0;
+              rlen = len0;
+              rdist = dist0;
+              rp = (w >> G) * 32u + rb;
+            }
+#endif
           }
         }
         if (tries == 0 && __popc(__ballot_sync(FULL, has)) >= 20) break;
       }
-      if (__ballot_sync(FULL, has || w < nwords) == 0u) break;
+      if (__ballot_sync(FULL, has || w < nitems) == 0u) break;
       if (has) {
         __threadfence_block();  // the bytes behind the clear bits are visible
         // overlapping run (dist < len, dist < STEP): [p - dist, p + k) is final and periodic, so any multiple of dist that
@@ -709,6 +758,7 @@ FP_DEV void fp_lz77_run(uint8_t *smem, uint32_t tid, uint32_t nthr, uint32_t ole
         has = false;
       }
     }
+#undef FP_ITEM_BITS
 }
 
 FP_DEV void fp_lz77(uint8_t *smem, uint32_t tid, uint32_t nthr, uint32_t olen, uint32_t wofs) {
@@ -777,7 +827,7 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
   }
   uint32_t phase = 0;
 #ifdef FP_PROF
-  long long tl_ = clock64();
+  long long tl_ = clock64(), ta_ = 0;
 #endif
   for (;;) {
     if (tid == 0) fp_store_wait_read();  // the previous unit's bulk store has read the window
@@ -1046,8 +1096,10 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
           }
         } while (0);
       }
+      FP_ARR();
       FP_DSYNC();
       FP_TICK(4);
+      FP_TICKW(0);
       // ---------------- pass A2: run on until one of my boundaries is one of a successor's ----------------
       {
         uint32_t succ = tid + 1u, succS = myS + L;
@@ -1114,8 +1166,10 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
           } while (0);
         }
       }
+      FP_ARR();
       FP_DSYNC();  // every lane is through with the bitmaps (they share the window with nothing live, but the lane arrays follow)
       FP_TICK(5);
+      FP_TICKW(1);
       // ---------------- the chain of meeting points from lane 0 is the true parse ----------------
       if (lane_on) {
         tgt_arr[tid] = tgt;
@@ -1221,8 +1275,10 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
       }
       if (lane == 31u) ctl->warp_tot[warp] = incl;
       if (incons) ctl->fb = 1;
+      FP_ARR();
       FP_DSYNC();
       FP_TICK(7);
+      FP_TICKW(2);
       uint32_t wbase = 0, total = 0;
 #pragma unroll
       for (int w = 0; w < NW; ++w) {
@@ -1300,8 +1356,10 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
         }
         if (trouble) ctl->fb = 1;
       }
+      FP_ARR();
       FP_DSYNC();
       FP_TICK(8);
+      FP_TICKW(3);
       if (ctl->fb) break;
       if (tid == 0) {
         ctl->olen = olen0 + total;
@@ -1350,8 +1408,11 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
 #endif
     fp_lz77_run(smem, tid, NTT, olen, wofs);
     fp_fence_async();
+    FP_ARR();
     FP_ASYNC();  // (B)
     FP_TICK(10);
+    FP_TICKW(4);
+    for (uint32_t i = tid; i < ((olen + 31u) >> 5); i += NT) flags[i] = 0;  // (pass C of the next unit is barriers away)
     // ---------------- output: one bulk store for the 16-byte aligned body, byte stores for the ragged ends ----------------
     {
       uint8_t *g = out_base + out_off[unit];

@@ -44,7 +44,7 @@ def main():
     for _ in range(3):
         step()
     torch.cuda.synchronize()
-    buf = (C.c_ulonglong * 16)()
+    buf = (C.c_ulonglong * 20)()
     L.b200z_debug_fast_prof(buf)
     reps = 5
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -59,6 +59,9 @@ def main():
     print(f"{os.environ.get('B200Z_LIB')}: {e0.elapsed_time(e1) / reps:.2f} ms per pass; clocks per unit {tot / k:.0f}")
     for i, name in enumerate(NAMES):
         print(f"  {name:28s} {buf[i] / k:9.0f}  {100.0 * buf[i] / tot:5.1f} %")
+    print("  waited at the closing barrier, mean over the 8 warps (clocks per unit; share of the phase):")
+    for j, (name, ph) in enumerate([("pass A", 4), ("pass A2", 5), ("pass A3 + scan", 7), ("pass C", 8), ("LZ77", 10)]):
+        print(f"  {name:28s} {buf[12 + j] / k / 8:9.0f}  {100.0 * buf[12 + j] / 8 / max(buf[ph], 1):5.1f} %")
 
 
 if __name__ == "__main__":
