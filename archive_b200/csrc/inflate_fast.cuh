@@ -778,7 +778,7 @@ __global__ void __launch_bounds__(fp::NTT, 2)
 k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__ in_off, const uint32_t *__restrict__ in_len,
                uint8_t *__restrict__ out_base, const uint64_t *__restrict__ out_off, const uint32_t *__restrict__ out_cap,
                uint32_t *__restrict__ out_len, int32_t *__restrict__ status, uint32_t *__restrict__ in_used, uint32_t n_units,
-               uint32_t *__restrict__ doneflag, uint32_t flag_stride) {
+               uint32_t *__restrict__ doneflag, uint32_t flag_stride, uint32_t *__restrict__ next_unit) {
   using namespace fp;
   FP_DYN_SMEM(fsmem);
   uint8_t *const smem = fsmem;
@@ -818,12 +818,12 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
     }
   }
   for (uint32_t i = tid; i < 2048u; i += NT) flags[i] = 0;
-  uint32_t next_u = blockIdx.x;  // (thread 0's copy is the one that counts)
+  // units come off a counter in global memory (zeroed by the launcher): a CTA that starts late -- behind a collective's
+  // kernel that holds part of an SM -- then simply takes fewer of them
   if (tid == 0) {
     fp_mbar_init(mbar, 1);
     ctl->ha_valid = 0;
-    fp_fetch_next(ctl, s_in, mbar, in_base, in_off, in_len, out_base, out_off, out_cap, n_units, next_u);
-        next_u += gridDim.x;
+    fp_fetch_next(ctl, s_in, mbar, in_base, in_off, in_len, out_base, out_off, out_cap, n_units, atomicAdd(next_unit, 1u));
   }
   uint32_t phase = 0;
 #ifdef FP_PROF
@@ -848,8 +848,7 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
       if (tid == 0) {
         doneflag[(size_t)unit * flag_stride] = 0;
         ctl->x_state = 1;
-        fp_fetch_next(ctl, s_in, mbar, in_base, in_off, in_len, out_base, out_off, out_cap, n_units, next_u);
-        next_u += gridDim.x;
+        fp_fetch_next(ctl, s_in, mbar, in_base, in_off, in_len, out_base, out_off, out_cap, n_units, atomicAdd(next_unit, 1u));
       }
       FP_ASYNC();  // (A)
       FP_ASYNC();  // (B)
@@ -1379,8 +1378,7 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
       ctl->x_wofs = wofs;
       ctl->lz_next = 0;
       // the staged input is dead: fetch the next unit behind the LZ77 pass
-      fp_fetch_next(ctl, s_in, mbar, in_base, in_off, in_len, out_base, out_off, out_cap, n_units, next_u);
-      next_u += gridDim.x;
+      fp_fetch_next(ctl, s_in, mbar, in_base, in_off, in_len, out_base, out_off, out_cap, n_units, atomicAdd(next_unit, 1u));
     }
     FP_ASYNC();  // (A)
     FP_TICK(9);

@@ -452,7 +452,7 @@ cudaError_t launch_inflate(const InflateBatch &b, cudaStream_t stream) {
     // when a batch is launched in quarters (profiles/r2_summary.md).
     const char *fe = getenv("B200Z_FAST");
     const int fast_on = fe ? atoi(fe) : 1;
-    if (fast_on && !b.count_only && b.ws.hist == 0 && b.ws.pieces != nullptr) {
+    if (fast_on && !b.count_only && b.ws.hist == 0 && b.ws.pieces != nullptr && b.ws.uscratch != nullptr) {
       static uint64_t attr_done = 0;  // one bit per device: function attributes belong to the device's context
       if (!((attr_done >> (cur_dev & 63)) & 1u)) {
         cudaError_t e = cudaFuncSetAttribute(k_inflate_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp::SMEM_BYTES);
@@ -467,9 +467,13 @@ cudaError_t launch_inflate(const InflateBatch &b, cudaStream_t stream) {
       if (spare < 0 || spare >= g_num_sms) spare = 0;
       uint64_t fblocks = (uint64_t)(g_num_sms - spare) * 2u;
       if (fblocks > b.n_units) fblocks = b.n_units;
+      // the unit counter: the first word of the exact kernels' scratch, which is dead until they run
+      uint32_t *next_unit = reinterpret_cast<uint32_t *>(b.ws.uscratch);
+      cudaError_t me = cudaMemsetAsync(next_unit, 0, sizeof(uint32_t), stream);
+      if (me != cudaSuccess) return me;
       k_inflate_fast<<<(unsigned)fblocks, fp::NTT, fp::SMEM_BYTES, stream>>>(b.in_base, b.in_off, b.in_len, b.out_base, b.out_off, b.out_cap,
                                                                         b.out_len, b.status, b.in_used, (uint32_t)b.n_units,
-                                                                        b.ws.pieces + 1, (uint32_t)PIECE_WORDS);
+                                                                        b.ws.pieces + 1, (uint32_t)PIECE_WORDS, next_unit);
       count_launch();
       cudaError_t e = cudaGetLastError();
       if (e != cudaSuccess) return e;

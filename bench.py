@@ -537,7 +537,14 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # the collective's kernel has to get onto the SMs BESIDE the decode of the next chunk (whose persistent CTAs would
+        # otherwise take every SM the moment the previous chunk drains): NCCL's stream gets the higher priority
+        opts = None
+        try:
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        except Exception:
+            pass
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
 
     from archive_b200 import _ffi, synth
     L = _ffi.ensure_init(local_rank)

@@ -41,7 +41,8 @@ extern "C" const uint32_t *emu_last_pieces() { return g_last_pieces.data(); }
 extern "C" int emu_inflate_fast(const uint8_t *in_base, const uint64_t *in_off, const uint32_t *in_len, uint8_t *out_base,
                                 const uint64_t *out_off, const uint32_t *out_cap, uint32_t *out_len, int32_t *status,
                                 uint32_t *in_used, uint32_t n_units, uint32_t blocks, uint32_t *flags) {
+  uint32_t next_unit = 0;
   B200Z_LAUNCH(k_inflate_fast, blocks, fp::NTT, 0, 0, in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, in_used,
-               n_units, flags, 1u);
+               n_units, flags, 1u, &next_unit);
   return 0;
 }
