@@ -31,6 +31,7 @@ static void set_err(const char *fmt, ...) {
 }
 
 static std::atomic<uint64_t> g_launches{0};
+static std::atomic<unsigned long long> g_bz2_fast_blocks{0}, g_bz2_exact_blocks{0};  // K7: blocks by the fast / the exact kernel
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 struct DevBuf {
@@ -1005,7 +1006,7 @@ static int bzip2_decode_impl(const uint8_t *in, size_t in_len, int verify, uint8
     struct A {
       unsigned long long *blk_bit, *end_bit, *block_out, *block_off;
       uint32_t *rec_val, *rec_pos, *n_rec, *nblock, *orig_ptr, *rnd, *chist, *tt, *seg_len, *seg_next, *seg_off, *slice_state,
-          *slice_out, *block_crc, *cycle_len;
+          *slice_out, *block_crc, *cycle_len, *fast;
       int32_t *status, *irregular;
       uint8_t *sym8, *raw;
       BzChainHost *chain;
@@ -1023,6 +1024,7 @@ static int bzip2_decode_impl(const uint8_t *in, size_t in_len, int verify, uint8
     a.irregular = c.take<int32_t>(nbk);
     a.block_crc = c.take<uint32_t>(nbk);
     a.cycle_len = c.take<uint32_t>(nbk);
+    a.fast = c.take<uint32_t>(nbk);
     a.chain = c.take<BzChainHost>(nbk);
     a.seg_len = c.take<uint32_t>((size_t)nbk * 4098);
     a.seg_next = c.take<uint32_t>((size_t)nbk * 4098);
@@ -1066,7 +1068,7 @@ static int bzip2_decode_impl(const uint8_t *in, size_t in_len, int verify, uint8
     e.nblock_max = nblock_max;
     // block k of this call uses slot k - k_lo of every per-block array
     e.rec_val = A.rec_val; e.rec_pos = A.rec_pos; e.n_rec = A.n_rec; e.nblock = A.nblock; e.orig_ptr = A.orig_ptr;
-    e.randomised = A.rnd; e.end_bit = A.end_bit; e.status = A.status;
+    e.randomised = A.rnd; e.end_bit = A.end_bit; e.status = A.status; e.fast_flag = A.fast;
     CU(bz2_launch_entropy(e, g.stream));
     const uint32_t m = k_hi - k_lo;
     auto fetch = [&]() -> int {
@@ -1081,6 +1083,14 @@ static int bzip2_decode_impl(const uint8_t *in, size_t in_len, int verify, uint8
     };
     rc = fetch();
     if (rc) return rc;
+    {
+      std::vector<uint32_t> h_fast(m);
+      CU(cudaMemcpy(h_fast.data(), A.fast, (size_t)m * 4, cudaMemcpyDeviceToHost));
+      unsigned long long nf = 0;
+      for (uint32_t v : h_fast) nf += v;
+      g_bz2_fast_blocks += nf;
+      g_bz2_exact_blocks += m - nf;
+    }
     // damaged blocks that the reference keeps decoding past a bad Huffman code (K7 status -3): decoded again the reference's
     // way, one thread each (bzip2_kernels.cu: k_bz2_entropy_literal); intact streams have none
     std::vector<uint32_t> quirk;
@@ -1921,6 +1931,11 @@ extern "C" {
 const char *b200z_version(void) { return "b200z 0.1 (sm_100a)"; }
 const char *b200z_last_error(void) { return t_err; }
 uint64_t b200z_launch_count(void) { return g_launches.load(); }
+// (debug, not part of the ABI) BZip2 candidate blocks decoded by k_bz2_entropy_fast / left to the exact kernel so far
+void b200z_debug_bz2_blocks(unsigned long long out[2]) {
+  out[0] = g_bz2_fast_blocks.load();
+  out[1] = g_bz2_exact_blocks.load();
+}
 
 int b200z_bzip2_decode(const uint8_t *in, size_t in_len, int verify, uint8_t *out, size_t out_cap, size_t *out_len) {
   int rc = require_init();

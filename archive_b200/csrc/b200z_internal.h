@@ -68,6 +68,7 @@ struct Bz2Entropy {  // K7, one warp per candidate block
   uint32_t *n_rec, *nblock, *orig_ptr, *randomised;
   unsigned long long *end_bit;
   int32_t *status;
+  uint32_t *fast_flag = nullptr;  // [n_blocks], may be null: 1 = the block was decoded by k_bz2_entropy_fast
 };
 struct Bz2Ibwt {  // K8 over the validated chain
   const void *chain;  // BzChain[n_chain] (device)

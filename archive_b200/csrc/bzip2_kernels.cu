@@ -17,6 +17,7 @@
 // bytes, a stable counting sort builds T, the single cycle of T is cut at ~4096 splitters and walked by one
 // thread per segment, and RLE1 + CRC are scans over a 5-state automaton / an associative CRC combine.
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "b200z_internal.h"
 #include "bz2_rnums.h"
@@ -108,6 +109,7 @@ struct BzSmem {
   uint8_t len[6][258];
   uint8_t minlen[6];
   uint8_t selector[BZ_MAX_SEL + 2];
+  __device__ __forceinline__ void set_sel(int i, uint8_t v) { selector[i] = v; }
   uint32_t mtfw[64];  // the MTF list, 4 entries per word (entry k = byte k%4 of word k/4)
   uint8_t seq2unseq[256];
 };
@@ -119,15 +121,160 @@ struct BzSmem {
 #define BZ_QUIRK (-3)   // _getMtfVal returned -1 after the first symbol: the reference does not look at that value and goes
                         // on with it (:387, :306) -- k_bz2_entropy_literal decodes such a block the reference's way
 
+// ---- block header (bzip2_decoder.dart:113-257): symbol map, selectors (MTF undone on the fly), code lengths, and
+// _hbCreateDecodeTables (:774-813) per table.  One thread; SM is the kernel's shared-memory block (seq2unseq, len, minlen,
+// perm, base, limit, set_sel).  Shared by the exact kernel and the fast one. ----
+struct BzHdr {
+  int n_groups, n_sel, alpha, n_in_use, err;
+  uint32_t optr, rnd;
+};
+template <class SM>
+__device__ void bz_parse_header(SM &S, BzBits &br, uint64_t blk_bit, uint64_t total_bits, BzHdr &h) {
+  int err = 0;
+  uint32_t rnd = 0, optr = 0;
+  int n_groups = 0, n_sel = 0, alpha = 0, n_in_use = 0;
+  // header: after the 48-bit magic and the 32-bit stored CRC (bzip2_decoder.dart:113-218)
+  br.seek(blk_bit + 48 + 32);
+  rnd = br.get(1);
+  optr = br.get(8);
+  optr = (optr << 8) | br.get(8);
+  optr = (optr << 8) | br.get(8);
+  uint32_t used16 = br.get(16);
+  for (int i = 0; i < 16; ++i) {
+    if (used16 & (0x8000u >> i)) {
+      uint32_t m = br.get(16);
+      for (int j = 0; j < 16; ++j)
+        if (m & (0x8000u >> j)) S.seq2unseq[n_in_use++] = (uint8_t)(i * 16 + j);
+    }
+  }
+  if (n_in_use == 0) err = BZ_DATA;
+  alpha = n_in_use + 2;
+  if (!err) {
+    n_groups = (int)br.get(3);
+    if (n_groups < 2 || n_groups > 6) err = BZ_DATA;
+  }
+  if (!err) {
+    n_sel = (int)br.get(15);
+    if (n_sel < 1) err = BZ_DATA;
+  }
+  if (!err) {
+    uint8_t pos[6];
+    for (int i = 0; i < n_groups; ++i) pos[i] = (uint8_t)i;
+    for (int i = 0; i < n_sel && !err; ++i) {
+      int j = 0;
+      while (br.get(1)) {
+        j++;
+        if (j >= n_groups) {
+          err = BZ_DATA;
+          break;
+        }
+      }
+      if (err) break;
+      if (i >= BZ_MAX_SEL) {  // _selectorMtf[i]: RangeError (bzip2_decoder.dart:168)
+        err = BZ_THROW;
+        break;
+      }
+      // undo the selector MTF on the fly (:172-186): same result as the reference's second loop
+      uint8_t tmp = pos[j];
+      for (int v = j; v > 0; --v) pos[v] = pos[v - 1];
+      pos[0] = tmp;
+      S.set_sel(i, tmp);
+      if (br.bitpos() > total_bits) {
+        err = BZ_THROW;
+        break;
+      }
+    }
+  }
+  if (!err) {
+    for (int t = 0; t < n_groups && !err; ++t) {
+      int c = (int)br.get(5);
+      for (int i = 0; i < alpha && !err; ++i) {
+        for (;;) {
+          if (c < 1 || c > 20) {
+            err = BZ_DATA;
+            break;
+          }
+          if (br.get(1) == 0) break;
+          if (br.get(1) == 0) c++;
+          else c--;
+        }
+        S.len[t][i] = (uint8_t)c;
+      }
+      if (br.bitpos() > total_bits) err = BZ_THROW;
+    }
+  }
+  if (!err) {
+    // _hbCreateDecodeTables (:774-813) per table
+    for (int t = 0; t < n_groups; ++t) {
+      int mn = 32, mx = 0;
+      for (int i = 0; i < alpha; ++i) {
+        int l = S.len[t][i];
+        mx = l > mx ? l : mx;
+        mn = l < mn ? l : mn;
+      }
+      S.minlen[t] = (uint8_t)mn;
+      for (int i = 0; i < 258; ++i) S.perm[t][i] = 0;  // Int32List(bzMaxAlphaSize) starts zeroed (:234)
+      int pp = 0;
+      for (int i = mn; i <= mx; i++)
+        for (int j = 0; j < alpha; j++)
+          if (S.len[t][j] == i) S.perm[t][pp++] = (uint16_t)j;
+      int32_t *base = S.base[t], *limit = S.limit[t];
+      for (int i = 0; i < 23; i++) base[i] = 0;
+      for (int i = 0; i < alpha; i++) base[S.len[t][i] + 1]++;
+      for (int i = 1; i < 23; i++) base[i] += base[i - 1];
+      for (int i = 0; i < 23; i++) limit[i] = 0;
+      int32_t vec = 0;
+      for (int i = mn; i <= mx; i++) {
+        vec += (base[i + 1] - base[i]);
+        limit[i] = vec - 1;
+        vec <<= 1;
+      }
+      for (int i = mn + 1; i <= mx; i++) base[i] = ((limit[i - 1] + 1) << 1) - base[i];
+    }
+  }
+  h.n_groups = n_groups;
+  h.n_sel = n_sel;
+  h.alpha = alpha;
+  h.n_in_use = n_in_use;
+  h.err = err;
+  h.optr = optr;
+  h.rnd = rnd;
+}
+
+// The decode LUTs, filled by `nthr` threads.  Entry for a 10-bit prefix = what _getMtfVal's limit/base walk (:747-771)
+// decides from those bits alone, so any code-length set (valid or not) decodes exactly as in the reference.
+template <class SM>
+__device__ void bz_fill_luts(SM &S, int n_groups, int tid, int nthr) {
+  for (int t = 0; t < n_groups; ++t) {
+    const int mn = S.minlen[t];
+    for (int v = tid; v < (1 << BZ_LUT_BITS); v += nthr) {
+      uint16_t e = 0;
+      for (int zn = mn; zn <= BZ_LUT_BITS; ++zn) {
+        if (zn < 1) continue;
+        int32_t zvec = v >> (BZ_LUT_BITS - zn);
+        if (zvec <= S.limit[t][zn]) {
+          int32_t idx = zvec - S.base[t][zn];
+          if (idx < 0 || idx >= 258) e = (uint16_t)((0x3ff << 5) | zn);  // data error marker
+          else e = (uint16_t)((S.perm[t][idx] << 5) | zn);
+          break;
+        }
+      }
+      S.lut[t][v] = e;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(32)
 k_bz2_entropy(const uint32_t *__restrict__ words, uint64_t n_bytes, const unsigned long long *__restrict__ blk_bit,
               uint32_t n_blocks, uint32_t nblock_max, uint32_t *__restrict__ rec_val, uint32_t *__restrict__ rec_pos,
               uint32_t *__restrict__ n_rec, uint32_t *__restrict__ nblock_out, uint32_t *__restrict__ orig_ptr,
-              uint32_t *__restrict__ randomised, unsigned long long *__restrict__ end_bit, int32_t *__restrict__ status) {
+              uint32_t *__restrict__ randomised, unsigned long long *__restrict__ end_bit, int32_t *__restrict__ status,
+              int only_redo) {
   extern __shared__ __align__(16) uint8_t smraw[];
   BzSmem &S = *reinterpret_cast<BzSmem *>(smraw);
   const uint32_t b = blockIdx.x;
   if (b >= n_blocks) return;
+  if (only_redo && status[b] != -9) return;  // (BZ_REDO) the fast kernel has decoded this block
   const int lane = threadIdx.x;
   const uint64_t total_bits = n_bytes * 8;
   __shared__ int s_groups, s_alpha, s_err, s_nsel, s_inuse;
@@ -142,105 +289,15 @@ k_bz2_entropy(const uint32_t *__restrict__ words, uint64_t n_bytes, const unsign
   int n_groups = 0, n_sel = 0, alpha = 0, n_in_use = 0;
 
   if (lane == 0) {
-    // header: after the 48-bit magic and the 32-bit stored CRC (bzip2_decoder.dart:113-218)
-    br.seek(blk_bit[b] + 48 + 32);
-    rnd = br.get(1);
-    optr = br.get(8);
-    optr = (optr << 8) | br.get(8);
-    optr = (optr << 8) | br.get(8);
-    uint32_t used16 = br.get(16);
-    for (int i = 0; i < 16; ++i) {
-      if (used16 & (0x8000u >> i)) {
-        uint32_t m = br.get(16);
-        for (int j = 0; j < 16; ++j)
-          if (m & (0x8000u >> j)) S.seq2unseq[n_in_use++] = (uint8_t)(i * 16 + j);
-      }
-    }
-    if (n_in_use == 0) err = BZ_DATA;
-    alpha = n_in_use + 2;
-    if (!err) {
-      n_groups = (int)br.get(3);
-      if (n_groups < 2 || n_groups > 6) err = BZ_DATA;
-    }
-    if (!err) {
-      n_sel = (int)br.get(15);
-      if (n_sel < 1) err = BZ_DATA;
-    }
-    if (!err) {
-      uint8_t pos[6];
-      for (int i = 0; i < n_groups; ++i) pos[i] = (uint8_t)i;
-      for (int i = 0; i < n_sel && !err; ++i) {
-        int j = 0;
-        while (br.get(1)) {
-          j++;
-          if (j >= n_groups) {
-            err = BZ_DATA;
-            break;
-          }
-        }
-        if (err) break;
-        if (i >= BZ_MAX_SEL) {  // _selectorMtf[i]: RangeError (bzip2_decoder.dart:168)
-          err = BZ_THROW;
-          break;
-        }
-        // undo the selector MTF on the fly (:172-186): same result as the reference's second loop
-        uint8_t tmp = pos[j];
-        for (int v = j; v > 0; --v) pos[v] = pos[v - 1];
-        pos[0] = tmp;
-        S.selector[i] = tmp;
-        if (br.bitpos() > total_bits) {
-          err = BZ_THROW;
-          break;
-        }
-      }
-    }
-    if (!err) {
-      for (int t = 0; t < n_groups && !err; ++t) {
-        int c = (int)br.get(5);
-        for (int i = 0; i < alpha && !err; ++i) {
-          for (;;) {
-            if (c < 1 || c > 20) {
-              err = BZ_DATA;
-              break;
-            }
-            if (br.get(1) == 0) break;
-            if (br.get(1) == 0) c++;
-            else c--;
-          }
-          S.len[t][i] = (uint8_t)c;
-        }
-        if (br.bitpos() > total_bits) err = BZ_THROW;
-      }
-    }
-    if (!err) {
-      // _hbCreateDecodeTables (:774-813) per table
-      for (int t = 0; t < n_groups; ++t) {
-        int mn = 32, mx = 0;
-        for (int i = 0; i < alpha; ++i) {
-          int l = S.len[t][i];
-          mx = l > mx ? l : mx;
-          mn = l < mn ? l : mn;
-        }
-        S.minlen[t] = (uint8_t)mn;
-        for (int i = 0; i < 258; ++i) S.perm[t][i] = 0;  // Int32List(bzMaxAlphaSize) starts zeroed (:234)
-        int pp = 0;
-        for (int i = mn; i <= mx; i++)
-          for (int j = 0; j < alpha; j++)
-            if (S.len[t][j] == i) S.perm[t][pp++] = (uint16_t)j;
-        int32_t *base = S.base[t], *limit = S.limit[t];
-        for (int i = 0; i < 23; i++) base[i] = 0;
-        for (int i = 0; i < alpha; i++) base[S.len[t][i] + 1]++;
-        for (int i = 1; i < 23; i++) base[i] += base[i - 1];
-        for (int i = 0; i < 23; i++) limit[i] = 0;
-        int32_t vec = 0;
-        for (int i = mn; i <= mx; i++) {
-          vec += (base[i + 1] - base[i]);
-          limit[i] = vec - 1;
-          vec <<= 1;
-        }
-        for (int i = mn + 1; i <= mx; i++) base[i] = ((limit[i - 1] + 1) << 1) - base[i];
-      }
-    }
+    BzHdr h;
+    bz_parse_header(S, br, blk_bit[b], total_bits, h);
+    n_groups = h.n_groups;
+    n_sel = h.n_sel;
+    alpha = h.alpha;
+    n_in_use = h.n_in_use;
+    err = h.err;
+    optr = h.optr;
+    rnd = h.rnd;
     s_groups = n_groups;
     s_alpha = alpha;
     s_err = err;
@@ -254,25 +311,7 @@ k_bz2_entropy(const uint32_t *__restrict__ words, uint64_t n_bytes, const unsign
   n_groups = s_groups;
   alpha = s_alpha;
   if (s_err == 0) {
-    // The whole warp fills the LUTs.  Entry for a 10-bit prefix = what _getMtfVal's limit/base walk (:747-771)
-    // decides from those bits alone, so any code-length set (valid or not) decodes exactly as in the reference.
-    for (int t = 0; t < n_groups; ++t) {
-      const int mn = S.minlen[t];
-      for (int v = lane; v < (1 << BZ_LUT_BITS); v += 32) {
-        uint16_t e = 0;
-        for (int zn = mn; zn <= BZ_LUT_BITS; ++zn) {
-          if (zn < 1) continue;
-          int32_t zvec = v >> (BZ_LUT_BITS - zn);
-          if (zvec <= S.limit[t][zn]) {
-            int32_t idx = zvec - S.base[t][zn];
-            if (idx < 0 || idx >= 258) e = (uint16_t)((0x3ff << 5) | zn);  // data error marker
-            else e = (uint16_t)((S.perm[t][idx] << 5) | zn);
-            break;
-          }
-        }
-        S.lut[t][v] = e;
-      }
-    }
+    bz_fill_luts(S, n_groups, lane, 32);
   }
   __syncwarp();
   // From here on EVERY lane walks the same bits with the same tables (shared-memory reads of one address are broadcasts),
@@ -433,6 +472,403 @@ k_bz2_entropy(const uint32_t *__restrict__ words, uint64_t n_bytes, const unsign
   randomised[b] = rnd;
   end_bit[b] = endp;
   status[b] = err;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K7f `k_bz2_entropy_fast`: the entropy stage of a CLEAN block without its serial chain per symbol.
+//
+// _getMtfVal (:732-772) is a chain of ~700 k dependent table look-ups per 900 kB block, the MTF list (:331-378) a second
+// one; the exact kernel above walks both with one warp (~130 ms per block on a B200).  Here a CTA of two warps splits the
+// block into batches of 32 selector groups (50 symbols each) and pipelines them:
+//   * the WALKER (warp 0) finds where every group starts.  For a group that starts at bit s with table t, lane l looks up
+//     the code at each of the bit offsets s + 8l .. s + 8l + 7 (E[b] = symbol, length: 256 look-ups at once, no chain), then
+//     J4[b] = where four symbols from b end (four dependent reads of E, eight independent chains per lane).  The only serial
+//     part left is ~13 hops over J4 per group; lane i then re-walks the four symbols behind mark i and writes them out.  A
+//     group longer than the 256-bit window takes another round from where the chain left it.
+//   * the WORKER (warp 1) undoes move-to-front for the previous batch, one group per lane: every lane runs its 50 symbols
+//     against a list that starts as the identity and records which INITIAL position each symbol refers to (a symbolic
+//     list, word-wise shifts in shared memory); the real list is then carried through the 32 groups by composing each
+//     lane's permutation (32 lanes gather), which also resolves the references.  RUNA/RUNB runs, record indices and block
+//     positions are prefix sums over per-lane summaries (a run may straddle two lanes: it belongs to the lane it ends in).
+// Output = the exact kernel's records.  Anything that is not an ordinary block -- header errors, an invalid code on the
+// parse, a run of more than 21 symbols, a block that overflows, selectors that run out, bits past the end of the input,
+// origPtr out of range -- sets status BZ_REDO and the exact kernel decodes the block again with the reference's verdicts.
+// ---------------------------------------------------------------------------------------------
+#define BZ_REDO (-9)
+constexpr int BZF_W = 256;  // bits of the walker's window
+constexpr uint32_t BZF_BADSYM = 0x3ffu;
+
+struct BzFast {
+  uint16_t lut[6][1 << BZ_LUT_BITS];
+  int32_t limit[6][24];
+  int32_t base[6][24];
+  uint16_t perm[6][258];
+  uint8_t len[6][258];
+  uint8_t minlen[8];
+  uint8_t selp[(BZ_MAX_SEL + 3) / 2 + 3];  // selectors, two per byte
+  uint8_t seq2unseq[256];
+  __device__ __forceinline__ void set_sel(int i, uint8_t v) {
+    const uint8_t c = selp[i >> 1];
+    selp[i >> 1] = (i & 1) ? (uint8_t)((c & 0x0fu) | (v << 4)) : (uint8_t)((c & 0xf0u) | v);
+  }
+  __device__ __forceinline__ int get_sel(int i) const { return (selp[i >> 1] >> ((i & 1) * 4)) & 15; }
+  uint16_t E[BZF_W];       // walker: (symbol << 5 | code length) of the code that starts at window bit b
+  uint16_t J4[BZF_W];      // walker: (position | symbols << 10) after up to four symbols from b (fewer: the window ended)
+  uint16_t syms[2][32][50];  // a batch: the symbols of 32 groups
+  uint8_t cnt[2][32];        // symbols in each group of the batch (50; fewer in the block's last group)
+  uint32_t mtf[64][32];      // worker: word w of lane l's symbolic list
+  uint8_t cur[256];          // worker: the block's MTF list at the start of the group being resolved
+  int ng[2], last[2];        // groups in the batch; the batch ends with the block's end-of-block code
+  int redo;
+  unsigned long long end_bit, hdr_bitpos;
+  BzHdr hdr;
+};
+static_assert(sizeof(BzFast) <= 45 * 1024, "five CTAs per SM");
+
+__global__ void __launch_bounds__(64)
+k_bz2_entropy_fast(const uint32_t *__restrict__ words, uint64_t n_bytes, const unsigned long long *__restrict__ blk_bit,
+                   uint32_t n_blocks, uint32_t nblock_max, uint32_t *__restrict__ rec_val, uint32_t *__restrict__ rec_pos,
+                   uint32_t *__restrict__ n_rec, uint32_t *__restrict__ nblock_out, uint32_t *__restrict__ orig_ptr,
+                   uint32_t *__restrict__ randomised, unsigned long long *__restrict__ end_bit, int32_t *__restrict__ status,
+                   uint32_t *__restrict__ fast_flag) {
+  __shared__ BzFast S;
+  const uint32_t b = blockIdx.x;
+  if (b >= n_blocks) return;
+  if (fast_flag && threadIdx.x == 0) fast_flag[b] = 0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned FULLW = 0xffffffffu;
+  const uint64_t total_bits = n_bytes * 8, n_words = (n_bytes + 3) >> 2;
+  if (tid == 0) {
+    BzBits br;
+    br.w = words;
+    br.n_words = n_words;
+    BzHdr h;
+    bz_parse_header(S, br, blk_bit[b], total_bits, h);
+    S.hdr = h;
+    S.hdr_bitpos = br.bitpos();
+    S.end_bit = 0;
+    S.redo = (h.err != 0 || br.bitpos() > total_bits) ? 1 : 0;
+  }
+  __syncthreads();
+  if (S.redo) {
+    if (tid == 0) status[b] = BZ_REDO;
+    return;
+  }
+  const BzHdr h = S.hdr;
+  bz_fill_luts(S, h.n_groups, tid, 64);
+  for (int i = tid; i < 256; i += 64) S.cur[i] = (uint8_t)i;
+  __syncthreads();
+
+  const uint32_t eob = (uint32_t)h.n_in_use + 1u;
+  // walker state (warp 0; the same in every lane)
+  uint64_t s = S.hdr_bitpos;  // bit the next group starts at
+  int g = 0;                  // its number
+  // worker state (warp 1; the same in every lane): what the exact kernel calls nrec, nblock, run_n, run_es, front
+  uint32_t st_nrec = 0, st_nblock = 0, st_n = 0, st_v = 0, st_front = 0;
+  uint32_t *const rv = rec_val + (size_t)b * nblock_max;
+  uint32_t *const rp = rec_pos + (size_t)b * nblock_max;
+
+  bool prev_last = false;
+  for (int bt = 0;; ++bt) {
+    const int buf = bt & 1;
+    if (warp == 0) {
+      if (!prev_last) {
+        // ---------------- walker: the groups of batch bt ----------------
+        int ngb = 0;
+        bool last = false, redo = false;
+        for (; ngb < 32 && !last && !redo; ++ngb, ++g) {
+          if (g >= h.n_sel) {  // the selectors ran out before the end-of-block code
+            redo = true;
+            break;
+          }
+          const int t = S.get_sel(g);
+          if (lane == 0 && (s >> 5) + 96 < n_words) asm volatile("prefetch.global.L1 [%0];" ::"l"(words + (s >> 5) + 96));
+          int need = 50, outi = 0;
+          while (need > 0 && !last && !redo) {
+            // E over [s, s + 256): my 64-bit window starts at byte (s >> 3) + lane
+            {
+              const uint64_t byte0 = (s >> 3) + (uint64_t)lane, w0 = byte0 >> 2;
+              const uint32_t bsh = (uint32_t)(byte0 & 3u) * 8u;
+              const uint32_t a0 = w0 < n_words ? __byte_perm(__ldg(words + w0), 0, 0x0123) : 0u;
+              const uint32_t a1 = w0 + 1 < n_words ? __byte_perm(__ldg(words + w0 + 1), 0, 0x0123) : 0u;
+              const uint32_t a2 = w0 + 2 < n_words ? __byte_perm(__ldg(words + w0 + 2), 0, 0x0123) : 0u;
+              const uint64_t win = ((uint64_t)__funnelshift_l(a1, a0, bsh) << 32) | __funnelshift_l(a2, a1, bsh);
+              const int o0 = (int)(s & 7u);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const uint64_t x = win << (o0 + j);
+                uint32_t e = S.lut[t][(uint32_t)(x >> (64 - BZ_LUT_BITS))];
+                if ((e & 31u) == 0u) {  // longer than the LUT: the limit / base walk from there on (:747-771)
+                  int zn = S.minlen[t] > BZ_LUT_BITS + 1 ? S.minlen[t] : BZ_LUT_BITS + 1;
+                  e = (BZF_BADSYM << 5) | 1u;
+                  for (; zn <= 20; ++zn) {
+                    const int32_t zvec = (int32_t)(x >> (64 - zn));
+                    if (zvec <= S.limit[t][zn]) {
+                      const int32_t idx = zvec - S.base[t][zn];
+                      if (idx >= 0 && idx < 258) e = ((uint32_t)S.perm[t][idx] << 5) | (uint32_t)zn;
+                      break;
+                    }
+                  }
+                }
+                S.E[8 * lane + j] = (uint16_t)e;
+              }
+            }
+            __syncwarp();
+            // J4: up to four symbols on from each bit of the window (eight independent chains per lane)
+            {
+              uint32_t p[8], c[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                p[j] = 8u * lane + j;
+                c[j] = 0;
+              }
+#pragma unroll
+              for (int hop = 0; hop < 4; ++hop) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  if (p[j] < (uint32_t)BZF_W) {
+                    p[j] += S.E[p[j]] & 31u;
+                    c[j]++;
+                  }
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) S.J4[8 * lane + j] = (uint16_t)(p[j] | (c[j] << 10));
+            }
+            __syncwarp();
+            // the chain: one hop per four symbols; lane i keeps mark i
+            int pos = 0, nm = 0, mark = 0;
+            while (pos < BZF_W && 4 * nm < need) {
+              if (lane == nm) mark = pos;
+              nm++;
+              pos = S.J4[pos] & 1023;
+            }
+            // lane i < nm: the (up to four) symbols behind its mark
+            int c = 0, p = mark;
+            bool sawe = false, sawbad = false;
+            if (lane < nm) {
+              const int hmax = need - 4 * lane < 4 ? need - 4 * lane : 4;
+              uint16_t *dst = &S.syms[buf][ngb][outi + 4 * lane];
+              while (c < hmax && p < BZF_W) {
+                const uint32_t e = S.E[p];
+                const uint32_t sym = e >> 5;
+                if (sym == BZF_BADSYM) {
+                  sawbad = true;
+                  break;
+                }
+                dst[c] = (uint16_t)sym;
+                c++;
+                p += (int)(e & 31u);
+                if (sym == eob) {
+                  sawe = true;
+                  break;
+                }
+              }
+            }
+            const unsigned em = __ballot_sync(FULLW, sawe), bm = __ballot_sync(FULLW, sawbad);
+            int src = nm - 1;
+            if (em) {
+              src = __ffs((int)em) - 1;
+              last = true;
+              if (bm & ((2u << src) - 1u)) redo = true;
+            } else if (bm) {
+              redo = true;
+            }
+            const int tot = 4 * src + __shfl_sync(FULLW, c, src);
+            s += (uint64_t)__shfl_sync(FULLW, p, src);
+            outi += tot;
+            need -= tot;
+            __syncwarp();
+          }
+          if (lane == 0) S.cnt[buf][ngb] = (uint8_t)(last ? outi - 1 : outi);  // without the end-of-block code
+        }
+        if (lane == 0) {
+          S.ng[buf] = ngb;
+          S.last[buf] = last ? 1 : 0;
+          if (last) S.end_bit = s;
+          if (redo) S.redo = 1;
+        }
+      }
+    } else if (bt > 0) {
+      // ---------------- worker: batch bt - 1 ----------------
+      const int wb = buf ^ 1;
+      const int ngb = S.ng[wb];
+      const bool lastb = S.last[wb] != 0;
+      bool lbad = false;
+      // (1) my group against a list that starts as the identity: symbols become references to initial positions
+      uint32_t lead_n = 0, lead_v = 0, trail_n = 0, trail_v = 0, recs_mid = 0, adv_mid = 0;
+      bool allrun = true;
+      int last_idx = -1, hiw = 0;
+      const int mycnt = lane < ngb ? (int)S.cnt[wb][lane] : 0;
+      uint16_t *const sy = S.syms[wb][lane];
+      {
+        uint32_t rn = 0, rvv = 0;
+        for (int k = 0; k < mycnt; ++k) {
+          const uint32_t sym = sy[k];
+          if (sym <= 1u) {
+            if (rn >= 21u) lbad = true;  // N >= 2*1024*1024 (:291)
+            else rvv += (sym + 1u) << rn;
+            rn++;
+            continue;
+          }
+          if (allrun) {
+            lead_n = rn;
+            lead_v = rvv;
+            allrun = false;
+          } else if (rn) {
+            recs_mid++;
+            adv_mid += rvv;
+          }
+          rn = 0;
+          rvv = 0;
+          recs_mid++;
+          adv_mid++;
+          last_idx = k;
+          const uint32_t nn = sym - 1u, wn = nn >> 2, bn = nn & 3u;
+          for (; hiw <= (int)wn; ++hiw) S.mtf[hiw][lane] = 0x03020100u + 0x04040404u * (uint32_t)hiw;
+          const uint32_t top = S.mtf[wn][lane];
+          const uint32_t uc = (top >> (8u * bn)) & 0xffu;
+          uint32_t carry = uc;
+          for (uint32_t w = 0; w < wn; ++w) {
+            const uint32_t tw = S.mtf[w][lane];
+            S.mtf[w][lane] = (tw << 8) | carry;
+            carry = tw >> 24;
+          }
+          const uint32_t mlow = bn == 3u ? 0xffffffffu : ((1u << (8u * (bn + 1u))) - 1u);
+          S.mtf[wn][lane] = (top & ~mlow) | (((top << 8) | carry) & mlow);
+          sy[k] = (uint16_t)(0x8000u | uc);
+        }
+        if (allrun) {
+          lead_n = rn;
+          lead_v = rvv;
+        } else {
+          trail_n = rn;
+          trail_v = rvv;
+        }
+      }
+      __syncwarp();
+      // (2) the real list, group by group: resolve the group's references, then list'[i] = list[P[i]]
+      for (int gi = 0; gi < ngb; ++gi) {
+        const int cg = (int)S.cnt[wb][gi];
+        const int hib = __shfl_sync(FULLW, hiw, gi) * 4;  // bytes of the group's list that may have moved
+        for (int k = lane; k < cg; k += 32) {
+          const uint32_t v = S.syms[wb][gi][k];
+          if (v & 0x8000u) S.syms[wb][gi][k] = (uint16_t)(0x8000u | S.cur[v & 0xffu]);
+        }
+        uint8_t nv[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+          const int i = lane + 32 * m;
+          nv[m] = 0;
+          if (i < hib) nv[m] = S.cur[(S.mtf[i >> 2][gi] >> (8 * (i & 3))) & 0xffu];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+          const int i = lane + 32 * m;
+          if (i < hib) S.cur[i] = nv[m];
+        }
+        __syncwarp();
+      }
+      // (3) every lane's starting state: records, block position, the open run and the list's front
+      const uint32_t lastv = last_idx >= 0 ? (uint32_t)(sy[last_idx] & 0xffu) : 0u;
+      uint32_t i_nrec = 0, i_nblock = 0, i_n = 0, i_v = 0, i_front = 0;
+      for (int gi = 0; gi < ngb; ++gi) {
+        if (lane == gi) {
+          i_nrec = st_nrec;
+          i_nblock = st_nblock;
+          i_n = st_n;
+          i_v = st_v;
+          i_front = st_front;
+        }
+        const bool ar = __shfl_sync(FULLW, (int)allrun, gi) != 0;
+        const uint32_t ln = __shfl_sync(FULLW, lead_n, gi), lv = __shfl_sync(FULLW, lead_v, gi);
+        if (st_n + ln > 21u) {
+          lbad = true;
+          break;
+        }
+        if (ar) {
+          st_v += lv << st_n;
+          st_n += ln;
+        } else {
+          if (st_n + ln) {
+            st_nrec++;
+            st_nblock += st_v + (lv << st_n);
+          }
+          st_nrec += __shfl_sync(FULLW, recs_mid, gi);
+          st_nblock += __shfl_sync(FULLW, adv_mid, gi);
+          st_n = __shfl_sync(FULLW, trail_n, gi);
+          st_v = __shfl_sync(FULLW, trail_v, gi);
+          st_front = __shfl_sync(FULLW, lastv, gi);
+        }
+      }
+      if (lastb && st_n) {  // the run that the end-of-block code closes (:306-321)
+        st_nrec++;
+        st_nblock += st_v;
+        st_n = 0;
+        st_v = 0;
+      }
+      // (4) the records of my group (:276-388 with the state above)
+      if (lane < ngb && !lbad) {
+        uint32_t nrec = i_nrec, nblock = i_nblock, rn = i_n, rvv = i_v, front = i_front;
+        for (int k = 0; k <= mycnt; ++k) {
+          const bool fin = k == mycnt;  // past my last symbol: only the block's last group has something to do here
+          if (fin && !(lastb && lane == ngb - 1)) break;
+          const uint32_t v = fin ? 0xffffu : (uint32_t)sy[k];
+          if (v <= 1u) {
+            rvv += (v + 1u) << rn;
+            rn++;
+            continue;
+          }
+          if (rn) {
+            if (nblock + rvv > nblock_max) {  // (:313-316)
+              lbad = true;
+              break;
+            }
+            rv[nrec] = (rvv << 8) | S.seq2unseq[front];
+            rp[nrec] = nblock;
+            nrec++;
+            nblock += rvv;
+            rn = 0;
+            rvv = 0;
+          }
+          if (fin) break;
+          if (nblock >= nblock_max) {  // (:326-329)
+            lbad = true;
+            break;
+          }
+          front = v & 0xffu;
+          rv[nrec] = (1u << 8) | S.seq2unseq[front];
+          rp[nrec] = nblock;
+          nrec++;
+          nblock++;
+        }
+      }
+      if (__any_sync(FULLW, lbad) && lane == 0) S.redo = 1;
+    }
+    __syncthreads();
+    const bool redo = S.redo != 0, cur_last = S.last[buf] != 0;
+    __syncthreads();
+    if (redo) {
+      if (tid == 0) status[b] = BZ_REDO;
+      return;
+    }
+    if (prev_last) break;  // the worker has just finished the block's last batch
+    prev_last = cur_last;
+  }
+  if (tid == 32) {
+    const unsigned long long endp = S.end_bit;
+    if (h.optr >= st_nblock || endp > total_bits) {  // (:399-402), a read past the end: the exact kernel's verdicts
+      status[b] = BZ_REDO;
+    } else {
+      n_rec[b] = st_nrec;
+      nblock_out[b] = st_nblock;
+      orig_ptr[b] = h.optr;
+      randomised[b] = h.rnd;
+      end_bit[b] = endp;
+      status[b] = BZ_OK;
+      if (fast_flag) fast_flag[b] = 1;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1238,9 +1674,19 @@ cudaError_t bz2_launch_entropy(const Bz2Entropy &a, cudaStream_t s) {
     attr = true;
   }
   if (a.n_blocks == 0) return cudaSuccess;
+  // clean blocks by the two-warp pipeline, whatever it leaves (status BZ_REDO) by the exact kernel; B200Z_BZ2_FAST=0: the
+  // exact kernel only (read at every launch)
+  const char *fe = getenv("B200Z_BZ2_FAST");
+  const int fast = !(fe && fe[0] == '0');
+  if (fast) {
+    k_bz2_entropy_fast<<<a.n_blocks, 64, 0, s>>>(a.words, a.n_bytes, a.blk_bit, a.n_blocks, a.nblock_max, a.rec_val, a.rec_pos,
+                                                 a.n_rec, a.nblock, a.orig_ptr, a.randomised, a.end_bit, a.status,
+                                                 a.fast_flag);
+    count_launch();
+  }
   k_bz2_entropy<<<a.n_blocks, 32, sizeof(BzSmem), s>>>(a.words, a.n_bytes, a.blk_bit, a.n_blocks, a.nblock_max, a.rec_val,
                                                        a.rec_pos, a.n_rec, a.nblock, a.orig_ptr, a.randomised, a.end_bit,
-                                                       a.status);
+                                                       a.status, fast);
   count_launch();
   return cudaGetLastError();
 }

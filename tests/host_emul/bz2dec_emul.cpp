@@ -17,7 +17,8 @@ void count_launch() {}
 #include <vector>
 
 using namespace b200z;
-static uint32_t g_last_quirk = 0;
+static uint32_t g_last_quirk = 0, g_last_fast = 0;
+extern "C" uint32_t emu_bzip2_last_fast() { return g_last_fast; }  // blocks of the last call that k_bz2_entropy_fast finished
 extern "C" uint32_t emu_bzip2_last_quirk() { return g_last_quirk; }  // blocks of the last call that took the literal path
 
 static uint32_t be32_at(const uint8_t *in, size_t n, uint64_t bit) {
@@ -86,7 +87,11 @@ extern "C" int emu_bzip2_blocks(const uint8_t *in, size_t in_len, uint8_t *out, 
     e.nblock_max = nblock_max;
     e.rec_val = rec_val.data(); e.rec_pos = rec_pos.data(); e.n_rec = n_rec.data(); e.nblock = nblock.data();
     e.orig_ptr = orig_ptr.data(); e.randomised = rnd.data(); e.end_bit = end_bit.data(); e.status = status.data();
+    std::vector<uint32_t> fastf(nb, 0u);
+    e.fast_flag = fastf.data();
     if (bz2_launch_entropy(e, nullptr) != cudaSuccess) return -9;
+    g_last_fast = 0;
+    for (uint32_t k = 0; k < nb; ++k) g_last_fast += fastf[k];
     std::vector<uint32_t> quirk;  // as in b200z_api.cu: damaged blocks the reference keeps decoding
     for (uint32_t k = 0; k < nb; ++k)
       if (status[k] == -3) quirk.push_back(k);

@@ -210,6 +210,11 @@ def emul_bzip2_last_quirk() -> int:
     return int(_BD.emu_bzip2_last_quirk()) if _BD is not None else 0
 
 
+def emul_bzip2_last_fast() -> int:
+    """Blocks of the last emul_bzip2_decode call that k_bz2_entropy_fast finished (the rest went to the exact kernel)."""
+    return int(_BD.emu_bzip2_last_fast()) if _BD is not None else 0
+
+
 _DE = None
 
 

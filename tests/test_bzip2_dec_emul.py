@@ -178,3 +178,25 @@ def test_fuzz_damage():
             seen["throw"] += st == orc.THROW
             seen["ok"] += st == orc.OK
     assert all(seen.values()), seen  # every path of interest was exercised
+
+
+def test_fast_kernel_takes_clean_blocks(monkeypatch):
+    """k_bz2_entropy_fast (two-warp pipeline: parallel bit walk + symbolic move-to-front) must finish every clean block --
+    and the exact kernel alone (B200Z_BZ2_FAST=0) must still give the same bytes."""
+    from archive_b200 import synth
+    rng = random.Random(5)
+    d1 = synth.text(260_000, stream=11).tobytes()
+    cases = [(d1, 1, 3), (bytes(rng.getrandbits(8) for _ in range(150000)), 1, 2), (b"ab" * 60000, 9, 1),
+             (bytes(range(256)) * 500, 9, 1), (bytes([7]) * 300000, 9, 1), (b"x", 9, 1),
+             (b"".join(bytes([rng.randrange(6)]) * rng.choice([1, 2, 3, 4, 5, 7, 50, 255, 300, 70000]) for _ in range(400)), 9, None)]
+    for d, level, nblocks in cases:
+        z = bz2.compress(d, level)
+        assert same(z) == (orc.OK, d)
+        nfast = orc.emul_bzip2_last_fast()
+        if nblocks is not None:
+            assert nfast == nblocks, (len(d), level, nfast)
+        else:
+            assert nfast >= 1
+    monkeypatch.setenv("B200Z_BZ2_FAST", "0")
+    assert same(bz2.compress(d1, 1)) == (orc.OK, d1)
+    assert orc.emul_bzip2_last_fast() == 0
