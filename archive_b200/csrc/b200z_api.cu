@@ -108,7 +108,7 @@ struct Ctx {
   cudaStream_t stream = nullptr, s_h2d = nullptr, s_d2h = nullptr;
   static const int kCompStreams = 8;
   cudaStream_t s_comp[kCompStreams] = {};
-  DevBuf d_in, d_out, d_ws, d_meta, d_small, d_bz;
+  DevBuf d_in, d_out, d_ws, d_meta, d_small, d_bz, d_tok;
   PinBuf h_meta;
 };
 static Ctx g;
@@ -1441,14 +1441,14 @@ static int deflate_staged(size_t n, int level, int window_bits, size_t *out_len)
 // overlap on the device.  Every member is compressed exactly as b200z_deflate_raw compresses it.
 // ---------------------------------------------------------------------------------------------
 static int deflate_member_on(const uint8_t *d_in, size_t n, int level, int window_bits, uint8_t *d_out, size_t cap, void *ws,
-                             size_t ws_bytes, cudaStream_t s, size_t *out_len, uint32_t *crc) {
+                             size_t ws_bytes, cudaStream_t s, size_t *out_len, uint32_t *crc, const DeflFastMember *pre = nullptr) {
   if (level == 0) {
     std::vector<DeflStoredBlock> bl;
     stored_block_list(n, window_bits, bl);
     CU(deflate_stored_device(d_in, bl.data(), (uint32_t)bl.size(), d_out, cap, ws, ws_bytes, out_len, s));
   } else {
     uint32_t stats[3];
-    CU(deflate_slow_device(d_in, n, level, window_bits, d_out, cap, ws, ws_bytes, out_len, stats, s));
+    CU(deflate_slow_device(d_in, n, level, window_bits, d_out, cap, ws, ws_bytes, out_len, stats, s, pre));
   }
   // the tile CRCs go to the front of the workspace: the encoder is done with it (both paths end synchronised)
   return device_crc32_on(d_in, n, (uint32_t *)ws, s, crc);
@@ -1495,8 +1495,10 @@ static int deflate_batch_impl(const uint8_t *in_base, const uint64_t *in_off, co
       CU(cudaMemcpyAsync((uint8_t *)g.d_in.p + din[i], in_base + in_off[i], (size_t)in_len[i], cudaMemcpyHostToDevice, g.s_h2d));
   CU(cudaEventRecord(staged, g.s_h2d));
   std::atomic<size_t> next{0};
+  size_t next_end = n_units;  // the lanes take members [next, next_end)
   std::vector<int> lane_rc(lanes, B200Z_OK);
   std::vector<std::string> lane_err(lanes);
+  std::vector<DeflFastMember> pre;  // levels 1-3: where the batch kernel has put every member's tokens
   const int device = g.device;
   auto lane = [&](size_t l) {
     auto fail = [&](int rc) {
@@ -1510,11 +1512,12 @@ static int deflate_batch_impl(const uint8_t *in_base, const uint64_t *in_off, co
     void *ws = (uint8_t *)g.d_ws.p + l * ws_lane;
     for (;;) {
       const size_t i = next.fetch_add(1);
-      if (i >= n_units) break;
+      if (i >= next_end) break;
       size_t olen = 0;
       uint32_t crc = 0;
       const int rc = deflate_member_on((const uint8_t *)g.d_in.p + din[i], (size_t)in_len[i], level, window_bits,
-                                       (uint8_t *)g.d_out.p + dout[i], dout[i + 1] - dout[i], ws, ws_lane, s, &olen, &crc);
+                                       (uint8_t *)g.d_out.p + dout[i], dout[i + 1] - dout[i], ws, ws_lane, s, &olen, &crc,
+                                       pre.empty() || in_len[i] == 0 ? nullptr : &pre[i]);
       if (rc) return fail(rc);
       out_len[i] = olen;
       if (crc32) crc32[i] = crc;
@@ -1529,13 +1532,73 @@ static int deflate_batch_impl(const uint8_t *in_base, const uint64_t *in_off, co
     }
     if (cudaStreamSynchronize(s) != cudaSuccess) fail(B200Z_E_NODEVICE);
   };
-  if (lanes == 1) {
-    lane(0);
+  auto run_lanes = [&]() {
+    if (lanes == 1) {
+      lane(0);
+    } else {
+      std::vector<std::thread> th;
+      for (size_t l = 1; l < lanes; ++l) th.emplace_back(lane, l);
+      lane(0);
+      for (auto &t : th) t.join();
+    }
+  };
+  if (level >= 1 && level <= 3) {
+    // _deflateFast is one serial chain per member; the batch is the parallel axis: ONE launch makes the tokens of a whole
+    // group of members (a warp per member, deflate_kernels.cu: k_defl_fast_batch), then the lanes cut the blocks, build
+    // the trees and emit the bits of each.  A group is as many members as the token store holds (12 bytes per input
+    // byte; B200Z_DEFLATE_TOK_MB, default 49152).
+    size_t budget = (size_t)48 << 30;
+    if (const char *e = getenv("B200Z_DEFLATE_TOK_MB")) budget = std::max<size_t>(1, (size_t)atoll(e)) << 20;
+    pre.assign(n_units, DeflFastMember());
+    size_t lo = 0;
+    auto failed = [&]() {
+      for (size_t l = 0; l < lanes; ++l)
+        if (lane_rc[l]) return true;
+      return false;
+    };
+    while (lo < n_units && !failed()) {
+      size_t hi = lo, bytes = 256;
+      std::vector<size_t> off;
+      while (hi < n_units) {
+        const size_t need = align_up(((size_t)in_len[hi] + 2) * 4, 256) * 3 + 256;
+        if (hi > lo && bytes + need > budget) break;
+        off.push_back(bytes);
+        bytes += need;
+        hi++;
+      }
+      const size_t list_off = align_up(bytes, 256);
+      bytes = list_off + (hi - lo) * sizeof(DeflFastMember);
+      CU(g.d_tok.reserve(bytes));
+      std::vector<DeflFastMember> order;
+      for (size_t i = lo; i < hi; ++i) {
+        const size_t n = (size_t)in_len[i], a = align_up((n + 2) * 4, 256);
+        uint8_t *base = (uint8_t *)g.d_tok.p + off[i - lo];
+        DeflFastMember m;
+        m.d = (const uint8_t *)g.d_in.p + din[i];
+        m.n = (uint32_t)n;
+        m.tok = (uint32_t *)base;
+        m.tally_ss = (uint32_t *)(base + a);
+        m.next_ss = (uint32_t *)(base + 2 * a);
+        m.ntok = (uint32_t *)(base + 3 * a);
+        pre[i] = m;
+        if (n) order.push_back(m);
+      }
+      std::stable_sort(order.begin(), order.end(), [](const DeflFastMember &x, const DeflFastMember &y) { return x.n > y.n; });
+      if (!order.empty()) {
+        CU(cudaStreamWaitEvent(g.stream, staged, 0));
+        CU(cudaMemcpyAsync((uint8_t *)g.d_tok.p + list_off, order.data(), order.size() * sizeof(DeflFastMember),
+                           cudaMemcpyHostToDevice, g.stream));
+        CU(deflate_fast_tokens_batch((const DeflFastMember *)((uint8_t *)g.d_tok.p + list_off), (uint32_t)order.size(), level,
+                                     window_bits, (uint32_t *)g.d_tok.p, g.stream));
+        CU(cudaStreamSynchronize(g.stream));
+      }
+      next.store(lo);
+      next_end = hi;
+      run_lanes();
+      lo = hi;
+    }
   } else {
-    std::vector<std::thread> th;
-    for (size_t l = 1; l < lanes; ++l) th.emplace_back(lane, l);
-    lane(0);
-    for (auto &t : th) t.join();
+    run_lanes();
   }
   cudaEventDestroy(staged);
   for (size_t l = 0; l < lanes; ++l)
@@ -2059,7 +2122,7 @@ void b200z_shutdown(void) {
   if (!g.inited) return;
   cudaSetDevice(g.device);
   cudaStreamSynchronize(g.stream);
-  g.d_in.release(); g.d_out.release(); g.d_ws.release(); g.d_meta.release(); g.d_small.release(); g.d_bz.release();
+  g.d_in.release(); g.d_out.release(); g.d_ws.release(); g.d_meta.release(); g.d_small.release(); g.d_bz.release(); g.d_tok.release();
   g.h_meta.release();
   cudaStreamDestroy(g.stream);
   cudaStreamDestroy(g.s_h2d);

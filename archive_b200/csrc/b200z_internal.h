@@ -122,9 +122,18 @@ struct DeflStoredBlock {
   uint32_t start, len, eof;
 };
 size_t deflate_bound(size_t n);
+// levels 1-3 over a batch (k_defl_fast_batch): where one member's bytes are and where its tokens go (device pointers;
+// tok / tally_ss / next_ss hold n + 2 words each)
+struct DeflFastMember {
+  const uint8_t *d = nullptr;
+  uint32_t n = 0, pad_ = 0;
+  uint32_t *tok = nullptr, *tally_ss = nullptr, *next_ss = nullptr, *ntok = nullptr;
+};
+cudaError_t deflate_fast_tokens_batch(const DeflFastMember *d_list, uint32_t n_mem, int level, int window_bits, uint32_t *d_counter,
+                                      cudaStream_t s);
 size_t deflate_workspace_bytes(size_t n);
 cudaError_t deflate_slow_device(const uint8_t *d_in, size_t n, int level, int window_bits, uint8_t *d_out, size_t out_cap,
-                                void *ws, size_t ws_bytes, size_t *out_len, uint32_t *stats, cudaStream_t s);
+                                void *ws, size_t ws_bytes, size_t *out_len, uint32_t *stats, cudaStream_t s, const DeflFastMember *pre = nullptr);
 cudaError_t deflate_stored_device(const uint8_t *d_in, const DeflStoredBlock *h_blocks, uint32_t n_blocks, uint8_t *d_out,
                                   size_t out_cap, void *ws, size_t ws_bytes, size_t *out_len, cudaStream_t s);
 cudaError_t crc32_tiles_device(const uint8_t *d_in, size_t n, uint32_t tile, uint32_t *d_part, cudaStream_t s);

@@ -513,7 +513,8 @@ struct BzFast {
   }
   __device__ __forceinline__ int get_sel(int i) const { return (selp[i >> 1] >> ((i & 1) * 4)) & 15; }
   uint16_t E[BZF_W];       // walker: (symbol << 5 | code length) of the code that starts at window bit b
-  uint16_t J4[BZF_W];      // walker: (position | symbols << 10) after up to four symbols from b (fewer: the window ended)
+  uint8_t EL[BZF_W + 64];  // walker: its length alone; 0 behind the window, so a hop from there stays where it is
+  uint16_t J4[BZF_W];      // walker: where four symbols from b end (a hop that starts behind the window does not move)
   uint16_t syms[2][32][50];  // a batch: the symbols of 32 groups
   uint8_t cnt[2][32];        // symbols in each group of the batch (50; fewer in the block's last group)
   uint32_t mtf[64][32];      // worker: word w of lane l's symbolic list
@@ -557,6 +558,7 @@ k_bz2_entropy_fast(const uint32_t *__restrict__ words, uint64_t n_bytes, const u
   const BzHdr h = S.hdr;
   bz_fill_luts(S, h.n_groups, tid, 64);
   for (int i = tid; i < 256; i += 64) S.cur[i] = (uint8_t)i;
+  if (tid < 64) S.EL[BZF_W + tid] = 0;
   __syncthreads();
 
   const uint32_t eob = (uint32_t)h.n_in_use + 1u;
@@ -592,17 +594,17 @@ k_bz2_entropy_fast(const uint32_t *__restrict__ words, uint64_t n_bytes, const u
               const uint32_t a0 = w0 < n_words ? __byte_perm(__ldg(words + w0), 0, 0x0123) : 0u;
               const uint32_t a1 = w0 + 1 < n_words ? __byte_perm(__ldg(words + w0 + 1), 0, 0x0123) : 0u;
               const uint32_t a2 = w0 + 2 < n_words ? __byte_perm(__ldg(words + w0 + 2), 0, 0x0123) : 0u;
-              const uint64_t win = ((uint64_t)__funnelshift_l(a1, a0, bsh) << 32) | __funnelshift_l(a2, a1, bsh);
+              const uint32_t whi = __funnelshift_l(a1, a0, bsh), wlo = __funnelshift_l(a2, a1, bsh);
               const int o0 = (int)(s & 7u);
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const uint64_t x = win << (o0 + j);
-                uint32_t e = S.lut[t][(uint32_t)(x >> (64 - BZ_LUT_BITS))];
+                const uint32_t x = __funnelshift_l(wlo, whi, (uint32_t)(o0 + j));  // 32 bits from window bit 8 * lane + j on
+                uint32_t e = S.lut[t][x >> (32 - BZ_LUT_BITS)];
                 if ((e & 31u) == 0u) {  // longer than the LUT: the limit / base walk from there on (:747-771)
                   int zn = S.minlen[t] > BZ_LUT_BITS + 1 ? S.minlen[t] : BZ_LUT_BITS + 1;
                   e = (BZF_BADSYM << 5) | 1u;
                   for (; zn <= 20; ++zn) {
-                    const int32_t zvec = (int32_t)(x >> (64 - zn));
+                    const int32_t zvec = (int32_t)(x >> (32 - zn));
                     if (zvec <= S.limit[t][zn]) {
                       const int32_t idx = zvec - S.base[t][zn];
                       if (idx >= 0 && idx < 258) e = ((uint32_t)S.perm[t][idx] << 5) | (uint32_t)zn;
@@ -611,28 +613,22 @@ k_bz2_entropy_fast(const uint32_t *__restrict__ words, uint64_t n_bytes, const u
                   }
                 }
                 S.E[8 * lane + j] = (uint16_t)e;
+                S.EL[8 * lane + j] = (uint8_t)(e & 31u);
               }
             }
             __syncwarp();
-            // J4: up to four symbols on from each bit of the window (eight independent chains per lane)
+            // J4: four symbols on from each bit of the window (eight independent chains per lane)
             {
-              uint32_t p[8], c[8];
+              uint32_t p[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                p[j] = 8u * lane + j;
-                c[j] = 0;
-              }
+              for (int j = 0; j < 8; ++j) p[j] = 8u * lane + j;
 #pragma unroll
               for (int hop = 0; hop < 4; ++hop) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  if (p[j] < (uint32_t)BZF_W) {
-                    p[j] += S.E[p[j]] & 31u;
-                    c[j]++;
-                  }
+                for (int j = 0; j < 8; ++j) p[j] += S.EL[p[j]];
               }
 #pragma unroll
-              for (int j = 0; j < 8; ++j) S.J4[8 * lane + j] = (uint16_t)(p[j] | (c[j] << 10));
+              for (int j = 0; j < 8; ++j) S.J4[8 * lane + j] = (uint16_t)p[j];
             }
             __syncwarp();
             // the chain: one hop per four symbols; lane i keeps mark i
@@ -640,7 +636,7 @@ k_bz2_entropy_fast(const uint32_t *__restrict__ words, uint64_t n_bytes, const u
             while (pos < BZF_W && 4 * nm < need) {
               if (lane == nm) mark = pos;
               nm++;
-              pos = S.J4[pos] & 1023;
+              pos = S.J4[pos];
             }
             // lane i < nm: the (up to four) symbols behind its mark
             int c = 0, p = mark;
@@ -695,55 +691,25 @@ k_bz2_entropy_fast(const uint32_t *__restrict__ words, uint64_t n_bytes, const u
       const bool lastb = S.last[wb] != 0;
       bool lbad = false;
       // (1) my group against a list that starts as the identity: symbols become references to initial positions
-      uint32_t lead_n = 0, lead_v = 0, trail_n = 0, trail_v = 0, recs_mid = 0, adv_mid = 0;
-      bool allrun = true;
-      int last_idx = -1, hiw = 0;
+      int hiw = 0;
       const int mycnt = lane < ngb ? (int)S.cnt[wb][lane] : 0;
       uint16_t *const sy = S.syms[wb][lane];
-      {
-        uint32_t rn = 0, rvv = 0;
-        for (int k = 0; k < mycnt; ++k) {
-          const uint32_t sym = sy[k];
-          if (sym <= 1u) {
-            if (rn >= 21u) lbad = true;  // N >= 2*1024*1024 (:291)
-            else rvv += (sym + 1u) << rn;
-            rn++;
-            continue;
-          }
-          if (allrun) {
-            lead_n = rn;
-            lead_v = rvv;
-            allrun = false;
-          } else if (rn) {
-            recs_mid++;
-            adv_mid += rvv;
-          }
-          rn = 0;
-          rvv = 0;
-          recs_mid++;
-          adv_mid++;
-          last_idx = k;
-          const uint32_t nn = sym - 1u, wn = nn >> 2, bn = nn & 3u;
-          for (; hiw <= (int)wn; ++hiw) S.mtf[hiw][lane] = 0x03020100u + 0x04040404u * (uint32_t)hiw;
-          const uint32_t top = S.mtf[wn][lane];
-          const uint32_t uc = (top >> (8u * bn)) & 0xffu;
-          uint32_t carry = uc;
-          for (uint32_t w = 0; w < wn; ++w) {
-            const uint32_t tw = S.mtf[w][lane];
-            S.mtf[w][lane] = (tw << 8) | carry;
-            carry = tw >> 24;
-          }
-          const uint32_t mlow = bn == 3u ? 0xffffffffu : ((1u << (8u * (bn + 1u))) - 1u);
-          S.mtf[wn][lane] = (top & ~mlow) | (((top << 8) | carry) & mlow);
-          sy[k] = (uint16_t)(0x8000u | uc);
+      for (int k = 0; k < mycnt; ++k) {
+        const uint32_t sym = sy[k];
+        if (sym <= 1u) continue;
+        const uint32_t nn = sym - 1u, wn = nn >> 2, bn = nn & 3u;
+        for (; hiw <= (int)wn; ++hiw) S.mtf[hiw][lane] = 0x03020100u + 0x04040404u * (uint32_t)hiw;
+        const uint32_t top = S.mtf[wn][lane];
+        const uint32_t uc = (top >> (8u * bn)) & 0xffu;
+        uint32_t carry = uc;
+        for (uint32_t w = 0; w < wn; ++w) {
+          const uint32_t tw = S.mtf[w][lane];
+          S.mtf[w][lane] = (tw << 8) | carry;
+          carry = tw >> 24;
         }
-        if (allrun) {
-          lead_n = rn;
-          lead_v = rvv;
-        } else {
-          trail_n = rn;
-          trail_v = rvv;
-        }
+        const uint32_t mlow = bn == 3u ? 0xffffffffu : ((1u << (8u * (bn + 1u))) - 1u);
+        S.mtf[wn][lane] = (top & ~mlow) | (((top << 8) | carry) & mlow);
+        sy[k] = (uint16_t)(0x8000u | uc);
       }
       __syncwarp();
       // (2) the real list, group by group: resolve the group's references, then list'[i] = list[P[i]]
@@ -769,79 +735,78 @@ k_bz2_entropy_fast(const uint32_t *__restrict__ words, uint64_t n_bytes, const u
         }
         __syncwarp();
       }
-      // (3) every lane's starting state: records, block position, the open run and the list's front
-      const uint32_t lastv = last_idx >= 0 ? (uint32_t)(sy[last_idx] & 0xffu) : 0u;
-      uint32_t i_nrec = 0, i_nblock = 0, i_n = 0, i_v = 0, i_front = 0;
-      for (int gi = 0; gi < ngb; ++gi) {
-        if (lane == gi) {
-          i_nrec = st_nrec;
-          i_nblock = st_nblock;
-          i_n = st_n;
-          i_v = st_v;
-          i_front = st_front;
+      // (3) the records (:276-388): the batch's symbols as ONE stream, 32 at a time.  A run symbol adds (sym + 1) << its
+      // index in the run; a symbol that is not a run symbol closes the run in front of it (one record, written at the
+      // position the run started at) and makes a record of its own.  Everything a lane needs -- its index in the run, the
+      // run's value, records and block positions in front of it -- is a ballot, a 5-step scan and two shuffles away.
+      const int total = ngb ? 50 * (ngb - 1) + (int)S.cnt[wb][ngb - 1] : 0;  // only the block's last group is short
+      const uint16_t *const flat = &S.syms[wb][0][0];
+      for (int base = 0; base < total; base += 32) {
+        const int i = base + lane;
+        const bool valid = i < total;
+        const uint32_t v = valid ? (uint32_t)flat[i] : 0xffffu;
+        const bool isrun = valid && v <= 1u, isnr = valid && v > 1u;
+        const unsigned NR = __ballot_sync(FULLW, isnr);
+        const unsigned below = NR & ((1u << lane) - 1u);
+        const int q = below ? 31 - __clz((int)below) : -1;  // the last symbol below me that is not a run symbol
+        const uint32_t before = q < 0 ? st_n + (uint32_t)lane : (uint32_t)(lane - q - 1);  // run symbols right in front of me
+        uint32_t a = 0;
+        if (isrun) {
+          if (before > 20u) lbad = true;  // N >= 2*1024*1024 (:291)
+          else a = (v + 1u) << before;
         }
-        const bool ar = __shfl_sync(FULLW, (int)allrun, gi) != 0;
-        const uint32_t ln = __shfl_sync(FULLW, lead_n, gi), lv = __shfl_sync(FULLW, lead_v, gi);
-        if (st_n + ln > 21u) {
-          lbad = true;
-          break;
+        uint32_t pa = a;  // inclusive scan
+#pragma unroll
+        for (int dlt = 1; dlt < 32; dlt <<= 1) {
+          const uint32_t tsh = __shfl_up_sync(FULLW, pa, dlt);
+          if (lane >= dlt) pa += tsh;
         }
-        if (ar) {
-          st_v += lv << st_n;
-          st_n += ln;
-        } else {
-          if (st_n + ln) {
-            st_nrec++;
-            st_nblock += st_v + (lv << st_n);
+        const uint32_t pa_q = __shfl_sync(FULLW, pa, q < 0 ? 0 : q);
+        const uint32_t fv = __shfl_sync(FULLW, v & 0xffu, q < 0 ? 0 : q);
+        const bool hasrun = isnr && before != 0u;
+        const unsigned HR = __ballot_sync(FULLW, hasrun);
+        if (isnr) {
+          const uint32_t runval = q < 0 ? st_v + pa : pa - pa_q;  // (a is 0 here: pa is the sum over what lies below me)
+          const uint32_t pos_sym = st_nblock + st_v + pa + (uint32_t)__popc(below);
+          uint32_t r = st_nrec + (uint32_t)__popc(below) + (uint32_t)__popc(HR & ((1u << lane) - 1u));
+          if (pos_sym >= nblock_max) {  // (:313-316, :326-329)
+            lbad = true;
+          } else {
+            if (hasrun) {
+              rv[r] = (runval << 8) | S.seq2unseq[q < 0 ? st_front : fv];
+              rp[r] = pos_sym - runval;
+              r++;
+            }
+            rv[r] = (1u << 8) | S.seq2unseq[v & 0xffu];
+            rp[r] = pos_sym;
           }
-          st_nrec += __shfl_sync(FULLW, recs_mid, gi);
-          st_nblock += __shfl_sync(FULLW, adv_mid, gi);
-          st_n = __shfl_sync(FULLW, trail_n, gi);
-          st_v = __shfl_sync(FULLW, trail_v, gi);
-          st_front = __shfl_sync(FULLW, lastv, gi);
+        }
+        const int nvalid = total - base < 32 ? total - base : 32;
+        const uint32_t pa_last = __shfl_sync(FULLW, pa, 31);
+        if (NR) {
+          const int ql = 31 - __clz((int)NR);
+          const uint32_t pa_ql = __shfl_sync(FULLW, pa, ql);
+          st_nrec += (uint32_t)(__popc(NR) + __popc(HR));
+          st_nblock += st_v + pa_ql + (uint32_t)__popc(NR);
+          st_v = pa_last - pa_ql;
+          st_n = (uint32_t)(nvalid - 1 - ql);
+          st_front = __shfl_sync(FULLW, v & 0xffu, ql);
+        } else {
+          st_v += pa_last;
+          st_n += (uint32_t)nvalid;
         }
       }
       if (lastb && st_n) {  // the run that the end-of-block code closes (:306-321)
+        if (st_n > 21u || st_nblock + st_v > nblock_max) {
+          lbad = true;
+        } else if (lane == 0) {
+          rv[st_nrec] = (st_v << 8) | S.seq2unseq[st_front];
+          rp[st_nrec] = st_nblock;
+        }
         st_nrec++;
         st_nblock += st_v;
         st_n = 0;
         st_v = 0;
-      }
-      // (4) the records of my group (:276-388 with the state above)
-      if (lane < ngb && !lbad) {
-        uint32_t nrec = i_nrec, nblock = i_nblock, rn = i_n, rvv = i_v, front = i_front;
-        for (int k = 0; k <= mycnt; ++k) {
-          const bool fin = k == mycnt;  // past my last symbol: only the block's last group has something to do here
-          if (fin && !(lastb && lane == ngb - 1)) break;
-          const uint32_t v = fin ? 0xffffu : (uint32_t)sy[k];
-          if (v <= 1u) {
-            rvv += (v + 1u) << rn;
-            rn++;
-            continue;
-          }
-          if (rn) {
-            if (nblock + rvv > nblock_max) {  // (:313-316)
-              lbad = true;
-              break;
-            }
-            rv[nrec] = (rvv << 8) | S.seq2unseq[front];
-            rp[nrec] = nblock;
-            nrec++;
-            nblock += rvv;
-            rn = 0;
-            rvv = 0;
-          }
-          if (fin) break;
-          if (nblock >= nblock_max) {  // (:326-329)
-            lbad = true;
-            break;
-          }
-          front = v & 0xffu;
-          rv[nrec] = (1u << 8) | S.seq2unseq[front];
-          rp[nrec] = nblock;
-          nrec++;
-          nblock++;
-        }
       }
       if (__any_sync(FULLW, lbad) && lane == 0) S.redo = 1;
     }

@@ -79,3 +79,24 @@ def test_fuzz():
             same(d, level, rng.choice([15, 15, 15, 9, 10, 12, 14]))
             n_cases += 1
     assert n_cases == 180
+
+
+def test_fast_levels_ring_and_rebase():
+    """Levels 1-3 (k_defl_fast_batch: a warp per member, head / prev as 16-bit offsets from a base that moves every
+    32 KiB, a 64 KiB byte ring refilled 16 KiB at a time): inputs long enough for several re-bases and ring wraps, matches
+    at the far edge of every window size, long runs (258-byte matches, interior positions not inserted)."""
+    import random
+    from archive_b200 import synth
+    rng = random.Random(12)
+    text = synth.text(230_000, stream=21).tobytes()
+    far = bytearray(rng.getrandbits(8) for _ in range(40_000))
+    for k in range(0, 200_000, 32_500):  # the same 40 bytes again just inside / outside every window
+        far += bytes(far[100:140]) + bytes(rng.getrandbits(8) for _ in range(32_460))
+    cases = [text, bytes(far), b"\0" * 150_000, (b"abcdefghij" * 30 + bytes(rng.getrandbits(8) for _ in range(50))) * 400,
+             text[:65_536 + 300], text[:131_072 + 2]]
+    for d in cases:
+        for level in (1, 2, 3):
+            same(d, level)
+    for wbits in (9, 12, 14):
+        same(text[:140_000], 1, wbits)
+        same(bytes(far[:150_000]), 3, wbits)

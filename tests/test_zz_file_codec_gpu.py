@@ -247,9 +247,17 @@ def test_deflate_batch_equals_one_by_one(a, monkeypatch):
             for it, (payload, crc) in zip(items, got):
                 d = a.Deflate(it, level=level)
                 assert payload == d.get_bytes() and crc == d.crc32 == zlib.crc32(it), (lanes, level, len(it))
-            if level == 6:
+            if level in (6, 1):
                 for it, (payload, _) in zip(items, got):
-                    assert payload == orc.deflate(it, 6)[1]
+                    assert payload == orc.deflate(it, level)[1]
+    # levels 1-3: the tokens of a whole group of members come from one k_defl_fast_batch launch; a small token store
+    # splits the batch into several groups
+    monkeypatch.setenv("B200Z_DEFLATE_TOK_MB", "1")
+    for level in (1, 2, 3):
+        got = deflate_batch(items, level)
+        for it, (payload, crc) in zip(items, got):
+            assert payload == orc.deflate(it, level)[1] and crc == zlib.crc32(it), (level, len(it))
+    monkeypatch.delenv("B200Z_DEFLATE_TOK_MB")
     assert deflate_batch([], 6) == []
     with pytest.raises(a.B200ZError):
         deflate_batch([b"abc"], 11)
