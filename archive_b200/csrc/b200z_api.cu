@@ -1190,6 +1190,7 @@ static int bzip2_decode_impl(const uint8_t *in, size_t in_len, int verify, uint8
   // ---- K8 on the chain ----
   const uint32_t nc = (uint32_t)chain.size();
   std::vector<unsigned long long> h_off(nc + 1, 0);
+  size_t early_copied = 0;  // bytes [0, early_copied) of the output are on their way to the host already (s_d2h)
   std::vector<uint32_t> h_crc(nc);
   std::vector<int32_t> h_irr(nc);
   if (nc) {
@@ -1202,11 +1203,41 @@ static int bzip2_decode_impl(const uint8_t *in, size_t in_len, int verify, uint8
     w.slice_state = A.slice_state; w.slice_out = A.slice_out; w.block_out = A.block_out; w.block_off = A.block_off;
     w.block_crc = A.block_crc; w.out = (uint8_t *)g.d_out.p; w.out_cap = out_cap;
     for (const BzChainHost &ce : chain) w.any_randomised = w.any_randomised || (ce.flags & 1u);
-    CU(bz2_launch_ibwt(w, g.stream));
+    // A long chain is decoded in groups: the bytes of a finished group go to the host (on the copy stream) while the next
+    // group is being decoded.  What the host may not keep -- blocks behind a failed check -- lies beyond *out_len anyway.
+    uint32_t groups = (!shard && nc >= 64) ? 4u : 1u;
+    if (const char *ge = getenv("B200Z_BZ2_GROUPS")) groups = (uint32_t)std::max(1, atoi(ge));
+    if (shard || groups > nc) groups = 1;
+    if (groups <= 1) {
+      CU(bz2_launch_ibwt(w, g.stream));
+    } else {
+      CU(g.h_meta.reserve((size_t)groups * 8));
+      volatile unsigned long long *h_end_off = (volatile unsigned long long *)g.h_meta.p;
+      std::vector<cudaEvent_t> ev(groups);
+      for (uint32_t gi = 0; gi < groups; ++gi) {
+        const uint32_t lo = (uint32_t)((uint64_t)nc * gi / groups), hi = (uint32_t)((uint64_t)nc * (gi + 1) / groups);
+        CU(bz2_launch_ibwt_group(w, lo, hi, g.stream));
+        CU(cudaMemcpyAsync((void *)(h_end_off + gi), A.block_off + hi, 8, cudaMemcpyDeviceToHost, g.stream));
+        CU(cudaEventCreateWithFlags(&ev[gi], cudaEventDisableTiming));
+        CU(cudaEventRecord(ev[gi], g.stream));
+      }
+      for (uint32_t gi = 0; gi < groups; ++gi) {
+        CU(cudaEventSynchronize(ev[gi]));
+        cudaEventDestroy(ev[gi]);
+        const unsigned long long eo = h_end_off[gi];
+        const size_t end = (size_t)(eo < (unsigned long long)out_cap ? eo : (unsigned long long)out_cap);
+        if (end > early_copied) {
+          CU(cudaMemcpyAsync(out + early_copied, (uint8_t *)g.d_out.p + early_copied, end - early_copied, cudaMemcpyDeviceToHost,
+                             g.s_d2h));
+          early_copied = end;
+        }
+      }
+    }
     CU(cudaMemcpyAsync(h_off.data(), A.block_off, (size_t)(nc + 1) * 8, cudaMemcpyDeviceToHost, g.stream));
     CU(cudaMemcpyAsync(h_crc.data(), A.block_crc, (size_t)nc * 4, cudaMemcpyDeviceToHost, g.stream));
     CU(cudaMemcpyAsync(h_irr.data(), A.irregular, (size_t)nc * 4, cudaMemcpyDeviceToHost, g.stream));
     CU(cudaStreamSynchronize(g.stream));
+    if (early_copied) CU(cudaStreamSynchronize(g.s_d2h));  // (no copy into the caller's buffer outlives this call)
   }
   if (getenv("B200Z_DEBUG"))
     for (uint32_t i = 0; i < nc && i < 16; ++i)
@@ -1292,7 +1323,9 @@ static int bzip2_decode_impl(const uint8_t *in, size_t in_len, int verify, uint8
     set_err("bzip2: output needs %zu bytes, out_cap %zu", n_out, out_cap);
     return B200Z_E_NOSPC;
   }
-  if (n_out) CU(cudaMemcpyAsync(out, g.d_out.p, n_out, cudaMemcpyDeviceToHost, g.stream));
+  if (n_out > early_copied)
+    CU(cudaMemcpyAsync(out + early_copied, (uint8_t *)g.d_out.p + early_copied, n_out - early_copied, cudaMemcpyDeviceToHost,
+                       g.stream));
   CU(cudaStreamSynchronize(g.stream));
   return final_rc;
 }

@@ -87,6 +87,7 @@ struct Bz2Ibwt {  // K8 over the validated chain
   uint8_t *out;
   unsigned long long out_cap;
   bool any_randomised = false;
+  bool carry_off = false;  // block_off[0] already holds the first block's offset (bz2_launch_ibwt_group)
 };
 struct BzChainHost {
   uint32_t cand, nblock, n_rec, orig_ptr;
@@ -99,6 +100,7 @@ cudaError_t bz2_launch_entropy(const Bz2Entropy &a, cudaStream_t s);
 // blocks K7 left with status -3 (a damaged block that the reference keeps decoding): d_list = their indices into a's arrays
 cudaError_t bz2_launch_entropy_literal(const Bz2Entropy &a, const uint32_t *d_list, uint32_t n_list, cudaStream_t s);
 cudaError_t bz2_launch_ibwt(const Bz2Ibwt &a, cudaStream_t s);
+cudaError_t bz2_launch_ibwt_group(const Bz2Ibwt &a, uint32_t lo, uint32_t hi, cudaStream_t s);
 void count_launch();
 void profile_enable(bool on);
 int profile_read(double *fast_ms, double *decode_ms, double *expand_ms, uint64_t *n);

@@ -1230,44 +1230,60 @@ k_bz2_walk_len(const BzChain *__restrict__ chain, const uint32_t *__restrict__ t
   sn[j] = (cur == g.tpos0) ? g.start_id : cur / g.stride;
 }
 
-// one thread per block: order of the segments along the cycle.  T (built by a stable counting sort) is always a
-// permutation, so the walk from tPos0 returns to tPos0; for a PERIODIC block (e.g. "abab...", or long runs after
-// RLE1) that happens after cycle_len < nblock steps and the reference simply keeps going round
-// (bzip2_decoder.dart:648-650): raw[i] = raw[i mod cycle_len].
-__global__ void k_bz2_walk_order(const BzChain *__restrict__ chain, uint32_t n_chain, const uint32_t *__restrict__ tt,
-                                 uint32_t nblock_max, const uint32_t *__restrict__ seg_len,
-                                 const uint32_t *__restrict__ seg_next, uint32_t *__restrict__ seg_off,
-                                 int32_t *__restrict__ irregular, uint32_t *__restrict__ cycle_len) {
-  const uint32_t bi = blockIdx.x * blockDim.x + threadIdx.x;
+// Order of the segments along the cycle, one CTA per block: the segment table (<= 4097 entries) is staged in shared memory,
+// one thread follows it there (a chain of shared-memory reads instead of global ones), the CTA writes the offsets back.
+// T (built by a stable counting sort) is always a permutation, so the walk from tPos0 returns to tPos0; for a PERIODIC
+// block (e.g. "abab...", or long runs after RLE1) that happens after cycle_len < nblock steps and the reference simply
+// keeps going round (bzip2_decoder.dart:648-650): raw[i] = raw[i mod cycle_len].
+__global__ void __launch_bounds__(128)
+k_bz2_walk_order(const BzChain *__restrict__ chain, uint32_t n_chain, const uint32_t *__restrict__ tt,
+                 uint32_t nblock_max, const uint32_t *__restrict__ seg_len,
+                 const uint32_t *__restrict__ seg_next, uint32_t *__restrict__ seg_off,
+                 int32_t *__restrict__ irregular, uint32_t *__restrict__ cycle_len) {
+  __shared__ uint32_t s_len[BZ_SPLIT + 2], s_off[BZ_SPLIT + 2];
+  __shared__ uint16_t s_next[BZ_SPLIT + 2];
+  const uint32_t bi = blockIdx.x;
   if (bi >= n_chain) return;
   const BzChain c = chain[bi];
-  irregular[bi] = 0;
-  cycle_len[bi] = c.nblock;
+  if (threadIdx.x == 0) {
+    irregular[bi] = 0;
+    cycle_len[bi] = c.nblock;
+  }
   if (c.nblock == 0) return;
   const uint32_t *T = tt + (size_t)bi * nblock_max;
   const BzWalkGeom g = bz_geom(c, T);
   const uint32_t *sl = seg_len + (size_t)bi * (BZ_SPLIT + 2), *sn = seg_next + (size_t)bi * (BZ_SPLIT + 2);
   uint32_t *so = seg_off + (size_t)bi * (BZ_SPLIT + 2);
-  for (uint32_t j = 0; j <= g.kb; ++j) so[j] = 0xffffffffu;
-  uint32_t seg = g.start_id, off = 0, visited = 0;
-  while (off < c.nblock) {
-    if (seg > g.kb) {
-      irregular[bi] = 1;
-      return;
-    }
-    if (so[seg] != 0xffffffffu) {  // back at the start: the cycle is shorter than the block
-      if (seg != g.start_id) irregular[bi] = 1;
-      cycle_len[bi] = off;
-      return;
-    }
-    if (sl[seg] == 0 || ++visited > g.kb + 1) {
-      irregular[bi] = 1;
-      return;
-    }
-    so[seg] = off;
-    off += sl[seg];
-    seg = sn[seg];
+  for (uint32_t j = threadIdx.x; j <= g.kb; j += blockDim.x) {
+    s_len[j] = sl[j];
+    const uint32_t nx = sn[j];
+    s_next[j] = (uint16_t)(nx > 0xffffu ? 0xffffu : nx);
+    s_off[j] = 0xffffffffu;
   }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t seg = g.start_id, off = 0, visited = 0;
+    while (off < c.nblock) {
+      if (seg > g.kb) {
+        irregular[bi] = 1;
+        break;
+      }
+      if (s_off[seg] != 0xffffffffu) {  // back at the start: the cycle is shorter than the block
+        if (seg != g.start_id) irregular[bi] = 1;
+        cycle_len[bi] = off;
+        break;
+      }
+      if (s_len[seg] == 0 || ++visited > g.kb + 1) {
+        irregular[bi] = 1;
+        break;
+      }
+      s_off[seg] = off;
+      off += s_len[seg];
+      seg = s_next[seg];
+    }
+  }
+  __syncthreads();
+  for (uint32_t j = threadIdx.x; j <= g.kb; j += blockDim.x) so[j] = s_off[j];
 }
 
 // periodic blocks: repeat the cycle
@@ -1422,9 +1438,9 @@ k_bz2_rle_count(const BzChain *__restrict__ chain, const uint8_t *__restrict__ r
 
 // exclusive scan of the block sizes (a few hundred values)
 __global__ void k_bz2_offsets(const unsigned long long *__restrict__ block_out, uint32_t n_chain,
-                              unsigned long long *__restrict__ block_off) {
+                              unsigned long long *__restrict__ block_off, int carry) {
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    unsigned long long run = 0;
+    unsigned long long run = carry ? block_off[0] : 0;  // (a later group of the chain goes on where the one before it ended)
     for (uint32_t i = 0; i < n_chain; ++i) {
       block_off[i] = run;
       run += block_out[i];
@@ -1458,20 +1474,41 @@ k_bz2_rle_emit(const BzChain *__restrict__ chain, const uint8_t *__restrict__ ra
   const unsigned long long o0 = block_off[blockIdx.x] + slice_out[(size_t)blockIdx.x * BZ_RLE_THREADS + t];
   unsigned long long o = o0;
   uint32_t crc = 0;  // register started at 0: R(0, slice)
+  // output bytes are gathered eight at a time and leave as one aligned 8-byte store (a thread's slice is contiguous in the
+  // output: byte stores from 1024 threads were 32 partial sectors per instruction, the larger half of this kernel's time)
+  uint64_t acc = 0;
+  uint32_t nacc = 0;
+  auto flush = [&]() {
+    const unsigned long long b0 = o - nacc;
+    if (nacc == 8u && b0 + 8u <= out_cap) {
+      *reinterpret_cast<uint64_t *>(out + b0) = acc;
+    } else {
+      for (uint32_t k = 0; k < nacc; ++k)
+        if (b0 + k < out_cap) out[b0 + k] = (uint8_t)(acc >> (8u * k));
+    }
+    acc = 0;
+    nacc = 0;
+  };
+  auto put = [&](uint8_t b) {
+    if (nacc == 0u && (o & 7ull) != 0ull) {  // up to the first aligned address: single bytes
+      if (o < out_cap) out[o] = b;
+      o++;
+    } else {
+      acc |= (uint64_t)b << (8u * nacc);
+      nacc++;
+      o++;
+      if (nacc == 8u) flush();
+    }
+    crc = (crc << 8) ^ crc_tab[(crc >> 24) ^ b];
+  };
   uint8_t prev = lo > 0 ? src[lo - 1] : 0;
   for (uint32_t i = lo; i < hi; ++i) {
     uint8_t x = src[i];
     bool eq = (i > 0) && x == prev;
     if (s == 4) {
-      for (uint32_t k = 0; k < x; ++k) {
-        if (o < out_cap) out[o] = prev;
-        o++;
-        crc = (crc << 8) ^ crc_tab[(crc >> 24) ^ prev];
-      }
+      for (uint32_t k = 0; k < x; ++k) put(prev);
     } else {
-      if (o < out_cap) out[o] = x;
-      o++;
-      crc = (crc << 8) ^ crc_tab[(crc >> 24) ^ x];
+      put(x);
     }
     s = rle_step(s, eq);
     prev = x;
@@ -1479,12 +1516,9 @@ k_bz2_rle_emit(const BzChain *__restrict__ chain, const uint8_t *__restrict__ ra
   if (t == BZ_RLE_THREADS - 1 && s == 4) {  // a run of 4 ends the block: its count is read past the end (k_bz2_rle_count)
     const uint32_t cl = cycle_len[blockIdx.x];
     const uint32_t extra = src[cl ? c.nblock % cl : 0u];
-    for (uint32_t k = 0; k < extra; ++k) {
-      if (o < out_cap) out[o] = prev;
-      o++;
-      crc = (crc << 8) ^ crc_tab[(crc >> 24) ^ prev];
-    }
+    for (uint32_t k = 0; k < extra; ++k) put(prev);
   }
+  flush();
   // combine: R(init, A||B) = R(init, A) * x^(8|B|) ^ R(0, B)
   sm_crc[t] = crc;
   sm_len[t] = (uint32_t)(o - o0);
@@ -1681,7 +1715,7 @@ cudaError_t bz2_launch_ibwt(const Bz2Ibwt &a, cudaStream_t s) {
   dim3 g3((BZ_SPLIT + 2 + 255) / 256, a.n_chain);
   k_bz2_walk_len<<<g3, 256, 0, s>>>(chain, a.tt, a.nblock_max, a.seg_len, a.seg_next);
   count_launch();
-  k_bz2_walk_order<<<(a.n_chain + 63) / 64, 64, 0, s>>>(chain, a.n_chain, a.tt, a.nblock_max, a.seg_len, a.seg_next,
+  k_bz2_walk_order<<<a.n_chain, 128, 0, s>>>(chain, a.n_chain, a.tt, a.nblock_max, a.seg_len, a.seg_next,
                                                          a.seg_off, a.irregular, a.cycle_len);
   count_launch();
   k_bz2_walk_emit<<<g3, 256, 0, s>>>(chain, a.tt, a.nblock_max, a.seg_len, a.seg_off, a.raw);
@@ -1696,7 +1730,7 @@ cudaError_t bz2_launch_ibwt(const Bz2Ibwt &a, cudaStream_t s) {
                                                            a.out_cap, a.out, a.block_crc, a.irregular, a.cycle_len);
     count_launch();
   }
-  k_bz2_offsets<<<1, 32, 0, s>>>(a.block_out, a.n_chain, a.block_off);
+  k_bz2_offsets<<<1, 32, 0, s>>>(a.block_out, a.n_chain, a.block_off, a.carry_off ? 1 : 0);
   count_launch();
   k_bz2_rle_emit<<<a.n_chain, BZ_RLE_THREADS, 0, s>>>(chain, a.raw, a.nblock_max, a.slice_state, a.slice_out, a.block_off,
                                                      a.out_cap, a.out, a.block_crc, a.cycle_len);
@@ -1707,6 +1741,34 @@ cudaError_t bz2_launch_ibwt(const Bz2Ibwt &a, cudaStream_t s) {
     count_launch();
   }
   return cudaGetLastError();
+}
+
+// K8 over the blocks [lo, hi) of the chain: every per-block array of `a` is shifted to the group's first block; the group's
+// output goes on where block lo - 1 ended (block_off[lo], written by the group before it).  Groups launched one after the
+// other on one stream give the result of one bz2_launch_ibwt over the whole chain -- and let the caller copy a finished
+// group's bytes to the host while the next group is being decoded.
+cudaError_t bz2_launch_ibwt_group(const Bz2Ibwt &a, uint32_t lo, uint32_t hi, cudaStream_t s) {
+  if (hi <= lo) return cudaSuccess;
+  const uint32_t chunks_max = (a.nblock_max + BZ_CHUNK - 1) / BZ_CHUNK;
+  Bz2Ibwt g = a;
+  g.chain = reinterpret_cast<const BzChain *>(a.chain) + lo;
+  g.n_chain = hi - lo;
+  g.sym8 = a.sym8 + (size_t)lo * a.nblock_max;
+  g.chist = a.chist + (size_t)lo * chunks_max * 256;
+  g.tt = a.tt + (size_t)lo * a.nblock_max;
+  g.seg_len = a.seg_len + (size_t)lo * (BZ_SPLIT + 2);
+  g.seg_next = a.seg_next + (size_t)lo * (BZ_SPLIT + 2);
+  g.seg_off = a.seg_off + (size_t)lo * (BZ_SPLIT + 2);
+  g.irregular = a.irregular + lo;
+  g.cycle_len = a.cycle_len + lo;
+  g.raw = a.raw + (size_t)lo * a.nblock_max;
+  g.slice_state = a.slice_state + (size_t)lo * BZ_RLE_THREADS;
+  g.slice_out = a.slice_out + (size_t)lo * BZ_RLE_THREADS;
+  g.block_out = a.block_out + lo;
+  g.block_off = a.block_off + lo;
+  g.block_crc = a.block_crc + lo;
+  g.carry_off = lo > 0;
+  return bz2_launch_ibwt(g, s);
 }
 
 }  // namespace b200z

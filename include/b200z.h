@@ -85,8 +85,9 @@ int b200z_zlib_decode(const uint8_t *in, size_t in_len, int verify, int raw, uin
 size_t b200z_gzip_bound(const uint8_t *in, size_t in_len);
 
 /* Deflate(bytes, level:, windowBits:).getBytes() and .crc32 -- deflate.dart:39-48,72-75,31.  Raw DEFLATE, byte-identical
- * to the reference at the same level and windowBits (9..15).  Levels 4-9 are data parallel; 1-3 (deflate_fast, whose hash
- * chains depend on the parse) run as one serial device thread per stream; 0 is stored.  Invalid level / windowBits
+ * to the reference at the same level and windowBits (9..15).  Levels 4-9 are data parallel inside a stream; 1-3
+ * (deflate_fast, whose hash chains depend on the parse) are one warp per stream with all state in shared memory -- their
+ * parallel axis is the batch (b200z_deflate_batch); 0 is stored.  Invalid level / windowBits
  * (Deflate._init returning false, :107-118) -> B200Z_E_ARG.                                                          */
 int b200z_deflate_raw(const uint8_t *in, size_t in_len, int level, int window_bits, uint8_t *out, size_t out_cap,
                       size_t *out_len, uint32_t *crc32_of_input);
@@ -95,8 +96,9 @@ size_t b200z_deflate_bound(size_t in_len); /* output capacity that always suffic
  * (zip_encoder.dart:185-259, platformZLibEncoder.encodeStream(raw: true) :244-249).  Unit u reads
  * in_base[in_off[u] .. +in_len[u]) and writes out_base[out_off[u] .. +out_cap[u]); out_len[u] = its compressed size,
  * crc32[u] (may be NULL) = CRC-32 of its input, status[u] = B200Z_OK or B200Z_U_NOSPC (out_len[u] = bytes needed).  All
- * inputs are staged at once and up to 8 members (B200Z_DEFLATE_LANES) are in flight on separate CUDA streams; every
- * stream is byte-identical to b200z_deflate_raw of the same input.                                                  */
+ * inputs are staged at once and up to 8 members (B200Z_DEFLATE_LANES) are in flight on separate CUDA streams; at levels
+ * 1-3 the match finding of ALL members runs first, as one launch with a warp per member.  Every stream is byte-identical
+ * to b200z_deflate_raw of the same input.                                                                            */
 int b200z_deflate_batch(const uint8_t *in_base, const uint64_t *in_off, const uint64_t *in_len, size_t n_units, int level,
                         int window_bits, uint8_t *out_base, const uint64_t *out_off, const uint64_t *out_cap,
                         uint64_t *out_len, uint32_t *crc32, int32_t *status);

@@ -38,7 +38,7 @@ o1 = np.empty(L.b200z_deflate_bound(n1), dtype=np.uint8); ol = C.c_size_t(0)
 best = 1e9
 for it in range(2):
     t0 = time.perf_counter()
-    rc = L.b200z_deflate_raw(p(one), n1, level, 15, p(o1), o1.size, C.byref(ol))
+    rc = L.b200z_deflate_raw(p(one), n1, level, 15, p(o1), o1.size, C.byref(ol), None)
     best = min(best, time.perf_counter() - t0)
     assert rc == 0
 assert o1[:ol.value].tobytes() == orc.deflate(one.tobytes(), level)[1]
