@@ -1203,9 +1203,11 @@ static int bzip2_decode_impl(const uint8_t *in, size_t in_len, int verify, uint8
     w.slice_state = A.slice_state; w.slice_out = A.slice_out; w.block_out = A.block_out; w.block_off = A.block_off;
     w.block_crc = A.block_crc; w.out = (uint8_t *)g.d_out.p; w.out_cap = out_cap;
     for (const BzChainHost &ce : chain) w.any_randomised = w.any_randomised || (ce.flags & 1u);
-    // A long chain is decoded in groups: the bytes of a finished group go to the host (on the copy stream) while the next
-    // group is being decoded.  What the host may not keep -- blocks behind a failed check -- lies beyond *out_len anyway.
-    uint32_t groups = (!shard && nc >= 64) ? 4u : 1u;
+    // B200Z_BZ2_GROUPS=n decodes a long chain in n groups, the bytes of a finished group on their way to the host (copy
+    // stream) while the next group is decoded.  Measured on a B200 (512 MiB, 597 blocks): 59.4 ms in one piece, 64.5 ms in
+    // 4 groups, 73.8 ms in 8 -- the pointer-chasing kernels of K8 are bound by latency, not by the number of blocks, so a
+    // group costs nearly what the whole chain costs.  Off by default.
+    uint32_t groups = 1u;
     if (const char *ge = getenv("B200Z_BZ2_GROUPS")) groups = (uint32_t)std::max(1, atoi(ge));
     if (shard || groups > nc) groups = 1;
     if (groups <= 1) {

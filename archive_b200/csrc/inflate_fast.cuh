@@ -67,6 +67,9 @@ constexpr uint32_t STEP = FP_STEP;    // bytes a lane copies per batch
 #ifndef FP_LOOK2
 #define FP_LOOK2 0  // LZ77: a look-up examines two pending matches of the item at once
 #endif
+#ifndef FP_LZBLK
+#define FP_LZBLK 1  // LZ77 by 2 KiB blocks (far matches at once, near ones by one warp); 0: per-byte readiness over the whole unit
+#endif
 #ifndef FP_HDRAHEAD
 #define FP_HDRAHEAD 1  // thread 0 parses the NEXT unit's first block header while the other warps start the LZ77 pass
 #endif
@@ -106,6 +109,7 @@ struct Ctl {
   uint32_t blk_end, blk_total;
   uint32_t x_state, x_olen, x_wofs;  // for the LZ77-only warps: 0 end, 1 nothing to do for this unit, 2 LZ77 over x_olen bytes
   uint32_t lz_next;                  // LZ77: the next bitmap word nobody has taken yet
+  uint32_t lz_bar;                   // LZ77 by blocks: arrivals at the pass's own barrier (emulation builds only)
   uint32_t ha_valid;                 // the unit being fetched already has its first block header parsed (lens in O_LENS2)
   uint32_t regmask[NW], validmask[NW], warp_tot[NW];
 };
@@ -766,6 +770,185 @@ FP_DEV void fp_lz77(uint8_t *smem, uint32_t tid, uint32_t nthr, uint32_t olen, u
   fp_lz77_run(smem, tid, nthr, olen, wofs);
 }
 
+// ---------------- LZ77 by blocks (the default, FP_LZBLK) ----------------
+// The pass above lets every thread retry the matches of its 16 bytes until their sources are final: with 4 KiB in flight
+// and a median distance of 3.4 KB three looks out of four fail.  Here the output is taken in blocks of 2 KiB, in order,
+// by warps 1 .. 7 (warp 0 parses the next unit's header meanwhile):
+//   * a match of block b whose source ends before block b - 1 reads final bytes whatever happens -- every block before
+//     b - 1 is complete -- and copies at once, no look, no retry (3 threads share a bitmap word: matches 0, 3, 6 .. of the
+//     word, 1, 4, 7 .., 2, 5, 8 ..);  a source that ends inside block b - 1 is final unless it touches a byte a NEAR match
+//     of that block still has to write (one look at that block's pending bitmap);
+//   * what is left -- sources that reach into the match's own block, or into pending bytes of the block before -- is a
+//     NEAR match: it is listed, its bytes are marked pending, and ONE warp resolves the list (per-byte readiness as above,
+//     but over 2 KiB and ~60 matches) while the other six warps already take the far matches of block b + 1.
+// One barrier (among the seven warps) per block.
+constexpr uint32_t LZ_BL = 2048u, LZ_WB = LZ_BL / 32u;  // bytes / bitmap words per block
+constexpr uint32_t LZ_NW = NW - 1u;                     // warps 1 .. NW - 1
+constexpr uint32_t LZ_PW = LZ_WB + 10u;                 // pending bitmap: the block and the 258 bytes behind it
+constexpr uint32_t LZ_NEAR_CAP = 704u;                  // near matches per block (a match is >= 3 bytes long: <= 683)
+static_assert(LZ_NW * 32u == 3u * LZ_WB + 32u, "six warps = three threads per bitmap word of a block");
+static_assert((2u * LZ_PW + 2u) * 4u + 2u * LZ_NEAR_CAP * 2u <= (O_LONG + 356u) - O_LUTL, "LZ77 scratch in the dead table space");
+
+FP_DEV void fp_lzsync(Ctl *ctl) {
+#if defined(B200Z_EMU)
+  const uint32_t n = LZ_NW * 32u;
+  const uint32_t t = atomicAdd(&ctl->lz_bar, 1u);
+  const uint32_t target = (t / n + 1u) * n;
+  while (FP_VOL(ctl->lz_bar) < target) FP_SPIN();
+#else
+  asm volatile("bar.sync 2, %0;" ::"n"(LZ_NW * 32) : "memory");
+#endif
+}
+
+// bits [a, e] (inclusive) of a bitmap: any set / set them / clear them
+FP_DEV uint32_t fp_bits_any(const uint32_t *bm, uint32_t a, uint32_t e) {
+  const uint32_t wa = a >> 5, wb = e >> 5;
+  const uint32_t mlo = 0xffffffffu << (a & 31u), mhi = 0xffffffffu >> (31u - (e & 31u));
+  if (wa == wb) return FP_VOL(bm[wa]) & mlo & mhi;
+  uint32_t busy = (FP_VOL(bm[wa]) & mlo) | (FP_VOL(bm[wb]) & mhi);
+  for (uint32_t q = wa + 1u; q < wb; ++q) busy |= FP_VOL(bm[q]);
+  return busy;
+}
+FP_DEV void fp_bits_or(uint32_t *bm, uint32_t a, uint32_t e) {
+  const uint32_t wa = a >> 5, wb = e >> 5;
+  const uint32_t mlo = 0xffffffffu << (a & 31u), mhi = 0xffffffffu >> (31u - (e & 31u));
+  if (wa == wb) {
+    atomicOr(&bm[wa], mlo & mhi);
+  } else {
+    atomicOr(&bm[wa], mlo);
+    for (uint32_t q = wa + 1u; q < wb; ++q) atomicOr(&bm[q], 0xffffffffu);
+    atomicOr(&bm[wb], mhi);
+  }
+}
+FP_DEV void fp_bits_clear(uint32_t *bm, uint32_t a, uint32_t e) {
+  const uint32_t wa = a >> 5, wb = e >> 5;
+  const uint32_t mlo = 0xffffffffu << (a & 31u), mhi = 0xffffffffu >> (31u - (e & 31u));
+  if (wa == wb) {
+    atomicAnd(&bm[wa], ~(mlo & mhi));
+  } else {
+    atomicAnd(&bm[wa], ~mlo);
+    for (uint32_t q = wa + 1u; q < wb; ++q) atomicAnd(&bm[q], 0u);
+    atomicAnd(&bm[wb], ~mhi);
+  }
+}
+
+// the copy of one match whose source is final (writeBackReference, output_memory_stream.dart:79-98): STEP bytes per batch,
+// loaded before they are stored.  Overlapping run (dist < len, dist < STEP): [p - dist, p + k) is final and periodic, so any
+// multiple of dist that does not reach back beyond p - dist serves as the distance: it doubles until a batch moves STEP bytes
+FP_DEV void fp_lz_copy(uint8_t *W, uint32_t rp, uint32_t rlen, uint32_t rdist) {
+  uint32_t back = rdist;
+  for (uint32_t k = 0; k < rlen;) {
+    if (back < STEP && 2u * back <= k + rdist) back <<= 1;
+    const uint32_t m = min(rlen - k, min(STEP, back));
+    const uint8_t *sp = W + rp + k - back;
+    uint8_t *dp = W + rp + k;
+    uint8_t r[STEP];
+#pragma unroll
+    for (uint32_t t = 0; t < STEP; ++t) r[t] = sp[t];  // (reading past the m-th byte is harmless)
+#pragma unroll
+    for (uint32_t t = 0; t < STEP; ++t)
+      if (t < m) dp[t] = r[t];
+    k += m;
+  }
+}
+
+// the 3-byte record at the first bytes of a match: len - 3, dist - 1
+FP_DEV void fp_lz_record(uint32_t s_Wr, uint32_t p, uint32_t &len, uint32_t &dist) {
+  const uint32_t ra = s_Wr + p;
+  const uint32_t rec = __funnelshift_r(FP_LDS32(ra & ~3u), FP_LDS32((ra & ~3u) + 4u), (ra & 3u) * 8u);
+  len = (rec & 0xffu) + 3u;
+  dist = ((rec >> 8) & 0xffffu) + 1u;
+}
+
+// warps 1 .. NW - 1 (tid >= 32)
+FP_DEV void fp_lz77_blocks(uint8_t *smem, uint32_t tid, uint32_t olen, uint32_t wofs) {
+  const unsigned FULL = 0xffffffffu;
+  Ctl *const ctl = reinterpret_cast<Ctl *>(smem + O_CTL);
+  const uint32_t *const flags = reinterpret_cast<const uint32_t *>(smem + O_FLAGS);
+  uint8_t *const W = smem + O_WIN + wofs;
+  uint32_t *const pend = reinterpret_cast<uint32_t *>(smem + O_LUTL);  // [2][LZ_PW]
+  uint32_t *const nnear = pend + 2u * LZ_PW;                            // [2]
+  uint16_t *const nearl = reinterpret_cast<uint16_t *>(nnear + 2);     // [2][LZ_NEAR_CAP]: position - start of the block
+  const uint32_t lt = tid - 32u, lw = lt >> 5, lane = lt & 31u;
+  const uint32_t s_Wr = FP_SA(W);
+  for (uint32_t i = lt; i < 2u * LZ_PW + 2u; i += LZ_NW * 32u) pend[i] = 0u;
+  fp_lzsync(ctl);
+  const uint32_t nwords = (olen + 31u) >> 5, nblk = (olen + LZ_BL - 1u) / LZ_BL;
+  for (uint32_t it = 0; it <= nblk; ++it) {
+    const uint32_t near_w = (it + LZ_NW - 1u) % LZ_NW;  // the warp that resolves the near matches of block it - 1
+    if (lw == near_w) {
+      if (it > 0u) {
+        // ---- the near matches of block it - 1: a lane owns entries lane, lane + 32, .. and goes round those still pending ----
+        const uint32_t b = (it - 1u) & 1u, bs = (it - 1u) * LZ_BL;
+        uint32_t *const pb = pend + b * LZ_PW;
+        const uint16_t *const nl = nearl + b * LZ_NEAR_CAP;
+        const uint32_t n = FP_VOL(nnear[b]);
+        uint32_t todo = 0u;
+        for (uint32_t i = lane, k = 0; i < n; i += 32u, ++k) todo |= 1u << k;
+        uint32_t cand = todo;
+        while (__ballot_sync(FULL, todo != 0u) != 0u) {
+          if (todo != 0u) {
+            if (cand == 0u) cand = todo;
+            const uint32_t k = (uint32_t)(__ffs((int)cand) - 1);
+            cand &= cand - 1u;
+            const uint32_t rel = nl[lane + 32u * k], p = bs + rel;
+            uint32_t len, dist;
+            fp_lz_record(s_Wr, p, len, dist);
+            const uint32_t src = p - dist, last = min(src + len, p) - 1u;
+            // (everything before this block is final by now: only bytes of the block itself can be pending)
+            const bool ready = last < bs || fp_bits_any(pb, (src > bs ? src : bs) - bs, last - bs) == 0u;
+            if (ready) {
+              __threadfence_block();  // the bytes behind the clear bits are visible
+              fp_lz_copy(W, p, len, dist);
+              __threadfence_block();  // ... before the bits say so
+              fp_bits_clear(pb, rel, rel + len - 1u);
+              todo &= ~(1u << k);
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0u) nnear[b] = 0u;
+      }
+    } else if (it < nblk) {
+      // ---- block `it`: far matches copy at once, near ones are listed ----
+      const uint32_t b = it & 1u, bs = it * LZ_BL, ps = bs - (it > 0u ? LZ_BL : 0u);
+      uint32_t *const pb = pend + b * LZ_PW;
+      const uint32_t *const pprev = pend + (b ^ 1u) * LZ_PW;
+      uint16_t *const nl = nearl + b * LZ_NEAR_CAP;
+      const uint32_t q = (lw < near_w ? lw : lw - 1u) * 32u + lane;  // 0 .. 191
+      const uint32_t w = q / 3u, gw = it * LZ_WB + w;
+      uint32_t c = q - 3u * w;  // my matches: set bits number c, c + 3, .. of the word
+      uint32_t f = gw < nwords ? flags[gw] : 0u;
+      while (f) {
+        const uint32_t bit = (uint32_t)(__ffs((int)f) - 1);
+        f &= f - 1u;
+        if (c != 0u) {
+          c--;
+          continue;
+        }
+        c = 2u;
+        const uint32_t p = gw * 32u + bit;
+        uint32_t len, dist;
+        fp_lz_record(s_Wr, p, len, dist);
+        const uint32_t src = p - dist, last = min(src + len, p) - 1u;
+        bool near = last >= bs;
+        if (!near && it > 0u && last >= ps)  // ends inside the block before: final unless a near match of that block is pending there
+          near = fp_bits_any(pprev, (src > ps ? src : ps) - ps, last - ps) != 0u;
+        if (near) {
+          const uint32_t slot = atomicAdd(&nnear[b], 1u);
+          nl[slot] = (uint16_t)(p - bs);
+          fp_bits_or(pb, p - bs, p - bs + len - 1u);
+        } else {
+          __threadfence_block();
+          fp_lz_copy(W, p, len, dist);
+        }
+      }
+    }
+    __threadfence_block();
+    fp_lzsync(ctl);
+  }
+}
+
 }  // namespace fp
 
 #ifdef B200Z_EMU
@@ -1377,6 +1560,7 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
       ctl->x_olen = olen;
       ctl->x_wofs = wofs;
       ctl->lz_next = 0;
+      ctl->lz_bar = 0;
       // the staged input is dead: fetch the next unit behind the LZ77 pass
       fp_fetch_next(ctl, s_in, mbar, in_base, in_off, in_len, out_base, out_off, out_cap, n_units, atomicAdd(next_unit, 1u));
     }
@@ -1388,6 +1572,25 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
       FP_ASYNC();  // (B)
       continue;
     }
+#if FP_LZBLK && FP_XT == 0
+    // Warp 0: the next unit's input is on its way (fetch_next above) and its first block header is a serial parse by one
+    // thread (measured: 36 k of a unit's 366 k clocks with everybody else at the barrier) -- it is parsed now, behind the
+    // LZ77 pass of the other seven warps.
+    if (warp == 0u) {
+      if (ctl->n_unit != NONE && ctl->n_elig != 0u) {
+        fp_mbar_wait(mbar, phase);  // (`phase` is the next load's parity by now; the wait at the top of the loop sees the same)
+        if (tid == 0) {
+          fp_unit_begin(ctl);
+          fp_parse_header(ctl, s_in, smem + O_LENS2, reinterpret_cast<uint32_t *>(smem + O_CL2));
+          if (!ctl->fb && !ctl->done && ctl->btype != 0u) fp_plan_lanes(ctl, ctl->n_wofs);
+          ctl->ha_valid = 1;
+        }
+        __syncwarp();
+      }
+    } else {
+      fp_lz77_blocks(smem, tid, olen, wofs);
+    }
+#else
     fp_lz77_prep(smem, tid, NTT, olen, wofs);
 #if FP_HDRAHEAD
     // The next unit's input is on its way (fetch_next above) and its first block header is a serial parse by one thread
@@ -1405,6 +1608,7 @@ k_inflate_fast(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__
     }
 #endif
     fp_lz77_run(smem, tid, NTT, olen, wofs);
+#endif
     fp_fence_async();
     FP_ARR();
     FP_ASYNC();  // (B)
