@@ -1006,7 +1006,7 @@ static int bzip2_decode_impl(const uint8_t *in, size_t in_len, int verify, uint8
     struct A {
       unsigned long long *blk_bit, *end_bit, *block_out, *block_off;
       uint32_t *rec_val, *rec_pos, *n_rec, *nblock, *orig_ptr, *rnd, *chist, *tt, *seg_len, *seg_next, *seg_off, *slice_state,
-          *slice_out, *block_crc, *cycle_len, *fast;
+          *slice_out, *block_crc, *cycle_len, *fast, *walk_ctr;
       int32_t *status, *irregular;
       uint8_t *sym8, *raw;
       BzChainHost *chain;
@@ -1025,6 +1025,7 @@ static int bzip2_decode_impl(const uint8_t *in, size_t in_len, int verify, uint8
     a.block_crc = c.take<uint32_t>(nbk);
     a.cycle_len = c.take<uint32_t>(nbk);
     a.fast = c.take<uint32_t>(nbk);
+    a.walk_ctr = c.take<uint32_t>(4);
     a.chain = c.take<BzChainHost>(nbk);
     a.seg_len = c.take<uint32_t>((size_t)nbk * 4098);
     a.seg_next = c.take<uint32_t>((size_t)nbk * 4098);
@@ -1199,7 +1200,7 @@ static int bzip2_decode_impl(const uint8_t *in, size_t in_len, int verify, uint8
     Bz2Ibwt w;
     w.chain = A.chain; w.n_chain = nc; w.nblock_max = nblock_max;
     w.rec_val = A.rec_val; w.rec_pos = A.rec_pos; w.sym8 = A.sym8; w.chist = A.chist; w.tt = A.tt;
-    w.seg_len = A.seg_len; w.seg_next = A.seg_next; w.seg_off = A.seg_off; w.irregular = A.irregular; w.cycle_len = A.cycle_len; w.raw = A.raw;
+    w.seg_len = A.seg_len; w.seg_next = A.seg_next; w.seg_off = A.seg_off; w.walk_ctr = A.walk_ctr; w.irregular = A.irregular; w.cycle_len = A.cycle_len; w.raw = A.raw;
     w.slice_state = A.slice_state; w.slice_out = A.slice_out; w.block_out = A.block_out; w.block_off = A.block_off;
     w.block_crc = A.block_crc; w.out = (uint8_t *)g.d_out.p; w.out_cap = out_cap;
     for (const BzChainHost &ce : chain) w.any_randomised = w.any_randomised || (ce.flags & 1u);

@@ -78,6 +78,7 @@ struct Bz2Ibwt {  // K8 over the validated chain
   uint32_t *chist;  // [n_chain][chunks_max][256]
   uint32_t *tt;     // [n_chain][nblock_max]
   uint32_t *seg_len, *seg_next, *seg_off;  // [n_chain][4098]
+  uint32_t *walk_ctr;                      // [2]: the work counters of k_bz2_walk_len / k_bz2_walk_emit
   int32_t *irregular;                      // [n_chain]
   uint32_t *cycle_len;                     // [n_chain]
   uint8_t *raw;                            // [n_chain][nblock_max]

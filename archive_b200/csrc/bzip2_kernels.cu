@@ -2,7 +2,7 @@
 //
 // Replaces (reference, paths relative to /root/reference/):
 //   lib/src/codecs/bzip2_decoder.dart:90-111    _readBlockType         -> k_bz2_scan      (K6)
-//   lib/src/codecs/bzip2_decoder.dart:113-388   _readCompressed part 1 -> k_bz2_entropy   (K7)
+//   lib/src/codecs/bzip2_decoder.dart:113-388   _readCompressed part 1 -> k_bz2_entropy_fast / k_bz2_entropy (K7)
 //       (symbol map, selectors, code lengths, _hbCreateDecodeTables :774-813, _getMtfVal :732-772,
 //        MTF + RUNA/RUNB)
 //   lib/src/codecs/bzip2_decoder.dart:397-439   cftab + T^-1            -> k_bz2_expand / k_bz2_chunk_hist /
@@ -11,13 +11,18 @@
 //                                                                          k_bz2_rle_count / k_bz2_rle_emit
 //   lib/src/codecs/bzip2/bzip2.dart:11-14       CRC (0x04c11db7, MSB first) -> inside k_bz2_rle_emit
 //
-// Shape of the work (DESIGN.md "K6-K8"): the entropy stage is one serial chain per block (a table switch
-// every 50 symbols + an MTF list), so K7 runs ONE WARP PER BLOCK -- the warp builds the decode LUTs together,
-// lane 0 walks the bits and emits (byte, run) records.  Everything after it is data parallel: records ->
-// bytes, a stable counting sort builds T, the single cycle of T is cut at ~4096 splitters and walked by one
-// thread per segment, and RLE1 + CRC are scans over a 5-state automaton / an associative CRC combine.
+// Shape of the work (DESIGN.md "K6-K8"): the entropy stage is a chain per block (a table switch every 50 symbols + an MTF
+// list).  k_bz2_entropy_fast breaks it up for clean blocks -- code look-ups at every bit offset of a window + four-symbol
+// jumps leave ~13 dependent hops per group of 50 symbols, move-to-front runs symbolically per group (32 groups at once) and
+// is composed across groups, records come from ballots and scans -- and k_bz2_entropy, one warp per block walking every
+// symbol, decodes whatever the fast kernel flags, with the reference's verdicts.  Everything after it is data parallel:
+// records -> bytes, a stable counting sort builds T, the single cycle of T is cut at ~4096 splitters whose segments are
+// walked by threads that take them off a counter, and RLE1 + CRC are scans over a 5-state automaton / an associative
+// CRC combine.
 #include <stdint.h>
 #include <stdlib.h>
+
+#include <algorithm>
 
 #include "b200z_internal.h"
 #include "bz2_rnums.h"
@@ -1205,29 +1210,39 @@ __device__ __forceinline__ BzWalkGeom bz_geom(const BzChain &c, const uint32_t *
   return g;
 }
 
+// Segments come off a counter: a thread whose segment ends takes the next one (of any block), so a CTA does not wait for the
+// longest of its 256 segments (lengths are geometric: the longest is ~5.5 x the mean).  Measured on a B200 (597 blocks): no
+// change against one segment per thread -- 6.9 ms for this kernel, 8.7 ms for k_bz2_walk_emit -- because the walk is bound
+// by the memory system, not by idle slots: every step is a 4-byte read at a random place of a 2.1 GB table, i.e. one
+// 32-byte sector from HBM per output byte (537 M sectors = 17 GB in 6.9 ms = 2.5 TB/s of sector traffic).
 __global__ void __launch_bounds__(256)
-k_bz2_walk_len(const BzChain *__restrict__ chain, const uint32_t *__restrict__ tt, uint32_t nblock_max,
-               uint32_t *__restrict__ seg_len, uint32_t *__restrict__ seg_next) {
-  const BzChain c = chain[blockIdx.y];
-  if (c.nblock == 0) return;
-  const uint32_t *T = tt + (size_t)blockIdx.y * nblock_max;
-  const BzWalkGeom g = bz_geom(c, T);
-  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j > g.kb) return;
-  uint32_t *sl = seg_len + (size_t)blockIdx.y * (BZ_SPLIT + 2), *sn = seg_next + (size_t)blockIdx.y * (BZ_SPLIT + 2);
-  if (j == g.kb && g.start_id != g.kb) {  // the start coincides with a regular splitter
-    sl[j] = 0;
-    sn[j] = g.start_id;
-    return;
+k_bz2_walk_len(const BzChain *__restrict__ chain, uint32_t n_chain, const uint32_t *__restrict__ tt, uint32_t nblock_max,
+               uint32_t *__restrict__ seg_len, uint32_t *__restrict__ seg_next, uint32_t *__restrict__ ctr) {
+  const uint32_t per = BZ_SPLIT + 2, total = n_chain * per;
+  for (;;) {
+    const uint32_t item = atomicAdd(ctr, 1u);
+    if (item >= total) return;
+    const uint32_t bi = item / per, j = item - bi * per;
+    const BzChain c = chain[bi];
+    if (c.nblock == 0) continue;
+    const uint32_t *T = tt + (size_t)bi * nblock_max;
+    const BzWalkGeom g = bz_geom(c, T);
+    if (j > g.kb) continue;
+    uint32_t *sl = seg_len + (size_t)bi * per, *sn = seg_next + (size_t)bi * per;
+    if (j == g.kb && g.start_id != g.kb) {  // the start coincides with a regular splitter
+      sl[j] = 0;
+      sn[j] = g.start_id;
+      continue;
+    }
+    uint32_t cur = (j == g.kb) ? g.tpos0 : j * g.stride;
+    uint32_t n = 0;
+    do {
+      cur = T[cur] >> 8;
+      n++;
+    } while (!(cur % g.stride == 0 || cur == g.tpos0) && n < c.nblock);
+    sl[j] = n;
+    sn[j] = (cur == g.tpos0) ? g.start_id : cur / g.stride;
   }
-  uint32_t cur = (j == g.kb) ? g.tpos0 : j * g.stride;
-  uint32_t n = 0;
-  do {
-    cur = T[cur] >> 8;
-    n++;
-  } while (!(cur % g.stride == 0 || cur == g.tpos0) && n < c.nblock);
-  sl[j] = n;
-  sn[j] = (cur == g.tpos0) ? g.start_id : cur / g.stride;
 }
 
 // Order of the segments along the cycle, one CTA per block: the segment table (<= 4097 entries) is staged in shared memory,
@@ -1298,24 +1313,30 @@ k_bz2_periodic_fill(const BzChain *__restrict__ chain, const uint32_t *__restric
 }
 
 __global__ void __launch_bounds__(256)
-k_bz2_walk_emit(const BzChain *__restrict__ chain, const uint32_t *__restrict__ tt, uint32_t nblock_max,
-                const uint32_t *__restrict__ seg_len, const uint32_t *__restrict__ seg_off, uint8_t *__restrict__ raw) {
-  const BzChain c = chain[blockIdx.y];
-  if (c.nblock == 0) return;
-  const uint32_t *T = tt + (size_t)blockIdx.y * nblock_max;
-  const BzWalkGeom g = bz_geom(c, T);
-  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j > g.kb) return;
-  const uint32_t off = seg_off[(size_t)blockIdx.y * (BZ_SPLIT + 2) + j];
-  if (off == 0xffffffffu) return;
-  uint32_t n = seg_len[(size_t)blockIdx.y * (BZ_SPLIT + 2) + j];
-  if (off + n > c.nblock) n = c.nblock - off;
-  uint32_t cur = (j == g.kb) ? g.tpos0 : j * g.stride;
-  uint8_t *dst = raw + (size_t)blockIdx.y * nblock_max + off;
-  for (uint32_t i = 0; i < n; ++i) {
-    uint32_t t = T[cur];
-    dst[i] = (uint8_t)t;
-    cur = t >> 8;
+k_bz2_walk_emit(const BzChain *__restrict__ chain, uint32_t n_chain, const uint32_t *__restrict__ tt, uint32_t nblock_max,
+                const uint32_t *__restrict__ seg_len, const uint32_t *__restrict__ seg_off, uint8_t *__restrict__ raw,
+                uint32_t *__restrict__ ctr) {
+  const uint32_t per = BZ_SPLIT + 2, total = n_chain * per;
+  for (;;) {
+    const uint32_t item = atomicAdd(ctr, 1u);
+    if (item >= total) return;
+    const uint32_t bi = item / per, j = item - bi * per;
+    const BzChain c = chain[bi];
+    if (c.nblock == 0) continue;
+    const uint32_t *T = tt + (size_t)bi * nblock_max;
+    const BzWalkGeom g = bz_geom(c, T);
+    if (j > g.kb) continue;
+    const uint32_t off = seg_off[(size_t)bi * per + j];
+    if (off == 0xffffffffu) continue;
+    uint32_t n = seg_len[(size_t)bi * per + j];
+    if (off + n > c.nblock) n = c.nblock - off;
+    uint32_t cur = (j == g.kb) ? g.tpos0 : j * g.stride;
+    uint8_t *dst = raw + (size_t)bi * nblock_max + off;
+    for (uint32_t i = 0; i < n; ++i) {
+      uint32_t t = T[cur];
+      dst[i] = (uint8_t)t;
+      cur = t >> 8;
+    }
   }
 }
 
@@ -1712,13 +1733,18 @@ cudaError_t bz2_launch_ibwt(const Bz2Ibwt &a, cudaStream_t s) {
   count_launch();
   k_bz2_build_tt<<<g2, 128, 0, s>>>(chain, a.sym8, a.nblock_max, chunks_max, a.chist, a.tt);
   count_launch();
-  dim3 g3((BZ_SPLIT + 2 + 255) / 256, a.n_chain);
-  k_bz2_walk_len<<<g3, 256, 0, s>>>(chain, a.tt, a.nblock_max, a.seg_len, a.seg_next);
+  // (persistent grids: segments come off a counter)
+  {
+    cudaError_t e = cudaMemsetAsync(a.walk_ctr, 0, 8, s);
+    if (e != cudaSuccess) return e;
+  }
+  const unsigned g3 = (unsigned)std::min<uint64_t>(((uint64_t)a.n_chain * (BZ_SPLIT + 2) + 255) / 256, 148u * 8u);
+  k_bz2_walk_len<<<g3, 256, 0, s>>>(chain, a.n_chain, a.tt, a.nblock_max, a.seg_len, a.seg_next, a.walk_ctr);
   count_launch();
   k_bz2_walk_order<<<a.n_chain, 128, 0, s>>>(chain, a.n_chain, a.tt, a.nblock_max, a.seg_len, a.seg_next,
                                                          a.seg_off, a.irregular, a.cycle_len);
   count_launch();
-  k_bz2_walk_emit<<<g3, 256, 0, s>>>(chain, a.tt, a.nblock_max, a.seg_len, a.seg_off, a.raw);
+  k_bz2_walk_emit<<<g3, 256, 0, s>>>(chain, a.n_chain, a.tt, a.nblock_max, a.seg_len, a.seg_off, a.raw, a.walk_ctr + 1);
   count_launch();
   k_bz2_periodic_fill<<<dim3(64, a.n_chain), 256, 0, s>>>(chain, a.cycle_len, a.nblock_max, a.raw);
   count_launch();

@@ -68,7 +68,7 @@ constexpr uint32_t STEP = FP_STEP;    // bytes a lane copies per batch
 #define FP_LOOK2 0  // LZ77: a look-up examines two pending matches of the item at once
 #endif
 #ifndef FP_LZBLK
-#define FP_LZBLK 1  // LZ77 by 2 KiB blocks (far matches at once, near ones by one warp); 0: per-byte readiness over the whole unit
+#define FP_LZBLK 0  // 1: LZ77 by 2 KiB blocks (far matches at once, near ones by one warp) -- measured 12.4 ms against 8.7; 0: per-byte readiness over the whole unit
 #endif
 #ifndef FP_HDRAHEAD
 #define FP_HDRAHEAD 1  // thread 0 parses the NEXT unit's first block header while the other warps start the LZ77 pass
@@ -770,7 +770,7 @@ FP_DEV void fp_lz77(uint8_t *smem, uint32_t tid, uint32_t nthr, uint32_t olen, u
   fp_lz77_run(smem, tid, nthr, olen, wofs);
 }
 
-// ---------------- LZ77 by blocks (the default, FP_LZBLK) ----------------
+// ---------------- LZ77 by blocks (-DFP_LZBLK=1; measured and NOT the default) ----------------
 // The pass above lets every thread retry the matches of its 16 bytes until their sources are final: with 4 KiB in flight
 // and a median distance of 3.4 KB three looks out of four fail.  Here the output is taken in blocks of 2 KiB, in order,
 // by warps 1 .. 7 (warp 0 parses the next unit's header meanwhile):
@@ -782,6 +782,11 @@ FP_DEV void fp_lz77(uint8_t *smem, uint32_t tid, uint32_t nthr, uint32_t olen, u
 //     NEAR match: it is listed, its bytes are marked pending, and ONE warp resolves the list (per-byte readiness as above,
 //     but over 2 KiB and ~60 matches) while the other six warps already take the far matches of block b + 1.
 // One barrier (among the seven warps) per block.
+// Measured on a B200 (config 2): the pass takes 253 k clocks per unit against 124 k for the per-byte pass above, the kernel
+// 12.4 ms against 8.7.  The chains of matches that feed each other (depth 42 per unit) are chains of NEAR matches, and here
+// they are walked block after block by one warp -- ~10 dependent rounds of ~770 clocks in each of 32 blocks -- where the
+// per-byte pass lets the chains of different regions advance side by side.  Kept as a build option (parity-green on the
+// emulation tier and on a B200 while it was the default: scripts/gpu_runs/r2_run21.sh).
 constexpr uint32_t LZ_BL = 2048u, LZ_WB = LZ_BL / 32u;  // bytes / bitmap words per block
 constexpr uint32_t LZ_NW = NW - 1u;                     // warps 1 .. NW - 1
 constexpr uint32_t LZ_PW = LZ_WB + 10u;                 // pending bitmap: the block and the 258 bytes behind it

@@ -111,6 +111,8 @@ extern "C" int emu_bzip2_blocks(const uint8_t *in, size_t in_len, uint8_t *out, 
     Bz2Ibwt w;
     w.chain = chain.data(); w.n_chain = nc; w.nblock_max = nblock_max;
     w.rec_val = rec_val.data(); w.rec_pos = rec_pos.data(); w.sym8 = sym8.data(); w.chist = chist.data(); w.tt = tt.data();
+    std::vector<uint32_t> walk_ctr(4, 0u);
+    w.walk_ctr = walk_ctr.data();
     w.seg_len = seg_len.data(); w.seg_next = seg_next.data(); w.seg_off = seg_off.data(); w.irregular = irregular.data();
     w.cycle_len = cycle_len.data(); w.raw = raw.data(); w.slice_state = slice_state.data(); w.slice_out = slice_out.data();
     w.block_out = block_out.data(); w.block_off = block_off.data(); w.block_crc = block_crc.data();
