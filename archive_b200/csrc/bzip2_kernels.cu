@@ -163,27 +163,28 @@ __device__ void bz_parse_header(SM &S, BzBits &br, uint64_t blk_bit, uint64_t to
     if (n_sel < 1) err = BZ_DATA;
   }
   if (!err) {
-    uint8_t pos[6];
-    for (int i = 0; i < n_groups; ++i) pos[i] = (uint8_t)i;
+    // (one thread parses up to 18 002 selectors: the run of ones is counted with one clz instead of bit by bit, and the
+    // MTF list of the <= 6 tables is six nibbles of a register)
+    uint32_t pl = 0x543210u;  // list entry k = nibble k
     for (int i = 0; i < n_sel && !err; ++i) {
-      int j = 0;
-      while (br.get(1)) {
-        j++;
-        if (j >= n_groups) {
-          err = BZ_DATA;
-          break;
-        }
+      br.refill();
+      const int j = __clz((int)~(uint32_t)(br.buf >> 32));  // ones in front of the first zero (:160-167)
+      if (j >= n_groups) {
+        err = BZ_DATA;
+        break;
       }
-      if (err) break;
+      br.buf <<= (j + 1);
+      br.cnt -= (j + 1);
       if (i >= BZ_MAX_SEL) {  // _selectorMtf[i]: RangeError (bzip2_decoder.dart:168)
         err = BZ_THROW;
         break;
       }
       // undo the selector MTF on the fly (:172-186): same result as the reference's second loop
-      uint8_t tmp = pos[j];
-      for (int v = j; v > 0; --v) pos[v] = pos[v - 1];
-      pos[0] = tmp;
-      S.set_sel(i, tmp);
+      const uint32_t sh = 4u * (uint32_t)j;
+      const uint32_t tmp = (pl >> sh) & 15u;
+      const uint32_t low = pl & ((1u << sh) - 1u);
+      pl = (pl & ~((16u << sh) - 1u)) | (low << 4) | tmp;
+      S.set_sel(i, (uint8_t)tmp);
       if (br.bitpos() > total_bits) {
         err = BZ_THROW;
         break;
@@ -483,24 +484,28 @@ k_bz2_entropy(const uint32_t *__restrict__ words, uint64_t n_bytes, const unsign
 // K7f `k_bz2_entropy_fast`: the entropy stage of a CLEAN block without its serial chain per symbol.
 //
 // _getMtfVal (:732-772) is a chain of ~700 k dependent table look-ups per 900 kB block, the MTF list (:331-378) a second
-// one; the exact kernel above walks both with one warp (~130 ms per block on a B200).  Here a CTA of two warps splits the
-// block into batches of 32 selector groups (50 symbols each) and pipelines them:
-//   * the WALKER (warp 0) finds where every group starts.  For a group that starts at bit s with table t, lane l looks up
-//     the code at each of the bit offsets s + 8l .. s + 8l + 7 (E[b] = symbol, length: 256 look-ups at once, no chain), then
-//     J4[b] = where four symbols from b end (four dependent reads of E, eight independent chains per lane).  The only serial
-//     part left is ~13 hops over J4 per group; lane i then re-walks the four symbols behind mark i and writes them out.  A
+// one; the exact kernel above walks both with one warp (~130 ms per block on a B200).  Here a CTA of three warps splits the
+// block into batches of 32 selector groups (50 symbols each) and pipelines them, a batch apart:
+//   * the WALKER (warp 0) finds where every group starts -- nothing else.  For a group that starts at bit s with table t,
+//     lane l looks up the code at each of the bit offsets s + 8l .. s + 8l + 7 (E[b] = the length of the code that would
+//     start there: 256 look-ups at once, no chain), then J4[b] = where four symbols from b end (four dependent reads of E,
+//     eight independent chains per lane; lengths read 0 behind the window, so a hop from there stays put, and a flag says
+//     whether all four hops started inside).  The only serial part left is 12 hops over J4 and two over E per group.  A
 //     group longer than the 256-bit window takes another round from where the chain left it.
-//   * the WORKER (warp 1) undoes move-to-front for the previous batch, one group per lane: every lane runs its 50 symbols
-//     against a list that starts as the identity and records which INITIAL position each symbol refers to (a symbolic
-//     list, word-wise shifts in shared memory); the real list is then carried through the 32 groups by composing each
-//     lane's permutation (32 lanes gather), which also resolves the references.  RUNA/RUNB runs, record indices and block
-//     positions are prefix sums over per-lane summaries (a run may straddle two lanes: it belongs to the lane it ends in).
+//   * the DECODER (warp 1), one group per lane: 32 lanes decode their groups' 50 symbols side by side from the start bits
+//     (the end-of-block code ends the block: the lowest lane that meets it), and undo move-to-front SYMBOLICALLY as they go:
+//     every lane runs against a list that starts as the identity and records which INITIAL position each symbol refers to
+//     (word-wise shifts in shared memory); the block's real list is then carried through the 32 groups by composing each
+//     lane's permutation (32 lanes gather), which also resolves the references.
+//   * the RECORDER (warp 2) takes the batch's resolved symbols as ONE stream, 32 at a time: RUNA/RUNB runs, record indices
+//     and block positions are a ballot, a 5-step scan and two shuffles away (a run may straddle passes and batches).
 // Output = the exact kernel's records.  Anything that is not an ordinary block -- header errors, an invalid code on the
 // parse, a run of more than 21 symbols, a block that overflows, selectors that run out, bits past the end of the input,
 // origPtr out of range -- sets status BZ_REDO and the exact kernel decodes the block again with the reference's verdicts.
 // ---------------------------------------------------------------------------------------------
 #define BZ_REDO (-9)
 constexpr int BZF_W = 256;  // bits of the walker's window
+constexpr int BZF_NT = 96;  // threads: walker, decoder, recorder
 constexpr uint32_t BZF_BADSYM = 0x3ffu;
 
 struct BzFast {
@@ -517,21 +522,22 @@ struct BzFast {
     selp[i >> 1] = (i & 1) ? (uint8_t)((c & 0x0fu) | (v << 4)) : (uint8_t)((c & 0xf0u) | v);
   }
   __device__ __forceinline__ int get_sel(int i) const { return (selp[i >> 1] >> ((i & 1) * 4)) & 15; }
-  uint16_t E[BZF_W];       // walker: (symbol << 5 | code length) of the code that starts at window bit b
-  uint8_t EL[BZF_W + 64];  // walker: its length alone; 0 behind the window, so a hop from there stays where it is
-  uint16_t J4[BZF_W];      // walker: where four symbols from b end (a hop that starts behind the window does not move)
-  uint16_t syms[2][32][50];  // a batch: the symbols of 32 groups
+  uint8_t EL[BZF_W + 64];  // walker: length of the code that starts at window bit b; 0 behind the window
+  uint16_t J4[BZF_W];      // walker: where four symbols from b end | 0x8000 when all four started inside the window
+  unsigned long long gstart[2][32];  // a batch: the bit every group starts at
+  int ngw[2];                        // groups the walker found for the batch
+  uint16_t syms[2][32][50];  // a batch: the symbols of 32 groups (references resolved to move-to-front VALUES | 0x8000)
   uint8_t cnt[2][32];        // symbols in each group of the batch (50; fewer in the block's last group)
-  uint32_t mtf[64][32];      // worker: word w of lane l's symbolic list
-  uint8_t cur[256];          // worker: the block's MTF list at the start of the group being resolved
-  int ng[2], last[2];        // groups in the batch; the batch ends with the block's end-of-block code
+  uint32_t mtf[64][32];      // decoder: word w of lane l's symbolic list
+  uint8_t cur[256];          // decoder: the block's MTF list at the start of the group being resolved
+  int ng[2], last[2];        // groups of the batch that belong to the block; the batch holds the end-of-block code
   int redo;
   unsigned long long end_bit, hdr_bitpos;
   BzHdr hdr;
 };
 static_assert(sizeof(BzFast) <= 45 * 1024, "five CTAs per SM");
 
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(BZF_NT)
 k_bz2_entropy_fast(const uint32_t *__restrict__ words, uint64_t n_bytes, const unsigned long long *__restrict__ blk_bit,
                    uint32_t n_blocks, uint32_t nblock_max, uint32_t *__restrict__ rec_val, uint32_t *__restrict__ rec_pos,
                    uint32_t *__restrict__ n_rec, uint32_t *__restrict__ nblock_out, uint32_t *__restrict__ orig_ptr,
@@ -554,6 +560,9 @@ k_bz2_entropy_fast(const uint32_t *__restrict__ words, uint64_t n_bytes, const u
     S.hdr_bitpos = br.bitpos();
     S.end_bit = 0;
     S.redo = (h.err != 0 || br.bitpos() > total_bits) ? 1 : 0;
+    S.ngw[0] = S.ngw[1] = 0;
+    S.ng[0] = S.ng[1] = 0;
+    S.last[0] = S.last[1] = 0;
   }
   __syncthreads();
   if (S.redo) {
@@ -561,8 +570,8 @@ k_bz2_entropy_fast(const uint32_t *__restrict__ words, uint64_t n_bytes, const u
     return;
   }
   const BzHdr h = S.hdr;
-  bz_fill_luts(S, h.n_groups, tid, 64);
-  for (int i = tid; i < 256; i += 64) S.cur[i] = (uint8_t)i;
+  bz_fill_luts(S, h.n_groups, tid, BZF_NT);
+  for (int i = tid; i < 256; i += BZF_NT) S.cur[i] = (uint8_t)i;
   if (tid < 64) S.EL[BZF_W + tid] = 0;
   __syncthreads();
 
@@ -570,262 +579,288 @@ k_bz2_entropy_fast(const uint32_t *__restrict__ words, uint64_t n_bytes, const u
   // walker state (warp 0; the same in every lane)
   uint64_t s = S.hdr_bitpos;  // bit the next group starts at
   int g = 0;                  // its number
-  // worker state (warp 1; the same in every lane): what the exact kernel calls nrec, nblock, run_n, run_es, front
+  bool walk_done = false;
+  // recorder state (warp 2; the same in every lane): what the exact kernel calls nrec, nblock, run_n, run_es, front
   uint32_t st_nrec = 0, st_nblock = 0, st_n = 0, st_v = 0, st_front = 0;
   uint32_t *const rv = rec_val + (size_t)b * nblock_max;
   uint32_t *const rp = rec_pos + (size_t)b * nblock_max;
+  auto ldw = [&](uint64_t i) -> uint32_t { return i < n_words ? __byte_perm(__ldg(words + i), 0, 0x0123) : 0u; };
 
-  bool prev_last = false;
+  bool dec_done = false;   // the decoder has met the end-of-block code (in an earlier iteration)
+  bool prev_last = false;  // ... and the batch the recorder takes in THIS iteration is the one that holds it
   for (int bt = 0;; ++bt) {
-    const int buf = bt & 1;
     if (warp == 0) {
-      if (!prev_last) {
-        // ---------------- walker: the groups of batch bt ----------------
+      if (walk_done || dec_done) {
+        if (lane == 0) S.ngw[bt & 1] = 0;
+      } else {
+        // ---------------- walker: where the groups of batch bt start ----------------
+        const int buf = bt & 1;
         int ngb = 0;
-        bool last = false, redo = false;
-        for (; ngb < 32 && !last && !redo; ++ngb, ++g) {
-          if (g >= h.n_sel) {  // the selectors ran out before the end-of-block code
-            redo = true;
-            break;
-          }
+        for (; ngb < 32 && g < h.n_sel; ++ngb, ++g) {
           const int t = S.get_sel(g);
-          if (lane == 0 && (s >> 5) + 96 < n_words) asm volatile("prefetch.global.L1 [%0];" ::"l"(words + (s >> 5) + 96));
-          int need = 50, outi = 0;
-          while (need > 0 && !last && !redo) {
-            // E over [s, s + 256): my 64-bit window starts at byte (s >> 3) + lane
+          if (lane == 0) {
+            S.gstart[buf][ngb] = s;
+            if ((s >> 5) + 96 < n_words) asm volatile("prefetch.global.L1 [%0];" ::"l"(words + (s >> 5) + 96));
+          }
+          int need = 50;
+          while (need > 0) {
+            // E over [s, s + 256): my window starts at byte (s >> 3) + lane
             {
               const uint64_t byte0 = (s >> 3) + (uint64_t)lane, w0 = byte0 >> 2;
               const uint32_t bsh = (uint32_t)(byte0 & 3u) * 8u;
-              const uint32_t a0 = w0 < n_words ? __byte_perm(__ldg(words + w0), 0, 0x0123) : 0u;
-              const uint32_t a1 = w0 + 1 < n_words ? __byte_perm(__ldg(words + w0 + 1), 0, 0x0123) : 0u;
-              const uint32_t a2 = w0 + 2 < n_words ? __byte_perm(__ldg(words + w0 + 2), 0, 0x0123) : 0u;
+              const uint32_t a0 = ldw(w0), a1 = ldw(w0 + 1), a2 = ldw(w0 + 2);
               const uint32_t whi = __funnelshift_l(a1, a0, bsh), wlo = __funnelshift_l(a2, a1, bsh);
               const int o0 = (int)(s & 7u);
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const uint32_t x = __funnelshift_l(wlo, whi, (uint32_t)(o0 + j));  // 32 bits from window bit 8 * lane + j on
-                uint32_t e = S.lut[t][x >> (32 - BZ_LUT_BITS)];
-                if ((e & 31u) == 0u) {  // longer than the LUT: the limit / base walk from there on (:747-771)
+                uint32_t zl = S.lut[t][x >> (32 - BZ_LUT_BITS)] & 31u;
+                if (zl == 0u) {  // longer than the LUT: the limit / base walk from there on (:747-771); no fit: 1 (the decoder flags it)
                   int zn = S.minlen[t] > BZ_LUT_BITS + 1 ? S.minlen[t] : BZ_LUT_BITS + 1;
-                  e = (BZF_BADSYM << 5) | 1u;
-                  for (; zn <= 20; ++zn) {
-                    const int32_t zvec = (int32_t)(x >> (32 - zn));
-                    if (zvec <= S.limit[t][zn]) {
-                      const int32_t idx = zvec - S.base[t][zn];
-                      if (idx >= 0 && idx < 258) e = ((uint32_t)S.perm[t][idx] << 5) | (uint32_t)zn;
+                  zl = 1u;
+                  for (; zn <= 20; ++zn)
+                    if ((int32_t)(x >> (32 - zn)) <= S.limit[t][zn]) {
+                      zl = (uint32_t)zn;
                       break;
                     }
-                  }
                 }
-                S.E[8 * lane + j] = (uint16_t)e;
-                S.EL[8 * lane + j] = (uint8_t)(e & 31u);
+                S.EL[8 * lane + j] = (uint8_t)zl;
               }
             }
             __syncwarp();
             // J4: four symbols on from each bit of the window (eight independent chains per lane)
             {
-              uint32_t p[8];
+              uint32_t p[8], p3[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) p[j] = 8u * lane + j;
 #pragma unroll
               for (int hop = 0; hop < 4; ++hop) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) p[j] += S.EL[p[j]];
+                for (int j = 0; j < 8; ++j) {
+                  if (hop == 3) p3[j] = p[j];
+                  p[j] += S.EL[p[j]];
+                }
               }
 #pragma unroll
-              for (int j = 0; j < 8; ++j) S.J4[8 * lane + j] = (uint16_t)p[j];
+              for (int j = 0; j < 8; ++j) S.J4[8 * lane + j] = (uint16_t)(p[j] | (p3[j] < (uint32_t)BZF_W ? 0x8000u : 0u));
             }
             __syncwarp();
-            // the chain: one hop per four symbols; lane i keeps mark i
-            int pos = 0, nm = 0, mark = 0;
-            while (pos < BZF_W && 4 * nm < need) {
-              if (lane == nm) mark = pos;
-              nm++;
-              pos = S.J4[pos];
+            // the chain: four symbols per hop while whole hops fit, single symbols for the rest
+            uint32_t pos = 0;
+            while (need >= 4 && pos < (uint32_t)BZF_W) {
+              const uint32_t j4 = S.J4[pos];
+              if (!(j4 & 0x8000u)) break;
+              pos = j4 & 0x7fffu;
+              need -= 4;
             }
-            // lane i < nm: the (up to four) symbols behind its mark
-            int c = 0, p = mark;
-            bool sawe = false, sawbad = false;
-            if (lane < nm) {
-              const int hmax = need - 4 * lane < 4 ? need - 4 * lane : 4;
-              uint16_t *dst = &S.syms[buf][ngb][outi + 4 * lane];
-              while (c < hmax && p < BZF_W) {
-                const uint32_t e = S.E[p];
-                const uint32_t sym = e >> 5;
-                if (sym == BZF_BADSYM) {
-                  sawbad = true;
-                  break;
-                }
-                dst[c] = (uint16_t)sym;
-                c++;
-                p += (int)(e & 31u);
-                if (sym == eob) {
-                  sawe = true;
+            while (need > 0 && pos < (uint32_t)BZF_W) {
+              pos += S.EL[pos];
+              need--;
+            }
+            s += pos;
+            __syncwarp();
+          }
+        }
+        if (lane == 0) S.ngw[buf] = ngb;
+        if (g >= h.n_sel) walk_done = true;  // (the encoder writes as many selectors as the block has groups)
+      }
+    } else if (warp == 1) {
+      if (bt >= 1 && !dec_done) {
+        // ---------------- decoder: batch bt - 1, a group per lane ----------------
+        const int wb = (bt - 1) & 1;
+        const int ngb = S.ngw[wb];
+        const int g0 = (bt - 1) * 32;
+        bool lbad = false, saw_eob = false;
+        unsigned long long my_end = 0;
+        int mycnt = 0, hiw = 0;
+        uint16_t *const sy = S.syms[wb][lane];
+        if (lane < ngb) {
+          const int t = S.get_sel(g0 + lane);
+          uint64_t sp = S.gstart[wb][lane];
+          for (int k = 0; k < 50; ++k) {
+            const uint64_t wi = sp >> 5;
+            const uint32_t x = __funnelshift_l(ldw(wi + 1), ldw(wi), (uint32_t)(sp & 31u));  // 32 bits from bit sp on
+            uint32_t e = S.lut[t][x >> (32 - BZ_LUT_BITS)];
+            if ((e & 31u) == 0u) {  // longer than the LUT: the limit / base walk from there on (:747-771)
+              int zn = S.minlen[t] > BZ_LUT_BITS + 1 ? S.minlen[t] : BZ_LUT_BITS + 1;
+              e = BZF_BADSYM << 5;
+              for (; zn <= 20; ++zn) {
+                const int32_t zvec = (int32_t)(x >> (32 - zn));
+                if (zvec <= S.limit[t][zn]) {
+                  const int32_t idx = zvec - S.base[t][zn];
+                  if (idx >= 0 && idx < 258) e = ((uint32_t)S.perm[t][idx] << 5) | (uint32_t)zn;
                   break;
                 }
               }
             }
-            const unsigned em = __ballot_sync(FULLW, sawe), bm = __ballot_sync(FULLW, sawbad);
-            int src = nm - 1;
-            if (em) {
-              src = __ffs((int)em) - 1;
-              last = true;
-              if (bm & ((2u << src) - 1u)) redo = true;
-            } else if (bm) {
-              redo = true;
+            const uint32_t sym = e >> 5;
+            if (sym == BZF_BADSYM) {
+              lbad = true;
+              break;
             }
-            const int tot = 4 * src + __shfl_sync(FULLW, c, src);
-            s += (uint64_t)__shfl_sync(FULLW, p, src);
-            outi += tot;
-            need -= tot;
-            __syncwarp();
+            sp += e & 31u;
+            if (sym == eob) {
+              saw_eob = true;
+              my_end = sp;
+              break;
+            }
+            mycnt = k + 1;
+            if (sym <= 1u) {
+              sy[k] = (uint16_t)sym;
+              continue;
+            }
+            // my group against a list that starts as the identity: the symbol becomes a reference to an initial position
+            const uint32_t nn = sym - 1u, wn = nn >> 2, bn = nn & 3u;
+            for (; hiw <= (int)wn; ++hiw) S.mtf[hiw][lane] = 0x03020100u + 0x04040404u * (uint32_t)hiw;
+            const uint32_t top = S.mtf[wn][lane];
+            const uint32_t uc = (top >> (8u * bn)) & 0xffu;
+            uint32_t carry = uc;
+            for (uint32_t w = 0; w < wn; ++w) {
+              const uint32_t tw = S.mtf[w][lane];
+              S.mtf[w][lane] = (tw << 8) | carry;
+              carry = tw >> 24;
+            }
+            const uint32_t mlow = bn == 3u ? 0xffffffffu : ((1u << (8u * (bn + 1u))) - 1u);
+            S.mtf[wn][lane] = (top & ~mlow) | (((top << 8) | carry) & mlow);
+            sy[k] = (uint16_t)(0x8000u | uc);
           }
-          if (lane == 0) S.cnt[buf][ngb] = (uint8_t)(last ? outi - 1 : outi);  // without the end-of-block code
         }
+        // the block ends in the lowest lane that met the end-of-block code; what the lanes above it decoded is not the block's
+        const unsigned em = __ballot_sync(FULLW, saw_eob);
+        const int el = em ? __ffs((int)em) - 1 : 31;
+        const int ngb_eff = em ? el + 1 : ngb;
+        if (__ballot_sync(FULLW, lbad && lane <= el && lane < ngb_eff) != 0u) {
+          if (lane == 0) S.redo = 1;
+        } else if (!em && ngb < 32) {
+          if (lane == 0) S.redo = 1;  // the selectors ran out before the end-of-block code
+        }
+        __syncwarp();
+        // the real list, group by group: resolve the group's references, then list'[i] = list[P[i]]
+        for (int gi = 0; gi < ngb_eff; ++gi) {
+          const int cg = __shfl_sync(FULLW, mycnt, gi);
+          const int hib = __shfl_sync(FULLW, hiw, gi) * 4;  // bytes of the group's list that may have moved
+          for (int k = lane; k < cg; k += 32) {
+            const uint32_t v = S.syms[wb][gi][k];
+            if (v & 0x8000u) S.syms[wb][gi][k] = (uint16_t)(0x8000u | S.cur[v & 0xffu]);
+          }
+          uint8_t nv[8];
+#pragma unroll
+          for (int m = 0; m < 8; ++m) {
+            const int i = lane + 32 * m;
+            nv[m] = 0;
+            if (i < hib) nv[m] = S.cur[(S.mtf[i >> 2][gi] >> (8 * (i & 3))) & 0xffu];
+          }
+          __syncwarp();
+#pragma unroll
+          for (int m = 0; m < 8; ++m) {
+            const int i = lane + 32 * m;
+            if (i < hib) S.cur[i] = nv[m];
+          }
+          __syncwarp();
+        }
+        if (lane < 32) S.cnt[wb][lane] = (uint8_t)mycnt;
         if (lane == 0) {
-          S.ng[buf] = ngb;
-          S.last[buf] = last ? 1 : 0;
-          if (last) S.end_bit = s;
-          if (redo) S.redo = 1;
+          S.ng[wb] = ngb_eff;
+          S.last[wb] = em ? 1 : 0;
         }
+        if (em && lane == el) S.end_bit = my_end;
       }
-    } else if (bt > 0) {
-      // ---------------- worker: batch bt - 1 ----------------
-      const int wb = buf ^ 1;
-      const int ngb = S.ng[wb];
-      const bool lastb = S.last[wb] != 0;
-      bool lbad = false;
-      // (1) my group against a list that starts as the identity: symbols become references to initial positions
-      int hiw = 0;
-      const int mycnt = lane < ngb ? (int)S.cnt[wb][lane] : 0;
-      uint16_t *const sy = S.syms[wb][lane];
-      for (int k = 0; k < mycnt; ++k) {
-        const uint32_t sym = sy[k];
-        if (sym <= 1u) continue;
-        const uint32_t nn = sym - 1u, wn = nn >> 2, bn = nn & 3u;
-        for (; hiw <= (int)wn; ++hiw) S.mtf[hiw][lane] = 0x03020100u + 0x04040404u * (uint32_t)hiw;
-        const uint32_t top = S.mtf[wn][lane];
-        const uint32_t uc = (top >> (8u * bn)) & 0xffu;
-        uint32_t carry = uc;
-        for (uint32_t w = 0; w < wn; ++w) {
-          const uint32_t tw = S.mtf[w][lane];
-          S.mtf[w][lane] = (tw << 8) | carry;
-          carry = tw >> 24;
-        }
-        const uint32_t mlow = bn == 3u ? 0xffffffffu : ((1u << (8u * (bn + 1u))) - 1u);
-        S.mtf[wn][lane] = (top & ~mlow) | (((top << 8) | carry) & mlow);
-        sy[k] = (uint16_t)(0x8000u | uc);
-      }
-      __syncwarp();
-      // (2) the real list, group by group: resolve the group's references, then list'[i] = list[P[i]]
-      for (int gi = 0; gi < ngb; ++gi) {
-        const int cg = (int)S.cnt[wb][gi];
-        const int hib = __shfl_sync(FULLW, hiw, gi) * 4;  // bytes of the group's list that may have moved
-        for (int k = lane; k < cg; k += 32) {
-          const uint32_t v = S.syms[wb][gi][k];
-          if (v & 0x8000u) S.syms[wb][gi][k] = (uint16_t)(0x8000u | S.cur[v & 0xffu]);
-        }
-        uint8_t nv[8];
+    } else {
+      if (bt >= 2) {
+        // ---------------- recorder: batch bt - 2 (:276-388) ----------------
+        // The batch's symbols as ONE stream, 32 at a time.  A run symbol adds (sym + 1) << its index in the run; a symbol
+        // that is not a run symbol closes the run in front of it (one record, written at the position the run started at)
+        // and makes a record of its own.  Everything a lane needs -- its index in the run, the run's value, records and
+        // block positions in front of it -- is a ballot, a 5-step scan and two shuffles away.
+        const int wb = bt & 1;  // (bt - 2) & 1
+        const int ngb = S.ng[wb];
+        const bool lastb = prev_last;
+        bool lbad = false;
+        const int total = ngb ? 50 * (ngb - 1) + (int)S.cnt[wb][ngb - 1] : 0;  // only the block's last group is short
+        const uint16_t *const flat = &S.syms[wb][0][0];
+        for (int base = 0; base < total; base += 32) {
+          const int i = base + lane;
+          const bool valid = i < total;
+          const uint32_t v = valid ? (uint32_t)flat[i] : 0xffffu;
+          const bool isrun = valid && v <= 1u, isnr = valid && v > 1u;
+          const unsigned NR = __ballot_sync(FULLW, isnr);
+          const unsigned below = NR & ((1u << lane) - 1u);
+          const int q = below ? 31 - __clz((int)below) : -1;  // the last symbol below me that is not a run symbol
+          const uint32_t before = q < 0 ? st_n + (uint32_t)lane : (uint32_t)(lane - q - 1);  // run symbols right in front of me
+          uint32_t a = 0;
+          if (isrun) {
+            if (before > 20u) lbad = true;  // N >= 2*1024*1024 (:291)
+            else a = (v + 1u) << before;
+          }
+          uint32_t pa = a;  // inclusive scan
 #pragma unroll
-        for (int m = 0; m < 8; ++m) {
-          const int i = lane + 32 * m;
-          nv[m] = 0;
-          if (i < hib) nv[m] = S.cur[(S.mtf[i >> 2][gi] >> (8 * (i & 3))) & 0xffu];
-        }
-        __syncwarp();
-#pragma unroll
-        for (int m = 0; m < 8; ++m) {
-          const int i = lane + 32 * m;
-          if (i < hib) S.cur[i] = nv[m];
-        }
-        __syncwarp();
-      }
-      // (3) the records (:276-388): the batch's symbols as ONE stream, 32 at a time.  A run symbol adds (sym + 1) << its
-      // index in the run; a symbol that is not a run symbol closes the run in front of it (one record, written at the
-      // position the run started at) and makes a record of its own.  Everything a lane needs -- its index in the run, the
-      // run's value, records and block positions in front of it -- is a ballot, a 5-step scan and two shuffles away.
-      const int total = ngb ? 50 * (ngb - 1) + (int)S.cnt[wb][ngb - 1] : 0;  // only the block's last group is short
-      const uint16_t *const flat = &S.syms[wb][0][0];
-      for (int base = 0; base < total; base += 32) {
-        const int i = base + lane;
-        const bool valid = i < total;
-        const uint32_t v = valid ? (uint32_t)flat[i] : 0xffffu;
-        const bool isrun = valid && v <= 1u, isnr = valid && v > 1u;
-        const unsigned NR = __ballot_sync(FULLW, isnr);
-        const unsigned below = NR & ((1u << lane) - 1u);
-        const int q = below ? 31 - __clz((int)below) : -1;  // the last symbol below me that is not a run symbol
-        const uint32_t before = q < 0 ? st_n + (uint32_t)lane : (uint32_t)(lane - q - 1);  // run symbols right in front of me
-        uint32_t a = 0;
-        if (isrun) {
-          if (before > 20u) lbad = true;  // N >= 2*1024*1024 (:291)
-          else a = (v + 1u) << before;
-        }
-        uint32_t pa = a;  // inclusive scan
-#pragma unroll
-        for (int dlt = 1; dlt < 32; dlt <<= 1) {
-          const uint32_t tsh = __shfl_up_sync(FULLW, pa, dlt);
-          if (lane >= dlt) pa += tsh;
-        }
-        const uint32_t pa_q = __shfl_sync(FULLW, pa, q < 0 ? 0 : q);
-        const uint32_t fv = __shfl_sync(FULLW, v & 0xffu, q < 0 ? 0 : q);
-        const bool hasrun = isnr && before != 0u;
-        const unsigned HR = __ballot_sync(FULLW, hasrun);
-        if (isnr) {
-          const uint32_t runval = q < 0 ? st_v + pa : pa - pa_q;  // (a is 0 here: pa is the sum over what lies below me)
-          const uint32_t pos_sym = st_nblock + st_v + pa + (uint32_t)__popc(below);
-          uint32_t r = st_nrec + (uint32_t)__popc(below) + (uint32_t)__popc(HR & ((1u << lane) - 1u));
-          if (pos_sym >= nblock_max) {  // (:313-316, :326-329)
-            lbad = true;
-          } else {
-            if (hasrun) {
-              rv[r] = (runval << 8) | S.seq2unseq[q < 0 ? st_front : fv];
-              rp[r] = pos_sym - runval;
-              r++;
+          for (int dlt = 1; dlt < 32; dlt <<= 1) {
+            const uint32_t tsh = __shfl_up_sync(FULLW, pa, dlt);
+            if (lane >= dlt) pa += tsh;
+          }
+          const uint32_t pa_q = __shfl_sync(FULLW, pa, q < 0 ? 0 : q);
+          const uint32_t fv = __shfl_sync(FULLW, v & 0xffu, q < 0 ? 0 : q);
+          const bool hasrun = isnr && before != 0u;
+          const unsigned HR = __ballot_sync(FULLW, hasrun);
+          if (isnr) {
+            const uint32_t runval = q < 0 ? st_v + pa : pa - pa_q;  // (a is 0 here: pa is the sum over what lies below me)
+            const uint32_t pos_sym = st_nblock + st_v + pa + (uint32_t)__popc(below);
+            uint32_t r = st_nrec + (uint32_t)__popc(below) + (uint32_t)__popc(HR & ((1u << lane) - 1u));
+            if (pos_sym >= nblock_max) {  // (:313-316, :326-329)
+              lbad = true;
+            } else {
+              if (hasrun) {
+                rv[r] = (runval << 8) | S.seq2unseq[q < 0 ? st_front : fv];
+                rp[r] = pos_sym - runval;
+                r++;
+              }
+              rv[r] = (1u << 8) | S.seq2unseq[v & 0xffu];
+              rp[r] = pos_sym;
             }
-            rv[r] = (1u << 8) | S.seq2unseq[v & 0xffu];
-            rp[r] = pos_sym;
+          }
+          const int nvalid = total - base < 32 ? total - base : 32;
+          const uint32_t pa_last = __shfl_sync(FULLW, pa, 31);
+          if (NR) {
+            const int ql = 31 - __clz((int)NR);
+            const uint32_t pa_ql = __shfl_sync(FULLW, pa, ql);
+            st_nrec += (uint32_t)(__popc(NR) + __popc(HR));
+            st_nblock += st_v + pa_ql + (uint32_t)__popc(NR);
+            st_v = pa_last - pa_ql;
+            st_n = (uint32_t)(nvalid - 1 - ql);
+            st_front = __shfl_sync(FULLW, v & 0xffu, ql);
+          } else {
+            st_v += pa_last;
+            st_n += (uint32_t)nvalid;
           }
         }
-        const int nvalid = total - base < 32 ? total - base : 32;
-        const uint32_t pa_last = __shfl_sync(FULLW, pa, 31);
-        if (NR) {
-          const int ql = 31 - __clz((int)NR);
-          const uint32_t pa_ql = __shfl_sync(FULLW, pa, ql);
-          st_nrec += (uint32_t)(__popc(NR) + __popc(HR));
-          st_nblock += st_v + pa_ql + (uint32_t)__popc(NR);
-          st_v = pa_last - pa_ql;
-          st_n = (uint32_t)(nvalid - 1 - ql);
-          st_front = __shfl_sync(FULLW, v & 0xffu, ql);
-        } else {
-          st_v += pa_last;
-          st_n += (uint32_t)nvalid;
+        if (lastb && st_n) {  // the run that the end-of-block code closes (:306-321)
+          if (st_n > 21u || st_nblock + st_v > nblock_max) {
+            lbad = true;
+          } else if (lane == 0) {
+            rv[st_nrec] = (st_v << 8) | S.seq2unseq[st_front];
+            rp[st_nrec] = st_nblock;
+          }
+          st_nrec++;
+          st_nblock += st_v;
+          st_n = 0;
+          st_v = 0;
         }
+        if (__any_sync(FULLW, lbad) && lane == 0) S.redo = 1;
       }
-      if (lastb && st_n) {  // the run that the end-of-block code closes (:306-321)
-        if (st_n > 21u || st_nblock + st_v > nblock_max) {
-          lbad = true;
-        } else if (lane == 0) {
-          rv[st_nrec] = (st_v << 8) | S.seq2unseq[st_front];
-          rp[st_nrec] = st_nblock;
-        }
-        st_nrec++;
-        st_nblock += st_v;
-        st_n = 0;
-        st_v = 0;
-      }
-      if (__any_sync(FULLW, lbad) && lane == 0) S.redo = 1;
     }
     __syncthreads();
-    const bool redo = S.redo != 0, cur_last = S.last[buf] != 0;
+    const bool redo = S.redo != 0;
+    const bool cur_last = bt >= 1 && !dec_done && S.last[(bt - 1) & 1] != 0;
     __syncthreads();
     if (redo) {
       if (tid == 0) status[b] = BZ_REDO;
       return;
     }
-    if (prev_last) break;  // the worker has just finished the block's last batch
+    if (prev_last) break;  // the recorder has just finished the block's last batch
     prev_last = cur_last;
+    if (cur_last) dec_done = true;
   }
-  if (tid == 32) {
+  if (tid == 64) {
     const unsigned long long endp = S.end_bit;
     if (h.optr >= st_nblock || endp > total_bits) {  // (:399-402), a read past the end: the exact kernel's verdicts
       status[b] = BZ_REDO;
@@ -1699,7 +1734,7 @@ cudaError_t bz2_launch_entropy(const Bz2Entropy &a, cudaStream_t s) {
   const char *fe = getenv("B200Z_BZ2_FAST");
   const int fast = !(fe && fe[0] == '0');
   if (fast) {
-    k_bz2_entropy_fast<<<a.n_blocks, 64, 0, s>>>(a.words, a.n_bytes, a.blk_bit, a.n_blocks, a.nblock_max, a.rec_val, a.rec_pos,
+    k_bz2_entropy_fast<<<a.n_blocks, BZF_NT, 0, s>>>(a.words, a.n_bytes, a.blk_bit, a.n_blocks, a.nblock_max, a.rec_val, a.rec_pos,
                                                  a.n_rec, a.nblock, a.orig_ptr, a.randomised, a.end_bit, a.status,
                                                  a.fast_flag);
     count_launch();
