@@ -1005,10 +1005,10 @@ static int bzip2_decode_impl(const uint8_t *in, size_t in_len, int verify, uint8
     Carver c(base);
     struct A {
       unsigned long long *blk_bit, *end_bit, *block_out, *block_off;
-      uint32_t *rec_val, *rec_pos, *n_rec, *nblock, *orig_ptr, *rnd, *chist, *tt, *seg_len, *seg_next, *seg_off, *slice_state,
+      uint32_t *rec_val, *rec_pos, *n_rec, *nblock, *orig_ptr, *rnd, *chist, *tt, *seg_len, *seg_next, *seg_off, *seg_resume, *slice_state,
           *slice_out, *block_crc, *cycle_len, *fast, *walk_ctr;
       int32_t *status, *irregular;
-      uint8_t *sym8, *raw;
+      uint8_t *sym8, *raw, *slots;
       BzChainHost *chain;
       size_t bytes;
     } a;
@@ -1030,6 +1030,7 @@ static int bzip2_decode_impl(const uint8_t *in, size_t in_len, int verify, uint8
     a.seg_len = c.take<uint32_t>((size_t)nbk * 4098);
     a.seg_next = c.take<uint32_t>((size_t)nbk * 4098);
     a.seg_off = c.take<uint32_t>((size_t)nbk * 4098);
+    a.seg_resume = c.take<uint32_t>((size_t)nbk * 4098);
     a.slice_state = c.take<uint32_t>((size_t)nbk * 1024);
     a.slice_out = c.take<uint32_t>((size_t)nbk * 1024);
     a.chist = c.take<uint32_t>((size_t)nbk * chunks_max * 256);
@@ -1038,6 +1039,7 @@ static int bzip2_decode_impl(const uint8_t *in, size_t in_len, int verify, uint8
     a.tt = c.take<uint32_t>((size_t)nbk * nblock_max);
     a.sym8 = c.take<uint8_t>((size_t)nbk * nblock_max);
     a.raw = c.take<uint8_t>((size_t)nbk * nblock_max);
+    a.slots = c.take<uint8_t>((size_t)nbk * bz2_slot_bytes_per_block());
     a.bytes = align_up(c.off, 256);
     return a;
   };
@@ -1200,7 +1202,7 @@ static int bzip2_decode_impl(const uint8_t *in, size_t in_len, int verify, uint8
     Bz2Ibwt w;
     w.chain = A.chain; w.n_chain = nc; w.nblock_max = nblock_max;
     w.rec_val = A.rec_val; w.rec_pos = A.rec_pos; w.sym8 = A.sym8; w.chist = A.chist; w.tt = A.tt;
-    w.seg_len = A.seg_len; w.seg_next = A.seg_next; w.seg_off = A.seg_off; w.walk_ctr = A.walk_ctr; w.irregular = A.irregular; w.cycle_len = A.cycle_len; w.raw = A.raw;
+    w.seg_len = A.seg_len; w.seg_next = A.seg_next; w.seg_off = A.seg_off; w.seg_resume = A.seg_resume; w.slots = A.slots; w.walk_ctr = A.walk_ctr; w.irregular = A.irregular; w.cycle_len = A.cycle_len; w.raw = A.raw;
     w.slice_state = A.slice_state; w.slice_out = A.slice_out; w.block_out = A.block_out; w.block_off = A.block_off;
     w.block_crc = A.block_crc; w.out = (uint8_t *)g.d_out.p; w.out_cap = out_cap;
     for (const BzChainHost &ce : chain) w.any_randomised = w.any_randomised || (ce.flags & 1u);

@@ -78,6 +78,8 @@ struct Bz2Ibwt {  // K8 over the validated chain
   uint32_t *chist;  // [n_chain][chunks_max][256]
   uint32_t *tt;     // [n_chain][nblock_max]
   uint32_t *seg_len, *seg_next, *seg_off;  // [n_chain][4098]
+  uint32_t *seg_resume;                    // [n_chain][4098]: where the walk of a segment stood when its slot was full
+  uint8_t *slots;                          // [n_chain][4098][bz2_slot_bytes_per_block() / 4098]: a segment's bytes before they are placed
   uint32_t *walk_ctr;                      // [2]: the work counters of k_bz2_walk_len / k_bz2_walk_emit
   int32_t *irregular;                      // [n_chain]
   uint32_t *cycle_len;                     // [n_chain]
@@ -100,6 +102,7 @@ cudaError_t bz2_launch_scan(const uint8_t *d_in, uint64_t n_bytes, unsigned long
 cudaError_t bz2_launch_entropy(const Bz2Entropy &a, cudaStream_t s);
 // blocks K7 left with status -3 (a damaged block that the reference keeps decoding): d_list = their indices into a's arrays
 cudaError_t bz2_launch_entropy_literal(const Bz2Entropy &a, const uint32_t *d_list, uint32_t n_list, cudaStream_t s);
+size_t bz2_slot_bytes_per_block();
 cudaError_t bz2_launch_ibwt(const Bz2Ibwt &a, cudaStream_t s);
 cudaError_t bz2_launch_ibwt_group(const Bz2Ibwt &a, uint32_t lo, uint32_t hi, cudaStream_t s);
 void count_launch();

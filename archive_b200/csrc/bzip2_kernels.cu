@@ -1245,14 +1245,21 @@ __device__ __forceinline__ BzWalkGeom bz_geom(const BzChain &c, const uint32_t *
   return g;
 }
 
-// Segments come off a counter: a thread whose segment ends takes the next one (of any block), so a CTA does not wait for the
-// longest of its 256 segments (lengths are geometric: the longest is ~5.5 x the mean).  Measured on a B200 (597 blocks): no
-// change against one segment per thread -- 6.9 ms for this kernel, 8.7 ms for k_bz2_walk_emit -- because the walk is bound
-// by the memory system, not by idle slots: every step is a 4-byte read at a random place of a 2.1 GB table, i.e. one
-// 32-byte sector from HBM per output byte (537 M sectors = 17 GB in 6.9 ms = 2.5 TB/s of sector traffic).
+// The walk is ONE pass (round 2; it was a length pass and an emit pass, 6.9 + 8.7 ms for 597 blocks, both bound by the
+// memory system: every step is a 4-byte read at a random place of a 2.1 GB table, i.e. one 32-byte sector from HBM per
+// output byte).  A segment's place in the output is known only once every segment's length is, so the bytes go to a SLOT
+// per segment first (BZ_SLOT bytes: segment lengths are geometric with mean nblock / 4096 ~ 220, so ~1 % overflow) and a
+// second, coalesced pass moves them (k_bz2_walk_emit); a segment longer than its slot records where the walk stood at the
+// slot's end and that kernel goes on from there.  Segments come off a counter (a thread whose segment ends takes the next
+// one, of any block) -- measured neutral against one segment per thread.
+#ifndef BZ_SLOT_BYTES
+#define BZ_SLOT_BYTES 1024  // (the emulation tier builds with 64, so that most segments overflow their slot there)
+#endif
+constexpr uint32_t BZ_SLOT = BZ_SLOT_BYTES;
 __global__ void __launch_bounds__(256)
 k_bz2_walk_len(const BzChain *__restrict__ chain, uint32_t n_chain, const uint32_t *__restrict__ tt, uint32_t nblock_max,
-               uint32_t *__restrict__ seg_len, uint32_t *__restrict__ seg_next, uint32_t *__restrict__ ctr) {
+               uint32_t *__restrict__ seg_len, uint32_t *__restrict__ seg_next, uint32_t *__restrict__ seg_resume,
+               uint8_t *__restrict__ slots, uint32_t *__restrict__ ctr) {
   const uint32_t per = BZ_SPLIT + 2, total = n_chain * per;
   for (;;) {
     const uint32_t item = atomicAdd(ctr, 1u);
@@ -1270,9 +1277,13 @@ k_bz2_walk_len(const BzChain *__restrict__ chain, uint32_t n_chain, const uint32
       continue;
     }
     uint32_t cur = (j == g.kb) ? g.tpos0 : j * g.stride;
+    uint8_t *slot = slots + (size_t)item * BZ_SLOT;
     uint32_t n = 0;
     do {
-      cur = T[cur] >> 8;
+      const uint32_t t = T[cur];
+      if (n < BZ_SLOT) slot[n] = (uint8_t)t;
+      else if (n == BZ_SLOT) seg_resume[item] = cur;  // (the byte of this step is still to be written)
+      cur = t >> 8;
       n++;
     } while (!(cur % g.stride == 0 || cur == g.tpos0) && n < c.nblock);
     sl[j] = n;
@@ -1347,30 +1358,36 @@ k_bz2_periodic_fill(const BzChain *__restrict__ chain, const uint32_t *__restric
   for (uint32_t i = cl + blockIdx.x * blockDim.x + threadIdx.x; i < c.nblock; i += gridDim.x * blockDim.x) dst[i] = dst[i % cl];
 }
 
+// one WARP per segment: the slot's bytes move to the segment's place in the block (coalesced); lane 0 walks on for the part
+// of a segment that did not fit its slot
 __global__ void __launch_bounds__(256)
 k_bz2_walk_emit(const BzChain *__restrict__ chain, uint32_t n_chain, const uint32_t *__restrict__ tt, uint32_t nblock_max,
-                const uint32_t *__restrict__ seg_len, const uint32_t *__restrict__ seg_off, uint8_t *__restrict__ raw,
-                uint32_t *__restrict__ ctr) {
+                const uint32_t *__restrict__ seg_len, const uint32_t *__restrict__ seg_off, const uint32_t *__restrict__ seg_resume,
+                const uint8_t *__restrict__ slots, uint8_t *__restrict__ raw) {
   const uint32_t per = BZ_SPLIT + 2, total = n_chain * per;
-  for (;;) {
-    const uint32_t item = atomicAdd(ctr, 1u);
-    if (item >= total) return;
+  const uint32_t lane = threadIdx.x & 31u, wpb = blockDim.x >> 5;
+  for (uint32_t item = blockIdx.x * wpb + (threadIdx.x >> 5); item < total; item += gridDim.x * wpb) {
     const uint32_t bi = item / per, j = item - bi * per;
     const BzChain c = chain[bi];
     if (c.nblock == 0) continue;
-    const uint32_t *T = tt + (size_t)bi * nblock_max;
-    const BzWalkGeom g = bz_geom(c, T);
-    if (j > g.kb) continue;
-    const uint32_t off = seg_off[(size_t)bi * per + j];
+    const uint32_t stride0 = (c.nblock + BZ_SPLIT - 1) / BZ_SPLIT, stride = stride0 ? stride0 : 1u;
+    if (j > (c.nblock + stride - 1) / stride) continue;  // (> kb)
+    const uint32_t off = seg_off[item];
     if (off == 0xffffffffu) continue;
-    uint32_t n = seg_len[(size_t)bi * per + j];
+    uint32_t n = seg_len[item];
     if (off + n > c.nblock) n = c.nblock - off;
-    uint32_t cur = (j == g.kb) ? g.tpos0 : j * g.stride;
     uint8_t *dst = raw + (size_t)bi * nblock_max + off;
-    for (uint32_t i = 0; i < n; ++i) {
-      uint32_t t = T[cur];
-      dst[i] = (uint8_t)t;
-      cur = t >> 8;
+    const uint8_t *slot = slots + (size_t)item * BZ_SLOT;
+    const uint32_t m = n < BZ_SLOT ? n : BZ_SLOT;
+    for (uint32_t i = lane; i < m; i += 32u) dst[i] = slot[i];
+    if (n > BZ_SLOT && lane == 0u) {
+      const uint32_t *T = tt + (size_t)bi * nblock_max;
+      uint32_t cur = seg_resume[item];
+      for (uint32_t i = BZ_SLOT; i < n; ++i) {
+        const uint32_t t = T[cur];
+        dst[i] = (uint8_t)t;
+        cur = t >> 8;
+      }
     }
   }
 }
@@ -1754,6 +1771,8 @@ cudaError_t bz2_launch_entropy_literal(const Bz2Entropy &a, const uint32_t *d_li
   return cudaGetLastError();
 }
 
+size_t bz2_slot_bytes_per_block() { return (size_t)(BZ_SPLIT + 2) * BZ_SLOT; }
+
 cudaError_t bz2_launch_ibwt(const Bz2Ibwt &a, cudaStream_t s) {
   if (a.n_chain == 0) return cudaSuccess;
   const BzChain *chain = reinterpret_cast<const BzChain *>(a.chain);
@@ -1774,12 +1793,12 @@ cudaError_t bz2_launch_ibwt(const Bz2Ibwt &a, cudaStream_t s) {
     if (e != cudaSuccess) return e;
   }
   const unsigned g3 = (unsigned)std::min<uint64_t>(((uint64_t)a.n_chain * (BZ_SPLIT + 2) + 255) / 256, 148u * 8u);
-  k_bz2_walk_len<<<g3, 256, 0, s>>>(chain, a.n_chain, a.tt, a.nblock_max, a.seg_len, a.seg_next, a.walk_ctr);
+  k_bz2_walk_len<<<g3, 256, 0, s>>>(chain, a.n_chain, a.tt, a.nblock_max, a.seg_len, a.seg_next, a.seg_resume, a.slots, a.walk_ctr);
   count_launch();
   k_bz2_walk_order<<<a.n_chain, 128, 0, s>>>(chain, a.n_chain, a.tt, a.nblock_max, a.seg_len, a.seg_next,
                                                          a.seg_off, a.irregular, a.cycle_len);
   count_launch();
-  k_bz2_walk_emit<<<g3, 256, 0, s>>>(chain, a.n_chain, a.tt, a.nblock_max, a.seg_len, a.seg_off, a.raw, a.walk_ctr + 1);
+  k_bz2_walk_emit<<<g3, 256, 0, s>>>(chain, a.n_chain, a.tt, a.nblock_max, a.seg_len, a.seg_off, a.seg_resume, a.slots, a.raw);
   count_launch();
   k_bz2_periodic_fill<<<dim3(64, a.n_chain), 256, 0, s>>>(chain, a.cycle_len, a.nblock_max, a.raw);
   count_launch();
@@ -1820,6 +1839,8 @@ cudaError_t bz2_launch_ibwt_group(const Bz2Ibwt &a, uint32_t lo, uint32_t hi, cu
   g.seg_len = a.seg_len + (size_t)lo * (BZ_SPLIT + 2);
   g.seg_next = a.seg_next + (size_t)lo * (BZ_SPLIT + 2);
   g.seg_off = a.seg_off + (size_t)lo * (BZ_SPLIT + 2);
+  g.seg_resume = a.seg_resume + (size_t)lo * (BZ_SPLIT + 2);
+  g.slots = a.slots + (size_t)lo * (BZ_SPLIT + 2) * BZ_SLOT;
   g.irregular = a.irregular + lo;
   g.cycle_len = a.cycle_len + lo;
   g.raw = a.raw + (size_t)lo * a.nblock_max;

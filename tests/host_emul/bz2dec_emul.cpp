@@ -11,6 +11,7 @@
 namespace b200z {
 void count_launch() {}
 }  // namespace b200z
+#define BZ_SLOT_BYTES 64  // K8: most segments of the test blocks overflow their slot, so both halves of the walk are covered
 #include "_gen/bzip2_kernels_emu.inc"
 
 #include <algorithm>
@@ -111,8 +112,11 @@ extern "C" int emu_bzip2_blocks(const uint8_t *in, size_t in_len, uint8_t *out, 
     Bz2Ibwt w;
     w.chain = chain.data(); w.n_chain = nc; w.nblock_max = nblock_max;
     w.rec_val = rec_val.data(); w.rec_pos = rec_pos.data(); w.sym8 = sym8.data(); w.chist = chist.data(); w.tt = tt.data();
-    std::vector<uint32_t> walk_ctr(4, 0u);
+    std::vector<uint32_t> walk_ctr(4, 0u), seg_resume((size_t)nbk * 4098);
+    std::vector<uint8_t> slots((size_t)nbk * bz2_slot_bytes_per_block());
     w.walk_ctr = walk_ctr.data();
+    w.seg_resume = seg_resume.data();
+    w.slots = slots.data();
     w.seg_len = seg_len.data(); w.seg_next = seg_next.data(); w.seg_off = seg_off.data(); w.irregular = irregular.data();
     w.cycle_len = cycle_len.data(); w.raw = raw.data(); w.slice_state = slice_state.data(); w.slice_out = slice_out.data();
     w.block_out = block_out.data(); w.block_off = block_off.data(); w.block_crc = block_crc.data();
