@@ -1995,13 +1995,35 @@ extern "C" int b200z_zip_extract(const uint8_t *z, size_t len, const b200z_zip_e
       }
     }
   }
+  size_t early_to = (size_t)lo;  // output bytes [lo, early_to) are on their way to the host already (copy stream)
   if (!u_idx.empty()) {
     const size_t m = u_idx.size();
     std::vector<uint32_t> r_len(m), r_used(m);
     std::vector<int32_t> r_st(m);
-    rc = run_batch_on_staged(u_in_off.data(), u_in_len.data(), u_out_off.data(), u_cap.data(), r_len.data(), r_st.data(),
-                             r_used.data(), m, (size_t)hi);
-    if (rc) return rc;
+    // A large archive is decoded in chunks of units (in output order), and the bytes of a finished chunk -- with the stored
+    // members that lie between its units -- go to the host on the copy stream while the next chunk is decoded
+    // (B200Z_ZIP_CHUNKS, default 8 from 512 MiB of output on; 1: one batch, one copy at the end).
+    size_t nchunks = (hi - lo) >= ((size_t)512 << 20) ? 8 : 1;
+    if (const char *ce = getenv("B200Z_ZIP_CHUNKS")) nchunks = (size_t)std::max(1, atoi(ce));
+    for (size_t k = 1; k < m && nchunks > 1; ++k)
+      if (u_out_off[k] < u_out_off[k - 1]) nchunks = 1;  // (units are made in output order; if ever not, no early copies)
+    if (nchunks > m) nchunks = m;
+    for (size_t c = 0, k0 = 0; c < nchunks; ++c) {
+      const size_t k1 = m * (c + 1) / nchunks;
+      if (k1 == k0) continue;
+      rc = run_batch_on_staged(u_in_off.data() + k0, u_in_len.data() + k0, u_out_off.data() + k0, u_cap.data() + k0, r_len.data() + k0,
+                               r_st.data() + k0, r_used.data() + k0, k1 - k0, (size_t)hi);
+      if (rc) {
+        if (early_to > lo) cudaStreamSynchronize(g.s_d2h);
+        return rc;
+      }
+      const size_t end = k1 < m ? (size_t)u_out_off[k1] : (size_t)hi;
+      if (nchunks > 1 && end > early_to && end <= hi) {
+        CU(cudaMemcpyAsync(out + early_to, (const uint8_t *)g.d_out.p + early_to, end - early_to, cudaMemcpyDeviceToHost, g.s_d2h));
+        early_to = end;
+      }
+      k0 = k1;
+    }
     for (size_t k = 0; k < m; ++k) {
       const uint32_t i = u_idx[k] & 0x7fffffffu;
       const bool inner = (u_idx[k] & 0x80000000u) != 0;  // a piece that is not the member's last
@@ -2014,8 +2036,10 @@ extern "C" int b200z_zip_extract(const uint8_t *z, size_t len, const b200z_zip_e
     }
   }
   if (any_dev) {
-    CU(cudaMemcpyAsync(out + lo, (const uint8_t *)g.d_out.p + lo, hi - lo, cudaMemcpyDeviceToHost, g.stream));
+    if (hi > early_to)
+      CU(cudaMemcpyAsync(out + early_to, (const uint8_t *)g.d_out.p + early_to, hi - early_to, cudaMemcpyDeviceToHost, g.stream));
     CU(cudaStreamSynchronize(g.stream));
+    if (early_to > lo) CU(cudaStreamSynchronize(g.s_d2h));
   }
   for (size_t i : bz_idx) {  // BZip2Decoder().decodeStream(_rawContent, output) (zip_file.dart:189-192,239-245)
     const b200z_zip_entry &e = entries[i];
