@@ -100,3 +100,24 @@ def test_fast_levels_ring_and_rebase():
     for wbits in (9, 12, 14):
         same(text[:140_000], 1, wbits)
         same(bytes(far[:150_000]), 3, wbits)
+
+
+def test_fast_levels_window_turns():
+    """Levels 1-3 take 32 positions per turn (k_defl_fast_batch: every lane assumes the window positions before its own were
+    entered in the hash chains; a step start whose same-hash predecessor lies inside a long match ends the window).  Data
+    made of short repeats, runs and small alphabets has such predecessors all the time."""
+    import random
+    rng = random.Random(99)
+    for it in range(24):
+        kind, n = it % 4, rng.choice([300, 1000, 5000, 40000])
+        if kind == 0:
+            d = bytes(rng.choice(b"ab") for _ in range(n))
+        elif kind == 1:
+            d = b"".join(bytes([rng.randrange(3)]) * rng.choice([1, 2, 3, 4, 5, 6, 7, 9, 20, 300]) for _ in range(n // 8))
+        elif kind == 2:
+            d = (b"abcabcabd" * 7 + bytes(rng.getrandbits(8) for _ in range(5))) * (n // 70)
+        else:
+            w = [bytes(rng.choice(b"etaoin shrdlu") for _ in range(rng.randrange(2, 9))) for _ in range(40)]
+            d = b"".join(rng.choice(w) for _ in range(n // 5))
+        for level in (1, 2, 3):
+            same(d, level, rng.choice([15, 15, 9, 12]))
