@@ -91,6 +91,7 @@ struct Bz2Ibwt {  // K8 over the validated chain
   unsigned long long out_cap;
   bool any_randomised = false;
   bool carry_off = false;  // block_off[0] already holds the first block's offset (bz2_launch_ibwt_group)
+  int phase = 0;           // 0: all of K8; 1: everything up to the blocks' output offsets; 2: the RLE1 output pass only
 };
 struct BzChainHost {
   uint32_t cand, nblock, n_rec, orig_ptr;

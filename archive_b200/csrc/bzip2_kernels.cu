@@ -1379,7 +1379,20 @@ k_bz2_walk_emit(const BzChain *__restrict__ chain, uint32_t n_chain, const uint3
     uint8_t *dst = raw + (size_t)bi * nblock_max + off;
     const uint8_t *slot = slots + (size_t)item * BZ_SLOT;
     const uint32_t m = n < BZ_SLOT ? n : BZ_SLOT;
-    for (uint32_t i = lane; i < m; i += 32u) dst[i] = slot[i];
+    // bytes up to the first 4-byte boundary of the destination, then whole words (the slot is read through two aligned
+    // words and a funnel shift: its base is aligned, the offset inside it is not), then the rest
+    const uint32_t headb = min(m, (uint32_t)((4u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u));
+    if (lane < headb) dst[lane] = slot[lane];
+    const uint32_t nwords = (m - headb) >> 2;
+    const uint32_t *s32 = reinterpret_cast<const uint32_t *>(slot);
+    uint32_t *d32 = reinterpret_cast<uint32_t *>(dst + headb);
+    const uint32_t sh = (headb & 3u) * 8u;
+    for (uint32_t w = lane; w < nwords; w += 32u) {
+      const uint32_t si = (headb >> 2) + w;  // (headb < 4: 0)
+      d32[w] = sh ? __funnelshift_r(s32[si], s32[si + 1u], sh) : s32[si];  // (no read behind the slot's last word)
+    }
+    const uint32_t done = headb + 4u * nwords;
+    if (done + lane < m) dst[done + lane] = slot[done + lane];
     if (n > BZ_SLOT && lane == 0u) {
       const uint32_t *T = tt + (size_t)bi * nblock_max;
       uint32_t cur = seg_resume[item];
@@ -1777,6 +1790,7 @@ cudaError_t bz2_launch_ibwt(const Bz2Ibwt &a, cudaStream_t s) {
   if (a.n_chain == 0) return cudaSuccess;
   const BzChain *chain = reinterpret_cast<const BzChain *>(a.chain);
   const uint32_t chunks_max = (a.nblock_max + BZ_CHUNK - 1) / BZ_CHUNK;
+  if (a.phase != 2) {
   dim3 g1(64, a.n_chain);
   k_bz2_expand<<<g1, 256, 0, s>>>(chain, a.rec_val, a.rec_pos, a.nblock_max, a.sym8);
   count_launch();
@@ -1812,6 +1826,8 @@ cudaError_t bz2_launch_ibwt(const Bz2Ibwt &a, cudaStream_t s) {
   }
   k_bz2_offsets<<<1, 32, 0, s>>>(a.block_out, a.n_chain, a.block_off, a.carry_off ? 1 : 0);
   count_launch();
+  }
+  if (a.phase == 1) return cudaGetLastError();
   k_bz2_rle_emit<<<a.n_chain, BZ_RLE_THREADS, 0, s>>>(chain, a.raw, a.nblock_max, a.slice_state, a.slice_out, a.block_off,
                                                      a.out_cap, a.out, a.block_crc, a.cycle_len);
   count_launch();
