@@ -1071,7 +1071,7 @@ static int bzip2_decode_impl(const uint8_t *in, size_t in_len, int verify, uint8
     e.nblock_max = nblock_max;
     // block k of this call uses slot k - k_lo of every per-block array
     e.rec_val = A.rec_val; e.rec_pos = A.rec_pos; e.n_rec = A.n_rec; e.nblock = A.nblock; e.orig_ptr = A.orig_ptr;
-    e.randomised = A.rnd; e.end_bit = A.end_bit; e.status = A.status; e.fast_flag = A.fast;
+    e.randomised = A.rnd; e.end_bit = A.end_bit; e.status = A.status; e.fast_flag = A.fast; e.sym8 = A.sym8;
     CU(bz2_launch_entropy(e, g.stream));
     const uint32_t m = k_hi - k_lo;
     auto fetch = [&]() -> int {
@@ -1206,6 +1206,8 @@ static int bzip2_decode_impl(const uint8_t *in, size_t in_len, int verify, uint8
     w.slice_state = A.slice_state; w.slice_out = A.slice_out; w.block_out = A.block_out; w.block_off = A.block_off;
     w.block_crc = A.block_crc; w.out = (uint8_t *)g.d_out.p; w.out_cap = out_cap;
     for (const BzChainHost &ce : chain) w.any_randomised = w.any_randomised || (ce.flags & 1u);
+    w.any_records = false;
+    for (const BzChainHost &ce : chain) w.any_records = w.any_records || ce.n_rec != 0;
     // B200Z_BZ2_GROUPS=n decodes a long chain in n groups, the bytes of a finished group on their way to the host (copy
     // stream) while the next group is decoded.  Measured on a B200 (512 MiB, 597 blocks): 59.4 ms in one piece, 64.5 ms in
     // 4 groups, 73.8 ms in 8 -- the pointer-chasing kernels of K8 are bound by latency, not by the number of blocks, so a

@@ -69,6 +69,7 @@ struct Bz2Entropy {  // K7, one warp per candidate block
   unsigned long long *end_bit;
   int32_t *status;
   uint32_t *fast_flag = nullptr;  // [n_blocks], may be null: 1 = the block was decoded by k_bz2_entropy_fast
+  uint8_t *sym8 = nullptr;        // [n_blocks][nblock_max]: K8's byte array, by candidate slot (the fast kernel writes it)
 };
 struct Bz2Ibwt {  // K8 over the validated chain
   const void *chain;  // BzChain[n_chain] (device)
@@ -91,6 +92,7 @@ struct Bz2Ibwt {  // K8 over the validated chain
   unsigned long long out_cap;
   bool any_randomised = false;
   bool carry_off = false;  // block_off[0] already holds the first block's offset (bz2_launch_ibwt_group)
+  bool any_records = true; // some block of the chain comes with records (the exact kernels'; long runs of the fast one)
   int phase = 0;           // 0: all of K8; 1: everything up to the blocks' output offsets; 2: the RLE1 output pass only
 };
 struct BzChainHost {

@@ -499,7 +499,8 @@ k_bz2_entropy(const uint32_t *__restrict__ words, uint64_t n_bytes, const unsign
 //     lane's permutation (32 lanes gather), which also resolves the references.
 //   * the RECORDER (warp 2) takes the batch's resolved symbols as ONE stream, 32 at a time: RUNA/RUNB runs, record indices
 //     and block positions are a ballot, a 5-step scan and two shuffles away (a run may straddle passes and batches).
-// Output = the exact kernel's records.  Anything that is not an ordinary block -- header errors, an invalid code on the
+// Output = the block's bytes (the L column of the BWT, K8's input; a run longer than 32 bytes as one of the exact kernel's
+// records, which k_bz2_expand turns into bytes).  Anything that is not an ordinary block -- header errors, an invalid code on the
 // parse, a run of more than 21 symbols, a block that overflows, selectors that run out, bits past the end of the input,
 // origPtr out of range -- sets status BZ_REDO and the exact kernel decodes the block again with the reference's verdicts.
 // ---------------------------------------------------------------------------------------------
@@ -507,6 +508,7 @@ k_bz2_entropy(const uint32_t *__restrict__ words, uint64_t n_bytes, const unsign
 constexpr int BZF_W = 256;  // bits of the walker's window
 constexpr int BZF_NT = 96;  // threads: walker, decoder, recorder
 constexpr uint32_t BZF_BADSYM = 0x3ffu;
+constexpr uint32_t BZF_INLINE_RUN = 32u;  // runs up to this length are written as bytes by the recorder, longer ones as a record
 
 struct BzFast {
   uint16_t lut[6][1 << BZ_LUT_BITS];
@@ -542,7 +544,7 @@ k_bz2_entropy_fast(const uint32_t *__restrict__ words, uint64_t n_bytes, const u
                    uint32_t n_blocks, uint32_t nblock_max, uint32_t *__restrict__ rec_val, uint32_t *__restrict__ rec_pos,
                    uint32_t *__restrict__ n_rec, uint32_t *__restrict__ nblock_out, uint32_t *__restrict__ orig_ptr,
                    uint32_t *__restrict__ randomised, unsigned long long *__restrict__ end_bit, int32_t *__restrict__ status,
-                   uint32_t *__restrict__ fast_flag) {
+                   uint32_t *__restrict__ fast_flag, uint8_t *__restrict__ sym8) {
   __shared__ BzFast S;
   const uint32_t b = blockIdx.x;
   if (b >= n_blocks) return;
@@ -584,6 +586,7 @@ k_bz2_entropy_fast(const uint32_t *__restrict__ words, uint64_t n_bytes, const u
   uint32_t st_nrec = 0, st_nblock = 0, st_n = 0, st_v = 0, st_front = 0;
   uint32_t *const rv = rec_val + (size_t)b * nblock_max;
   uint32_t *const rp = rec_pos + (size_t)b * nblock_max;
+  uint8_t *const s8 = sym8 + (size_t)b * nblock_max;  // the block's bytes (L of the BWT), written here directly
   auto ldw = [&](uint64_t i) -> uint32_t { return i < n_words ? __byte_perm(__ldg(words + i), 0, 0x0123) : 0u; };
 
   bool dec_done = false;   // the decoder has met the end-of-block code (in an earlier iteration)
@@ -801,21 +804,27 @@ k_bz2_entropy_fast(const uint32_t *__restrict__ words, uint64_t n_bytes, const u
           const uint32_t pa_q = __shfl_sync(FULLW, pa, q < 0 ? 0 : q);
           const uint32_t fv = __shfl_sync(FULLW, v & 0xffu, q < 0 ? 0 : q);
           const bool hasrun = isnr && before != 0u;
-          const unsigned HR = __ballot_sync(FULLW, hasrun);
+          // The bytes go straight to the block's byte array (what k_bz2_expand made of the records); only a LONG run stays a
+          // record for that kernel (its fill would hold a lane, and the warp with it, for up to 2 M iterations).
+          const uint32_t runval = q < 0 ? st_v + pa : pa - pa_q;  // (a is 0 in a closing lane: pa is the sum over what lies below it)
+          const bool longrun = hasrun && runval > BZF_INLINE_RUN;
+          const unsigned LR = __ballot_sync(FULLW, longrun);
           if (isnr) {
-            const uint32_t runval = q < 0 ? st_v + pa : pa - pa_q;  // (a is 0 here: pa is the sum over what lies below me)
             const uint32_t pos_sym = st_nblock + st_v + pa + (uint32_t)__popc(below);
-            uint32_t r = st_nrec + (uint32_t)__popc(below) + (uint32_t)__popc(HR & ((1u << lane) - 1u));
             if (pos_sym >= nblock_max) {  // (:313-316, :326-329)
               lbad = true;
             } else {
               if (hasrun) {
-                rv[r] = (runval << 8) | S.seq2unseq[q < 0 ? st_front : fv];
-                rp[r] = pos_sym - runval;
-                r++;
+                const uint32_t rb = S.seq2unseq[q < 0 ? st_front : fv];
+                if (longrun) {
+                  const uint32_t r = st_nrec + (uint32_t)__popc(LR & ((1u << lane) - 1u));
+                  rv[r] = (runval << 8) | rb;
+                  rp[r] = pos_sym - runval;
+                } else {
+                  for (uint32_t z = pos_sym - runval; z < pos_sym; ++z) s8[z] = (uint8_t)rb;
+                }
               }
-              rv[r] = (1u << 8) | S.seq2unseq[v & 0xffu];
-              rp[r] = pos_sym;
+              s8[pos_sym] = S.seq2unseq[v & 0xffu];
             }
           }
           const int nvalid = total - base < 32 ? total - base : 32;
@@ -823,7 +832,7 @@ k_bz2_entropy_fast(const uint32_t *__restrict__ words, uint64_t n_bytes, const u
           if (NR) {
             const int ql = 31 - __clz((int)NR);
             const uint32_t pa_ql = __shfl_sync(FULLW, pa, ql);
-            st_nrec += (uint32_t)(__popc(NR) + __popc(HR));
+            st_nrec += (uint32_t)__popc(LR);
             st_nblock += st_v + pa_ql + (uint32_t)__popc(NR);
             st_v = pa_last - pa_ql;
             st_n = (uint32_t)(nvalid - 1 - ql);
@@ -836,11 +845,15 @@ k_bz2_entropy_fast(const uint32_t *__restrict__ words, uint64_t n_bytes, const u
         if (lastb && st_n) {  // the run that the end-of-block code closes (:306-321)
           if (st_n > 21u || st_nblock + st_v > nblock_max) {
             lbad = true;
-          } else if (lane == 0) {
-            rv[st_nrec] = (st_v << 8) | S.seq2unseq[st_front];
-            rp[st_nrec] = st_nblock;
+          } else if (st_v > BZF_INLINE_RUN) {
+            if (lane == 0) {
+              rv[st_nrec] = (st_v << 8) | S.seq2unseq[st_front];
+              rp[st_nrec] = st_nblock;
+            }
+            st_nrec++;
+          } else {
+            if ((uint32_t)lane < st_v) s8[st_nblock + lane] = S.seq2unseq[st_front];
           }
-          st_nrec++;
           st_nblock += st_v;
           st_n = 0;
           st_v = 0;
@@ -1131,7 +1144,7 @@ k_bz2_expand(const BzChain *__restrict__ chain, const uint32_t *__restrict__ rec
              uint32_t nblock_max, uint8_t *__restrict__ sym8) {
   const BzChain c = chain[blockIdx.y];
   const uint32_t *rv = rec_val + (size_t)c.cand * nblock_max, *rp = rec_pos + (size_t)c.cand * nblock_max;
-  uint8_t *dst = sym8 + (size_t)blockIdx.y * nblock_max;
+  uint8_t *dst = sym8 + (size_t)c.cand * nblock_max;  // (by candidate slot: k_bz2_entropy_fast writes its blocks' bytes there itself)
   for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < c.n_rec; r += gridDim.x * blockDim.x) {
     uint32_t v = rv[r], p = rp[r];
     uint8_t ch = (uint8_t)v;
@@ -1152,7 +1165,7 @@ k_bz2_chunk_hist(const BzChain *__restrict__ chain, const uint8_t *__restrict__ 
   for (int i = lane; i < 256; i += 32) h[warp][i] = 0;
   __syncwarp();
   const uint32_t lo = chunk * BZ_CHUNK;
-  const uint8_t *src = sym8 + (size_t)blockIdx.y * nblock_max;
+  const uint8_t *src = sym8 + (size_t)c.cand * nblock_max;
   if (lo < c.nblock) {
     uint32_t hi = min(lo + BZ_CHUNK, c.nblock);
     for (uint32_t i = lo + lane; i < hi; i += 32) atomicAdd(&h[warp][src[i]], 1u);
@@ -1206,7 +1219,7 @@ k_bz2_build_tt(const BzChain *__restrict__ chain, const uint8_t *__restrict__ sy
   const uint32_t *cb = chist + ((size_t)blockIdx.y * chunks_max + chunk) * 256;
   for (int i = lane; i < 256; i += 32) cnt[warp][i] = cb[i];
   __syncwarp();
-  const uint8_t *src = sym8 + (size_t)blockIdx.y * nblock_max;
+  const uint8_t *src = sym8 + (size_t)c.cand * nblock_max;
   uint32_t *T = tt + (size_t)blockIdx.y * nblock_max;
   const uint32_t hi = min(lo + BZ_CHUNK, c.nblock);
   for (uint32_t g = lo; g < hi; g += 32) {
@@ -1766,7 +1779,7 @@ cudaError_t bz2_launch_entropy(const Bz2Entropy &a, cudaStream_t s) {
   if (fast) {
     k_bz2_entropy_fast<<<a.n_blocks, BZF_NT, 0, s>>>(a.words, a.n_bytes, a.blk_bit, a.n_blocks, a.nblock_max, a.rec_val, a.rec_pos,
                                                  a.n_rec, a.nblock, a.orig_ptr, a.randomised, a.end_bit, a.status,
-                                                 a.fast_flag);
+                                                 a.fast_flag, a.sym8);
     count_launch();
   }
   k_bz2_entropy<<<a.n_blocks, 32, sizeof(BzSmem), s>>>(a.words, a.n_bytes, a.blk_bit, a.n_blocks, a.nblock_max, a.rec_val,
@@ -1791,9 +1804,11 @@ cudaError_t bz2_launch_ibwt(const Bz2Ibwt &a, cudaStream_t s) {
   const BzChain *chain = reinterpret_cast<const BzChain *>(a.chain);
   const uint32_t chunks_max = (a.nblock_max + BZ_CHUNK - 1) / BZ_CHUNK;
   if (a.phase != 2) {
-  dim3 g1(64, a.n_chain);
-  k_bz2_expand<<<g1, 256, 0, s>>>(chain, a.rec_val, a.rec_pos, a.nblock_max, a.sym8);
-  count_launch();
+  if (a.any_records) {  // (38 k CTAs that find nothing to do still cost 1.5 ms)
+    dim3 g1(64, a.n_chain);
+    k_bz2_expand<<<g1, 256, 0, s>>>(chain, a.rec_val, a.rec_pos, a.nblock_max, a.sym8);
+    count_launch();
+  }
   dim3 g2((chunks_max + 3) / 4, a.n_chain);
   k_bz2_chunk_hist<<<g2, 128, 0, s>>>(chain, a.sym8, a.nblock_max, chunks_max, a.chist);
   count_launch();
@@ -1849,7 +1864,6 @@ cudaError_t bz2_launch_ibwt_group(const Bz2Ibwt &a, uint32_t lo, uint32_t hi, cu
   Bz2Ibwt g = a;
   g.chain = reinterpret_cast<const BzChain *>(a.chain) + lo;
   g.n_chain = hi - lo;
-  g.sym8 = a.sym8 + (size_t)lo * a.nblock_max;
   g.chist = a.chist + (size_t)lo * chunks_max * 256;
   g.tt = a.tt + (size_t)lo * a.nblock_max;
   g.seg_len = a.seg_len + (size_t)lo * (BZ_SPLIT + 2);

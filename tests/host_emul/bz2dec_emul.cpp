@@ -90,6 +90,7 @@ extern "C" int emu_bzip2_blocks(const uint8_t *in, size_t in_len, uint8_t *out, 
     e.orig_ptr = orig_ptr.data(); e.randomised = rnd.data(); e.end_bit = end_bit.data(); e.status = status.data();
     std::vector<uint32_t> fastf(nb, 0u);
     e.fast_flag = fastf.data();
+    e.sym8 = sym8.data();
     if (bz2_launch_entropy(e, nullptr) != cudaSuccess) return -9;
     g_last_fast = 0;
     for (uint32_t k = 0; k < nb; ++k) g_last_fast += fastf[k];
