@@ -96,6 +96,37 @@ def test_scale_multiblock(a):
     assert len(out) == len(d) and out == d
 
 
+def test_decode_paths_agree(a, monkeypatch):
+    """The ways K7 / K8 can be run give the same bytes and verdicts: the fast entropy kernel (default) or the exact kernel alone
+    (B200Z_BZ2_FAST=0); the RLE1 output pass in one piece or in groups with early copies (B200Z_BZ2_EMIT_GROUPS); the whole
+    of K8 in groups (B200Z_BZ2_GROUPS).  Long runs (records beside the bytes the fast kernel writes itself), a damaged
+    block in the middle and a stream that ends early are in the set."""
+    from archive_b200 import synth
+    text = synth.text(3_000_000, stream=14).tobytes()
+    runs = (b"\0" * 200_000 + text[:150_000] + b"ab" * 90_000 + bytes([9]) * 70_000) * 3
+    z_text, z_runs = bz2.compress(text, 9), bz2.compress(runs, 3)
+    bad = bytearray(bz2.compress(text, 2))
+    bad[len(bad) * 5 // 8] ^= 0x10
+    streams = [z_text, z_runs, bytes(bad), z_text[:len(z_text) * 2 // 3]]
+
+    def run(z):
+        out = a.OutputMemoryStream()
+        try:
+            ok = a.BZip2Decoder().decode_stream(a.InputMemoryStream(z), out, verify=True)
+        except a.DartRangeError:
+            ok = "throw"
+        return ok, out.get_bytes()
+
+    want = [run(z) for z in streams]
+    assert want[0] == (True, text) and want[1] == (True, runs)
+    for env in ({"B200Z_BZ2_FAST": "0"}, {"B200Z_BZ2_EMIT_GROUPS": "1"}, {"B200Z_BZ2_EMIT_GROUPS": "3"}, {"B200Z_BZ2_GROUPS": "2"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        assert [run(z) for z in streams] == want, env
+        for k in env:
+            monkeypatch.delenv(k)
+
+
 def test_randomised_blocks(a):
     """The obsolete randomised-block bit (no encoder has set it since bzip2 0.9.5): the reference decodes such blocks with its
     own variant of the de-randomisation (bzip2_decoder.dart:492-608, SURVEY Q6 -- it differs from libbzip2, so libbz2 is no

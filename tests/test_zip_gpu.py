@@ -149,6 +149,27 @@ def test_large_members_one_batch(a):
         assert zlib.crc32(f.content) == zlib.crc32(txt[i * size:(i + 1) * size].tobytes())
 
 
+def test_extraction_in_chunks_equals_one_batch(a, monkeypatch):
+    """b200z_zip_extract decodes a large archive in chunks of units and copies a finished chunk's bytes (with the stored
+    members that lie between its units) to the host while the next chunk is decoded (B200Z_ZIP_CHUNKS; default: 8 chunks
+    from 512 MiB of output on).  Forced on a small archive with deflated, stored and empty members in between: the same
+    contents as one batch."""
+    from archive_b200 import synth
+    txt = synth.text(14 * 300_000, stream=955).tobytes()
+    buf = io.BytesIO()
+    want = {}
+    with zipfile.ZipFile(buf, "w") as z:
+        for i in range(14):
+            body = txt[i * 300_000:(i + 1) * 300_000] if i % 5 != 4 else b""
+            kind = zipfile.ZIP_STORED if i % 3 == 1 else zipfile.ZIP_DEFLATED
+            z.writestr(f"m{i}", body, compress_type=kind, compresslevel=6)
+            want[f"m{i}"] = body
+    for chunks in ("1", "3", "5", "64"):
+        monkeypatch.setenv("B200Z_ZIP_CHUNKS", chunks)
+        arc = a.ZipDecoder().decode_bytes(buf.getvalue())
+        assert {f.name: f.content for f in arc.files} == want, chunks
+
+
 def test_flush_points_split_members(a):
     """Members written with Z_FULL_FLUSH points are decoded piece by piece (proven by a sizing pass); Z_SYNC_FLUSH points
     look the same but keep the window, so those members must come out right as well (decoded whole), and a flush-point
