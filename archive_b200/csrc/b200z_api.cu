@@ -1616,6 +1616,10 @@ static int deflate_batch_impl(const uint8_t *in_base, const uint64_t *in_off, co
     // the trees and emit the bits of each.  A group is as many members as the token store holds (12 bytes per input
     // byte; B200Z_DEFLATE_TOK_MB, default 49152).
     size_t budget = (size_t)48 << 30;
+    {
+      size_t free_b = 0, total_b = 0;  // (never more than 60 % of what the device has free right now)
+      if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b) budget = std::min(budget, free_b / 10 * 6 + g.d_tok.cap);
+    }
     if (const char *e = getenv("B200Z_DEFLATE_TOK_MB")) budget = std::max<size_t>(1, (size_t)atoll(e)) << 20;
     pre.assign(n_units, DeflFastMember());
     size_t lo = 0;
