@@ -785,8 +785,9 @@ FP_DEV void fp_lz77(uint8_t *smem, uint32_t tid, uint32_t nthr, uint32_t olen, u
 // Measured on a B200 (config 2): the pass takes 253 k clocks per unit against 124 k for the per-byte pass above, the kernel
 // 12.4 ms against 8.7.  The chains of matches that feed each other (depth 42 per unit) are chains of NEAR matches, and here
 // they are walked block after block by one warp -- ~10 dependent rounds of ~770 clocks in each of 32 blocks -- where the
-// per-byte pass lets the chains of different regions advance side by side.  Kept as a build option (parity-green on the
-// emulation tier and on a B200 while it was the default: scripts/gpu_runs/r2_run21.sh).
+// per-byte pass lets the chains of different regions advance side by side.  Kept as a build option (parity-green on a B200
+// while it was the default: scripts/gpu_runs/r2_run21.sh; the emulation tier builds and checks it in
+// tests/test_inflate_fast_emul.py::test_lz77_by_blocks_build_option).
 constexpr uint32_t LZ_BL = 2048u, LZ_WB = LZ_BL / 32u;  // bytes / bitmap words per block
 constexpr uint32_t LZ_NW = NW - 1u;                     // warps 1 .. NW - 1
 constexpr uint32_t LZ_PW = LZ_WB + 10u;                 // pending bitmap: the block and the 258 bytes behind it

@@ -31,6 +31,11 @@ def pytest_configure(config):
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
         subprocess.run(["g++", "-O2", "-g", "-fPIC", "-shared", "-std=c++17", "-I", emul, "-I",
                         os.path.join(ROOT, "archive_b200", "csrc"), src, "-o", so], check=True)
+    # ... and the same kernels with k_inflate_fast's LZ77 pass by blocks (a build option of inflate_fast.cuh, -DFP_LZBLK=1)
+    so = os.path.join(emul, "libinflate_emul_lzblk.so")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
+        subprocess.run(["g++", "-O2", "-g", "-fPIC", "-shared", "-std=c++17", "-DFP_LZBLK=1", "-I", emul, "-I",
+                        os.path.join(ROOT, "archive_b200", "csrc"), src, "-o", so], check=True)
     # the BZip2 encoder kernels, compiled against the CUDA execution-model emulation (tests/host_emul/cuda_emu.h)
     csrc = os.path.join(ROOT, "archive_b200", "csrc")
     src = os.path.join(emul, "bz2enc_emul.cpp")

@@ -205,3 +205,16 @@ def test_seeded_fuzz_small_windows_and_levels():
         units.append(z + bytes(rng.choice([0, 2, 8])))
         caps.append(len(p) + rng.choice([0, 0, 100]))
     check_against_oracle(units, caps, must_finish=20)
+
+
+def test_lz77_by_blocks_build_option(monkeypatch):
+    """inflate_fast.cuh keeps a second LZ77 pass as a build option (-DFP_LZBLK=1: blocks of 2 KiB in order, far matches copy
+    at once, near ones are listed and resolved by one warp; measured slower on a B200, so not the default).  The same units
+    must come out the same through it."""
+    import sys
+    me = sys.modules[__name__]
+    monkeypatch.setattr(me, "_E", C.CDLL(os.path.join(ROOT, "tests", "host_emul", "libinflate_emul_lzblk.so")))
+    test_benchmark_shape_units_all_finish_here()
+    test_block_types_sizes_and_multi_block()
+    test_flush_pieces_end_of_stream_without_final_block()
+    test_distance_before_start_is_left()
