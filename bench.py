@@ -722,7 +722,7 @@ def main():
                else "k_inflate_decode + k_inflate_expand (B200Z_FAST=0)",
                "value": world * U_bytes / (ms_a / args.steps * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": ms_a / args.steps,
                "all_units_ok": bool((d_status.cpu().numpy() == 0).all()),
-               "dram_bytes_per_pass": 1437029000 if other == "1" else 6980970000,
+               "dram_bytes_per_pass": 1431698328 if other == "1" else 6980970000,
                "note": "decode only, same buffers; DRAM bytes from profiles/ (ncu)"}
     finally:
         if was is None:
