@@ -200,3 +200,25 @@ def test_fast_kernel_takes_clean_blocks(monkeypatch):
     monkeypatch.setenv("B200Z_BZ2_FAST", "0")
     assert same(bz2.compress(d1, 1)) == (orc.OK, d1)
     assert orc.emul_bzip2_last_fast() == 0
+
+
+def test_fast_kernel_long_codes_and_deep_lists():
+    """Codes longer than the 10-bit look-up table (the walker's and the decoder's limit / base walk) and move-to-front
+    positions deep in the list (the symbolic lists' lazy initialisation, up to all 64 words): 250 distinct bytes, most of
+    the text a few frequent ones, the rest rare -- the rare list positions get codes of 11 .. 15 bits (694 of the first block's 6 x 188 codes are longer than 10)."""
+    rng = random.Random(77)
+    common = bytes(rng.choice(b"etaoinshr ") for _ in range(64))
+    out = bytearray()
+    while len(out) < 260_000:
+        out += bytes(rng.choice(common) for _ in range(rng.randrange(20, 400)))
+        if rng.random() < 0.7:
+            out += bytes([rng.randrange(250)]) * rng.choice([1, 1, 2, 5])
+    d = bytes(out)
+    for level in (1, 3):
+        z = bz2.compress(d, level)
+        assert same(z) == (orc.OK, d)
+        assert orc.emul_bzip2_last_fast() >= 1
+    # every byte value in turn, again and again: list positions 255 all the time
+    d2 = bytes(range(256)) * 700 + bytes(reversed(range(256))) * 300
+    z2 = bz2.compress(d2, 9)
+    assert same(z2) == (orc.OK, d2) and orc.emul_bzip2_last_fast() == 1
